@@ -1,0 +1,115 @@
+"""GPU parity of the reference-bin search (K4+K5+K6) against the oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+import c_oracle
+import wc_oracle
+from wisecondor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_search(X, bins, r0, r1, k):
+    from wisecondor_b200 import device
+    return device.newref_topk_host(X, bins, r0, r1, k)
+
+
+def _assert_same(idx, dist, oidx, odist):
+    assert idx.shape == oidx.shape and dist.shape == odist.shape
+    bad = np.flatnonzero((idx != oidx).any(axis=1))
+    assert bad.size == 0, "index rows differ: %s (first: %s vs %s)" % (bad[:8], idx[bad[0]][:10], oidx[bad[0]][:10])
+    assert np.array_equal(dist, odist), "distances not bit-identical: max rel %g" % np.max(
+        np.abs(dist - odist) / np.maximum(np.abs(odist), 1e-300))
+
+
+def test_small_genome_vs_numpy_oracle(small_bins):
+    X = synth.corrected_like(small_bins, 40, seed=3)
+    sums = np.cumsum(small_bins)
+    oidx, odist = wc_oracle.get_reference(X, small_bins, sums, 20, 1, 1)
+    idx, dist = _gpu_search(X, small_bins, 0, X.shape[0], 20)
+    _assert_same(idx, dist, oidx, odist)
+
+
+@pytest.mark.parametrize("S,k", [(20, 100), (37, 100), (600, 100), (64, 7), (130, 128), (50, 200)])
+def test_medium_vs_c_oracle(S, k):
+    bins = [int(b) for b in np.maximum(1, np.array(synth.chrom_bins(250000)) // 4)]
+    X = synth.corrected_like(bins, S, seed=11 + S)
+    n = X.shape[0]
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, n, k)
+    idx, dist = _gpu_search(X, bins, 0, n, k)
+    _assert_same(idx, dist, oidx, odist)
+
+
+def test_parts_concatenate_to_whole(small_bins):
+    """README.md:144-145 / wisetools.py:358-361: single- and multi-part runs are identical."""
+    from wisecondor_b200 import wisetools
+    X = synth.corrected_like(small_bins, 30, seed=5)
+    sums = list(np.cumsum(small_bins))
+    whole_i, whole_d = wisetools.getReference(X, small_bins, sums, 25, 1, 1)
+    for parts in (2, 3, 7):
+        pi, pd = [], []
+        for p in range(1, parts + 1):
+            i, d = wisetools.getReference(X, small_bins, sums, 25, p, parts)
+            pi.append(i)
+            pd.append(d)
+        assert np.array_equal(np.concatenate(pi), whole_i)
+        assert np.array_equal(np.concatenate(pd), whole_d)
+
+
+def test_too_few_candidates_leaves_fillers():
+    bins = [30, 4, 3]       # rows of chromosome 1 have only 7 candidates
+    X = synth.corrected_like(bins, 16, seed=2)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, 37, 12)
+    idx, dist = _gpu_search(X, bins, 0, 37, 12)
+    _assert_same(idx, dist, oidx, odist)
+    assert (idx[:30, 7:] == -1).all() and (dist[:30, 7:] == 1e10).all()
+
+
+def test_ties_and_duplicates_fall_back_exactly():
+    """Hundreds of identical bins: every distance ties; the order must be by index (wisetools.py:314-320)."""
+    bins = [40, 700, 60]
+    rng = np.random.default_rng(9)
+    X = synth.corrected_like(bins, 24, seed=4)
+    X[40:740] = X[40]                       # chromosome 2 = 700 copies of one bin
+    X[5] = X[40]                            # and a target on chromosome 1 identical to them (distance 0)
+    X[750] = X[3] + rng.normal(0, 1e-9, 24)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, X.shape[0], 100)
+    idx, dist = _gpu_search(X, bins, 0, X.shape[0], 100)
+    _assert_same(idx, dist, oidx, odist)
+
+
+def test_nan_and_inf_rows_are_never_selected():
+    bins = [50, 60, 40]
+    X = synth.corrected_like(bins, 20, seed=6)
+    X[10, 3] = np.nan
+    X[70, 0] = np.inf
+    X[120] = 1e6                            # distances ~ 2e13 >= 1e10: never inserted (wisetools.py:312-314)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, X.shape[0], 30)
+    idx, dist = _gpu_search(X, bins, 0, X.shape[0], 30)
+    _assert_same(idx, dist, oidx, odist)
+    assert (idx[10] == -1).all() and (idx[70] == -1).all()
+
+
+def test_row_range_and_empty_range(small_bins):
+    X = synth.corrected_like(small_bins, 20, seed=8)
+    n = X.shape[0]
+    oidx, odist = c_oracle.get_reference_rows(X, small_bins, 100, 333, 10)
+    idx, dist = _gpu_search(X, small_bins, 100, 333, 10)
+    _assert_same(idx, dist, oidx, odist)
+    idx, dist = _gpu_search(X, small_bins, 50, 50, 10)
+    assert idx.shape == (0, 10) and dist.shape == (0, 10)
+    assert n == sum(small_bins)
+
+
+def test_config2_shape_sampled_rows():
+    """BASELINE config 2 shape (N=11537, S=600, refsize 100): full GPU search, oracle on sampled row ranges."""
+    bins = synth.chrom_bins(250000)
+    X = synth.corrected_like(bins, 600, seed=4)
+    n = X.shape[0]
+    idx, dist = _gpu_search(X, bins, 0, n, 100)
+    # size-independent properties over every row
+    assert (np.diff(dist, axis=1) >= 0).all()
+    assert (idx >= 0).all() and (idx < n - np.repeat(bins, bins)[:, None]).all()
+    for r0 in (0, 990, 5000, n - 64):
+        oidx, odist = c_oracle.get_reference_rows(X, bins, r0, r0 + 64, 100)
+        _assert_same(idx[r0:r0 + 64], dist[r0:r0 + 64], oidx, odist)

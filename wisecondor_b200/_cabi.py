@@ -1,0 +1,105 @@
+"""ctypes binding of libwisecondor_b200.so (the C ABI declared in include/wisecondor_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that is impossible, or no B200 is
+present when a compute entry point is called, the call raises.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_LIB = None
+
+SYMBOLS = [
+    "wc_create", "wc_destroy", "wc_last_error", "wc_version", "wc_sm_count", "wc_last_phase_ms",
+    "wc_last_counter", "wc_newref_topk", "wc_newref_topk_host", "wc_normalize_mask", "wc_gather_masked",
+    "wc_pca_gram", "wc_pca_finish", "wc_test_prep", "wc_test_batch", "wc_segment_batch",
+]
+
+
+class WcCall(ctypes.Structure):
+    _fields_ = [("sample", ctypes.c_int32), ("chrom", ctypes.c_int32), ("x", ctypes.c_int32),
+                ("y", ctypes.c_int32), ("z", ctypes.c_double)]
+
+
+class WisecondorError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (building first if needed) the shared library and declare the prototypes."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build_library()
+    L = ctypes.CDLL(path)
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    L.wc_create.restype = vp
+    L.wc_create.argtypes = [ci]
+    L.wc_destroy.restype = None
+    L.wc_destroy.argtypes = [vp]
+    L.wc_last_error.restype = ctypes.c_char_p
+    L.wc_version.restype = ctypes.c_char_p
+    L.wc_sm_count.restype = ci
+    L.wc_sm_count.argtypes = [vp]
+    L.wc_last_phase_ms.restype = cd
+    L.wc_last_phase_ms.argtypes = [vp, ci]
+    L.wc_last_counter.restype = ctypes.c_longlong
+    L.wc_last_counter.argtypes = [vp, ci]
+    L.wc_newref_topk.restype = ci
+    L.wc_newref_topk.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, vp]
+    L.wc_newref_topk_host.restype = ci
+    L.wc_newref_topk_host.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp]
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise WisecondorError("wisecondor_b200 error %d: %s" % (rc, lib().wc_last_error().decode()))
+
+
+class Context(object):
+    """One wc_ctx per CUDA device; owns the grow-only device workspaces."""
+
+    def __init__(self, device=0):
+        self._h = lib().wc_create(int(device))
+        if not self._h:
+            raise WisecondorError("wc_create(%d) failed: %s" % (device, lib().wc_last_error().decode()))
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sm_count(self):
+        return lib().wc_sm_count(self._h)
+
+    def phase_ms(self, which):
+        return lib().wc_last_phase_ms(self._h, which)
+
+    def counter(self, which):
+        return lib().wc_last_counter(self._h, which)
+
+    def close(self):
+        if self._h:
+            lib().wc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_CONTEXTS = {}
+
+
+def context(device=0):
+    ctx = _CONTEXTS.get(device)
+    if ctx is None:
+        ctx = _CONTEXTS[device] = Context(device)
+    return ctx

@@ -1,0 +1,113 @@
+// wisecondor_b200 - context, error text and workspace management behind the C ABI.
+#include "wc_common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+
+void wc_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* wc_last_error(void) { return g_err; }
+extern "C" const char* wc_version(void) { return "wisecondor_b200 0.1 (sm_100a)"; }
+
+extern "C" wc_ctx* wc_create(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        wc_set_error("no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        wc_set_error("device %d out of range (have %d)", device, ndev);
+        return nullptr;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        wc_set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        wc_set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (prop.major != 10) {
+        wc_set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    wc_ctx* ctx = new wc_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 2 * WC_NPHASE; ++i) {
+        if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) {
+            wc_set_error("cudaEventCreate failed");
+            delete ctx;
+            return nullptr;
+        }
+    }
+    for (int i = 0; i < WC_NPHASE; ++i) ctx->phase_ms[i] = 0.0;
+    for (int i = 0; i < WC_NCOUNTER; ++i) ctx->counter[i] = 0;
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        ctx->encode_tiled = fn;
+    return ctx;
+}
+
+extern "C" void wc_destroy(wc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < WC_NBUF; ++i)
+        if (ctx->buf[i].p) cudaFree(ctx->buf[i].p);
+    for (int i = 0; i < 2 * WC_NPHASE; ++i) cudaEventDestroy(ctx->ev[i]);
+    delete ctx;
+}
+
+extern "C" int wc_sm_count(const wc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" double wc_last_phase_ms(const wc_ctx* ctx, int which) {
+    if (!ctx || which < 0 || which >= WC_NPHASE) return -1.0;
+    return ctx->phase_ms[which];
+}
+
+extern "C" long long wc_last_counter(const wc_ctx* ctx, int which) {
+    if (!ctx || which < 0 || which >= WC_NCOUNTER) return -1;
+    return ctx->counter[which];
+}
+
+int wc_reserve(wc_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (slot < 0 || slot >= WC_NBUF) {
+        wc_set_error("workspace slot %d out of range", slot);
+        return WC_ERR_INTERNAL;
+    }
+    wc_buf& b = ctx->buf[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.bytes < bytes) {
+        if (b.p) {
+            cudaDeviceSynchronize();
+            cudaFree(b.p);
+            b.p = nullptr;
+            b.bytes = 0;
+        }
+        size_t want = bytes + bytes / 8;   // a little slack so slightly larger follow-up calls do not reallocate
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&b.p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            wc_set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            b.p = nullptr;
+            return WC_ERR_NOMEM;
+        }
+        b.bytes = want;
+    }
+    *out = b.p;
+    return WC_OK;
+}

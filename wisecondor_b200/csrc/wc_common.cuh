@@ -1,0 +1,125 @@
+// wisecondor_b200 - shared device/host helpers (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/wisecondor_b200.h"
+
+// ---- error plumbing -----------------------------------------------------------------------------------
+void wc_set_error(const char* fmt, ...);
+
+#define WC_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            wc_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);   \
+            return WC_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+
+#define WC_CHECK_ARG(cond)                                                                              \
+    do {                                                                                                \
+        if (!(cond)) {                                                                                  \
+            wc_set_error("bad argument: %s (%s:%d)", #cond, __FILE__, __LINE__);                        \
+            return WC_ERR_ARG;                                                                          \
+        }                                                                                               \
+    } while (0)
+
+// ---- context ------------------------------------------------------------------------------------------
+// Grow-only device workspace: the search/test paths ask for named slots; memory is reused across calls.
+struct wc_buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+enum { WC_NBUF = 24, WC_NPHASE = 8, WC_NCOUNTER = 8 };
+
+struct wc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    wc_buf buf[WC_NBUF];
+    cudaEvent_t ev[2 * WC_NPHASE];
+    double phase_ms[WC_NPHASE];
+    long long counter[WC_NCOUNTER];
+    void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)
+};
+
+int wc_reserve(wc_ctx* ctx, int slot, size_t bytes, void** out);
+
+// ---- small PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 2-D TMA tile load, global -> shared, completion on an mbarrier (SASS: UTMALDG).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// Shared-space 64-bit load from a 32-bit shared address.  `volatile` only pins its order against the mbarrier
+// wait at the NVVM level; ptxas still schedules the resulting ld.shared freely among the DMMAs.
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8)   (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_cg_s32(const int* p) {
+    int v;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
