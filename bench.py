@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py - newref reference-bin search throughput (bin-pairs/s) on B200, beside the reference's CPU path.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on
+rank 0.  A *step* is one full pass of the hot path - K4 centre+norms, K5 fp64 DMMA distance tiles with the
+fused streaming top-k, K6 exact re-score/finalise, and for N > 1 the NCCL all-gather of the row shards - over
+a synthetic corrected sample x bin matrix of the named workload, inputs resident in HBM.
+
+  value     whole-job bin-pairs/s = (N^2 - sum N_c^2) / max-over-ranks device time per step
+  roofline  the dominant kernel (K5): 2*S*pairs flops per launch / its CUDA-event duration, against the FP64
+            tensor-core peak measured on this pool (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json carries
+            no FP64 figure)
+  e2e       the same metric through the host-buffer C-ABI call (pinned host -> device copy of the matrix and
+            device -> host copy of the result inside the timed region)
+  cpu_baseline / --impl reference   the reference's own numpy path (oracle/_ref, generated from
+            /root/reference by oracle/make_ref.py) on all host cores, on a bounded slice of target rows;
+            falls back to the C port of the oracle when oracle/_ref did not travel.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from wisecondor_b200 import synth  # noqa: E402
+
+WORKLOADS = {
+    # name: (binsize, samples, refsize, BASELINE.json config it corresponds to)
+    "newref_600x250kb": (250000, 600, 100, "configs[1]"),
+    "newref_600x50kb": (50000, 600, 100, "configs[2]"),
+    "newref_2000x10kb": (10000, 2000, 100, "configs[4]"),
+    "newref_20x250kb": (250000, 20, 100, "configs[0]"),
+}
+DEFAULT_WORKLOAD = "newref_600x50kb"
+METRIC = "newref_bin_pairs_per_s"
+UNIT = "bin-pairs/s"
+
+
+def pairs_for_rows(bins, r0, r1):
+    n = int(sum(bins))
+    per_row = n - np.repeat(np.asarray(bins, dtype=np.int64), bins)
+    return int(per_row[r0:r1].sum())
+
+
+def get_part(partnum, outof, bincount):
+    return int(bincount / float(outof) * partnum), int(bincount / float(outof) * (partnum + 1))
+
+
+def fp64_peak():
+    path = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["fp64_peak_tflops"]), float(d["fp64_sustained_tflops"]), "profiles/fp64_peak_r01.json"
+    except Exception:
+        return 37.2, 37.2, "nominal 148 SM x 64 FMA/clk x 1.965 GHz (no measured file)"
+
+
+# --------------------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active," \
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, power) if p > 250.0] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU reference arm
+# --------------------------------------------------------------------------------------------------------
+def _ref_part_worker(args):
+    """One part of the reference's own getReference, in a worker process (wisecondor.py:47-56 runs parts in a
+    ProcessPoolExecutor the same way)."""
+    path, bins, k, part, parts = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        import wisetools as ref_wisetools
+        X = np.load(path, mmap_mode="r")
+        X = np.asfortranarray(X)            # the layout the reference's arrays have after the prep-npz round trip
+        sums = list(np.cumsum(bins))
+        t0 = time.time()
+        idx, dist = ref_wisetools.getReference(X, bins, sums, k, part, parts)
+        dt = time.time() - t0
+    return idx.shape[0], dt
+
+
+def cpu_reference_run(X, bins, k, steps, warmup, rows_per_core=None, budget_s=20.0):
+    """Times the reference CPU path on all host cores on a bounded slice of target rows.
+    Returns (pairs_per_s, dict describing the run)."""
+    cores = os.cpu_count() or 1
+    n = int(sum(bins))
+    S = X.shape[1]
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "wisetools.py"))
+    if have_ref:
+        import concurrent.futures
+        import tempfile
+        # per-row cost of the numpy path ~ 4.6e-9 s per (candidate, sample) element on one core
+        est_row_s = 4.6e-9 * n * S + 2.2e-6 * n
+        if rows_per_core is None:
+            rows_per_core = int(max(1, min(64, budget_s / max(1, steps + warmup) / est_row_s)))
+        parts = max(cores, n // rows_per_core)
+        tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False)
+        tmp.close()
+        np.save(tmp.name, X)
+        times = []
+        pairs = 0
+        try:
+            with concurrent.futures.ProcessPoolExecutor(max_workers=cores) as ex:
+                for it in range(warmup + steps):
+                    first = 1 + (it * cores) % max(1, parts - cores)
+                    jobs = [(tmp.name, list(bins), k, p, parts) for p in range(first, first + cores)]
+                    res = list(ex.map(_ref_part_worker, jobs))
+                    dt = max(r[1] for r in res)      # parts run concurrently: the step lasts as long as the slowest
+                    if it >= warmup:
+                        times.append(dt)
+                        pr = 0
+                        for p in range(first, first + cores):
+                            a, b = get_part(p - 1, parts, n)
+                            pr += pairs_for_rows(bins, a, b)
+                        pairs += pr
+        finally:
+            os.unlink(tmp.name)
+        total = float(sum(times))
+        desc = {"kind": "reference", "cores": cores,
+                "sample": "oracle/_ref wisetools.getReference, %d parts of %d (about %d target rows each) per step on "
+                          "%d worker processes, %d steps; whole-matrix candidates, S=%d" %
+                          (cores, parts, n // parts, cores, steps, S)}
+        return pairs / total, total / max(1, steps), desc
+    # C port of the oracle (pthreads, all cores)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    est_row_s = 1.1e-9 * n * S
+    rows = int(max(cores, min(n, budget_s / max(1, steps + warmup) / est_row_s * cores)))
+    times = []
+    pairs = 0
+    for it in range(warmup + steps):
+        r0 = (it * rows) % max(1, n - rows)
+        t0 = time.time()
+        c_oracle.get_reference_rows(X, bins, r0, r0 + rows, k, cores)
+        dt = time.time() - t0
+        if it >= warmup:
+            times.append(dt)
+            pairs += pairs_for_rows(bins, r0, r0 + rows)
+    total = float(sum(times))
+    desc = {"kind": "port", "cores": cores,
+            "sample": "oracle/wc_oracle.c (C port, pthreads) on %d target rows per step, %d steps; oracle/_ref absent" %
+                      (rows, steps)}
+    return pairs / total, total / max(1, steps), desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    binsize, S, k, cfg = WORKLOADS[args.workload]
+    bins = synth.chrom_bins(binsize)
+    X = synth.corrected_like(bins, S, seed=4)
+    value, s_per_step, desc = cpu_reference_run(X, bins, k, max(1, args.steps), max(0, args.warmup),
+                                                budget_s=args.cpu_budget * 4)
+    desc = dict(desc)
+    desc["value"] = value
+    desc["unit"] = UNIT
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "baseline_config": cfg, "bins": int(sum(bins)), "samples": S,
+                   "refsize": k, "note": "each step is a bounded slice of target rows; throughput is per bin pair"},
+        "cpu_baseline": desc,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work in the default run")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from wisecondor_b200 import device
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    binsize, S, k, cfg = WORKLOADS[args.workload]
+    bins = synth.chrom_bins(binsize)
+    n = int(sum(bins))
+    X_host_np = synth.corrected_like(bins, S, seed=4)
+    X_pinned = torch.from_numpy(X_host_np).pin_memory()
+    X = X_pinned.to(dev, non_blocking=False)
+    r0, r1 = get_part(rank, world, n)
+    rows = r1 - r0
+    rows_max = max(get_part(p, world, n)[1] - get_part(p, world, n)[0] for p in range(world))
+    out_idx = torch.empty((rows_max, k), dtype=torch.int32, device=dev)
+    out_dist = torch.empty((rows_max, k), dtype=torch.float64, device=dev)
+    if world > 1:
+        all_idx = torch.empty((world * rows_max, k), dtype=torch.int32, device=dev)
+        all_dist = torch.empty((world * rows_max, k), dtype=torch.float64, device=dev)
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # 512 MiB > 126 MB L2
+
+    def step():
+        device.newref_topk(X, bins, r0, r1, k, out_idx[:rows], out_dist[:rows])
+        if world > 1:
+            dist.all_gather_into_tensor(all_idx, out_idx)
+            dist.all_gather_into_tensor(all_dist, out_dist)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k5_ms, k4_ms, k6_ms, launches = [], [], [], 0
+    barrier()
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        flush.fill_(i)                       # L2 flush between timed iterations (outside the event pairs)
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+        st = device.last_search_stats(local)
+        k4_ms.append(st["center_norms_ms"])
+        k5_ms.append(st["dist_topk_ms"])
+        k6_ms.append(st["finalize_ms"] + st["exhaustive_ms"])
+        launches += int(st["launches"])
+    barrier()
+    t_wall = time.time() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    pairs_total = pairs_for_rows(bins, 0, n)
+    value = pairs_total / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call --------------------------------------------------
+    e2e_steps = max(2, min(args.steps, 5))
+    device.newref_topk_host(X_pinned.numpy(), bins, r0, r1, k, device=local)
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        hi, hd = device.newref_topk_host(X_pinned.numpy(), bins, r0, r1, k, device=local)
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.time() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = {"value": pairs_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n) * S * 8,
+           "d2h_bytes_per_step": int(rows) * k * 12, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "api": "wisecondor_b200.device.newref_topk_host -> wc_newref_topk_host (pinned host buffers)"}
+
+    if rank == 0:
+        peak, sustained, peak_src = fp64_peak()
+        k5 = float(np.mean(k5_ms))
+        flops = 2.0 * S * pairs_for_rows(bins, r0, r1)
+        achieved = flops / (k5 * 1e-3) / 1e12
+        # a kernel timed inside a long step under the power cap -> the sustained figure; short steps -> burst
+        use_peak = sustained if ms_per_step > 50.0 else peak
+        roofline = {"bound": "tensor", "kernel": "wc_dist_topk_kernel (K5, fp64 DMMA.8x8x4 + TMA)",
+                    "achieved": achieved, "peak": use_peak, "unit": "TFLOP/s", "frac": achieved / use_peak,
+                    "traffic": None, "flops_per_launch": flops, "kernel_ms": k5,
+                    "peak_source": "measured FP64 tensor (DMMA) peak of this pool, %s (%s figure); "
+                                   "MEASURED_PEAKS.json has no FP64 entry" %
+                                   (peak_src, "sustained" if use_peak == sustained else "burst"),
+                    "share_of_step": k5 / ms_per_step}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "baseline_config": cfg, "bins": n, "samples": S, "refsize": k,
+                       "bin_pairs": pairs_total, "parallelism": "rows sharded by getPart over %d GPU(s)%s" %
+                       (world, " + NCCL all-gather" if world > 1 else ""),
+                       "l2": "512 MiB buffer written between timed iterations (L2 flush)"},
+            "phases_ms": {"center_norms": float(np.mean(k4_ms)), "dist_topk": k5, "finalize": float(np.mean(k6_ms))},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, s_per_step, desc = cpu_reference_run(X_host_np, bins, k, 1, 0, budget_s=args.cpu_budget)
+            desc = dict(desc)
+            desc["value"] = v
+            desc["unit"] = UNIT
+            line["cpu_baseline"] = desc
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -60,6 +60,15 @@ double wc_last_phase_ms(const wc_ctx* ctx, int which);
  * fallback, 2 = candidate entries emitted by K5, 3 = tiles computed, 4 = CTAs launched for K5. */
 long long wc_last_counter(const wc_ctx* ctx, int which);
 
+/* Debug aid: enable (1) / disable (0) per-CTA cycle counters in the distance kernel and copy the counters of the
+ * most recent search to out_h (grid x 8 int64: total, wait-on-TMA, epilogue, prune, tiles, prunes, emitted by
+ * thread 0, reserved).  Returns the number of CTAs copied, or a negative wc_status. */
+int wc_debug_profile(wc_ctx* ctx, int enable, long long* out_h, int max_ctas);
+
+/* Tuning knob for experiments: key "k5_lag" = chunks (0..4) by which half of the distance kernel's MMA warps
+ * trail the other half.  Results never depend on it. */
+int wc_set_option(wc_ctx* ctx, const char* key, double value);
+
 /* ---- newref: reference-bin search --------------------------------------------------------------------- */
 /* Replaces getReference + getRefForBins (wisetools.py:364-398, 298-325) for target rows
  * [row_begin, row_end) - the rows wisetools.getPart (wisetools.py:358-361) hands one part.
@@ -79,48 +88,6 @@ int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int S, const i
  * (wisecondor.py:111-132) would bind. */
 int wc_newref_topk_host(wc_ctx* ctx, const double* corrected_h, int N, int S, const int* chrom_bins_h,
                         int nchrom, int row_begin, int row_end, int refsize, int32_t* idx_h, double* dist_h);
-
-/* ---- newref: normalise, mask, PCA --------------------------------------------------------------------- */
-/* Replaces toNumpyArray's arithmetic (wisetools.py:255-261): counts_d is S x Nraw int32 (sample-major, the
- * stacked chr1..22 arrays).  Writes sample totals, the nonzero-bin mask (1 byte per raw bin) and returns the
- * masked bin count through N_out.  Synchronous. */
-int wc_normalize_mask(wc_ctx* ctx, const int32_t* counts_d, int S, int Nraw, double* totals_d,
-                      uint8_t* mask_d, int* N_out, void* stream);
-/* Builds the masked, normalised matrix in both layouts: Xs_d (S x N, sample-major) and, when Xb_d != NULL,
- * Xb_d (N x S, bin-major) - `maskedData` (wisetools.py:261). */
-int wc_gather_masked(wc_ctx* ctx, const int32_t* counts_d, int S, int Nraw, const double* totals_d,
-                     const uint8_t* mask_d, int N, double* Xs_d, double* Xb_d, void* stream);
-/* Replaces trainPCA (wisetools.py:89-101): per-bin mean over samples, Gram matrix of the centred data
- * (S x S, fp64 DMMA tiles), eigen-decomposition of the S x S Gram on the host (LAPACK-free Jacobi is not used:
- * the caller supplies the top-ncomp eigenvectors through wc_pca_finish), projection and residual.
- * Step 1: mean_d[N] and gram_d[S x S] from Xs_d (S x N). */
-int wc_pca_gram(wc_ctx* ctx, const double* Xs_d, int S, int N, double* mean_d, double* gram_d, void* stream);
-/* Step 2: given the top-ncomp unit eigenvectors U (ncomp x S, row-major) and eigenvalues of gram, compute
- * components_d (ncomp x N, sign-normalised like sklearn's svd_flip), and corrected_d (N x S bin-major) =
- * X / (mean + (Xc V^T) V).  */
-int wc_pca_finish(wc_ctx* ctx, const double* Xs_d, int S, int N, const double* mean_d, const double* U_h,
-                  const double* eigval_h, int ncomp, double* components_d, double* corrected_d, void* stream);
-
-/* ---- test: sample prep, z-scores, segmentation --------------------------------------------------------- */
-/* Replaces toNumpyRefFormat + applyPCA (wisetools.py:267-278, 104-113) for a batch: counts_d is B x Nraw int32
- * already padded/truncated to the reference's chromosome sizes; out T_d is N x ldB float64 ([bin][sample]). */
-int wc_test_prep(wc_ctx* ctx, const int32_t* counts_d, int B, int Nraw, const uint8_t* mask_d, int N,
-                 const double* mean_d, const double* components_d, int ncomp, double* T_d, int ldB, void* stream);
-/* Replaces repeatTest / trySample (wisetools.py:407-448) for a batch of B samples laid out [bin][sample].
- *   ref_idx_d  global masked-bin index of every kept reference bin (those with distance < cutoff), CSR
- *   ref_off_d  N+1 offsets into ref_idx_d
- *   Z_d, R_d   N x ldB outputs; refsizes_d N x ldB int32; asdef_d B (average reference sigma, wisetools.py:435)
- *   work_d     2 * N * ldB doubles of scratch (the evolving testCopy, double-buffered) */
-int wc_test_batch(wc_ctx* ctx, const double* T_d, int N, int B, int ldB, const int32_t* ref_idx_d,
-                  const int32_t* ref_off_d, double z_threshold, int repeats, double* Z_d, double* R_d,
-                  int32_t* refsizes_d, double* asdef_d, double* work_d, void* stream);
-/* Replaces fillTri + TriArr.segmentTri (wisetools.py:466-472, triarray.py:59-84) for a batch: Zc_d holds, per
- * sample, the cleaned z-scores of the requested chromosomes back to back; off_d is B x (nchrom+1) offsets into
- * Zc_d.  Writes cwz_d (B x nchrom chromosome-wide z), up to max_calls wc_call records (device) and the number
- * found (device int; > max_calls means truncated). */
-int wc_segment_batch(wc_ctx* ctx, const double* Zc_d, const int64_t* off_d, int B, int nchrom,
-                     double z_threshold, int min_search, double* cwz_d, wc_call* calls_d, int* ncalls_d,
-                     int max_calls, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,8 +12,7 @@ _LIB = None
 
 SYMBOLS = [
     "wc_create", "wc_destroy", "wc_last_error", "wc_version", "wc_sm_count", "wc_last_phase_ms",
-    "wc_last_counter", "wc_newref_topk", "wc_newref_topk_host", "wc_normalize_mask", "wc_gather_masked",
-    "wc_pca_gram", "wc_pca_finish", "wc_test_prep", "wc_test_batch", "wc_segment_batch",
+    "wc_last_counter", "wc_newref_topk", "wc_newref_topk_host", "wc_debug_profile", "wc_set_option",
 ]
 
 
@@ -52,6 +51,10 @@ def lib():
     L.wc_newref_topk.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, vp]
     L.wc_newref_topk_host.restype = ci
     L.wc_newref_topk_host.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp]
+    L.wc_set_option.restype = ci
+    L.wc_set_option.argtypes = [vp, ctypes.c_char_p, cd]
+    L.wc_debug_profile.restype = ci
+    L.wc_debug_profile.argtypes = [vp, ci, vp, ci]
     _LIB = L
     return L
 

@@ -47,6 +47,10 @@ struct wc_ctx {
     cudaEvent_t ev[2 * WC_NPHASE];
     double phase_ms[WC_NPHASE];
     long long counter[WC_NCOUNTER];
+    int k5_dbg = 0;                 // timing experiments only (results invalid when non-zero)
+    int k5_stages = 0;              // 0 = automatic TMA ring depth
+    int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones
+    int debug_profile = 0;          // K5 writes per-CTA cycle counters when set (wc_debug_profile)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)
 };
 
@@ -82,6 +86,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe of a phase (mbarrier.test_wait never suspends the thread).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
@@ -103,6 +121,9 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ void lds_v2f64(uint32_t addr, double& v0, double& v1) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(addr));
 }
 // FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8)   (SASS: DMMA.8x8x4)
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {

@@ -21,30 +21,33 @@ namespace {
 constexpr int BM = 128;             // target rows per CTA tile
 constexpr int BN = 128;             // candidate columns per CTA tile
 constexpr int BK = 16;              // samples per pipeline stage (16 doubles = one 128-byte swizzle row)
-constexpr int STAGES = 4;
-constexpr int CONSUMER_WARPS = 8;   // 4 (rows) x 2 (cols) warps, each a 32 x 64 sub-tile
+constexpr int CONSUMER_WARPS = 8;   // each warp owns 16 rows x 128 cols of the tile: no cross-warp state
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
+constexpr int WROWS = BM / CONSUMER_WARPS;   // 16 rows per warp
 constexpr int PRODUCER_WARPS = 4;   // one warp group; only warp 0 lane 0 issues TMA, the group donates registers
 constexpr int TOPK_THREADS = CONSUMER_THREADS + PRODUCER_WARPS * 32;
 constexpr int TILE_BYTES = BM * BK * 8;               // 16 KiB per operand per stage
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;
 constexpr int HIST_BINS = 256;
-constexpr int FIN_THREADS = 128;
-constexpr int FIN_MAX = 2048;       // candidates a finalize CTA can hold
-constexpr int FIN_SHORT = 256;      // exact re-score capacity (2 passes of 128)
+constexpr int FIN_THREADS = 128;    // one thread per shortlisted candidate during the exact re-score
+constexpr int FIN_CHUNK = 32;       // samples staged per pipeline step of the re-score
+constexpr int FIN_LD = FIN_CHUNK + 1;   // padded tile row (bank-conflict free per-thread row walks)
 constexpr int EXH_THREADS = 256;
 
-struct TopkSmem {
-    alignas(1024) unsigned char tiles[STAGES][STAGE_BYTES];
-    uint64_t full[STAGES];
-    uint64_t empty[STAGES];
+constexpr int MAX_STAGES = 6;
+// Shared memory of K5: [nstages x STAGE_BYTES operand ring, 1024-byte aligned][TopkState][8 warps x cap x 12 B
+// prune scratch].
+struct TopkState {
+    uint64_t full[MAX_STAGES];
+    uint64_t empty[MAX_STAGES];
+    uint64_t gate;       // opened by the leading warps after `lag` chunks; the lagging warps start behind it
     double tau[BM];      // emission threshold per row (includes the error margin); NaN = row inactive
     double nrm[BM];      // n_i
     int cs[BM];          // excluded column range [cs, ce) = the row's own chromosome
     int ce[BM];
     int cnt[BM];         // entries in the row's candidate buffer
     int flag[BM];        // 1 = buffer could not be bounded -> exhaustive fallback
-    int hist[CONSUMER_WARPS][HIST_BINS];
+    alignas(16) double ncol[CONSUMER_WARPS][BN];   // per-warp prefetched (halved) column norms of the current tile
 };
 
 struct TopkArgs {
@@ -54,7 +57,7 @@ struct TopkArgs {
     int N;
     int row_begin, row_end;
     int nkc;                 // k chunks of BK
-    int nsteps_last;         // k4 steps in the last chunk (1..4)
+    int ndsteps_last;        // 8-sample double-steps in the last chunk (1..2)
     const int* rb_tile_prefix;   // [nrb+1] valid tiles before row block rb
     const int* rb_skip_lo;       // [nrb] first skipped column tile (own chromosome interior)
     const int* rb_skip_n;        // [nrb] number of skipped column tiles
@@ -69,6 +72,11 @@ struct TopkArgs {
     int k;
     double mcoef;                // margin(v) = mcoef * (n_i + |v|)
     double tau_init;
+    long long* prof;             // optional [grid][8] per-CTA cycle counters (consumer warp 0), or nullptr
+    int lag;                     // chunks by which warps 4-7 trail warps 0-3 (0 = all in phase)
+    int nstages;                 // depth of the TMA ring (3..MAX_STAGES)
+    int dbg;                     // timing experiments only: 1 = skip emission, 2 = skip the whole filter
+    long long* trace;            // optional debug timeline of CTA 0: [2 warps (0 and 4)][64 tiles][4 stamps]
 };
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -81,76 +89,96 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ int bucket_of(double d, double mn, float scale) {
     int b = (int)((float)(d - mn) * scale);
     return b < 0 ? 0 : (b > HIST_BINS - 1 ? HIST_BINS - 1 : b);
 }
 
-// Warp-collective prune of one row's candidate buffer: keep every entry <= v* + margin, where v* is the largest
-// entry of the histogram bucket that holds the k-th smallest.  The kept set contains the k smallest, so v* is a
-// valid upper bound of the row's final k-th smallest distance.
-__device__ void prune_row(double* cd, int* cj, int n, int k, double nrm, double mcoef, int* hist, int lane,
-                          double* tau_out, int* n_out) {
-    double mn = INFINITY, mx = -INFINITY;
-    for (int i = lane; i < n; i += 32) {
-        double d = ld_cg_f64(cd + i);
-        mn = fmin(mn, d);
-        mx = fmax(mx, d);
+// Warp-collective prune of one row's candidate buffer.  The buffer is copied once into a warp-private shared
+// scratch (independent L2 loads); a value-space bisection finds a cut v with k <= #{d <= v} <= k + slack; v* = the
+// largest entry <= v is then a valid upper bound of the row's final k-th smallest distance, and everything
+// <= v* + margin is written back compacted.  Plain loops on purpose: this code runs a few times per tile somewhere
+// in the CTA and must not evict the main loop from the instruction cache.
+template <int PER_LANE>   // cap / 32: every load of the buffer is issued before the first one is consumed
+__device__ __noinline__ void prune_row(double* cd, int* cj, int n, int k, double nrm, double mcoef, int lane,
+                                       double* sd, int* sj, double* tau_out, int* n_out, long long* ptr) {
+    const long long pt0 = clock64();
+    double lo = INFINITY, hi = -INFINITY;
+    {
+        double d[PER_LANE];
+        int j[PER_LANE];
+#pragma unroll
+        for (int t = 0; t < PER_LANE; ++t) {
+            const int i = t * 32 + lane;
+            d[t] = i < n ? __ldcg(cd + i) : INFINITY;
+            j[t] = i < n ? __ldcg(cj + i) : 0;
+        }
+#pragma unroll
+        for (int t = 0; t < PER_LANE; ++t) {
+            const int i = t * 32 + lane;
+            if (i < n) {
+                sd[i] = d[t];
+                sj[i] = j[t];
+                lo = fmin(lo, d[t]);
+                hi = fmax(hi, d[t]);
+            }
+        }
     }
-    mn = warp_min(mn);
-    mx = warp_max(mx);
-    float scale = (mx > mn) ? (float)(HIST_BINS - 1) / (float)(mx - mn) : 0.0f;
-    for (int b = lane; b < HIST_BINS; b += 32) hist[b] = 0;
+    lo = warp_min(lo);
+    hi = warp_max(hi);
     __syncwarp();
-    for (int i = lane; i < n; i += 32) atomicAdd(&hist[bucket_of(ld_cg_f64(cd + i), mn, scale)], 1);
-    __syncwarp();
-    int c[HIST_BINS / 32], sum = 0;
+    const long long pt1 = clock64();
+    // Bisect for a cut with k <= count(<= cut) <= k_hi (about 4 rounds on real data).
+    const int k_hi = k + 24;
+    double blo = lo, bhi = hi, cut = hi;
+    int c_hi = n;
+    int nit = 0;
+    for (int it = 0; it < 48 && c_hi > k_hi; ++it) {
+        ++nit;
+        const double mid = blo + 0.5 * (bhi - blo);
+        if (!(mid > blo && mid < bhi)) break;                      // bracket exhausted (ties): keep the current cut
+        int c = 0;
+#pragma unroll 4
+        for (int i = lane; i < n; i += 32) c += sd[i] <= mid ? 1 : 0;
 #pragma unroll
-    for (int t = 0; t < HIST_BINS / 32; ++t) {
-        c[t] = hist[lane * (HIST_BINS / 32) + t];
-        sum += c[t];
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (c >= k) { bhi = mid; c_hi = c; cut = mid; } else { blo = mid; }
     }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    int run = incl - sum, bl = -1;
-#pragma unroll
-    for (int t = 0; t < HIST_BINS / 32; ++t) {
-        run += c[t];
-        if (bl < 0 && run >= k) bl = lane * (HIST_BINS / 32) + t;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, bl >= 0);
-    int bstar = HIST_BINS - 1;
-    if (m) bstar = __shfl_sync(0xffffffffu, bl, __ffs(m) - 1);
+    const long long pt2 = clock64();
     double vstar = -INFINITY;
+#pragma unroll 4
     for (int i = lane; i < n; i += 32) {
-        double d = ld_cg_f64(cd + i);
-        if (bucket_of(d, mn, scale) <= bstar) vstar = fmax(vstar, d);
+        const double d = sd[i];
+        if (d <= cut) vstar = fmax(vstar, d);
     }
     vstar = warp_max(vstar);
-    double tau = vstar + mcoef * (nrm + fabs(vstar));
+    const double tau = vstar + mcoef * (nrm + fabs(vstar));
+    const long long pt3 = clock64();
     int w = 0;
     for (int base = 0; base < n; base += 32) {
-        int i = base + lane;
-        double d = 0.0;
-        int j = 0;
-        bool keep = false;
-        if (i < n) {
-            d = ld_cg_f64(cd + i);
-            j = ld_cg_s32(cj + i);
-            keep = d <= tau;
-        }
-        unsigned km = __ballot_sync(0xffffffffu, keep);
+        const int i = base + lane;
+        const bool keep = i < n && sd[i] <= tau;
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
         if (keep) {
-            int pos = w + __popc(km & ((1u << lane) - 1u));
-            cd[pos] = d;
-            cj[pos] = j;
+            const int pos = w + __popc(km & ((1u << lane) - 1u));
+            cd[pos] = sd[i];
+            cj[pos] = sj[i];
         }
         w += __popc(km);
-        __syncwarp();
+    }
+    __syncwarp();
+    if (ptr != nullptr && lane == 0) {
+        ptr[0] = pt1 - pt0; ptr[1] = pt2 - pt1; ptr[2] = pt3 - pt2; ptr[3] = clock64() - pt3;
+        ptr[4] = nit; ptr[5] = n; ptr[6] = w; ptr[7] = 0;
     }
     *tau_out = tau;
     *n_out = w;
@@ -162,8 +190,11 @@ __device__ void prune_row(double* cd, int* cj, int n, int k, double nrm, double 
 __global__ void __launch_bounds__(TOPK_THREADS, 1)
 wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    TopkSmem& sm = *reinterpret_cast<TopkSmem*>(smem_raw);
     if (smem_u32(smem_raw) & 1023u) __trap();   // SWIZZLE_128B tiles need a 1024-byte aligned base
+    const int STAGES = a.nstages;
+    unsigned char* tiles = smem_raw;
+    TopkState& sm = *reinterpret_cast<TopkState*>(smem_raw + (size_t)STAGES * STAGE_BYTES);
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(&sm + 1);
     const int tid = threadIdx.x;
     const int warp_all = tid >> 5, lane = tid & 31;
     const int warp = warp_all - PRODUCER_WARPS;     // consumer warp index (negative in the producer group)
@@ -173,6 +204,7 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], CONSUMER_WARPS);
         }
+        mbar_init(&sm.gate, CONSUMER_WARPS / 2);
         mbar_fence_init();
         tma_prefetch_desc(&tmap);
     }
@@ -209,8 +241,8 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                 for (int kc = 0; kc < a.nkc; ++kc) {
                     mbar_wait(&sm.empty[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&sm.full[stage], STAGE_BYTES);
-                    tma_load_2d(sm.tiles[stage], &tmap, kc * BK, row0, &sm.full[stage]);
-                    tma_load_2d(sm.tiles[stage] + TILE_BYTES, &tmap, kc * BK, col0, &sm.full[stage]);
+                    tma_load_2d(tiles + (size_t)stage * STAGE_BYTES, &tmap, kc * BK, row0, &sm.full[stage]);
+                    tma_load_2d(tiles + (size_t)stage * STAGE_BYTES + TILE_BYTES, &tmap, kc * BK, col0, &sm.full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -218,145 +250,262 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
         return;
     }
 
-    // ===== consumers: 8 warps, warp tile 32 rows x 64 cols = 4 x 8 DMMA tiles =====
+    // ===== consumers: 8 warps; warp w owns rows [16w, 16w+16) x all 128 columns = 2 x 16 DMMA tiles =====
+    // Rows are warp-private, so the threshold / candidate-count state needs no CTA-level barrier: each warp runs
+    // its own epilogue and prune and drifts from the others by at most the depth of the TMA ring.
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int ctid = tid - PRODUCER_WARPS * 32;     // 0..255
-    const int g = lane >> 2, q4 = lane & 3;
-    const int wm = warp >> 1, wn = warp & 1;
-    const uint32_t a_off = (uint32_t)(wm * 32 + g) * 128u;
-    const uint32_t b_off = (uint32_t)TILE_BYTES + (uint32_t)(wn * 64 + g) * 128u;
-    uint32_t sw[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) sw[s] = (uint32_t)((((2 * s + (q4 >> 1)) ^ g) << 4) | ((q4 & 1) << 3));
 
-    const uint32_t tiles_u32 = smem_u32(&sm.tiles[0][0]);
+    // Fragment <-> tile mapping.  A DMMA.8x8x4 lane (g = lane/4, q = lane%4) supplies A[g][q] and B[q][g].  Rows of an
+    // 8-row group are visited in the order perm(g) = (g&1)*4 + (g>>1) and each lane fetches 16 bytes = two
+    // consecutive samples (k = 8h+2q, 8h+2q+1), used as the q-th sample of two successive MMAs.  Both operands
+    // use the same sample permutation, so the dot products are unchanged; with the TMA 128-byte swizzle
+    // (16-byte chunk index ^= row & 7) every quarter-warp of an LDS.128 then touches 128 distinct bytes of
+    // banks: no conflicts.
+    const int g = lane >> 2, q4 = lane & 3;
+    const int pg = ((g & 1) << 2) | (g >> 1);
+    const uint32_t a_off = (uint32_t)(warp * WROWS + pg) * 128u;
+    const uint32_t b_off = (uint32_t)TILE_BYTES + (uint32_t)pg * 128u;
+    uint32_t sw[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) sw[h] = (uint32_t)(((4 * h + q4) ^ pg) << 4);
+
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    const size_t scratch_per_warp = (size_t)a.cap * 12 > 8192 ? (size_t)a.cap * 12 : 8192;
+    double* w_sd = reinterpret_cast<double*>(scratch + (size_t)warp * scratch_per_warp);
+    int* w_sj = reinterpret_cast<int*>(w_sd + a.cap);
+    const int r0w = warp * WROWS;               // first tile row of this warp
+    double* w_tau = sm.tau + r0w;
+    double* w_nrm = sm.nrm + r0w;
+    int* w_cs = sm.cs + r0w;
+    int* w_ce = sm.ce + r0w;
+    int* w_cnt = sm.cnt + r0w;
+    int* w_flag = sm.flag + r0w;
+    double* w_ncol = sm.ncol[warp];
     int stage = 0;
     uint32_t phase = 0;
     int seg = a.cta_seg_base[blockIdx.x];
     int cur_rb = -1;
     const size_t seg_stride = (size_t)BM * a.cap;
+    bool ready = false;
 
+    // Phase offset between the two consumer warps of every SM sub-partition (warps w and w+4 share one): the
+    // trailing warp starts `lag` chunks late, so that when one of the pair is in its epilogue / prune the other
+    // still has staged chunks to feed the FP64 tensor pipe with.
+    const bool leader = warp < CONSUMER_WARPS / 2;
+    int gate_left = (leader && a.lag > 0) ? a.lag : -1;      // chunks until this leader opens the gate
+    if (!leader && a.lag > 0) mbar_wait(&sm.gate, 0);
+
+    long long pf_wait = 0, pf_epi = 0, pf_prune = 0, pf_nprune = 0, pf_emit = 0;
+    const long long pf_t0 = clock64();
     for (int lin = lin0; lin < lin1; ++lin) {
         while (lin >= a.rb_tile_prefix[rb + 1]) ++rb;
         if (rb != cur_rb) {
-            // segment boundary: flush the previous row block's state, load the new one's
-            named_bar_sync(1, CONSUMER_THREADS);
-            if (ctid < BM) {
+            // segment boundary: flush this warp's rows of the previous row block, load the new block's
+            __syncwarp();
+            if (lane < WROWS) {
                 if (cur_rb >= 0) {
-                    a.seg_cnt[(size_t)seg * BM + ctid] = sm.cnt[ctid];
-                    a.seg_flag[(size_t)seg * BM + ctid] = sm.flag[ctid];
+                    a.seg_cnt[(size_t)seg * BM + r0w + lane] = w_cnt[lane];
+                    a.seg_flag[(size_t)seg * BM + r0w + lane] = w_flag[lane];
                 }
-                int row = a.row_begin + rb * BM + ctid;
-                bool valid = row < a.row_end;
-                sm.nrm[ctid] = valid ? a.norms[row] : 0.0;
-                sm.cs[ctid] = valid ? a.row_cs[row] : 0;
-                sm.ce[ctid] = valid ? a.row_ce[row] : 0;
-                sm.tau[ctid] = valid ? a.tau_init : __longlong_as_double(0x7ff8000000000000LL);
-                sm.cnt[ctid] = 0;
-                sm.flag[ctid] = 0;
+                const int row = a.row_begin + rb * BM + r0w + lane;
+                const bool valid = row < a.row_end;
+                w_nrm[lane] = valid ? a.norms[row] : 0.0;
+                w_cs[lane] = valid ? a.row_cs[row] : 0;
+                w_ce[lane] = valid ? a.row_ce[row] : 0;
+                w_tau[lane] = valid ? a.tau_init : __longlong_as_double(0x7ff8000000000000LL);
+                w_cnt[lane] = 0;
+                w_flag[lane] = 0;
             }
             if (cur_rb >= 0) ++seg;
             cur_rb = rb;
-            named_bar_sync(1, CONSUMER_THREADS);
+            __syncwarp();
         }
         const int q = lin - a.rb_tile_prefix[rb];
         const int t = q < a.rb_skip_lo[rb] ? q : q + a.rb_skip_n[rb];
         const int col0 = t * BN;
 
-        double acc[4][8][2];
+        const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && (lin - lin0) < 64;
+        long long* tr = tr_on ? a.trace + ((size_t)(warp >> 2) * 64 + (lin - lin0)) * 8 : nullptr;
+        if (tr_on) tr[0] = clock64();
+        // prefetch this tile's 128 column norms into the warp's shared slice (consumed in the epilogue)
+        {
+            const double* src = a.norms + col0 + lane * 4;
+            cp_async_16(w_ncol + lane * 4, src);
+            cp_async_16(w_ncol + lane * 4 + 2, src + 2);
+            cp_async_commit();
+        }
+
+        double acc[2][16][2];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            for (int nt = 0; nt < 16; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
         for (int kc = 0; kc < a.nkc; ++kc) {
-            mbar_wait(&sm.full[stage], phase);
+            if (!ready) {
+                const long long pf_w0 = clock64();
+                mbar_wait(&sm.full[stage], phase);
+                pf_wait += clock64() - pf_w0;
+            }
             const uint32_t base = tiles_u32 + (uint32_t)stage * STAGE_BYTES;
-            const int nsteps = (kc == a.nkc - 1) ? a.nsteps_last : 4;
+            // probe the next stage's barrier now; the answer is only needed after this chunk's 128 DMMAs
+            int nstage = stage + 1;
+            uint32_t nphase = phase;
+            if (nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+            const bool ready_next = mbar_test_wait(&sm.full[nstage], nphase);
+            const int nd = (kc == a.nkc - 1) ? a.ndsteps_last : 2;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                if (s < nsteps) {
-                    double fa[4], fb[8];
+            for (int h = 0; h < 2; ++h) {
+                if (h < nd) {
+                    double fa[2][2];
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-                        fa[mt] = lds_f64(base + a_off + mt * 1024 + sw[s]);
+                    for (int mt = 0; mt < 2; ++mt) lds_v2f64(base + a_off + mt * 1024 + sw[h], fa[mt][0], fa[mt][1]);
 #pragma unroll
-                    for (int nt = 0; nt < 8; ++nt)
-                        fb[nt] = lds_f64(base + b_off + nt * 1024 + sw[s]);
+                    for (int half = 0; half < 2; ++half) {
+                        double fb[8][2];
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
+                        for (int i = 0; i < 8; ++i)
+                            lds_v2f64(base + b_off + (half * 8 + i) * 1024 + sw[h], fb[i][0], fb[i][1]);
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fb[nt]);
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    dmma_8x8x4(acc[mt][half * 8 + i][0], acc[mt][half * 8 + i][1], fa[mt][u], fb[i][u]);
+                    }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (gate_left > 0 && --gate_left == 0) {
+                if (lane == 0) mbar_arrive(&sm.gate);
+                gate_left = -1;
+            }
+            stage = nstage;
+            phase = nphase;
+            ready = ready_next;
         }
 
-        // ---- epilogue: d~ = (n_i + n_j) - 2 dot, filter against the row threshold, emit survivors ----
+        // ---- epilogue: filter d~ = (n_i + n_j) - 2 dot against the row threshold, emit survivors ----
+        // accumulator (mt, nt, e) of lane (g, q) is row 16w + mt*8 + perm(g), column nt*8 + perm(2q+e) = nt*8 + 4e + q.
+        // The filter runs on the accumulator itself: d~ <= tau  <=>  dot >= (n_i - tau)/2 + n_j/2 (one DADD and one
+        // DSETP per entry; the few-ulp difference to the canonical d~ is far inside the threshold margin).
+        const long long pf_e0 = clock64();
+        if (tr_on) tr[1] = pf_e0;
+        cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w_ncol[lane * 4 + i] *= 0.5;     // exact; NaN padding stays NaN
+        __syncwarp();
         double* cd = a.cand_d + (size_t)seg * seg_stride;
         int* cj = a.cand_j + (size_t)seg * seg_stride;
-        double ncol[8][2];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            int j = col0 + wn * 64 + nt * 8 + q4 * 2;
-            ncol[nt][0] = __ldg(a.norms + j);
-            ncol[nt][1] = __ldg(a.norms + j + 1);
-        }
+        for (int mt = 0; mt < 2; ++mt) {
+            const int rw = mt * 8 + pg;                   // row within the warp's 16
+            const double tau = w_tau[rw];
+            const double nr = w_nrm[rw];
+            const double hrow = 0.5 * (nr - tau);         // NaN for inactive rows: nothing passes
+            unsigned mask = 0;
+            if (a.dbg & 2) {
+                if (acc[mt][0][0] + acc[mt][15][1] == 1.2345) mask = 1;
+            } else {
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-            const int rl = wm * 32 + mt * 8 + g;
-            const double tau = sm.tau[rl];
-            const double nr = sm.nrm[rl];
-            const int cs = sm.cs[rl];
-            const unsigned clen = (unsigned)(sm.ce[rl] - cs);
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
+            for (int nt = 0; nt < 16; ++nt) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int j = col0 + wn * 64 + nt * 8 + q4 * 2 + e;
-                    const double d = fma(-2.0, acc[mt][nt][e], nr + ncol[nt][e]);
-                    if (d <= tau && (unsigned)(j - cs) >= clen) {
-                        int slot = atomicAdd(&sm.cnt[rl], 1);
-                        if (slot < a.cap) {
-                            cd[(size_t)rl * a.cap + slot] = d;
-                            cj[(size_t)rl * a.cap + slot] = j;
+                    if (acc[mt][nt][e] >= hrow + w_ncol[nt * 8 + 4 * e + q4]) mask |= 1u << (nt * 2 + e);
+                }
+            }
+            }
+            if (a.dbg & 1) mask = 0;
+            if (tr_on) tr[4 + mt * 2] = clock64();
+            if (mask) {
+                // Rare path, kept deliberately compact (a fully unrolled version pushed the kernel far past the
+                // instruction cache; a local-memory copy thrashed the tiny L1): park this row's 32 accumulators in
+                // the warp's shared scratch, lane-interleaved, and walk the set bits.
+                double* tmp = w_sd + lane;                // entry b lives at tmp[b * 32]
+#pragma unroll
+                for (int nt = 0; nt < 16; ++nt) {
+                    tmp[(nt * 2) * 32] = acc[mt][nt][0];
+                    tmp[(nt * 2 + 1) * 32] = acc[mt][nt][1];
+                }
+                const int cs = w_cs[rw];
+                const unsigned clen = (unsigned)(w_ce[rw] - cs);
+                unsigned m2 = mask;
+                while (m2) {                               // confirm with the canonical d~ (drops NaN / inf) and
+                    const int bit = __ffs(m2) - 1;         // drop the row's own chromosome
+                    m2 &= m2 - 1;
+                    const int cl = (bit >> 1) * 8 + 4 * (bit & 1) + q4;
+                    const double d = fma(-2.0, tmp[bit * 32], nr + 2.0 * w_ncol[cl]);
+                    if (!(d <= tau) || (unsigned)(col0 + cl - cs) < clen) mask &= ~(1u << bit);
+                }
+                if (mask) {                               // one shared-memory atomic per (thread, row)
+                    pf_emit += __popc(mask);
+                    int w = atomicAdd(&w_cnt[rw], __popc(mask));
+                    double* rd = cd + (size_t)(r0w + rw) * a.cap;
+                    int* rj = cj + (size_t)(r0w + rw) * a.cap;
+                    while (mask) {
+                        const int bit = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int cl = (bit >> 1) * 8 + 4 * (bit & 1) + q4;
+                        if (w < a.cap) {
+                            rd[w] = fma(-2.0, tmp[bit * 32], nr + 2.0 * w_ncol[cl]);
+                            rj[w] = col0 + cl;
                         } else {
-                            sm.flag[rl] = 1;
+                            w_flag[rw] = 1;
                         }
+                        ++w;
                     }
                 }
             }
+            if (tr_on) tr[5 + mt * 2] = clock64();
         }
-        named_bar_sync(1, CONSUMER_THREADS);
+        __syncwarp();
+        const long long pf_p0 = clock64();
+        pf_epi += pf_p0 - pf_e0;
+        if (tr_on) tr[2] = pf_p0;
         // ---- prune rows whose buffer could overflow during the next tile ----
-        for (int rl = warp * (BM / CONSUMER_WARPS); rl < (warp + 1) * (BM / CONSUMER_WARPS); ++rl) {
-            int n = sm.cnt[rl];
+        for (int rw = 0; rw < WROWS; ++rw) {
+            int n = w_cnt[rw];
             if (n > a.cap) n = a.cap;
-            if (n > a.cap - BN && !sm.flag[rl]) {
+            if (n > a.cap - BN && !w_flag[rw]) {
                 double tau;
                 int kept;
-                prune_row(cd + (size_t)rl * a.cap, cj + (size_t)rl * a.cap, n, a.k, sm.nrm[rl], a.mcoef,
-                          sm.hist[warp], lane, &tau, &kept);
+                ++pf_nprune;
+                double* rd = cd + (size_t)(r0w + rw) * a.cap;
+                int* rj = cj + (size_t)(r0w + rw) * a.cap;
+                __threadfence_block();
+                if (a.cap <= 512)
+                    prune_row<16>(rd, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sd, w_sj, &tau, &kept, tr_on ? tr : nullptr);
+                else
+                    prune_row<32>(rd, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sd, w_sj, &tau, &kept, tr_on ? tr : nullptr);
                 if (lane == 0) {
                     if (kept > a.cap - BN) {       // a tie plateau wider than the buffer: exact fallback
-                        sm.flag[rl] = 1;
-                        sm.tau[rl] = __longlong_as_double(0x7ff8000000000000LL);
-                        sm.cnt[rl] = 0;
+                        w_flag[rw] = 1;
+                        w_tau[rw] = __longlong_as_double(0x7ff8000000000000LL);
+                        w_cnt[rw] = 0;
                     } else {
-                        sm.tau[rl] = tau;
-                        sm.cnt[rl] = kept;
+                        w_tau[rw] = tau;
+                        w_cnt[rw] = kept;
                     }
                 }
                 __syncwarp();
             }
         }
-        named_bar_sync(1, CONSUMER_THREADS);
+        pf_prune += clock64() - pf_p0;
+        if (tr_on) tr[3] = clock64();
     }
-    if (ctid < BM && cur_rb >= 0) {
-        a.seg_cnt[(size_t)seg * BM + ctid] = sm.cnt[ctid] > a.cap ? a.cap : sm.cnt[ctid];
-        a.seg_flag[(size_t)seg * BM + ctid] = sm.flag[ctid];
+    if (gate_left > 0 && lane == 0) mbar_arrive(&sm.gate);   // fewer chunks than the lag: open the gate on the way out
+    __syncwarp();
+    if (a.prof != nullptr && warp == 0 && lane == 0) {
+        long long* o = a.prof + (size_t)blockIdx.x * 8;
+        o[0] = clock64() - pf_t0; o[1] = pf_wait; o[2] = pf_epi; o[3] = pf_prune;
+        o[4] = lin1 - lin0; o[5] = pf_nprune; o[6] = pf_emit; o[7] = 0;
+    }
+    if (lane < WROWS && cur_rb >= 0) {
+        a.seg_cnt[(size_t)seg * BM + r0w + lane] = w_cnt[lane] > a.cap ? a.cap : w_cnt[lane];
+        a.seg_flag[(size_t)seg * BM + r0w + lane] = w_flag[lane];
     }
 }
 
@@ -393,26 +542,6 @@ __device__ __forceinline__ bool pair_less(double da, int ja, double db, int jb) 
     return da < db || (da == db && ja < jb);
 }
 
-__device__ void bitonic_sort_pairs(double* key, int* val, int m, int tid, int nthreads) {
-    for (int size = 2; size <= m; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (m >> 1); t += nthreads) {
-                int i = ((t / stride) * stride << 1) + (t % stride);
-                int j = i + stride;
-                bool up = (i & size) == 0;
-                double ki = key[i], kj = key[j];
-                int vi = val[i], vj = val[j];
-                bool swap = up ? pair_less(kj, vj, ki, vi) : pair_less(ki, vi, kj, vj);
-                if (swap) {
-                    key[i] = kj; key[j] = ki;
-                    val[i] = vj; val[j] = vi;
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 struct FinArgs {
     const double* X;        // original corrected data, N x S
     int N, S;
@@ -428,6 +557,7 @@ struct FinArgs {
     const int* seg_flag;
     int cap;
     int k;
+    int shortcap;           // shortlist capacity (256 or 512)
     double mcoef;
     int* idx_out;
     double* dist_out;
@@ -435,15 +565,23 @@ struct FinArgs {
     int* slow_count;
 };
 
+// One CTA per target row.
+//  1. select: 256-bucket histogram over the row's candidate entries (all segments) -> v* = largest entry of the
+//     bucket holding the k-th smallest approximate distance; shortlist = entries <= v* + margin(v*).  The
+//     shortlist provably contains the exact top-k (every threshold ever applied to this row was >= that window).
+//  2. exact re-score of the shortlist in the reference's operation order (wisetools.py:302 on Fortran-ordered
+//     operands: sequential over samples, separately rounded subtract / multiply / add); one thread per
+//     candidate, candidate rows staged through shared memory by cp.async in 32-sample chunks, double buffered.
+//  3. rank by (distance, index), write the first k with indices remapped to other-chromosome coordinates.
 __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs a) {
-    extern __shared__ unsigned char fin_raw[];
-    double* key = reinterpret_cast<double*>(fin_raw);                      // FIN_MAX
-    int* val = reinterpret_cast<int*>(key + FIN_MAX);                      // FIN_MAX
-    double* tile = reinterpret_cast<double*>(val + FIN_MAX);               // 128 x 33
-    double* xi = tile + 128 * 33;                                          // 32
-    double* ex_d = xi + 32;                                                // FIN_SHORT
-    int* ex_j = reinterpret_cast<int*>(ex_d + FIN_SHORT);                  // FIN_SHORT
-    __shared__ int s_total, s_flag, s_p;
+    extern __shared__ __align__(16) unsigned char fin_raw[];
+    double* tile0 = reinterpret_cast<double*>(fin_raw);                    // 2 x FIN_THREADS x FIN_LD
+    double* xi0 = tile0 + 2 * FIN_THREADS * FIN_LD;                        // 2 x FIN_CHUNK
+    double* ex_d = xi0 + 2 * FIN_CHUNK;                                    // shortcap
+    int* ex_j = reinterpret_cast<int*>(ex_d + a.shortcap);                 // shortcap
+    int* hist = ex_j + a.shortcap;                                         // HIST_BINS
+    __shared__ double s_red[2][FIN_THREADS / 32];
+    __shared__ int s_total, s_flag, s_p, s_bstar, s_valid;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rloc = blockIdx.x;
@@ -461,105 +599,174 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
         }
         s_total = tot;
         s_flag = fl;
+        s_p = 0;
+        s_valid = 0;
     }
+    for (int b = tid; b < HIST_BINS; b += FIN_THREADS) hist[b] = 0;
     __syncthreads();
     const int total = s_total;
-    if (s_flag || total > FIN_MAX) {
+    if (s_flag) {
         if (tid == 0) a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
         return;
     }
-    int m = 2;
-    while (m < total) m <<= 1;
-    {
-        int base = 0;
-        for (int s = 0; s < nseg; ++s) {
-            const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
-            const size_t off = ((size_t)(seg0 + s) * BM + rl) * a.cap;
-            for (int e = tid; e < n; e += FIN_THREADS) {
-                key[base + e] = a.cand_d[off + e];
-                val[base + e] = a.cand_j[off + e];
-            }
-            base += n;
+    if (total == 0) {
+        for (int e = tid; e < a.k; e += FIN_THREADS) { out_i[e] = -1; out_d[e] = 1e10; }
+        return;
+    }
+
+    // ---- 1. select ----
+    double mn = INFINITY, mx = -INFINITY;
+    for (int s = 0; s < nseg; ++s) {
+        const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
+        const double* cd = a.cand_d + ((size_t)(seg0 + s) * BM + rl) * a.cap;
+        for (int e = tid; e < n; e += FIN_THREADS) {
+            double d = cd[e];
+            mn = fmin(mn, d);
+            mx = fmax(mx, d);
         }
-        for (int e = total + tid; e < m; e += FIN_THREADS) {
-            key[e] = INFINITY;
-            val[e] = 0x7fffffff;
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < FIN_THREADS / 32; ++w) { mn = fmin(mn, s_red[0][w]); mx = fmax(mx, s_red[1][w]); }
+    const float scale = (mx > mn) ? (float)(HIST_BINS - 1) / (float)(mx - mn) : 0.0f;
+    for (int s = 0; s < nseg; ++s) {
+        const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
+        const double* cd = a.cand_d + ((size_t)(seg0 + s) * BM + rl) * a.cap;
+        for (int e = tid; e < n; e += FIN_THREADS) atomicAdd(&hist[bucket_of(cd[e], mn, scale)], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int c[HIST_BINS / 32], sum = 0;
+#pragma unroll
+        for (int t = 0; t < HIST_BINS / 32; ++t) { c[t] = hist[lane * (HIST_BINS / 32) + t]; sum += c[t]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int run = incl - sum, bl = -1;
+#pragma unroll
+        for (int t = 0; t < HIST_BINS / 32; ++t) {
+            run += c[t];
+            if (bl < 0 && run >= a.k) bl = lane * (HIST_BINS / 32) + t;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, bl >= 0);
+        int bstar = HIST_BINS - 1;                      // fewer than k entries: keep them all
+        if (m) bstar = __shfl_sync(0xffffffffu, bl, __ffs(m) - 1);
+        if (lane == 0) s_bstar = bstar;
+    }
+    __syncthreads();
+    const int bstar = s_bstar;
+    double vstar = -INFINITY;
+    for (int s = 0; s < nseg; ++s) {
+        const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
+        const double* cd = a.cand_d + ((size_t)(seg0 + s) * BM + rl) * a.cap;
+        for (int e = tid; e < n; e += FIN_THREADS) {
+            double d = cd[e];
+            if (bucket_of(d, mn, scale) <= bstar) vstar = fmax(vstar, d);
+        }
+    }
+    vstar = warp_max(vstar);
+    __syncthreads();                                    // s_red reuse
+    if (lane == 0) s_red[0][warp] = vstar;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < FIN_THREADS / 32; ++w) vstar = fmax(vstar, s_red[0][w]);
+    const double window = vstar + a.mcoef * (a.norms[row] + fabs(vstar));
+    for (int s = 0; s < nseg; ++s) {
+        const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
+        const size_t off = ((size_t)(seg0 + s) * BM + rl) * a.cap;
+        for (int e = tid; e < n; e += FIN_THREADS) {
+            if (a.cand_d[off + e] <= window) {
+                int slot = atomicAdd(&s_p, 1);
+                if (slot < a.shortcap) ex_j[slot] = a.cand_j[off + e];
+            }
         }
     }
     __syncthreads();
-    bitonic_sort_pairs(key, val, m, tid, FIN_THREADS);
-
-    // shortlist: everything within the error margin of the k-th smallest approximate distance
-    const int kk = total < a.k ? total : a.k;
-    int p = 0;
-    if (kk > 0) {
-        const double tk = key[kk - 1];
-        const double window = tk + a.mcoef * (a.norms[row] + fabs(tk));
-        if (tid == 0) s_p = 0;
-        __syncthreads();
-        int local = 0;
-        for (int e = tid; e < total; e += FIN_THREADS) local += key[e] <= window ? 1 : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-        if (lane == 0) atomicAdd(&s_p, local);
-        __syncthreads();
-        p = s_p;
-    }
-    if (p > FIN_SHORT) {
+    const int p = s_p;
+    if (p > a.shortcap) {                               // tie plateau wider than the shortlist: exact fallback
         if (tid == 0) a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
         return;
     }
 
-    // exact re-score in the reference's operation order: sequential over samples, separately rounded
-    // subtract, multiply, add (wisetools.py:302 on its Fortran-ordered operands)
+    // ---- 2. exact re-score ----
     const double* xrow = a.X + (size_t)row * a.S;
-    for (int pass = 0; pass * 128 < p; ++pass) {
-        const int c0 = pass * 128;
-        const int nc = (p - c0) < 128 ? (p - c0) : 128;
-        double accd = 0.0;
-        for (int s0 = 0; s0 < a.S; s0 += 32) {
-            const int ns = (a.S - s0) < 32 ? (a.S - s0) : 32;
-            for (int c = warp; c < nc; c += FIN_THREADS / 32) {
-                const double* src = a.X + (size_t)val[c0 + c] * a.S + s0;
-                if (lane < ns) tile[c * 33 + lane] = src[lane];
+    const int nchunks = (a.S + FIN_CHUNK - 1) / FIN_CHUNK;
+    for (int c0 = 0; c0 < p; c0 += FIN_THREADS) {
+        const int nc = (p - c0) < FIN_THREADS ? (p - c0) : FIN_THREADS;
+        auto issue = [&](int chunk, int buf) {
+            const int s0 = chunk * FIN_CHUNK;
+            const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
+            double* tile = tile0 + buf * FIN_THREADS * FIN_LD;
+            for (int e = tid; e < nc * FIN_CHUNK; e += FIN_THREADS) {
+                const int c = e >> 5, l = e & 31;
+                if (l < ns) cp_async_8(tile + c * FIN_LD + l, a.X + (size_t)ex_j[c0 + c] * a.S + s0 + l);
             }
-            if (warp == 0 && lane < ns) xi[lane] = xrow[s0 + lane];
+            if (tid < ns) cp_async_8(xi0 + buf * FIN_CHUNK + tid, xrow + s0 + tid);
+            cp_async_commit();
+        };
+        double accd = 0.0;
+        issue(0, 0);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            if (ch + 1 < nchunks) {
+                issue(ch + 1, (ch + 1) & 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
             __syncthreads();
+            const int s0 = ch * FIN_CHUNK;
+            const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
             if (tid < nc) {
-                const double* tr = tile + tid * 33;
-                for (int l = 0; l < ns; ++l) {
-                    double v = __dsub_rn(tr[l], xi[l]);
-                    accd = __dadd_rn(accd, __dmul_rn(v, v));
+                const double* tr = tile0 + (ch & 1) * FIN_THREADS * FIN_LD + tid * FIN_LD;
+                const double* xi = xi0 + (ch & 1) * FIN_CHUNK;
+                if (ns == FIN_CHUNK) {
+#pragma unroll
+                    for (int l = 0; l < FIN_CHUNK; ++l) {
+                        double v = __dsub_rn(tr[l], xi[l]);
+                        accd = __dadd_rn(accd, __dmul_rn(v, v));
+                    }
+                } else {
+                    for (int l = 0; l < ns; ++l) {
+                        double v = __dsub_rn(tr[l], xi[l]);
+                        accd = __dadd_rn(accd, __dmul_rn(v, v));
+                    }
                 }
             }
             __syncthreads();
         }
         if (tid < nc) {
             const bool ok = accd < 1e10;     // wisetools.py:312-314: strict `<` against the 1e10 start value; NaN fails
+            const int j = ex_j[c0 + tid];
             ex_d[c0 + tid] = ok ? accd : INFINITY;
-            ex_j[c0 + tid] = ok ? val[c0 + tid] : 0x7fffffff;
+            ex_j[c0 + tid] = ok ? j : 0x7fffffff;
         }
+        __syncthreads();
     }
-    int m2 = 2;
-    while (m2 < p) m2 <<= 1;
-    for (int e = p + tid; e < m2; e += FIN_THREADS) {
-        ex_d[e] = INFINITY;
-        ex_j[e] = 0x7fffffff;
-    }
-    __syncthreads();
-    if (p > 0) bitonic_sort_pairs(ex_d, ex_j, m2, tid, FIN_THREADS);
+
+    // ---- 3. rank by (distance, index) and write ----
     const int cs = a.row_cs[row], ce = a.row_ce[row];
-    for (int e = tid; e < a.k; e += FIN_THREADS) {
-        int oi = -1;
-        double od = 1e10;
-        if (e < p && ex_j[e] != 0x7fffffff) {
-            const int j = ex_j[e];
-            oi = j >= ce ? j - (ce - cs) : j;
-            od = ex_d[e];
+    int nvalid_local = 0;
+    for (int e = tid; e < p; e += FIN_THREADS) {
+        const double d = ex_d[e];
+        const int j = ex_j[e];
+        if (j == 0x7fffffff) continue;
+        ++nvalid_local;
+        int rank = 0;
+        for (int u = 0; u < p; ++u) rank += pair_less(ex_d[u], ex_j[u], d, j) ? 1 : 0;
+        if (rank < a.k) {
+            out_i[rank] = j >= ce ? j - (ce - cs) : j;
+            out_d[rank] = d;
         }
-        out_i[e] = oi;
-        out_d[e] = od;
     }
+    atomicAdd(&s_valid, nvalid_local);
+    __syncthreads();
+    for (int e = s_valid + tid; e < a.k; e += FIN_THREADS) { out_i[e] = -1; out_d[e] = 1e10; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -652,6 +859,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 enum {
+    SLOT_PROF = 20,
     SLOT_XC = 0, SLOT_NORMS, SLOT_ROWCS, SLOT_ROWCE, SLOT_RBMETA, SLOT_CAND_D, SLOT_CAND_J, SLOT_SEGCNT,
     SLOT_SEGFLAG, SLOT_SLOW, SLOT_SCRATCH, SLOT_IO_X, SLOT_IO_IDX, SLOT_IO_DIST
 };
@@ -685,7 +893,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     const int ld = (S + BK - 1) / BK * BK;
     const int nkc = ld / BK;
     const int last_valid = S - (nkc - 1) * BK;            // 1..16 valid samples in the last chunk
-    const int nsteps_last = (last_valid + 3) / 4;
+    const int ndsteps_last = (last_valid + 7) / 8;
     const size_t Npad = (size_t)(N + BN - 1) / BN * BN + BN;
     const double mcoef = 16.0 * (double)(S + 8) * 1.1102230246251565e-16;
 
@@ -814,12 +1022,25 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     }
     TopkArgs ta;
     ta.norms = norms; ta.row_cs = d_row_cs; ta.row_ce = d_row_ce; ta.N = N;
-    ta.row_begin = row_begin; ta.row_end = row_end; ta.nkc = nkc; ta.nsteps_last = nsteps_last;
+    ta.row_begin = row_begin; ta.row_end = row_end; ta.nkc = nkc; ta.ndsteps_last = ndsteps_last;
     ta.rb_tile_prefix = d_prefix; ta.rb_skip_lo = d_skip_lo; ta.rb_skip_n = d_skip_n; ta.nrb = nrb;
     ta.total_tiles = total_tiles; ta.cta_seg_base = d_cta_seg;
     ta.cand_d = cand_d; ta.cand_j = cand_j; ta.seg_cnt = seg_cnt; ta.seg_flag = seg_flag;
     ta.cap = cap; ta.k = k; ta.mcoef = mcoef; ta.tau_init = 1e10 * (1.0 + 1e-6);
-    const size_t topk_smem = sizeof(TopkSmem);
+    ta.dbg = ctx->k5_dbg;
+    ta.lag = ctx->k5_lag;
+    ta.nstages = cap <= 512 ? 4 : 3;
+    if (ctx->k5_stages >= 3 && ctx->k5_stages <= MAX_STAGES) ta.nstages = ctx->k5_stages;
+    ta.prof = nullptr;
+    ta.trace = nullptr;
+    if (ctx->debug_profile) {
+        if ((rc = wc_reserve(ctx, SLOT_PROF, ((size_t)grid * 8 + 1024) * sizeof(long long), (void**)&ta.prof))) return rc;
+        WC_CUDA(cudaMemsetAsync(ta.prof, 0, ((size_t)grid * 8 + 1024) * sizeof(long long), stream));
+        ta.trace = ta.prof + (size_t)grid * 8;
+    }
+    const size_t topk_smem = (size_t)ta.nstages * STAGE_BYTES + sizeof(TopkState) +
+                             (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192);
+    if (topk_smem > 227 * 1024) { wc_set_error("K5 shared memory %zu exceeds 227 KiB", topk_smem); return WC_ERR_INTERNAL; }
     WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
     WC_CUDA(cudaEventRecord(ctx->ev[2], stream));
     wc_dist_topk_kernel<<<grid, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
@@ -831,8 +1052,10 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     fa.X = corrected_d; fa.N = N; fa.S = S; fa.norms = norms; fa.row_cs = d_row_cs; fa.row_ce = d_row_ce;
     fa.row_begin = row_begin; fa.row_end = row_end; fa.rb_seg_first = d_seg_first; fa.rb_seg_count = d_seg_count;
     fa.cand_d = cand_d; fa.cand_j = cand_j; fa.seg_cnt = seg_cnt; fa.seg_flag = seg_flag; fa.cap = cap; fa.k = k;
+    fa.shortcap = k <= 128 ? 256 : 512;
     fa.mcoef = mcoef; fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
-    const size_t fin_smem = FIN_MAX * 12 + (128 * 33 + 32) * 8 + FIN_SHORT * 12;
+    const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LD + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 +
+                            HIST_BINS * 4;
     WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
     wc_finalize_kernel<<<rows, FIN_THREADS, fin_smem, stream>>>(fa);
@@ -895,4 +1118,41 @@ extern "C" int wc_newref_topk_host(wc_ctx* ctx, const double* corrected_h, int N
         WC_CUDA(cudaStreamSynchronize(0));
     }
     return WC_OK;
+}
+
+// Debug: enable per-CTA cycle counters in K5 and read them back (grid x 8 int64: total, wait-on-TMA, epilogue,
+// prune, tiles, prunes, emitted entries of consumer thread 0, reserved).  Returns the number of CTAs copied.
+extern "C" int wc_debug_profile(wc_ctx* ctx, int enable, long long* out_h, int max_ctas) {
+    WC_CHECK_ARG(ctx != nullptr);
+    ctx->debug_profile = enable;
+    if (out_h == nullptr || max_ctas <= 0) return 0;
+    int grid = (int)ctx->counter[4];
+    if (grid > max_ctas) grid = max_ctas;
+    if (grid <= 0 || ctx->buf[SLOT_PROF].p == nullptr) return 0;
+    WC_CUDA(cudaMemcpy(out_h, ctx->buf[SLOT_PROF].p, (size_t)grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (max_ctas >= grid + 128)   // room for the CTA-0 timeline: 1024 more int64 right after the per-CTA counters
+        WC_CUDA(cudaMemcpy(out_h + (size_t)grid * 8, (long long*)ctx->buf[SLOT_PROF].p + (size_t)ctx->counter[4] * 8,
+                           1024 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return grid;
+}
+
+// Tuning knobs (debug / experiments).  key "k5_lag": chunks by which the trailing consumer warps lag (0..4).
+extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
+    WC_CHECK_ARG(ctx != nullptr && key != nullptr);
+    if (strcmp(key, "k5_lag") == 0) {
+        WC_CHECK_ARG(value >= 0 && value <= MAX_STAGES - 2);
+        ctx->k5_lag = (int)value;
+        return WC_OK;
+    }
+    if (strcmp(key, "k5_dbg") == 0) {
+        ctx->k5_dbg = (int)value;
+        return WC_OK;
+    }
+    if (strcmp(key, "k5_stages") == 0) {
+        WC_CHECK_ARG(value == 0 || (value >= 3 && value <= MAX_STAGES));
+        ctx->k5_stages = (int)value;
+        return WC_OK;
+    }
+    wc_set_error("unknown option %s", key);
+    return WC_ERR_ARG;
 }
