@@ -19,7 +19,7 @@ ctx = _cabi.context(0)
 _cabi.lib().wc_debug_profile(ctx.handle, 1, None, 0)
 if len(sys.argv) > 2:
     _cabi.check(_cabi.lib().wc_set_option(ctx.handle, b"k5_lag", float(sys.argv[2])))
-for kv in sys.argv[3:]:
+for kv in [x for x in sys.argv[3:] if '=' in x]:
     key, val = kv.split("=")
     _cabi.check(_cabi.lib().wc_set_option(ctx.handle, key.encode(), float(val)))
 for _ in range(2):
@@ -36,11 +36,11 @@ out = {"workload": name, "lag": (sys.argv[2] if len(sys.argv) > 2 else "default"
        "emitted_thread0_mean": p[:, 6].mean(),
        "ideal_cycles_per_tile": 128 * 128 * S / 64.0}
 print(json.dumps(out))
-if g + 128 <= 320:
-    tl = buf.reshape(-1)[g * 8: g * 8 + 1024].reshape(2, 64, 8).astype(np.int64)
-    for i in range(8, 54):
+if g + 64 <= 320 and "-t" in sys.argv:
+    tl = buf.reshape(-1)[g * 8: g * 8 + 512].reshape(2, 64, 4).astype(np.int64)
+    for i in list(range(4, 8)) + list(range(36, 50)):
+        row = []
         for w in (0, 1):
             t = tl[w, i]
-            if 0 < t[5] <= 1024 and 0 < t[4] < 64:    # slots overwritten by the last prune of that tile
-                print("tile %2d warp%d PRUNE: load %6d bisect %6d (%d rounds) vstar %6d compact %6d  n %d -> %d" %
-                      (i, w * 4, t[0], t[1], t[4], t[2], t[3], t[5], t[6]))
+            row.append("warp%d main %7d epi %6d prune %6d" % (w * 4, t[1] - t[0], t[2] - t[1], t[3] - t[2]))
+        print("tile %2d  " % i + " | ".join(row))

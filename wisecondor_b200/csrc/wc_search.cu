@@ -5,18 +5,28 @@
 // smallest ordered by (distance, index).
 //
 // Kernels
-//   K4 wc_center_norms_kernel   X' = X - 1 (padded, TMA-friendly) and n_i = sum_s X'[i][s]^2          (HBM bound)
-//   K5 wc_dist_topk_kernel      fp64 tensor-core contraction d~ = n_i + n_j - 2 X'_i . X'_j on 128x128 tiles,
-//                               operands staged by TMA (SWIZZLE_128B) through a 4-stage mbarrier ring, fused
-//                               with a streaming per-row threshold filter: only entries that can still be among
-//                               the row's k smallest leave the SM.  The distance matrix never exists. (FP64 bound)
-//   K6 wc_finalize_kernel       per row: shortlist = entries within an error margin of the k-th smallest d~,
-//                               exact re-score in the reference's operation order, sort by (d, index), remap
-//                               to other-chromosome coordinates                                       (L2 bound)
-//   K6b wc_exhaustive_kernel    exact brute force for rows the streaming path could not bound (massive ties)
+//   K4 wc_prepare_kernel      X' = X - 1 (padded, TMA-friendly), n_i = sum_s X'[i][s]^2, and two extra "samples"
+//                             per row, (1, -n_i/2), so that the contraction itself yields the score
+//                             s_ij = X'_i.X'_j - (n_i + n_j)/2 = -d~_ij/2                                (HBM bound)
+//   K5 wc_dist_topk_kernel    fp64 tensor-core contraction (DMMA.8x8x4) on 128x128 tiles, operands staged by TMA
+//                             (SWIZZLE_128B) through an mbarrier ring, fused with a streaming per-row threshold
+//                             filter on the raw accumulator bits: only entries that can still be among the row's
+//                             k smallest leave the SM.  The distance matrix never exists.              (FP64 bound)
+//   K6 wc_finalize_kernel     per row: shortlist = entries within an error margin of the k-th smallest d~, exact
+//                             re-score in the reference's operation order, rank by (d, index), remap to
+//                             other-chromosome coordinates                                              (L2 bound)
+//   K6b wc_exhaustive_kernel  exact brute force for rows the streaming path could not bound (massive ties)
+//
+// Why the filter works on integer bit patterns: on B200 plain FP64 instructions (DADD/DSETP/DFMA) share the FP64
+// pipe with DMMA and are starved ~20x while another warp of the same SM sub-partition streams DMMAs (measured,
+// tools/dmma_coissue.cu); integer and shared-memory instructions are not.  With the score in the accumulator,
+// "d~ <= tau" is one unsigned 64-bit compare per entry, and the candidate buffers, the prune and the emission
+// path need no FP64 arithmetic at all.
 #include "wc_common.cuh"
 
 namespace {
+
+typedef unsigned long long u64;
 
 constexpr int BM = 128;             // target rows per CTA tile
 constexpr int BN = 128;             // candidate columns per CTA tile
@@ -28,43 +38,41 @@ constexpr int PRODUCER_WARPS = 4;   // one warp group; only warp 0 lane 0 issues
 constexpr int TOPK_THREADS = CONSUMER_THREADS + PRODUCER_WARPS * 32;
 constexpr int TILE_BYTES = BM * BK * 8;               // 16 KiB per operand per stage
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;
+constexpr int MAX_STAGES = 6;
 constexpr int HIST_BINS = 256;
 constexpr int FIN_THREADS = 128;    // one thread per shortlisted candidate during the exact re-score
 constexpr int FIN_CHUNK = 32;       // samples staged per pipeline step of the re-score
 constexpr int FIN_LD = FIN_CHUNK + 1;   // padded tile row (bank-conflict free per-thread row walks)
 constexpr int EXH_THREADS = 256;
+constexpr u64 KEY_NEVER = 0ull;     // threshold key of an inactive row: no finite negative score passes
 
-constexpr int MAX_STAGES = 6;
-// Shared memory of K5: [nstages x STAGE_BYTES operand ring, 1024-byte aligned][TopkState][8 warps x cap x 12 B
-// prune scratch].
+// Shared memory of K5: [nstages x STAGE_BYTES operand ring, 1024-byte aligned][TopkState][8 warps x scratch]
 struct TopkState {
     uint64_t full[MAX_STAGES];
     uint64_t empty[MAX_STAGES];
     uint64_t gate;       // opened by the leading warps after `lag` chunks; the lagging warps start behind it
-    double tau[BM];      // emission threshold per row (includes the error margin); NaN = row inactive
+    u64 thr[BM];         // per-row threshold key = bits(-tau/2); an entry passes iff bits(score) <= thr (unsigned)
     double nrm[BM];      // n_i
-    int cs[BM];          // excluded column range [cs, ce) = the row's own chromosome
-    int ce[BM];
     int cnt[BM];         // entries in the row's candidate buffer
-    int flag[BM];        // 1 = buffer could not be bounded -> exhaustive fallback
-    alignas(16) double ncol[CONSUMER_WARPS][BN];   // per-warp prefetched (halved) column norms of the current tile
+    unsigned char flag[BM];   // 1 = buffer could not be bounded -> exhaustive fallback
 };
 
 struct TopkArgs {
-    const double* norms;     // [Npad], NaN beyond N
+    const double* norms;     // [Npad]
     const int* row_cs;       // [N]
     const int* row_ce;       // [N]
     int N;
     int row_begin, row_end;
-    int nkc;                 // k chunks of BK
-    int ndsteps_last;        // 8-sample double-steps in the last chunk (1..2)
+    int nkc;                 // k chunks of BK, the last one holding the two extra samples
+    int nd_last;             // data double-steps (8 samples each) in the last chunk: 0 or 1
+    int extra_h;             // 8-sample block of the last chunk that holds (1, -n/2)
     const int* rb_tile_prefix;   // [nrb+1] valid tiles before row block rb
     const int* rb_skip_lo;       // [nrb] first skipped column tile (own chromosome interior)
     const int* rb_skip_n;        // [nrb] number of skipped column tiles
     int nrb;
     int total_tiles;
     const int* cta_seg_base;     // [grid] first segment id of each CTA
-    double* cand_d;              // [nseg][BM][cap]
+    u64* cand_key;               // [nseg][BM][cap] score bit patterns
     int* cand_j;
     int* seg_cnt;                // [nseg][BM]
     int* seg_flag;               // [nseg][BM]
@@ -73,10 +81,9 @@ struct TopkArgs {
     double mcoef;                // margin(v) = mcoef * (n_i + |v|)
     double tau_init;
     long long* prof;             // optional [grid][8] per-CTA cycle counters (consumer warp 0), or nullptr
+    long long* trace;            // optional debug timeline of CTA 0: [2 warps (0 and 4)][64 tiles][4 stamps]
     int lag;                     // chunks by which warps 4-7 trail warps 0-3 (0 = all in phase)
     int nstages;                 // depth of the TMA ring (3..MAX_STAGES)
-    int dbg;                     // timing experiments only: 1 = skip emission, 2 = skip the whole filter
-    long long* trace;            // optional debug timeline of CTA 0: [2 warps (0 and 4)][64 tiles][4 stamps]
 };
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -89,11 +96,18 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { u64 t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ u64 warp_max_u64(u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { u64 t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -102,90 +116,87 @@ __device__ __forceinline__ int bucket_of(double d, double mn, float scale) {
     int b = (int)((float)(d - mn) * scale);
     return b < 0 ? 0 : (b > HIST_BINS - 1 ? HIST_BINS - 1 : b);
 }
+// threshold key for "d~ <= tau": bits(-tau/2); tau is kept strictly positive so the key has its sign bit set and
+// every score >= +0 (d~ <= 0, rounding noise of duplicates) passes the unsigned compare.
+__device__ __forceinline__ u64 key_of_tau(double tau) { return (u64)__double_as_longlong(-0.5 * tau); }
+__device__ __forceinline__ double dist_of_key(u64 key) { return -2.0 * __longlong_as_double((long long)key); }
 
-// Warp-collective prune of one row's candidate buffer.  The buffer is copied once into a warp-private shared
-// scratch (independent L2 loads); a value-space bisection finds a cut v with k <= #{d <= v} <= k + slack; v* = the
-// largest entry <= v is then a valid upper bound of the row's final k-th smallest distance, and everything
-// <= v* + margin is written back compacted.  Plain loops on purpose: this code runs a few times per tile somewhere
-// in the CTA and must not evict the main loop from the instruction cache.
+// Warp-collective prune of one row's candidate buffer, on score keys (unsigned order == distance order).  The
+// buffer is copied once into the warp's shared scratch with independent L2 loads; an integer bisection finds a
+// cut with k <= #{key <= cut} <= k + 24 (about 5 rounds on real data); v* = the largest key <= cut bounds the row's
+// final k-th smallest distance from above, and everything within the error margin of it is written back compacted.
+// Integer-only apart from the five FP64 operations that turn v* into the new threshold.
 template <int PER_LANE>   // cap / 32: every load of the buffer is issued before the first one is consumed
-__device__ __noinline__ void prune_row(double* cd, int* cj, int n, int k, double nrm, double mcoef, int lane,
-                                       double* sd, int* sj, double* tau_out, int* n_out, long long* ptr) {
-    const long long pt0 = clock64();
-    double lo = INFINITY, hi = -INFINITY;
+__device__ __noinline__ void prune_row(u64* ck, int* cj, int n, int k, double nrm, double mcoef, int lane, u64* sk,
+                                       int* sj, u64* thr_out, int* n_out) {
+    u64 lo = ~0ull, hi = 0ull;
     {
-        double d[PER_LANE];
+        u64 d[PER_LANE];
         int j[PER_LANE];
 #pragma unroll
         for (int t = 0; t < PER_LANE; ++t) {
             const int i = t * 32 + lane;
-            d[t] = i < n ? __ldcg(cd + i) : INFINITY;
+            d[t] = i < n ? __ldcg(ck + i) : ~0ull;
             j[t] = i < n ? __ldcg(cj + i) : 0;
         }
 #pragma unroll
         for (int t = 0; t < PER_LANE; ++t) {
             const int i = t * 32 + lane;
             if (i < n) {
-                sd[i] = d[t];
+                sk[i] = d[t];
                 sj[i] = j[t];
-                lo = fmin(lo, d[t]);
-                hi = fmax(hi, d[t]);
+                lo = d[t] < lo ? d[t] : lo;
+                hi = d[t] > hi ? d[t] : hi;
             }
         }
     }
-    lo = warp_min(lo);
-    hi = warp_max(hi);
+    lo = warp_min_u64(lo);
+    hi = warp_max_u64(hi);
     __syncwarp();
-    const long long pt1 = clock64();
-    // Bisect for a cut with k <= count(<= cut) <= k_hi (about 4 rounds on real data).
     const int k_hi = k + 24;
-    double blo = lo, bhi = hi, cut = hi;
+    u64 blo = lo, bhi = hi, cut = hi;           // count(<= cut) >= k throughout
     int c_hi = n;
-    int nit = 0;
-    for (int it = 0; it < 48 && c_hi > k_hi; ++it) {
-        ++nit;
-        const double mid = blo + 0.5 * (bhi - blo);
-        if (!(mid > blo && mid < bhi)) break;                      // bracket exhausted (ties): keep the current cut
+    for (int it = 0; it < 70 && c_hi > k_hi; ++it) {
+        if (bhi - blo < 2) break;               // bracket exhausted (ties): keep the current cut
+        const u64 mid = blo + ((bhi - blo) >> 1);
         int c = 0;
 #pragma unroll 4
-        for (int i = lane; i < n; i += 32) c += sd[i] <= mid ? 1 : 0;
+        for (int i = lane; i < n; i += 32) c += sk[i] <= mid ? 1 : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (c >= k) { bhi = mid; c_hi = c; cut = mid; } else { blo = mid; }
     }
-    const long long pt2 = clock64();
-    double vstar = -INFINITY;
+    u64 vstar = 0ull;
 #pragma unroll 4
     for (int i = lane; i < n; i += 32) {
-        const double d = sd[i];
-        if (d <= cut) vstar = fmax(vstar, d);
+        const u64 d = sk[i];
+        if (d <= cut && d > vstar) vstar = d;
     }
-    vstar = warp_max(vstar);
-    const double tau = vstar + mcoef * (nrm + fabs(vstar));
-    const long long pt3 = clock64();
+    vstar = warp_max_u64(vstar);
+    const double dv = dist_of_key(vstar);
+    double tau = dv + mcoef * (nrm + fabs(dv));
+    const double tiny = fmax(mcoef * nrm, 1e-300);
+    if (!(tau > tiny)) tau = tiny;
+    const u64 thr = key_of_tau(tau);
     int w = 0;
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
-        const bool keep = i < n && sd[i] <= tau;
+        const bool keep = i < n && sk[i] <= thr;
         const unsigned km = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int pos = w + __popc(km & ((1u << lane) - 1u));
-            cd[pos] = sd[i];
+            ck[pos] = sk[i];
             cj[pos] = sj[i];
         }
         w += __popc(km);
     }
     __syncwarp();
-    if (ptr != nullptr && lane == 0) {
-        ptr[0] = pt1 - pt0; ptr[1] = pt2 - pt1; ptr[2] = pt3 - pt2; ptr[3] = clock64() - pt3;
-        ptr[4] = nit; ptr[5] = n; ptr[6] = w; ptr[7] = 0;
-    }
-    *tau_out = tau;
+    *thr_out = thr;
     *n_out = w;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K5: distance tiles on the FP64 tensor cores + streaming top-k filter
+// K5: score tiles on the FP64 tensor cores + streaming top-k filter
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TOPK_THREADS, 1)
 wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) {
@@ -268,19 +279,18 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     uint32_t sw[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) sw[h] = (uint32_t)(((4 * h + q4) ^ pg) << 4);
+    const uint32_t swx = a.extra_h ? sw[1] : sw[0];
 
     const uint32_t tiles_u32 = smem_u32(tiles);
     const size_t scratch_per_warp = (size_t)a.cap * 12 > 8192 ? (size_t)a.cap * 12 : 8192;
-    double* w_sd = reinterpret_cast<double*>(scratch + (size_t)warp * scratch_per_warp);
-    int* w_sj = reinterpret_cast<int*>(w_sd + a.cap);
+    u64* w_sk = reinterpret_cast<u64*>(scratch + (size_t)warp * scratch_per_warp);
+    int* w_sj = reinterpret_cast<int*>(w_sk + a.cap);
     const int r0w = warp * WROWS;               // first tile row of this warp
-    double* w_tau = sm.tau + r0w;
+    u64* w_thr = sm.thr + r0w;
     double* w_nrm = sm.nrm + r0w;
-    int* w_cs = sm.cs + r0w;
-    int* w_ce = sm.ce + r0w;
     int* w_cnt = sm.cnt + r0w;
-    int* w_flag = sm.flag + r0w;
-    double* w_ncol = sm.ncol[warp];
+    unsigned char* w_flag = sm.flag + r0w;
+    int my_cs[2] = {0, 0}, my_ce[2] = {0, 0};   // excluded column range [cs, ce) of this lane's two rows
     int stage = 0;
     uint32_t phase = 0;
     int seg = a.cta_seg_base[blockIdx.x];
@@ -288,9 +298,7 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     const size_t seg_stride = (size_t)BM * a.cap;
     bool ready = false;
 
-    // Phase offset between the two consumer warps of every SM sub-partition (warps w and w+4 share one): the
-    // trailing warp starts `lag` chunks late, so that when one of the pair is in its epilogue / prune the other
-    // still has staged chunks to feed the FP64 tensor pipe with.
+    // Optional phase offset between the two consumer warps of every SM sub-partition (warps w and w+4 share one).
     const bool leader = warp < CONSUMER_WARPS / 2;
     int gate_left = (leader && a.lag > 0) ? a.lag : -1;      // chunks until this leader opens the gate
     if (!leader && a.lag > 0) mbar_wait(&sm.gate, 0);
@@ -310,30 +318,27 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                 const int row = a.row_begin + rb * BM + r0w + lane;
                 const bool valid = row < a.row_end;
                 w_nrm[lane] = valid ? a.norms[row] : 0.0;
-                w_cs[lane] = valid ? a.row_cs[row] : 0;
-                w_ce[lane] = valid ? a.row_ce[row] : 0;
-                w_tau[lane] = valid ? a.tau_init : __longlong_as_double(0x7ff8000000000000LL);
+                w_thr[lane] = valid ? key_of_tau(a.tau_init) : KEY_NEVER;
                 w_cnt[lane] = 0;
                 w_flag[lane] = 0;
             }
             if (cur_rb >= 0) ++seg;
             cur_rb = rb;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int row = a.row_begin + rb * BM + r0w + mt * 8 + pg;
+                const bool valid = row < a.row_end;
+                my_cs[mt] = valid ? a.row_cs[row] : 0;
+                my_ce[mt] = valid ? a.row_ce[row] : 0;
+            }
             __syncwarp();
         }
         const int q = lin - a.rb_tile_prefix[rb];
         const int t = q < a.rb_skip_lo[rb] ? q : q + a.rb_skip_n[rb];
         const int col0 = t * BN;
-
         const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && (lin - lin0) < 64;
-        long long* tr = tr_on ? a.trace + ((size_t)(warp >> 2) * 64 + (lin - lin0)) * 8 : nullptr;
+        long long* tr = tr_on ? a.trace + ((size_t)(warp >> 2) * 64 + (lin - lin0)) * 4 : nullptr;
         if (tr_on) tr[0] = clock64();
-        // prefetch this tile's 128 column norms into the warp's shared slice (consumed in the epilogue)
-        {
-            const double* src = a.norms + col0 + lane * 4;
-            cp_async_16(w_ncol + lane * 4, src);
-            cp_async_16(w_ncol + lane * 4 + 2, src + 2);
-            cp_async_commit();
-        }
 
         double acc[2][16][2];
 #pragma unroll
@@ -348,12 +353,13 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                 pf_wait += clock64() - pf_w0;
             }
             const uint32_t base = tiles_u32 + (uint32_t)stage * STAGE_BYTES;
-            // probe the next stage's barrier now; the answer is only needed after this chunk's 128 DMMAs
+            // probe the next stage's barrier now; the answer is only needed after this chunk's DMMAs
             int nstage = stage + 1;
             uint32_t nphase = phase;
             if (nstage == STAGES) { nstage = 0; nphase ^= 1u; }
             const bool ready_next = mbar_test_wait(&sm.full[nstage], nphase);
-            const int nd = (kc == a.nkc - 1) ? a.ndsteps_last : 2;
+            const bool last = kc == a.nkc - 1;
+            const int nd = last ? a.nd_last : 2;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (h < nd) {
@@ -376,6 +382,27 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                     }
                 }
             }
+            if (last) {
+                // The two extra samples (1, -n/2) sit in one 16-byte slot of the row.  Feeding the B operand with
+                // the pair swapped makes the step add 1*(-n_j/2) + (-n_i/2)*1 to the dot product.
+                double fa[2][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) lds_v2f64(base + a_off + mt * 1024 + swx, fa[mt][0], fa[mt][1]);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    double fb[8][2];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        lds_v2f64(base + b_off + (half * 8 + i) * 1024 + swx, fb[i][0], fb[i][1]);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                dmma_8x8x4(acc[mt][half * 8 + i][0], acc[mt][half * 8 + i][1], fa[mt][u], fb[i][1 - u]);
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);
             if (gate_left > 0 && --gate_left == 0) {
@@ -387,70 +414,54 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             ready = ready_next;
         }
 
-        // ---- epilogue: filter d~ = (n_i + n_j) - 2 dot against the row threshold, emit survivors ----
+        // ---- epilogue: one unsigned compare per accumulator against the row's threshold key ----
         // accumulator (mt, nt, e) of lane (g, q) is row 16w + mt*8 + perm(g), column nt*8 + perm(2q+e) = nt*8 + 4e + q.
-        // The filter runs on the accumulator itself: d~ <= tau  <=>  dot >= (n_i - tau)/2 + n_j/2 (one DADD and one
-        // DSETP per entry; the few-ulp difference to the canonical d~ is far inside the threshold margin).
         const long long pf_e0 = clock64();
         if (tr_on) tr[1] = pf_e0;
-        cp_async_wait<0>();
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w_ncol[lane * 4 + i] *= 0.5;     // exact; NaN padding stays NaN
-        __syncwarp();
-        double* cd = a.cand_d + (size_t)seg * seg_stride;
+        u64* ck = a.cand_key + (size_t)seg * seg_stride;
         int* cj = a.cand_j + (size_t)seg * seg_stride;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             const int rw = mt * 8 + pg;                   // row within the warp's 16
-            const double tau = w_tau[rw];
-            const double nr = w_nrm[rw];
-            const double hrow = 0.5 * (nr - tau);         // NaN for inactive rows: nothing passes
+            const u64 thr = w_thr[rw];
             unsigned mask = 0;
-            if (a.dbg & 2) {
-                if (acc[mt][0][0] + acc[mt][15][1] == 1.2345) mask = 1;
-            } else {
 #pragma unroll
             for (int nt = 0; nt < 16; ++nt) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    if (acc[mt][nt][e] >= hrow + w_ncol[nt * 8 + 4 * e + q4]) mask |= 1u << (nt * 2 + e);
-                }
+                for (int e = 0; e < 2; ++e)
+                    if ((u64)__double_as_longlong(acc[mt][nt][e]) <= thr) mask |= 1u << (nt * 2 + e);
             }
-            }
-            if (a.dbg & 1) mask = 0;
-            if (tr_on) tr[4 + mt * 2] = clock64();
             if (mask) {
                 // Rare path, kept deliberately compact (a fully unrolled version pushed the kernel far past the
                 // instruction cache; a local-memory copy thrashed the tiny L1): park this row's 32 accumulators in
                 // the warp's shared scratch, lane-interleaved, and walk the set bits.
-                double* tmp = w_sd + lane;                // entry b lives at tmp[b * 32]
+                u64* tmp = w_sk + lane;                   // entry b lives at tmp[b * 32]
 #pragma unroll
                 for (int nt = 0; nt < 16; ++nt) {
-                    tmp[(nt * 2) * 32] = acc[mt][nt][0];
-                    tmp[(nt * 2 + 1) * 32] = acc[mt][nt][1];
+                    tmp[(nt * 2) * 32] = (u64)__double_as_longlong(acc[mt][nt][0]);
+                    tmp[(nt * 2 + 1) * 32] = (u64)__double_as_longlong(acc[mt][nt][1]);
                 }
-                const int cs = w_cs[rw];
-                const unsigned clen = (unsigned)(w_ce[rw] - cs);
+                const int cs = my_cs[mt];
+                const unsigned clen = (unsigned)(my_ce[mt] - cs);
                 unsigned m2 = mask;
-                while (m2) {                               // confirm with the canonical d~ (drops NaN / inf) and
-                    const int bit = __ffs(m2) - 1;         // drop the row's own chromosome
+                while (m2) {                               // drop inf / NaN scores and the row's own chromosome
+                    const int bit = __ffs(m2) - 1;
                     m2 &= m2 - 1;
                     const int cl = (bit >> 1) * 8 + 4 * (bit & 1) + q4;
-                    const double d = fma(-2.0, tmp[bit * 32], nr + 2.0 * w_ncol[cl]);
-                    if (!(d <= tau) || (unsigned)(col0 + cl - cs) < clen) mask &= ~(1u << bit);
+                    const unsigned hi32 = (unsigned)(tmp[bit * 32] >> 32);
+                    if ((hi32 & 0x7ff00000u) == 0x7ff00000u || (unsigned)(col0 + cl - cs) < clen) mask &= ~(1u << bit);
                 }
                 if (mask) {                               // one shared-memory atomic per (thread, row)
                     pf_emit += __popc(mask);
                     int w = atomicAdd(&w_cnt[rw], __popc(mask));
-                    double* rd = cd + (size_t)(r0w + rw) * a.cap;
+                    u64* rk = ck + (size_t)(r0w + rw) * a.cap;
                     int* rj = cj + (size_t)(r0w + rw) * a.cap;
                     while (mask) {
                         const int bit = __ffs(mask) - 1;
                         mask &= mask - 1;
                         const int cl = (bit >> 1) * 8 + 4 * (bit & 1) + q4;
                         if (w < a.cap) {
-                            rd[w] = fma(-2.0, tmp[bit * 32], nr + 2.0 * w_ncol[cl]);
+                            rk[w] = tmp[bit * 32];
                             rj[w] = col0 + cl;
                         } else {
                             w_flag[rw] = 1;
@@ -459,7 +470,6 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                     }
                 }
             }
-            if (tr_on) tr[5 + mt * 2] = clock64();
         }
         __syncwarp();
         const long long pf_p0 = clock64();
@@ -470,23 +480,23 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             int n = w_cnt[rw];
             if (n > a.cap) n = a.cap;
             if (n > a.cap - BN && !w_flag[rw]) {
-                double tau;
+                u64 thr;
                 int kept;
                 ++pf_nprune;
-                double* rd = cd + (size_t)(r0w + rw) * a.cap;
+                u64* rk = ck + (size_t)(r0w + rw) * a.cap;
                 int* rj = cj + (size_t)(r0w + rw) * a.cap;
                 __threadfence_block();
                 if (a.cap <= 512)
-                    prune_row<16>(rd, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sd, w_sj, &tau, &kept, tr_on ? tr : nullptr);
+                    prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sk, w_sj, &thr, &kept);
                 else
-                    prune_row<32>(rd, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sd, w_sj, &tau, &kept, tr_on ? tr : nullptr);
+                    prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sk, w_sj, &thr, &kept);
                 if (lane == 0) {
                     if (kept > a.cap - BN) {       // a tie plateau wider than the buffer: exact fallback
                         w_flag[rw] = 1;
-                        w_tau[rw] = __longlong_as_double(0x7ff8000000000000LL);
+                        w_thr[rw] = KEY_NEVER;
                         w_cnt[rw] = 0;
                     } else {
-                        w_tau[rw] = tau;
+                        w_thr[rw] = thr;
                         w_cnt[rw] = kept;
                     }
                 }
@@ -510,29 +520,33 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K4: centre at 1.0 and row norms
+// K4: centre at 1.0, row norms, the two extra samples; padding rows get (1, -inf) so they never pass the filter
 // ---------------------------------------------------------------------------------------------------------
-__global__ void wc_center_norms_kernel(const double* __restrict__ X, int N, int S, int ld, double* __restrict__ Xc,
-                                       double* __restrict__ norms) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void wc_prepare_kernel(const double* __restrict__ X, int N, int Npad, int S, int ld, int Sx,
+                                  double* __restrict__ Xc, double* __restrict__ norms) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= N) return;
-    const double* src = X + (size_t)warp * S;
-    double* dst = Xc + (size_t)warp * ld;
+    if (row >= Npad) return;
+    double* dst = Xc + (size_t)row * ld;
     double acc = 0.0;
-    for (int s = lane; s < ld; s += 32) {
-        double v = s < S ? src[s] - 1.0 : 0.0;
-        dst[s] = v;
-        acc = fma(v, v, acc);
+    if (row < N) {
+        const double* src = X + (size_t)row * S;
+        for (int s = lane; s < ld; s += 32) {
+            double v = s < S ? src[s] - 1.0 : 0.0;
+            dst[s] = v;
+            acc = fma(v, v, acc);
+        }
+    } else {
+        for (int s = lane; s < ld; s += 32) dst[s] = 0.0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) norms[warp] = acc;
-}
-
-__global__ void wc_fill_f64_kernel(double* p, size_t n, double v) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+    __syncwarp();
+    if (lane == 0) {
+        norms[row] = row < N ? acc : 0.0;
+        dst[Sx] = 1.0;
+        dst[Sx + 1] = row < N ? -0.5 * acc : -INFINITY;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -551,7 +565,7 @@ struct FinArgs {
     int row_begin, row_end;
     const int* rb_seg_first;
     const int* rb_seg_count;
-    const double* cand_d;
+    const u64* cand_key;
     const int* cand_j;
     const int* seg_cnt;
     const int* seg_flag;
@@ -618,9 +632,9 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     double mn = INFINITY, mx = -INFINITY;
     for (int s = 0; s < nseg; ++s) {
         const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
-        const double* cd = a.cand_d + ((size_t)(seg0 + s) * BM + rl) * a.cap;
+        const u64* cd = a.cand_key + ((size_t)(seg0 + s) * BM + rl) * a.cap;
         for (int e = tid; e < n; e += FIN_THREADS) {
-            double d = cd[e];
+            double d = dist_of_key(cd[e]);
             mn = fmin(mn, d);
             mx = fmax(mx, d);
         }
@@ -634,8 +648,8 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     const float scale = (mx > mn) ? (float)(HIST_BINS - 1) / (float)(mx - mn) : 0.0f;
     for (int s = 0; s < nseg; ++s) {
         const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
-        const double* cd = a.cand_d + ((size_t)(seg0 + s) * BM + rl) * a.cap;
-        for (int e = tid; e < n; e += FIN_THREADS) atomicAdd(&hist[bucket_of(cd[e], mn, scale)], 1);
+        const u64* cd = a.cand_key + ((size_t)(seg0 + s) * BM + rl) * a.cap;
+        for (int e = tid; e < n; e += FIN_THREADS) atomicAdd(&hist[bucket_of(dist_of_key(cd[e]), mn, scale)], 1);
     }
     __syncthreads();
     if (warp == 0) {
@@ -664,9 +678,9 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     double vstar = -INFINITY;
     for (int s = 0; s < nseg; ++s) {
         const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
-        const double* cd = a.cand_d + ((size_t)(seg0 + s) * BM + rl) * a.cap;
+        const u64* cd = a.cand_key + ((size_t)(seg0 + s) * BM + rl) * a.cap;
         for (int e = tid; e < n; e += FIN_THREADS) {
-            double d = cd[e];
+            double d = dist_of_key(cd[e]);
             if (bucket_of(d, mn, scale) <= bstar) vstar = fmax(vstar, d);
         }
     }
@@ -681,7 +695,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
         const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
         const size_t off = ((size_t)(seg0 + s) * BM + rl) * a.cap;
         for (int e = tid; e < n; e += FIN_THREADS) {
-            if (a.cand_d[off + e] <= window) {
+            if (dist_of_key(a.cand_key[off + e]) <= window) {
                 int slot = atomicAdd(&s_p, 1);
                 if (slot < a.shortcap) ex_j[slot] = a.cand_j[off + e];
             }
@@ -890,12 +904,15 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
 
     const int k = refsize;
     const int cap = k <= 128 ? 512 : 1024;
-    const int ld = (S + BK - 1) / BK * BK;
-    const int nkc = ld / BK;
-    const int last_valid = S - (nkc - 1) * BK;            // 1..16 valid samples in the last chunk
-    const int ndsteps_last = (last_valid + 7) / 8;
+    // sample axis: nblocks 8-sample blocks of data, then one block holding the two extra samples (1, -n/2)
+    const int nblocks = (S + 7) / 8;
+    const int Sx = nblocks * 8;
+    const int nkc = nblocks / 2 + 1;
+    const int nd_last = nblocks - 2 * (nkc - 1);          // 0 or 1 data double-steps in the last chunk
+    const int extra_h = nd_last;
+    const int ld = nkc * BK;
     const size_t Npad = (size_t)(N + BN - 1) / BN * BN + BN;
-    const double mcoef = 16.0 * (double)(S + 8) * 1.1102230246251565e-16;
+    const double mcoef = 16.0 * (double)(S + 16) * 1.1102230246251565e-16;
 
     // ---- per-row exclusion ranges and the (row block, column tile) work list -----------------------------
     std::vector<int> row_cs(N), row_ce(N);
@@ -956,7 +973,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
 
     // ---- workspace ----------------------------------------------------------------------------------------
     double* Xc; double* norms; int* d_row_cs; int* d_row_ce; int* d_meta;
-    double* cand_d; int* cand_j; int* seg_cnt; int* seg_flag; int* slow;
+    u64* cand_key; int* cand_j; int* seg_cnt; int* seg_flag; int* slow;
     int rc;
     if ((rc = wc_reserve(ctx, SLOT_XC, Npad * ld * sizeof(double), (void**)&Xc))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_NORMS, Npad * sizeof(double), (void**)&norms))) return rc;
@@ -965,7 +982,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     const size_t meta_ints = (size_t)(nrb + 1) + 4 * (size_t)nrb + grid;
     if ((rc = wc_reserve(ctx, SLOT_RBMETA, meta_ints * sizeof(int), (void**)&d_meta))) return rc;
     const size_t cand_n = (size_t)std::max(nseg, 1) * BM * cap;
-    if ((rc = wc_reserve(ctx, SLOT_CAND_D, cand_n * sizeof(double), (void**)&cand_d))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_CAND_D, cand_n * sizeof(u64), (void**)&cand_key))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_CAND_J, cand_n * sizeof(int), (void**)&cand_j))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_SEGCNT, (size_t)std::max(nseg, 1) * BM * sizeof(int), (void**)&seg_cnt))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_SEGFLAG, (size_t)std::max(nseg, 1) * BM * sizeof(int), (void**)&seg_flag))) return rc;
@@ -991,12 +1008,9 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
 
     // ---- K4 -------------------------------------------------------------------------------------------------
     WC_CUDA(cudaEventRecord(ctx->ev[0], stream));
-    WC_CUDA(cudaMemsetAsync(Xc + (size_t)N * ld, 0, (Npad - N) * ld * sizeof(double), stream));
     {
-        size_t n = Npad - N;
-        wc_fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(norms + N, n, NAN);
-        int blocks = (N * 32 + 255) / 256;
-        wc_center_norms_kernel<<<blocks, 256, 0, stream>>>(corrected_d, N, S, ld, Xc, norms);
+        const int blocks = (int)((Npad * 32 + 255) / 256);
+        wc_prepare_kernel<<<blocks, 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ld, Sx, Xc, norms);
     }
     WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[1], stream));
@@ -1022,20 +1036,19 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     }
     TopkArgs ta;
     ta.norms = norms; ta.row_cs = d_row_cs; ta.row_ce = d_row_ce; ta.N = N;
-    ta.row_begin = row_begin; ta.row_end = row_end; ta.nkc = nkc; ta.ndsteps_last = ndsteps_last;
+    ta.row_begin = row_begin; ta.row_end = row_end; ta.nkc = nkc; ta.nd_last = nd_last; ta.extra_h = extra_h;
     ta.rb_tile_prefix = d_prefix; ta.rb_skip_lo = d_skip_lo; ta.rb_skip_n = d_skip_n; ta.nrb = nrb;
     ta.total_tiles = total_tiles; ta.cta_seg_base = d_cta_seg;
-    ta.cand_d = cand_d; ta.cand_j = cand_j; ta.seg_cnt = seg_cnt; ta.seg_flag = seg_flag;
+    ta.cand_key = cand_key; ta.cand_j = cand_j; ta.seg_cnt = seg_cnt; ta.seg_flag = seg_flag;
     ta.cap = cap; ta.k = k; ta.mcoef = mcoef; ta.tau_init = 1e10 * (1.0 + 1e-6);
-    ta.dbg = ctx->k5_dbg;
     ta.lag = ctx->k5_lag;
-    ta.nstages = cap <= 512 ? 4 : 3;
+    ta.nstages = cap <= 512 ? 5 : 3;
     if (ctx->k5_stages >= 3 && ctx->k5_stages <= MAX_STAGES) ta.nstages = ctx->k5_stages;
     ta.prof = nullptr;
     ta.trace = nullptr;
     if (ctx->debug_profile) {
-        if ((rc = wc_reserve(ctx, SLOT_PROF, ((size_t)grid * 8 + 1024) * sizeof(long long), (void**)&ta.prof))) return rc;
-        WC_CUDA(cudaMemsetAsync(ta.prof, 0, ((size_t)grid * 8 + 1024) * sizeof(long long), stream));
+        if ((rc = wc_reserve(ctx, SLOT_PROF, ((size_t)grid * 8 + 512) * sizeof(long long), (void**)&ta.prof))) return rc;
+        WC_CUDA(cudaMemsetAsync(ta.prof, 0, ((size_t)grid * 8 + 512) * sizeof(long long), stream));
         ta.trace = ta.prof + (size_t)grid * 8;
     }
     const size_t topk_smem = (size_t)ta.nstages * STAGE_BYTES + sizeof(TopkState) +
@@ -1051,7 +1064,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     FinArgs fa;
     fa.X = corrected_d; fa.N = N; fa.S = S; fa.norms = norms; fa.row_cs = d_row_cs; fa.row_ce = d_row_ce;
     fa.row_begin = row_begin; fa.row_end = row_end; fa.rb_seg_first = d_seg_first; fa.rb_seg_count = d_seg_count;
-    fa.cand_d = cand_d; fa.cand_j = cand_j; fa.seg_cnt = seg_cnt; fa.seg_flag = seg_flag; fa.cap = cap; fa.k = k;
+    fa.cand_key = cand_key; fa.cand_j = cand_j; fa.seg_cnt = seg_cnt; fa.seg_flag = seg_flag; fa.cap = cap; fa.k = k;
     fa.shortcap = k <= 128 ? 256 : 512;
     fa.mcoef = mcoef; fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
     const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LD + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 +
@@ -1130,9 +1143,9 @@ extern "C" int wc_debug_profile(wc_ctx* ctx, int enable, long long* out_h, int m
     if (grid > max_ctas) grid = max_ctas;
     if (grid <= 0 || ctx->buf[SLOT_PROF].p == nullptr) return 0;
     WC_CUDA(cudaMemcpy(out_h, ctx->buf[SLOT_PROF].p, (size_t)grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
-    if (max_ctas >= grid + 128)   // room for the CTA-0 timeline: 1024 more int64 right after the per-CTA counters
+    if (max_ctas >= grid + 64)   // room for the CTA-0 timeline: 512 more int64 right after the per-CTA counters
         WC_CUDA(cudaMemcpy(out_h + (size_t)grid * 8, (long long*)ctx->buf[SLOT_PROF].p + (size_t)ctx->counter[4] * 8,
-                           1024 * sizeof(long long), cudaMemcpyDeviceToHost));
+                           512 * sizeof(long long), cudaMemcpyDeviceToHost));
     return grid;
 }
 
@@ -1142,10 +1155,6 @@ extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
     if (strcmp(key, "k5_lag") == 0) {
         WC_CHECK_ARG(value >= 0 && value <= MAX_STAGES - 2);
         ctx->k5_lag = (int)value;
-        return WC_OK;
-    }
-    if (strcmp(key, "k5_dbg") == 0) {
-        ctx->k5_dbg = (int)value;
         return WC_OK;
     }
     if (strcmp(key, "k5_stages") == 0) {
