@@ -195,6 +195,46 @@ def get_optimal_cutoff(distances, repeats=3):
     return cut
 
 
+def pairwise_sum(a):
+    """numpy's float64 add.reduce over a contiguous 1-D array, restated (the third-party arithmetic behind
+    np_mean / np_std / np_sum at wisetools.py:426-427, 471; numpy `pairwise_sum` in loops_utils.h): n < 8
+    sequential from 0.0... precisely: n < 8 -> left-to-right sum starting from a[0]'s block; n <= 128 -> eight
+    interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the n%8 tail added
+    sequentially; larger n -> split at n/2 rounded down to a multiple of 8 and recurse.  The CUDA z-score and
+    segmentation kernels implement exactly this order; tests pin it against numpy itself."""
+    n = len(a)
+    if n < 8:
+        res = 0.0
+        for v in a:
+            res = res + float(v)
+        return res
+    if n <= 128:
+        r = [float(a[j]) for j in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] = r[j] + float(a[i + j])
+            i += 8
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+        while i < n:
+            res = res + float(a[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return pairwise_sum(a[:n2]) + pairwise_sum(a[n2:])
+
+
+def mean_std_model(a):
+    """np.mean / np.std (ddof 0) of a 1-D float64 array in numpy's operation order: mean = pairwise_sum / n;
+    std = sqrt(pairwise_sum((a - mean)^2) / n) with separately rounded subtract and multiply."""
+    n = len(a)
+    m = pairwise_sum(a) / n
+    dev = [float(v) - m for v in a]
+    sq = [d * d for d in dev]
+    return m, float(np.sqrt(pairwise_sum(sq) / n))
+
+
 def try_sample(test, test_copy, indexes, distances, chrom_bins, chrom_bin_sums, cutoff):
     """One z-score pass (wisetools.py:407-435).  Per bin: reference values = test_copy without the bin's
     own chromosome, gathered at indexes[i][distances[i] < cutoff], negatives dropped; z = (x-mean)/std,
