@@ -55,9 +55,10 @@ int wc_sm_count(const wc_ctx* ctx);
 /* Device-time (ms, CUDA events on `stream`) of the named phases of the most recent call:
  * which: 0 = centre+norms (K4), 1 = distance+streaming top-k (K5), 2 = exact re-score/finalise (K6),
  *        3 = exhaustive fallback rows, 4 = z-score passes (K8), 5 = segmentation (K9), 6 = prep (K1-K3). */
-double wc_last_phase_ms(const wc_ctx* ctx, int which);
-/* Counters of the most recent wc_newref_topk call: which: 0 = kernel launches, 1 = rows sent to the exhaustive
- * fallback, 2 = candidate entries emitted by K5, 3 = tiles computed, 4 = CTAs launched for K5. */
+double wc_last_phase_ms(wc_ctx* ctx, int which);
+/* Counters of the most recent calls: which: 0 = kernel launches of wc_newref_topk, 1 = its rows sent to the exhaustive
+ * fallback, 2 = candidate entries emitted by K5, 3 = tiles computed, 4 = CTAs launched for K5, 5 = kernel launches of
+ * the last wc_zscore_batch, 6 = of the last wc_segment_batch, 7 = of the last wc_newref_prep. */
 long long wc_last_counter(const wc_ctx* ctx, int which);
 
 /* Debug aid: enable (1) / disable (0) per-CTA cycle counters in the distance kernel and copy the counters of the
@@ -88,6 +89,56 @@ int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int S, const i
  * (wisecondor.py:111-132) would bind. */
 int wc_newref_topk_host(wc_ctx* ctx, const double* corrected_h, int N, int S, const int* chrom_bins_h,
                         int nchrom, int row_begin, int row_end, int refsize, int32_t* idx_h, double* dist_h);
+
+/* ---- test: batched sample preparation, within-sample z-scores, Stouffer segmentation ------------------------ */
+/* Layout: the batch's corrected values are T[bin][sample] with leading dimension ldb (a multiple of 32, >= B). */
+
+/* Once per reference: replaces the per-bin `index[distances[i] < cutoff]` selection and the other-chromosome
+ * concatenation trySample rebuilds per chromosome (wisetools.py:420-424).
+ *   indexes_d/distances_d DEVICE N x k: the reference npz's `indexes`, `distances` (wisecondor.py:164-165)
+ *   cutoff                getOptimalCutoff's value (wisetools.py:328-336; sample independent, host numpy)
+ *   table_d  DEVICE N x k int32: table[i][0..count[i]) = GLOBAL masked-bin ids of bin i's usable reference bins
+ *   count_d  DEVICE N int32 */
+int wc_test_table(wc_ctx* ctx, const int32_t* indexes_d, const double* distances_d, int N, int k,
+                  const int* chrom_bins_h, int nchrom, double cutoff, int32_t* table_d, int32_t* count_d,
+                  void* stream);
+
+/* Replaces toNumpyRefFormat + applyPCA (wisetools.py:267-278, 104-113) for B samples.
+ *   counts_d     DEVICE B x Nraw int32: per sample the autosomal read counts, each chromosome zero-padded /
+ *                truncated to the reference's `chromosome_sizes` (wisetools.py:270-272; the host does that and
+ *                scaleSample, wisetools.py:220-237)
+ *   masked_raw_d DEVICE N int32: raw position of every masked-in bin (np.flatnonzero(mask))
+ *   pca_mean_d N, pca_components_d ncomp x N: the reference npz's PCA (wisecondor.py:168-169)
+ *   test_d       DEVICE N x ldb float64 out: x / ((x - mean) C^T C + mean), sample-minor.  Asynchronous. */
+int wc_test_prep(wc_ctx* ctx, const int32_t* counts_d, int B, int Nraw, const int32_t* masked_raw_d, int N,
+                 const double* pca_mean_d, const double* pca_components_d, int ncomp, double* test_d, int ldb,
+                 void* stream);
+
+/* applyPCA alone (wisetools.py:104-113) on already normalised, masked vectors x_d (DEVICE B x N float64). */
+int wc_apply_pca(wc_ctx* ctx, const double* x_d, int B, int N, const double* pca_mean_d,
+                 const double* pca_components_d, int ncomp, double* test_d, int ldb, void* stream);
+
+/* Replaces repeatTest / trySample (wisetools.py:438-448, 407-435) for B samples: `repeats` passes, bins with
+ * abs(z) >= z_threshold are marked -1 between passes and stop serving as reference values.
+ *   z_d, r_d DEVICE B x N float64 (sample-major), refsizes_d DEVICE B x N int32: resultsZ, resultsR, refSizes of
+ *   the last pass;  asdef_d DEVICE B float64: stdDevSum / stdDevNum.  Bit-identical to the reference (numpy's
+ *   summation order).  copy_init_d (DEVICE N x ldb, or NULL = test_d) is trySample's `testCopy`: the values the
+ *   reference bins are gathered from in the first pass, -1 where already marked.  Asynchronous. */
+int wc_zscore_batch(wc_ctx* ctx, const double* test_d, const double* copy_init_d, int N, int B, int ldb, const int32_t* table_d,
+                    const int32_t* count_d, int k, double z_threshold, int repeats, double* z_d, double* r_d,
+                    int32_t* refsizes_d, double* asdef_d, void* stream);
+
+/* Replaces the chromosome loop of toolTest (wisecondor.py:233-238): fillTri (wisetools.py:466-472) +
+ * TriArr.segmentTri (triarray.py:59-84) on the bins with refsizes >= minrefbins (wisecondor.py:215-218), for the
+ * chromosomes listed (0-based) in chromosomes_h.
+ *   cwz_d          DEVICE B x nsel float64: zTriangle.getValue(0, n-1) (wisecondor.py:237)
+ *   cleaned_bins_d DEVICE B x nsel int32: kept bins of each listed chromosome (`cleanedBins`, wisecondor.py:220-222)
+ *   calls_d        DEVICE B x max_calls wc_call, ncalls_d DEVICE B int32: unordered; sort by (chrom, x)
+ * mineffectsize != 0 (fillTriMin, wisetools.py:475-487) is not implemented here.  Synchronous. */
+int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* refsizes_d, int N, int B,
+                     const int* chrom_bins_h, int nchrom, const int* chromosomes_h, int nsel, int minrefbins,
+                     double z_threshold, int min_search, double* cwz_d, int32_t* cleaned_bins_d, wc_call* calls_d,
+                     int32_t* ncalls_d, int max_calls, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,197 @@
+"""GPU parity of the batched test path - sample preparation (K7), within-sample z-scores (K8) and Stouffer
+segmentation (K9) - against the oracle and the golden vectors produced by the reference, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+import c_oracle
+import wc_oracle
+from wisecondor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _same(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def _close(a, b, rel=1e-9):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    assert a.shape == b.shape
+    ok = (np.isnan(a) & np.isnan(b)) | (a == b) | (np.abs(a - b) <= rel * np.maximum(np.abs(a), np.abs(b)))
+    assert ok.all(), "max rel err %g" % np.nanmax(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def fn():
+    return np.load(os.path.join(GOLD, "functions.npz"), allow_pickle=True)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    return np.load(os.path.join(GOLD, "tiny_cli.npz"), allow_pickle=True)
+
+
+# ---- z-scores ----------------------------------------------------------------------------------------------
+def test_zscores_golden_bit_exact(fn):
+    from wisecondor_b200 import wisetools
+    bins = [int(b) for b in fn['z_bins']]
+    sums = list(np.cumsum(bins))
+    cutoff = float(fn['z_cutoff'])
+    test = fn['z_test']
+    z, r, s, sd = wisetools.trySample(test, np.copy(test), fn['z_idx'], fn['z_dst'], bins, sums, cutoff)
+    assert _same(np.array([z, r, s]), fn['z_pass1']) and sd == float(fn['z_pass1_sd'])
+    z, r, s, sd = wisetools.repeatTest(np.copy(test), fn['z_idx'], fn['z_dst'], bins, sums, cutoff, 3.0, 5)
+    assert _same(np.array([z, r, s]), fn['z_pass5']) and sd == float(fn['z_pass5_sd'])
+    # trySample on a pre-marked copy (the state repeatTest hands its second pass)
+    copy = np.copy(test)
+    copy[np.abs(fn['z_pass1'][0]) >= 3.0] = -1
+    want = wc_oracle.try_sample(test, copy, fn['z_idx'], fn['z_dst'], bins, sums, cutoff)
+    got = wisetools.trySample(test, copy, fn['z_idx'], fn['z_dst'], bins, sums, cutoff)
+    assert _same(got[0], want[0]) and _same(got[1], want[1]) and _same(got[2], want[2]) and got[3] == want[3]
+
+
+@pytest.mark.parametrize("B,k,S", [(1, 100, 30), (37, 100, 30), (70, 20, 16), (5, 150, 24), (3, 300, 24)])
+def test_zscores_batch_vs_oracle(B, k, S):
+    """Medium genome, batches that do not fill a warp tile, refsize below and above numpy's 128-element block."""
+    from wisecondor_b200 import wisetools
+    bins = [int(b) for b in np.maximum(2, np.array(synth.chrom_bins(250000)) // 6)]
+    n = sum(bins)
+    sums = list(np.cumsum(bins))
+    X = synth.corrected_like(bins, S, seed=7 + B)
+    idx, dst = c_oracle.get_reference_rows(X, bins, 0, n, k)
+    cutoff = wc_oracle.get_optimal_cutoff(dst, 3)
+    rng = np.random.default_rng(B)
+    tests = 1.0 + rng.normal(0, 0.03, size=(B, n))
+    for b in range(B):
+        a = int(rng.integers(0, n - 60))
+        tests[b, a:a + int(rng.integers(5, 60))] *= rng.choice([0.7, 1.3])       # aberrations -> marks -> -1 gathers
+    tests[0, 5] = 0.0
+    z, r, s, sd = wisetools.repeatTestBatch(tests, idx, dst, bins, sums, cutoff, 3.2, 4)
+    for b in sorted(set([0, B // 2, B - 1])):
+        want = wc_oracle.repeat_test(tests[b], idx, dst, bins, sums, cutoff, 3.2, 4)
+        assert _same(z[b], want[0]), "sample %d z" % b
+        assert _same(r[b], want[1]) and _same(s[b], want[2]) and sd[b] == want[3]
+
+
+def test_zscores_empty_and_constant_references():
+    """Bins without usable reference bins give NaN / refsize 0; identical reference values give sigma 0 -> inf z
+    (wisetools.py:426-433 under np.seterr('ignore'))."""
+    from wisecondor_b200 import wisetools
+    bins = [20, 15, 10]
+    n = sum(bins)
+    sums = list(np.cumsum(bins))
+    X = synth.corrected_like(bins, 12, seed=1)
+    idx, dst = c_oracle.get_reference_rows(X, bins, 0, n, 8)
+    dst[3, :] = 5.0                                   # every distance above the cutoff: no reference bins for bin 3
+    cutoff = 1.0
+    dst[dst >= cutoff] = 5.0
+    test = 1.0 + np.random.default_rng(0).normal(0, 0.02, size=n)
+    test[20:35] = 1.0                                 # chromosome 2 constant: bins referencing only it get sigma 0
+    want = wc_oracle.repeat_test(test, idx, dst, bins, sums, cutoff, 4.0, 3)
+    got = wisetools.repeatTest(test, idx, dst, bins, sums, cutoff, 4.0, 3)
+    assert _same(got[0], want[0]) and _same(got[1], want[1]) and _same(got[2], want[2])
+    assert (got[3] == want[3]) or (np.isnan(got[3]) and np.isnan(want[3]))
+    assert got[2][3] == 0 and np.isnan(got[0][3])
+
+
+# ---- sample preparation ------------------------------------------------------------------------------------------
+def test_prep_matches_reference(fn, tiny):
+    from wisecondor_b200 import wisetools
+    bins = [int(b) for b in tiny['bins']]
+    samples = [synth.counts_to_sample_dict(tiny['test_counts'][t], bins, 50000000) for t in range(4)]
+    sizes, mask = tiny['ref_chromosome_sizes'], tiny['ref_mask']
+    for t in range(4):
+        want = wc_oracle.to_numpy_ref_format(samples[t], sizes, mask)
+        assert _same(wisetools.toNumpyRefFormat(samples[t], sizes, mask), want)      # integer / integer: exact
+        _close(wisetools.applyPCA(want, tiny['ref_pca_mean'], tiny['ref_pca_components']),
+               wc_oracle.apply_pca(want, tiny['ref_pca_mean'], tiny['ref_pca_components']), 1e-12)
+    T = wisetools.prepSamples(samples, sizes, mask, tiny['ref_pca_mean'], tiny['ref_pca_components'])
+    for t in range(4):
+        want = wc_oracle.apply_pca(wc_oracle.to_numpy_ref_format(samples[t], sizes, mask), tiny['ref_pca_mean'],
+                                   tiny['ref_pca_components'])
+        _close(T[:, t], want, 1e-12)
+    # pad / truncate path and the golden vector of the reference
+    s2 = [synth.counts_to_sample_dict(fn['ingest_counts'][i], list(fn['ingest_bins']), 50000000) for i in range(3)]
+    chrom_bins = [len(s2[0][str(c)]) for c in range(1, 23)]
+    odd = [b + (1 if i % 2 else -1) for i, b in enumerate(chrom_bins)]
+    assert _same(wisetools.toNumpyRefFormat(s2[1], odd, np.ones(sum(odd), dtype=bool)), fn['ingest_padtrunc'])
+    assert _same(wisetools.toNumpyRefFormat(s2[2], chrom_bins, fn['ingest_mask']), fn['ingest_tref'])
+    _close(wisetools.applyPCA(fn['ingest_tref'], fn['ingest_mean'], fn['ingest_components']), fn['ingest_applied'], 1e-12)
+
+
+# ---- segmentation --------------------------------------------------------------------------------------------
+def _segment(zlist, thr, min_search=3):
+    """Each region as one 'sample' with a single chromosome."""
+    from wisecondor_b200 import wisetools
+    out = []
+    for zreg in zlist:
+        n = len(zreg)
+        cwz, cleaned, calls = wisetools.segmentChromosomes(zreg[None, :], np.full((1, n), 100), [n], [1], 25, thr, min_search)
+        out.append((cwz[0, 0], int(cleaned[0, 0]), [(float(c['z']), (int(c['x']), int(c['y']))) for c in calls]))
+    return out
+
+
+def test_segmentation_golden_exact(fn):
+    offs = np.concatenate(([0], np.cumsum(fn['seg_n'])))
+    regions = [fn['seg_z'][offs[i]:offs[i + 1]] for i in range(len(fn['seg_n']))]
+    got = _segment(regions, 3.5)
+    calls = fn['seg_calls']
+    for i, (cw, n, segs) in enumerate(got):
+        assert cw == fn['seg_cw'][i] and n == len(regions[i])
+        want = calls[calls[:, 0] == i][:, 1:]
+        have = np.array([[s[1][0], s[1][1], s[0]] for s in segs], dtype=float).reshape(-1, 3)
+        assert np.array_equal(have, want), "region %d: %s vs %s" % (i, have, want)
+    (cw, n, segs), = _segment([np.full(25, 2.0)], 3.5)
+    assert np.array_equal(np.array([[s[1][0], s[1][1], s[0]] for s in segs], dtype=float), fn['seg_flat_calls'])
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (5, 2), (159, 3), (160, 4), (161, 5), (700, 6), (1300, 7)])
+def test_segmentation_vs_oracle(n, seed):
+    rng = np.random.default_rng(seed)
+    z = rng.normal(0, 1, size=n)
+    if n > 10:
+        for _ in range(3):
+            a = int(rng.integers(0, n - 4))
+            z[a:a + int(rng.integers(2, max(3, n // 5)))] += rng.choice([-1.5, 1.5, 3.0])
+    else:
+        z += 5.0
+    (cw, m, segs), = _segment([z], 4.0)
+    wcw, wsegs = wc_oracle.segment_region(z, 4.0, 3) if n <= 400 else wc_oracle.segment_region_prefix(z, 4.0, 3)
+    assert [s[1] for s in segs] == [s[1] for s in wsegs]
+    if n <= 400:
+        assert cw == wcw and [s[0] for s in segs] == [s[0] for s in wsegs]
+    else:
+        _close([cw] + [s[0] for s in segs], [wcw] + [s[0] for s in wsegs], 1e-12)
+        # exact values of the called runs in numpy's own order
+        assert cw == np.sum(z) / np.sqrt(n)
+        for v, (x, y) in segs:
+            assert v == np.sum(z[x:y + 1]) / np.sqrt(y - x + 1)
+
+
+def test_segmentation_batch_keep_mask_and_chromosome_list():
+    """Several samples, several chromosomes, bins dropped by minrefbins, a chromosome subset (-chromosomes)."""
+    from wisecondor_b200 import wisetools
+    rng = np.random.default_rng(12)
+    bins = [90, 40, 200, 7, 130]
+    n = sum(bins)
+    B = 6
+    z = rng.normal(0, 1, size=(B, n))
+    z[1, 100:120] += 2.5
+    z[2, 140:300] -= 1.0
+    z[4, 335:] += 3.0
+    sizes = rng.integers(20, 40, size=(B, n))
+    chroms = [1, 3, 4, 5]
+    cwz, cleaned, calls = wisetools.segmentChromosomes(z, sizes, bins, chroms, 25, 3.8, 3)
+    starts = np.concatenate(([0], np.cumsum(bins)))
+    for b in range(B):
+        for slot, c in enumerate(chroms):
+            keep = sizes[b, starts[c - 1]:starts[c]] >= 25
+            zc = z[b, starts[c - 1]:starts[c]][keep]
+            assert cleaned[b, slot] == keep.sum()
+            wcw, wsegs = wc_oracle.segment_region(zc, 3.8, 3)
+            assert cwz[b, slot] == wcw
+            mine = calls[(calls['sample'] == b) & (calls['chrom'] == slot)]
+            assert [(float(m['z']), (int(m['x']), int(m['y']))) for m in mine] == [(float(v), xy) for v, xy in wsegs]

@@ -13,6 +13,7 @@ _LIB = None
 SYMBOLS = [
     "wc_create", "wc_destroy", "wc_last_error", "wc_version", "wc_sm_count", "wc_last_phase_ms",
     "wc_last_counter", "wc_newref_topk", "wc_newref_topk_host", "wc_debug_profile", "wc_set_option",
+    "wc_test_table", "wc_test_prep", "wc_apply_pca", "wc_zscore_batch", "wc_segment_batch",
 ]
 
 
@@ -55,6 +56,17 @@ def lib():
     L.wc_set_option.argtypes = [vp, ctypes.c_char_p, cd]
     L.wc_debug_profile.restype = ci
     L.wc_debug_profile.argtypes = [vp, ci, vp, ci]
+    i32 = ci
+    L.wc_test_table.restype = ci
+    L.wc_test_table.argtypes = [vp, vp, vp, i32, i32, vp, i32, cd, vp, vp, vp]
+    L.wc_test_prep.restype = ci
+    L.wc_test_prep.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, vp]
+    L.wc_apply_pca.restype = ci
+    L.wc_apply_pca.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, i32, vp]
+    L.wc_zscore_batch.restype = ci
+    L.wc_zscore_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, cd, i32, vp, vp, vp, vp, vp]
+    L.wc_segment_batch.restype = ci
+    L.wc_segment_batch.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, i32, i32, cd, i32, vp, vp, vp, vp, i32, vp]
     _LIB = L
     return L
 

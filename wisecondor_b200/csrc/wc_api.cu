@@ -69,8 +69,16 @@ extern "C" void wc_destroy(wc_ctx* ctx) {
 
 extern "C" int wc_sm_count(const wc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
-extern "C" double wc_last_phase_ms(const wc_ctx* ctx, int which) {
+extern "C" double wc_last_phase_ms(wc_ctx* ctx, int which) {
     if (!ctx || which < 0 || which >= WC_NPHASE) return -1.0;
+    if (ctx->timed_mask & (1u << which)) {      // recorded by an asynchronous call: wait for the end event now
+        float ms = 0.f;
+        cudaSetDevice(ctx->device);
+        if (cudaEventSynchronize(ctx->ev[2 * which + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, ctx->ev[2 * which], ctx->ev[2 * which + 1]) == cudaSuccess)
+            ctx->phase_ms[which] = ms;
+        ctx->timed_mask &= ~(1u << which);
+    }
     return ctx->phase_ms[which];
 }
 

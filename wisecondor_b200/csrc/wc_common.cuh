@@ -38,7 +38,17 @@ struct wc_buf {
     size_t bytes = 0;
 };
 
-enum { WC_NBUF = 24, WC_NPHASE = 8, WC_NCOUNTER = 8 };
+enum { WC_NBUF = 48, WC_NPHASE = 8, WC_NCOUNTER = 8 };
+
+// Workspace slots (one grow-only device buffer each).
+enum {
+    SLOT_XC = 0, SLOT_NORMS, SLOT_ROWCS, SLOT_ROWCE, SLOT_RBMETA, SLOT_CAND_D, SLOT_CAND_J, SLOT_SEGCNT,
+    SLOT_SEGFLAG, SLOT_SLOW, SLOT_SCRATCH, SLOT_IO_X, SLOT_IO_IDX, SLOT_IO_DIST,                       // search
+    SLOT_PROF = 20,
+    SLOT_T_COPY = 24, SLOT_T_ZT, SLOT_T_RT, SLOT_T_NT, SLOT_T_SD, SLOT_T_FLAGS, SLOT_T_TOTALS, SLOT_T_PROJ,   // test
+    SLOT_S_ISQ = 32, SLOT_S_META, SLOT_S_STATUS,                                                       // segmentation
+    SLOT_P_FIRST = 36                                                                                  // newref prep
+};
 
 struct wc_ctx {
     int device = 0;
@@ -47,6 +57,7 @@ struct wc_ctx {
     cudaEvent_t ev[2 * WC_NPHASE];
     double phase_ms[WC_NPHASE];
     long long counter[WC_NCOUNTER];
+    unsigned timed_mask = 0;        // phases whose event pair is recorded but not yet read (asynchronous calls)
     int k5_dbg = 0;                 // timing experiments only (results invalid when non-zero)
     int k5_stages = 0;              // 0 = automatic TMA ring depth
     int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones

@@ -872,12 +872,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-enum {
-    SLOT_PROF = 20,
-    SLOT_XC = 0, SLOT_NORMS, SLOT_ROWCS, SLOT_ROWCE, SLOT_RBMETA, SLOT_CAND_D, SLOT_CAND_J, SLOT_SEGCNT,
-    SLOT_SEGFLAG, SLOT_SLOW, SLOT_SCRATCH, SLOT_IO_X, SLOT_IO_IDX, SLOT_IO_DIST
-};
-
 }  // namespace
 
 extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int S, const int* chrom_bins_h,
@@ -896,8 +890,9 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     WC_CHECK_ARG(tot == N);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     WC_CUDA(cudaSetDevice(ctx->device));
-    for (int i = 0; i < WC_NPHASE; ++i) ctx->phase_ms[i] = 0.0;
-    for (int i = 0; i < WC_NCOUNTER; ++i) ctx->counter[i] = 0;
+    for (int i = 0; i < 4; ++i) ctx->phase_ms[i] = 0.0;
+    for (int i = 0; i < 5; ++i) ctx->counter[i] = 0;
+    ctx->timed_mask &= ~0xfu;
     const int rows = row_end - row_begin;
     if (rows == 0) return WC_OK;
     WC_CHECK_ARG(idx_d != nullptr && dist_d != nullptr);

@@ -73,3 +73,150 @@ def last_search_stats(device=0):
         "exhaustive_ms": ctx.phase_ms(3), "launches": ctx.counter(0), "exhaustive_rows": ctx.counter(1),
         "tiles": ctx.counter(3), "ctas": ctx.counter(4),
     }
+
+
+# ------------------------------------------------------------------------------------------------------------
+# test: batched sample preparation, z-scores, segmentation
+# ------------------------------------------------------------------------------------------------------------
+CALL_DTYPE = np.dtype([("sample", np.int32), ("chrom", np.int32), ("x", np.int32), ("y", np.int32), ("z", np.float64)])
+
+
+def _dev_index(dev):
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+def _ints(values):
+    arr = np.ascontiguousarray(values, dtype=np.int32)
+    return arr, arr.ctypes.data_as(ctypes.c_void_p)
+
+
+def pad32(b):
+    return (int(b) + 31) // 32 * 32
+
+
+class ReferenceTable(object):
+    """Device-resident form of a reference npz for the test path: per bin the global ids of its usable reference
+    bins (`index[distances < cutoff]` mapped out of other-chromosome coordinates, wisetools.py:420-424)."""
+
+    def __init__(self, indexes, distances, masked_sizes, cutoff, device=0):
+        dev = torch.device("cuda", device)
+        self.device = dev
+        self.masked_sizes = [int(v) for v in masked_sizes]
+        self.n, self.k = int(indexes.shape[0]), int(indexes.shape[1])
+        self.cutoff = float(cutoff)
+        idx = torch.as_tensor(np.ascontiguousarray(indexes, dtype=np.int32), device=dev)
+        dst = torch.as_tensor(np.ascontiguousarray(distances, dtype=np.float64), device=dev)
+        self.table = torch.empty((self.n, self.k), dtype=torch.int32, device=dev)
+        self.count = torch.empty((self.n,), dtype=torch.int32, device=dev)
+        cb, cbp = _ints(self.masked_sizes)
+        ctx = _cabi.context(_dev_index(dev))
+        rc = _cabi.lib().wc_test_table(ctx.handle, _ptr(idx), _ptr(dst), self.n, self.k, cbp, len(cb), self.cutoff,
+                                       _ptr(self.table), _ptr(self.count), _stream_ptr(dev))
+        _cabi.check(rc)
+        torch.cuda.current_stream(dev).synchronize()
+
+
+def test_prep(counts, masked_raw, pca_mean, pca_components, nsamples=None):
+    """toNumpyRefFormat's normalise+mask and applyPCA (wisetools.py:275-276, 104-113) for a batch.
+
+    counts: CUDA int32 [B][Nraw] (chromosomes already padded/truncated to the reference sizes); masked_raw: CUDA
+    int32 [N]; pca_mean CUDA f64 [N]; pca_components CUDA f64 [ncomp][N].  Returns T: CUDA f64 [N][pad32(B)]."""
+    _require_cuda(counts, torch.int32, "counts")
+    _require_cuda(masked_raw, torch.int32, "masked_raw")
+    b, nraw = counts.shape
+    n = masked_raw.shape[0]
+    dev = counts.device
+    if pca_components is None:        # normalise + mask only (toNumpyRefFormat)
+        ncomp = 0
+        pca_mean = pca_components = torch.empty((0,), dtype=torch.float64, device=dev)
+    else:
+        _require_cuda(pca_mean, torch.float64, "pca_mean")
+        _require_cuda(pca_components, torch.float64, "pca_components")
+        ncomp = pca_components.shape[0]
+    ldb = pad32(b)
+    out = torch.empty((n, ldb), dtype=torch.float64, device=dev)
+    ctx = _cabi.context(_dev_index(dev))
+    rc = _cabi.lib().wc_test_prep(ctx.handle, _ptr(counts), b, nraw, _ptr(masked_raw), n, _ptr(pca_mean),
+                                  _ptr(pca_components), ncomp, _ptr(out), ldb, _stream_ptr(dev))
+    _cabi.check(rc)
+    return out
+
+
+def apply_pca(x, pca_mean, pca_components):
+    """applyPCA (wisetools.py:104-113) for a batch of normalised masked vectors x: CUDA f64 [B][N].
+    Returns T: CUDA f64 [N][pad32(B)] (sample-minor)."""
+    _require_cuda(x, torch.float64, "x")
+    _require_cuda(pca_mean, torch.float64, "pca_mean")
+    _require_cuda(pca_components, torch.float64, "pca_components")
+    b, n = x.shape
+    dev = x.device
+    ldb = pad32(b)
+    out = torch.empty((n, ldb), dtype=torch.float64, device=dev)
+    ctx = _cabi.context(_dev_index(dev))
+    rc = _cabi.lib().wc_apply_pca(ctx.handle, _ptr(x), b, n, _ptr(pca_mean), _ptr(pca_components),
+                                  pca_components.shape[0], _ptr(out), ldb, _stream_ptr(dev))
+    _cabi.check(rc)
+    return out
+
+
+def zscore_batch(test, nsamples, table, z_threshold, repeats, copy_init=None):
+    """repeatTest (wisetools.py:438-448) for a batch.  test: CUDA f64 [N][ldb] sample-minor; table: ReferenceTable;
+    copy_init: optional CUDA f64 [N][ldb], trySample's pre-marked `testCopy`.
+    Returns (z [B][N], r [B][N], refsizes int32 [B][N], asdef [B]) on the device."""
+    _require_cuda(test, torch.float64, "test")
+    if copy_init is not None:
+        _require_cuda(copy_init, torch.float64, "copy_init")
+        if copy_init.shape != test.shape:
+            raise _cabi.WisecondorError("copy_init must have the shape of test")
+    n, ldb = test.shape
+    b = int(nsamples)
+    dev = test.device
+    z = torch.empty((b, n), dtype=torch.float64, device=dev)
+    r = torch.empty((b, n), dtype=torch.float64, device=dev)
+    sizes = torch.empty((b, n), dtype=torch.int32, device=dev)
+    asdef = torch.empty((b,), dtype=torch.float64, device=dev)
+    ctx = _cabi.context(_dev_index(dev))
+    rc = _cabi.lib().wc_zscore_batch(ctx.handle, _ptr(test), _ptr(copy_init) if copy_init is not None else None, n, b, ldb, _ptr(table.table), _ptr(table.count), table.k,
+                                     float(z_threshold), int(repeats), _ptr(z), _ptr(r), _ptr(sizes), _ptr(asdef),
+                                     _stream_ptr(dev))
+    _cabi.check(rc)
+    return z, r, sizes, asdef
+
+
+def segment_batch(z, refsizes, masked_sizes, chromosomes, minrefbins, z_threshold, min_search=3, max_calls=256):
+    """The chromosome loop of toolTest (wisecondor.py:233-238) for a batch.  z: CUDA f64 [B][N]; refsizes: CUDA
+    int32 [B][N]; chromosomes: 0-based indices.  Returns (cwz [B][nsel] CUDA, cleaned_bins int32 [B][nsel] CUDA,
+    calls: numpy structured array (sample, chrom, x, y, z) sorted by (sample, chrom, x))."""
+    _require_cuda(z, torch.float64, "z")
+    _require_cuda(refsizes, torch.int32, "refsizes")
+    b, n = z.shape
+    dev = z.device
+    cb, cbp = _ints(masked_sizes)
+    sel, selp = _ints(chromosomes)
+    cwz = torch.empty((b, len(sel)), dtype=torch.float64, device=dev)
+    cleaned = torch.empty((b, len(sel)), dtype=torch.int32, device=dev)
+    ctx = _cabi.context(_dev_index(dev))
+    while True:
+        calls = torch.empty((b, max_calls * CALL_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        ncalls = torch.empty((b,), dtype=torch.int32, device=dev)
+        rc = _cabi.lib().wc_segment_batch(ctx.handle, _ptr(z), _ptr(refsizes), n, b, cbp, len(cb), selp, len(sel),
+                                          int(minrefbins), float(z_threshold), int(min_search), _ptr(cwz), _ptr(cleaned),
+                                          _ptr(calls), _ptr(ncalls), int(max_calls), _stream_ptr(dev))
+        if rc != 0 and b"max_calls" in _cabi.lib().wc_last_error() and max_calls < (1 << 16):
+            max_calls *= 8
+            continue
+        _cabi.check(rc)
+        break
+    nc = ncalls.cpu().numpy()
+    raw = calls.cpu().numpy().view(CALL_DTYPE).reshape(b, max_calls)
+    rows = [raw[i, :nc[i]] for i in range(b)]
+    flat = np.concatenate(rows) if rows else np.zeros(0, dtype=CALL_DTYPE)
+    flat = flat[np.lexsort((flat["x"], flat["chrom"], flat["sample"]))]
+    return cwz, cleaned, flat
+
+
+def last_test_stats(device=0):
+    """Device timings (ms) of the most recent prep / z-score / segmentation calls on `device`."""
+    ctx = _cabi.context(device)
+    return {"prep_ms": ctx.phase_ms(6), "zscore_ms": ctx.phase_ms(4), "segment_ms": ctx.phase_ms(5),
+            "zscore_launches": ctx.counter(5), "segment_launches": ctx.counter(6)}
