@@ -54,7 +54,8 @@ const char* wc_version(void);
 int wc_sm_count(const wc_ctx* ctx);
 /* Device-time (ms, CUDA events on `stream`) of the named phases of the most recent call:
  * which: 0 = centre+norms (K4), 1 = distance+streaming top-k (K5), 2 = exact re-score/finalise (K6),
- *        3 = exhaustive fallback rows, 4 = z-score passes (K8), 5 = segmentation (K9), 6 = prep (K1-K3). */
+ *        3 = exhaustive fallback rows, 4 = z-score passes (K8), 5 = segmentation (K9), 6 = test sample prep (K7),
+ *        7 = PCA bin means + Gram matrix (K2).  Phases of asynchronous calls are read lazily (this call waits). */
 double wc_last_phase_ms(wc_ctx* ctx, int which);
 /* Counters of the most recent calls: which: 0 = kernel launches of wc_newref_topk, 1 = its rows sent to the exhaustive
  * fallback, 2 = candidate entries emitted by K5, 3 = tiles computed, 4 = CTAs launched for K5, 5 = kernel launches of
@@ -89,6 +90,31 @@ int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int S, const i
  * (wisecondor.py:111-132) would bind. */
 int wc_newref_topk_host(wc_ctx* ctx, const double* corrected_h, int N, int S, const int* chrom_bins_h,
                         int nchrom, int row_begin, int row_end, int refsize, int32_t* idx_h, double* dist_h);
+
+/* ---- newref: normalisation, mask, PCA residual ------------------------------------------------------------ */
+/* Together these replace toNumpyArray (wisetools.py:240-264) and trainPCA (wisetools.py:89-101) as called from
+ * toolNewrefPrep (wisecondor.py:91-96).  counts_d: DEVICE S x Nraw int32, one row per sample = its autosomal count
+ * arrays concatenated (all samples must have equal chromosome lengths, as wisetools.py:250 requires). */
+
+/* mask_d (DEVICE Nraw uint8) = sumPerBin > 0 (wisetools.py:259-260): some sample has a read in the bin. */
+int wc_newref_mask(wc_ctx* ctx, const int32_t* counts_d, int S, int Nraw, uint8_t* mask_d, void* stream);
+
+/* masked_d (DEVICE N x S float64, bin-major) = counts / per-sample total at the masked-in bins masked_raw_d
+ * (wisetools.py:255-256, 261). */
+int wc_newref_normalize(wc_ctx* ctx, const int32_t* counts_d, int S, int Nraw, const int32_t* masked_raw_d, int N,
+                        double* masked_d, void* stream);
+
+/* First half of PCA(n_components).fit (wisetools.py:90-92): mean_d (DEVICE N) = per-bin mean over samples (numpy's
+ * summation order: bit-identical to pca.mean_), gram_d (DEVICE S x S) = Xc^T Xc of the centred matrix.  The caller
+ * takes the top eigenpairs of gram_d on the host (numpy/scipy LAPACK; S is 600..2000). */
+int wc_pca_gram(wc_ctx* ctx, const double* masked_d, int N, int S, double* mean_d, double* gram_d, void* stream);
+
+/* Second half + transform / inverse_transform / divide (wisetools.py:94-96): eigvec_d DEVICE S x ncomp (columns =
+ * eigenvectors of the Gram matrix, largest first), sigma_h HOST ncomp singular values (sqrt of the eigenvalues).
+ * components_d DEVICE ncomp x N (pca.components_, sign not normalised), corrected_d DEVICE N x S (bin-major:
+ * `correctedData`, wisecondor.py:106). */
+int wc_pca_apply(wc_ctx* ctx, const double* masked_d, int N, int S, const double* mean_d, const double* eigvec_d,
+                 const double* sigma_h, int ncomp, double* components_d, double* corrected_d, void* stream);
 
 /* ---- test: batched sample preparation, within-sample z-scores, Stouffer segmentation ------------------------ */
 /* Layout: the batch's corrected values are T[bin][sample] with leading dimension ldb (a multiple of 32, >= B). */

@@ -1,0 +1,179 @@
+"""GPU: the drop-in command line (wisecondor.py newrefprep/newrefpart/newrefpost/newref/test/testbatch) and the newref
+preparation kernels (K1-K3) against what the reference's own CLI produced on the same sample files
+(tests/golden/tiny_cli.npz, functions.npz)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import wc_oracle
+from wisecondor_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, os.path.join(GOLD))
+
+
+def _close(a, b, rel=1e-9):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    ok = (np.isnan(a) & np.isnan(b)) | (a == b) | (np.abs(a - b) <= rel * np.maximum(np.abs(a), np.abs(b)))
+    assert ok.all(), "max rel err %g" % np.nanmax(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def _components_close(a, b):
+    for x, y in zip(a, b):
+        s = np.sign(np.dot(x, y))
+        assert np.max(np.abs(x * s - y)) <= 1e-9 * np.max(np.abs(y))
+
+
+def _run(argv):
+    import wisecondor
+    try:
+        wisecondor.main(argv)
+    except SystemExit as e:
+        assert e.code in (0, None), "wisecondor.py %s exited with %s" % (argv[0], e.code)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    return np.load(os.path.join(GOLD, "tiny_cli.npz"), allow_pickle=True)
+
+
+@pytest.fixture(scope="module")
+def fn():
+    return np.load(os.path.join(GOLD, "functions.npz"), allow_pickle=True)
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory, tiny):
+    from make_golden import TINY_BINSIZE, write_sample_npz
+    d = tmp_path_factory.mktemp("wc_cli")
+    bins = [int(b) for b in tiny['bins']]
+    for i in range(tiny['ref_counts'].shape[0]):
+        write_sample_npz(str(d / ("r%02d.npz" % i)), tiny['ref_counts'][i], bins, TINY_BINSIZE)
+    for t in range(tiny['test_counts'].shape[0]):
+        write_sample_npz(str(d / ("t%d.npz" % t)), tiny['test_counts'][t], bins, TINY_BINSIZE)
+    # the reference npz exactly as the reference wrote it (arrays from the golden file)
+    np.savez_compressed(str(d / "goldref.npz"), arguments={}, runtime={}, binsize=tiny['ref_binsize'],
+                        indexes=tiny['ref_indexes'], distances=tiny['ref_distances'],
+                        chromosome_sizes=tiny['ref_chromosome_sizes'], mask=tiny['ref_mask'],
+                        masked_sizes=tiny['ref_masked_sizes'], pca_components=tiny['ref_pca_components'],
+                        pca_mean=tiny['ref_pca_mean'])
+    return d
+
+
+def test_prep_kernels_vs_reference(fn):
+    from wisecondor_b200 import wisetools
+    bins = list(fn['ingest_bins'])
+    samples = [synth.counts_to_sample_dict(fn['ingest_counts'][i], bins, 50000000) for i in range(fn['ingest_counts'].shape[0])]
+    masked, chrom_bins, mask = wisetools.toNumpyArray(samples)
+    assert np.array_equal(mask, fn['ingest_mask']) and chrom_bins == [len(samples[0][str(c)]) for c in range(1, 23)]
+    assert np.array_equal(masked, fn['ingest_masked'])                  # integer / integer-valued total: exact
+    corrected, pca = wisetools.trainPCA(masked)
+    assert np.array_equal(pca.mean_, fn['ingest_mean'])                 # numpy's summation order on the device
+    _close(corrected, fn['ingest_corrected'])
+    _components_close(pca.components_, fn['ingest_components'])
+    with pytest.raises(ValueError):
+        bad = dict(samples[0])
+        bad['3'] = bad['3'][:-1]
+        wisetools.toNumpyArray([samples[1], bad])
+
+
+def test_newref_cluster_steps_match_reference(workdir, tiny):
+    refs = [str(workdir / ("r%02d.npz" % i)) for i in range(tiny['ref_counts'].shape[0])]
+    prep = str(workdir / "ref_prep.npz")
+    _run(["newrefprep"] + refs + [prep])
+    for part in (1, 2, 3):
+        _run(["newrefpart", prep, str(workdir / "ref_part"), str(part), "3", "-refsize", "40"])
+    _run(["newrefpost", prep, str(workdir / "ref_part"), "3", str(workdir / "ref.npz")])
+    p = np.load(prep, allow_pickle=True)
+    assert np.array_equal(p['mask'], tiny['prep_mask'])
+    assert np.array_equal(p['maskedChromBins'], tiny['prep_maskedChromBins'])
+    assert np.array_equal(p['maskedChromBinSums'], tiny['prep_maskedChromBinSums'])
+    assert np.array_equal(p['maskedData'], tiny['prep_maskedData'])
+    _close(p['correctedData'], tiny['prep_correctedData'])
+    assert set(p.files) == {'arguments', 'runtime', 'binsize', 'chromosomeBins', 'maskedData', 'mask', 'maskedChromBins',
+                            'maskedChromBinSums', 'correctedData', 'pca_components', 'pca_mean'}
+    r = np.load(str(workdir / "ref.npz"), allow_pickle=True)
+    assert set(r.files) == {'arguments', 'runtime', 'binsize', 'indexes', 'distances', 'chromosome_sizes', 'mask',
+                            'masked_sizes', 'pca_components', 'pca_mean'}
+    assert r['indexes'].dtype == np.int32 and r['distances'].dtype == np.float64
+    assert np.array_equal(r['indexes'], tiny['ref_indexes'])
+    _close(r['distances'], tiny['ref_distances'])
+    assert np.array_equal(r['chromosome_sizes'], tiny['ref_chromosome_sizes'])
+    assert np.array_equal(r['masked_sizes'], tiny['ref_masked_sizes'])
+    assert np.array_equal(r['pca_mean'], tiny['ref_pca_mean'])
+    _components_close(r['pca_components'], tiny['ref_pca_components'])
+    assert r['binsize'].item() == tiny['ref_binsize'].item()
+    assert r['arguments'].item()['func'].__name__ == 'toolNewrefPost'
+    # distances are bit-identical to the oracle's on the *same* corrected matrix (exact re-score, K6)
+    import c_oracle
+    mb = [int(b) for b in p['maskedChromBins']]
+    oidx, odst = c_oracle.get_reference_rows(p['correctedData'], mb, 0, sum(mb), 40)
+    assert np.array_equal(r['indexes'], oidx) and np.array_equal(r['distances'], odst)
+
+
+def test_newref_single_command_resumes_and_cleans_up(workdir, tiny):
+    refs = [str(workdir / ("r%02d.npz" % i)) for i in range(tiny['ref_counts'].shape[0])]
+    out = str(workdir / "whole.npz")
+    _run(["newref"] + refs + [out, "-refsize", "40", "-parts", "2"])
+    assert not os.path.exists(str(workdir / "whole_prep.npz")) and not os.path.exists(str(workdir / "whole_part_1.npz"))
+    r = np.load(out, allow_pickle=True)
+    assert np.array_equal(r['indexes'], tiny['ref_indexes'])
+    _close(r['distances'], tiny['ref_distances'])
+
+
+def _check_result(res, tiny, t):
+    _close(np.concatenate(list(res['results_z'])), tiny['res%d_z' % t])
+    _close(np.concatenate(list(res['results_r'])), tiny['res%d_r' % t])
+    _close(res['results_cwz'], tiny['res%d_cwz' % t])
+    calls = np.asarray(res['results_calls'], dtype=float).reshape(-1, 5)
+    want = tiny['res%d_calls' % t]
+    assert calls.shape == want.shape
+    assert np.array_equal(calls[:, :3], want[:, :3])                     # chromosome, start bin, end bin: exact
+    _close(calls[:, 3:], want[:, 3:])
+    _close([res['threshold_z'], res['asdef'], res['aasdef']], tiny['res%d_scalars' % t])
+    assert [len(a) for a in res['results_z']] == [int(v) for v in tiny['ref_chromosome_sizes']]
+
+
+def test_test_tool_matches_reference(workdir, tiny):
+    """`test` against the reference npz the reference itself wrote."""
+    for t in range(tiny['test_counts'].shape[0]):
+        out = str(workdir / ("o%d.npz" % t))
+        extra = ["-minrefbins", "10"] + (["-repeats", "3"] if t == 2 else [])
+        _run(["test", str(workdir / ("t%d.npz" % t)), out, str(workdir / "goldref.npz")] + extra)
+        res = np.load(out, allow_pickle=True)
+        assert set(res.files) == {'arguments', 'runtime', 'binsize', 'results_r', 'results_z', 'results_cwz',
+                                  'results_calls', 'threshold_z', 'asdef', 'aasdef'}
+        _check_result(res, tiny, t)
+
+
+def test_testbatch_equals_single_runs(workdir, tiny):
+    outdir = str(workdir / "batch")
+    tests = [str(workdir / ("t%d.npz" % t)) for t in (0, 1, 3)]
+    _run(["testbatch"] + tests + [outdir, str(workdir / "goldref.npz"), "-minrefbins", "10"])
+    for t in (0, 1, 3):
+        res = np.load(os.path.join(outdir, "t%d.npz" % t), allow_pickle=True)
+        _check_result(res, tiny, t)
+        single = np.load(str(workdir / ("o%d.npz" % t)), allow_pickle=True)
+        assert np.array_equal(np.concatenate(list(res['results_z'])), np.concatenate(list(single['results_z'])), equal_nan=True)
+        assert np.array_equal(np.asarray(res['results_calls']), np.asarray(single['results_calls']))
+
+
+def test_own_reference_then_test_end_to_end(workdir, tiny):
+    """newref and test both from this build: calls land where the reference's do."""
+    out = str(workdir / "e2e.npz")
+    _run(["test", str(workdir / "t1.npz"), out, str(workdir / "ref.npz"), "-minrefbins", "10"])
+    res = np.load(out, allow_pickle=True)
+    _check_result(res, tiny, 1)
+
+
+def test_host_only_tools_say_so(workdir):
+    import wisecondor
+    with pytest.raises(SystemExit) as e:
+        wisecondor.main(["convert", "x.bam", "x.npz"])
+    assert e.value.code == 2
+    assert wc_oracle is not None

@@ -1,0 +1,144 @@
+"""CPU: host-side logic (row/sample partition, scaling, inflate, CLI surface), the C-ABI library (loads, exports every
+symbol the header declares, fails loudly without a GPU) and the world_size-2 gather over gloo."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import wc_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from wisecondor_b200 import _cabi, build
+    path = build.build_library()
+    L = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "wisecondor_b200.h")).read()
+    declared = set(re.findall(r"\b(wc_[a-z0-9_]+)\s*\(", header))
+    declared -= {"wc_call", "wc_ctx", "wc_status"}
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(L, name), "libwisecondor_b200.so lacks %s" % name
+    assert set(_cabi.SYMBOLS) == declared, "binding list and header differ: %s" % (set(_cabi.SYMBOLS) ^ declared)
+    assert b"sm_100a" in _cabi.lib().wc_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from wisecondor_b200 import _cabi, wisetools
+    with pytest.raises(_cabi.WisecondorError):
+        _cabi.Context(0)
+    X = np.ones((10, 4))
+    with pytest.raises(Exception):
+        wisetools.getReference(X, [5, 5], [5, 10], 3, 1, 1)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no product source imports, loads or links it."""
+    bad = re.compile(r"^\s*(import|from)\s+\S*(wc_oracle|c_oracle)|libwc_oracle|sys\.path.*oracle|#include.*oracle", re.M)
+    files = [os.path.join(ROOT, "wisecondor.py")]
+    for dirpath, _, names in os.walk(os.path.join(ROOT, "wisecondor_b200")):
+        files += [os.path.join(dirpath, f) for f in names if f.endswith((".py", ".cu", ".cuh", ".h"))]
+    for f in files:
+        assert not bad.search(open(f).read()), f
+
+
+def test_get_part_matches_reference_formula():
+    from wisecondor_b200 import shard, wisetools
+    for n in (7, 716, 11537, 57633, 288113):
+        for parts in (1, 2, 3, 4, 7, 8):
+            edges = [wisetools.getPart(p, parts, n) for p in range(parts)]
+            assert edges == [wc_oracle.get_part(p, parts, n) for p in range(parts)]
+            assert edges == [shard.row_shard(p, parts, n) for p in range(parts)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(parts - 1))
+    for n in (0, 1, 5, 10000):
+        for w in (1, 2, 8):
+            blocks = [shard.sample_shard(r, w, n) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1
+
+
+def test_scale_inflate_cutoff_host_functions():
+    from wisecondor_b200 import wisetools
+    rng = np.random.default_rng(0)
+    sample = {str(c): rng.integers(0, 50, size=int(rng.integers(1, 40))).astype(np.int32) for c in range(1, 23)}
+    assert wisetools.scaleSample(sample, 5, 5) is sample and wisetools.scaleSample(sample, 5, None) is sample
+    got, want = wisetools.scaleSample(sample, 2, 10), wc_oracle.scale_sample(sample, 2, 10)
+    for c in sample:
+        assert np.array_equal(got[c], want[c]) and got[c].dtype == np.int32
+    with pytest.raises(SystemExit):
+        wisetools.scaleSample(sample, 3, 10)
+    mask = rng.random(50) > 0.3
+    keep = rng.random(int(mask.sum())) > 0.2
+    vals = rng.normal(size=int(keep.sum()))
+    assert np.array_equal(wisetools.inflateArrayMulti(vals, [mask, keep]), wc_oracle.inflate_multi(vals, [mask, keep]))
+    d = rng.gamma(2.0, 1.0, size=(40, 9))
+    assert wisetools.getOptimalCutoff(d, 3)[0] == wc_oracle.get_optimal_cutoff(d, 3)
+    counts = wisetools._refFormatCounts(sample, [len(sample[str(c)]) + (c % 3) - 1 for c in range(1, 23)])
+    assert counts.dtype == np.int32 and counts.shape[0] == sum(len(sample[str(c)]) + (c % 3) - 1 for c in range(1, 23))
+
+
+def test_cli_surface_matches_reference():
+    import wisecondor
+    p = wisecondor.buildParser()
+    a = p.parse_args(["newref", "a.npz", "b.npz", "out.npz"])
+    assert (a.infiles, a.outfile, a.refsize, a.binsize, a.cpus, a.parts) == (["a.npz", "b.npz"], "out.npz", 100, None, 1, 1)
+    assert a.func is wisecondor.toolNewref
+    a = p.parse_args(["newrefpart", "p.npz", "part", "2", "5", "-refsize", "50"])
+    assert a.part == [2, 5] and a.refsize == 50 and a.func is wisecondor.toolNewrefPart
+    a = p.parse_args(["newrefpost", "p.npz", "part", "5", "out.npz"])
+    assert a.parts == 5
+    a = p.parse_args(["test", "s.npz", "o.npz", "r.npz"])
+    assert (a.minzscore, a.mineffectsize, a.multitest, a.minrefbins, a.repeats) == (None, 0, 1000, 25, 5)
+    assert list(a.chromosomes) == list(range(1, 23))
+    a = p.parse_args(["test", "s.npz", "o.npz", "r.npz", "-chromosomes", "1,13,21", "-minzscore", "4.5"])
+    assert a.chromosomes == [1, 13, 21] and a.minzscore == 4.5
+    a = p.parse_args(["convert", "x.bam", "x.npz"])
+    assert a.binsize == 1e6 and a.retdist == 4 and a.retthres == 4
+    # the tool functions keep the reference's names: npz `arguments` pickles args.func by name
+    for name in ("toolConvert", "toolNewref", "toolNewrefPrep", "toolNewrefPart", "toolNewrefPost", "toolTest",
+                 "toolPlot", "toolReport"):
+        assert callable(getattr(wisecondor, name))
+
+
+def _gather_worker(rank, world, port, n, k, q):
+    import torch
+    import torch.distributed as dist
+    from wisecondor_b200 import shard
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        a, b = shard.row_shard(rank, world, n)
+        rows = torch.arange(a, b, dtype=torch.int32)[:, None] * 1000 + torch.arange(k, dtype=torch.int32)[None, :]
+        idx, dst = shard.allgather_rows(rows, rows.to(torch.float64) * 0.5, n)
+        want = torch.arange(n, dtype=torch.int32)[:, None] * 1000 + torch.arange(k, dtype=torch.int32)[None, :]
+        q.put((rank, bool(torch.equal(idx, want) and torch.equal(dst, want.to(torch.float64) * 0.5))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 101), (3, 100)])
+def test_row_sharded_gather_over_gloo(world, n):
+    """The N>1 newref path on CPU: every rank's getPart rows all-gathered into the whole table on every rank."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, n, 6, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=10) for _ in range(world))
+    assert got == [(r, True) for r in range(world)]

@@ -220,3 +220,68 @@ def last_test_stats(device=0):
     ctx = _cabi.context(device)
     return {"prep_ms": ctx.phase_ms(6), "zscore_ms": ctx.phase_ms(4), "segment_ms": ctx.phase_ms(5),
             "zscore_launches": ctx.counter(5), "segment_launches": ctx.counter(6)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# newref preparation: normalise, mask, PCA residual
+# ------------------------------------------------------------------------------------------------------------
+def newref_normalize(counts):
+    """toNumpyArray's arithmetic (wisetools.py:255-261).  counts: CUDA int32 [S][Nraw].
+    Returns (maskedData CUDA f64 [N][S] bin-major, mask numpy bool [Nraw])."""
+    _require_cuda(counts, torch.int32, "counts")
+    s, nraw = counts.shape
+    dev = counts.device
+    ctx = _cabi.context(_dev_index(dev))
+    mask_d = torch.empty((nraw,), dtype=torch.uint8, device=dev)
+    _cabi.check(_cabi.lib().wc_newref_mask(ctx.handle, _ptr(counts), s, nraw, _ptr(mask_d), _stream_ptr(dev)))
+    mask = mask_d.cpu().numpy().astype(bool)
+    masked_raw = torch.as_tensor(np.flatnonzero(mask).astype(np.int32), device=dev)
+    n = int(masked_raw.shape[0])
+    masked = torch.empty((n, s), dtype=torch.float64, device=dev)
+    if n > 0:
+        _cabi.check(_cabi.lib().wc_newref_normalize(ctx.handle, _ptr(counts), s, nraw, _ptr(masked_raw), n, _ptr(masked),
+                                                    _stream_ptr(dev)))
+    return masked, mask
+
+
+def top_eigenpairs(gram, ncomp):
+    """Largest `ncomp` eigenpairs of the symmetric S x S Gram matrix (host LAPACK; the only N-independent step
+    of the PCA).  Returns (eigenvectors S x ncomp, largest first; singular values = sqrt(eigenvalues))."""
+    s = gram.shape[0]
+    try:
+        from scipy.linalg import eigh
+        w, v = eigh(gram, subset_by_index=[max(0, s - ncomp), s - 1])
+    except ImportError:                                   # pragma: no cover
+        w, v = np.linalg.eigh(gram)
+        w, v = w[-ncomp:], v[:, -ncomp:]
+    order = np.argsort(w)[::-1]
+    w, v = w[order], v[:, order]
+    return np.ascontiguousarray(v), np.sqrt(np.maximum(w, 0.0))
+
+
+def pca_fit_apply(masked, ncomp=3):
+    """trainPCA (wisetools.py:89-101) with the exact top-`ncomp` principal subspace.  masked: CUDA f64 [N][S].
+    Returns (corrected CUDA f64 [N][S], components numpy [ncomp][N] with scikit-learn's sign convention,
+    mean numpy [N])."""
+    _require_cuda(masked, torch.float64, "masked")
+    n, s = masked.shape
+    dev = masked.device
+    ctx = _cabi.context(_dev_index(dev))
+    mean = torch.empty((n,), dtype=torch.float64, device=dev)
+    gram = torch.empty((s, s), dtype=torch.float64, device=dev)
+    _cabi.check(_cabi.lib().wc_pca_gram(ctx.handle, _ptr(masked), n, s, _ptr(mean), _ptr(gram), _stream_ptr(dev)))
+    vec, sigma = top_eigenpairs(gram.cpu().numpy(), ncomp)
+    if not (sigma > 0).all():
+        raise _cabi.WisecondorError("PCA: fewer than %d non-zero singular values (degenerate sample matrix)" % ncomp)
+    vec_d = torch.as_tensor(vec, device=dev)
+    comps = torch.empty((ncomp, n), dtype=torch.float64, device=dev)
+    corrected = torch.empty((n, s), dtype=torch.float64, device=dev)
+    sig = np.ascontiguousarray(sigma, dtype=np.float64)
+    _cabi.check(_cabi.lib().wc_pca_apply(ctx.handle, _ptr(masked), n, s, _ptr(mean), _ptr(vec_d),
+                                         sig.ctypes.data_as(ctypes.c_void_p), ncomp, _ptr(comps), _ptr(corrected),
+                                         _stream_ptr(dev)))
+    comps_h = comps.cpu().numpy()
+    # scikit-learn svd_flip(u_based_decision=False): the largest-magnitude entry of every component is positive
+    signs = np.sign(comps_h[np.arange(ncomp), np.argmax(np.abs(comps_h), axis=1)])
+    signs[signs == 0] = 1.0
+    return corrected, comps_h * signs[:, None], mean.cpu().numpy()

@@ -4,6 +4,8 @@ Same function names, argument meaning and return values as the reference; the bo
 through wisecondor_b200._cabi / wisecondor_b200.device.  Functions the north star keeps on the host
 (scaleSample, getOptimalCutoff, getPart, splitByChrom, inflateArray) are plain numpy.
 """
+import time
+
 import numpy as np
 
 from . import device as _dev
@@ -16,23 +18,77 @@ def getPart(partnum, outof, bincount):
     return int(bincount / float(outof) * partnum), int(bincount / float(outof) * (partnum + 1))
 
 
-def getReference(correctedData, chromosomeBins, chromosomeBinSums, selectRefAmount=100, part=1, splitParts=1):
+def getReference(correctedData, chromosomeBins, chromosomeBinSums, selectRefAmount=100, part=1, splitParts=1,
+                 device=None):
     """Reference bins for the rows of 1-based `part` of `splitParts` (reference wisetools.py:364-398).
 
     Returns (indexArray int32 rows x selectRefAmount, distanceArray float64 rows x selectRefAmount): per target
     bin the positions, within the concatenation of all other chromosomes, of the selectRefAmount nearest bins
     ordered by (squared distance, index), and those distances.  The chromosome split of the reference's
-    splitByChrom/getRefForBins loop happens inside the kernel (per-row exclusion ranges).
+    splitByChrom/getRefForBins loop happens inside the kernel (per-row exclusion ranges).  correctedData may be a
+    numpy array [N][S] or a CUDA tensor; `device` overrides the module-level DEVICE (one host thread per GPU).
     """
+    timeStart = time.time()
     bincount = int(chromosomeBinSums[-1])
     startNum, endNum = getPart(part - 1, splitParts, bincount)
     print('Working on part', part, 'of', splitParts, 'meaning bins', startNum, 'up to', endNum)
-    X = np.ascontiguousarray(correctedData, dtype=np.float64)
-    if X.shape[0] != bincount:
-        raise ValueError("correctedData has %d bins, chromosomeBinSums says %d" % (X.shape[0], bincount))
-    idx, dist = _dev.newref_topk_host(X, [int(b) for b in chromosomeBins], startNum, endNum,
-                                      int(selectRefAmount), device=DEVICE)
+    dev = DEVICE if device is None else device
+    bins = [int(b) for b in chromosomeBins]
+    if not isinstance(correctedData, np.ndarray) and hasattr(correctedData, "is_cuda"):
+        if correctedData.shape[0] != bincount:
+            raise ValueError("correctedData has %d bins, chromosomeBinSums says %d" % (correctedData.shape[0], bincount))
+        idx, dist = _dev.newref_topk(correctedData, bins, startNum, endNum, int(selectRefAmount))
+        idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    else:
+        X = np.ascontiguousarray(correctedData, dtype=np.float64)
+        if X.shape[0] != bincount:
+            raise ValueError("correctedData has %d bins, chromosomeBinSums says %d" % (X.shape[0], bincount))
+        idx, dist = _dev.newref_topk_host(X, bins, startNum, endNum, int(selectRefAmount), device=dev)
+    print('Time spent:', int(time.time() - timeStart), 'seconds')
     return idx, dist
+
+
+class _FittedPCA(object):
+    """What the reference reads from the scikit-learn object trainPCA returns (wisecondor.py:107-108)."""
+
+    def __init__(self, components, mean):
+        self.components_ = components
+        self.mean_ = mean
+        self.n_components_ = components.shape[0]
+
+
+def _stackCounts(samples):
+    """Host part of toNumpyArray (reference wisetools.py:244-253): chromosomes 1..22 of every sample, stacked
+    sample-major [S][Nraw] int32.  Like the reference, samples whose chromosome lengths differ are an error."""
+    chromBins = []
+    for chromosome in range(1, 23):
+        lens = set(int(np.asarray(s[str(chromosome)]).shape[0]) for s in samples)
+        if len(lens) != 1:
+            raise ValueError("could not broadcast: chromosome %d has differing bin counts %s" % (chromosome, sorted(lens)))
+        chromBins.append(lens.pop())
+    counts = np.empty((len(samples), sum(chromBins)), dtype=np.int32)
+    for i, s in enumerate(samples):
+        counts[i] = np.concatenate([np.asarray(s[str(c)]) for c in range(1, 23)])
+    return counts, chromBins
+
+
+def toNumpyArray(samples, as_device=False):
+    """reference wisetools.py:240-264.  Returns (maskedData [N][S], chromBins, mask)."""
+    torch = _torch()
+    counts, chromBins = _stackCounts(samples)
+    masked, mask = _dev.newref_normalize(torch.as_tensor(counts, device=torch.device("cuda", DEVICE)))
+    print('Applying nonzero mask on the data:', (counts.shape[1], counts.shape[0]), 'becomes', tuple(masked.shape))
+    return (masked if as_device else masked.cpu().numpy()), chromBins, mask
+
+
+def trainPCA(refData, pcacomp=3, as_device=False):
+    """reference wisetools.py:89-101.  refData: [N][S] numpy or CUDA tensor.  Returns (corrected [N][S], pca) where
+    pca carries components_ and mean_."""
+    torch = _torch()
+    dev = torch.device("cuda", DEVICE)
+    X = refData if isinstance(refData, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(refData, dtype=np.float64), device=dev)
+    corrected, comps, mean = _dev.pca_fit_apply(X, pcacomp)
+    return (corrected if as_device else corrected.cpu().numpy()), _FittedPCA(comps, mean)
 
 
 def getOptimalCutoff(reference, repeats):
@@ -200,3 +256,66 @@ def segmentChromosomes(cleanedZ_or_z, refSizes, masked_sizes, chromosomes, minre
     cwz, cleaned, calls = _dev.segment_batch(z, sizes, masked_sizes, [c - 1 for c in chromosomes], minrefbins,
                                              z_threshold, min_search)
     return cwz.cpu().numpy(), cleaned.cpu().numpy(), calls
+
+
+def testSamples(samples, ref, z_threshold, chromosomes=tuple(range(1, 23)), mineffectsize=0, minrefbins=25, repeats=5,
+                min_search=3, batch=1024):
+    """The computation of toolTest (reference wisecondor.py:196-268) for a list of sample dicts already scaled to
+    the reference's binsize.  `ref` holds the reference-npz entries.  Returns one dict per sample with the
+    result-npz entries results_r, results_z, results_cwz, results_calls, threshold_z, asdef, aasdef.
+
+    Device: prepSample (K7), repeatTest (K8), fillTri + segmentTri (K9).  Host: getOptimalCutoff (once per
+    reference), the cleaned->raw coordinate walk and the per-call median of R (wisecondor.py:241-257), inflate."""
+    if mineffectsize != 0:
+        raise NotImplementedError("-mineffectsize != 0 (fillTriMin's run-median filter, reference "
+                                  "wisetools.py:475-487) is not implemented on the device yet")
+    torch = _torch()
+    chromosome_sizes = [int(v) for v in ref['chromosome_sizes']]
+    masked_sizes = [int(v) for v in ref['masked_sizes']]
+    mask = np.asarray(ref['mask'], dtype=bool)
+    optimalCutoff, _ = getOptimalCutoff(ref['distances'], 3)
+    table = _table(ref['indexes'], ref['distances'], masked_sizes, optimalCutoff)
+    masked_raw = np.flatnonzero(mask)
+    raw_starts = np.concatenate(([0], np.cumsum(chromosome_sizes)))
+    masked_starts = np.concatenate(([0], np.cumsum(masked_sizes)))
+    sel = [c - 1 for c in chromosomes]
+    out = []
+    timeStartTest = time.time()
+    for first in range(0, len(samples), batch):
+        chunk = samples[first:first + batch]
+        nb = len(chunk)
+        T = prepSamples(chunk, chromosome_sizes, mask, ref['pca_mean'], ref['pca_components'], as_device=True)
+        z_d, r_d, sizes_d, asdef_d = _dev.zscore_batch(T, nb, table, z_threshold, repeats)
+        cwz_d, cleaned_d, calls = _dev.segment_batch(z_d, sizes_d, masked_sizes, sel, minrefbins, z_threshold, min_search)
+        z_h, r_h, sizes_h = z_d.cpu().numpy(), r_d.cpu().numpy(), sizes_d.cpu().numpy()
+        asdef_h, cwz_h = asdef_d.cpu().numpy(), cwz_d.cpu().numpy()
+        call_lo = np.searchsorted(calls['sample'], np.arange(nb), side='left')
+        call_hi = np.searchsorted(calls['sample'], np.arange(nb), side='right')
+        for b in range(nb):
+            keep = sizes_h[b] >= minrefbins                                  # infinite_mask, wisecondor.py:215
+            cleanedR = r_h[b][keep]
+            kept_raw = masked_raw[keep]                                      # raw bin of every cleaned bin
+            kept_starts = np.searchsorted(kept_raw, raw_starts)              # cleaned offset of every chromosome
+            inflatedZ = np.zeros(mask.shape[0])
+            inflatedR = np.zeros(mask.shape[0])
+            inflatedZ[kept_raw] = z_h[b][keep]
+            inflatedR[kept_raw] = cleanedR - 1
+            stouffCalls = []
+            for c in calls[call_lo[b]:call_hi[b]]:
+                chrom = sel[int(c['chrom'])]
+                x, y = int(c['x']), int(c['y'])
+                base = kept_starts[chrom]
+                pos = kept_raw[base:kept_starts[chrom + 1]] - raw_starts[chrom]
+                start_raw = int(pos[x])
+                end_raw = int(pos[y - 1]) + 1 if y > x else start_raw        # the walk of wisecondor.py:242-253
+                stouffCalls.append([chrom + 1, start_raw, end_raw, float(c['z']),
+                                    np.median(cleanedR[base + x:base + y + 1]) - 1])
+            asdef = float(asdef_h[b])
+            out.append(dict(
+                results_z=[inflatedZ[raw_starts[i]:raw_starts[i + 1]] for i in range(len(chromosome_sizes))],
+                results_r=[inflatedR[raw_starts[i]:raw_starts[i + 1]] for i in range(len(chromosome_sizes))],
+                results_cwz=cwz_h[b].copy(), results_calls=np.array(stouffCalls), threshold_z=z_threshold,
+                asdef=asdef, aasdef=asdef * z_threshold))
+    del masked_starts
+    print('Time spent on obtaining z-scores and stouffers z-scores:', int(time.time() - timeStartTest), 'seconds')
+    return out
