@@ -230,6 +230,106 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------
+# test half of the path: samples/s of the batched z-score + segmentation kernels (sample-sharded, no communication)
+# --------------------------------------------------------------------------------------------------------
+def synthetic_test_counts(nsamples, nraw, seed):
+    """Per-sample raw count vectors [B][Nraw] int32: Poisson around a shared bin profile with one aberrant stretch."""
+    rng = np.random.default_rng(seed)
+    lam = rng.gamma(20.0, 8.7, size=nraw)
+    out = rng.poisson(lam, size=(nsamples, nraw)).astype(np.int32)
+    for b in range(nsamples):
+        a = int(rng.integers(0, nraw - 500))
+        w = int(rng.integers(20, 400))
+        out[b, a:a + w] = (out[b, a:a + w] * rng.choice([0.8, 1.25])).astype(np.int32)
+    return out
+
+
+def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins, k, idx_full, dist_full):
+    n = int(sum(bins))
+    B = int(args.test_batch)
+    dist_h = dist_full.cpu().numpy()
+    cut = float("inf")
+    for _ in range(3):                              # getOptimalCutoff (wisetools.py:328-336), once per reference
+        sel = dist_h[dist_h < cut]
+        cut = np.average(sel) + 3 * np.std(sel)
+    table = device.ReferenceTable(idx_full.cpu().numpy(), dist_h, bins, cut, device=local)
+    counts_pinned = torch.from_numpy(synthetic_test_counts(B, n, seed=100 + rank)).pin_memory()
+    masked_raw = torch.arange(n, dtype=torch.int32, device=dev)          # synthetic reference: nothing masked out
+    mean = X.mean(dim=1) / X.mean(dim=1).sum()                            # a plausible pca_mean (normalised profile)
+    comps = torch.zeros((3, n), dtype=torch.float64, device=dev)
+    comps[0, 0::3] = 1.0
+    comps[1, 1::3] = 1.0
+    comps[2, 2::3] = 1.0
+    comps /= comps.norm(dim=1, keepdim=True)
+    thr = 5.4                                                             # norm.ppf(1 - 1/(57633*0.5*1000))
+    host_z = torch.empty((B, n), dtype=torch.float64).pin_memory()
+    host_r = torch.empty((B, n), dtype=torch.float64).pin_memory()
+    host_n = torch.empty((B, n), dtype=torch.int32).pin_memory()
+
+    def run(from_host):
+        counts = counts_pinned.to(dev, non_blocking=True) if from_host else counts_dev
+        T = device.test_prep(counts, masked_raw, mean, comps)
+        z, r, sizes, asdef = device.zscore_batch(T, B, table, thr, 5)
+        cwz, cleaned, calls = device.segment_batch(z, sizes, bins, list(range(22)), 25, thr, 3)
+        if from_host:
+            host_z.copy_(z, non_blocking=True)
+            host_r.copy_(r, non_blocking=True)
+            host_n.copy_(sizes, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        return len(calls)
+
+    counts_dev = counts_pinned.to(dev)
+    for _ in range(2):
+        ncalls = run(False)
+    torch.cuda.synchronize(dev)
+    steps = max(2, min(args.steps, 5))
+    zs, sg, pr = [], [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(steps):
+        run(False)
+        st = device.last_test_stats(local)
+        zs.append(st["zscore_ms"]); sg.append(st["segment_ms"]); pr.append(st["prep_ms"])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    dev_ms = e0.elapsed_time(e1) / steps
+    t0 = time.time()
+    for _ in range(steps):
+        run(True)
+    e2e_s = (time.time() - t0) / steps
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        return None
+    zms, sms = float(np.mean(zs)), float(np.mean(sg))
+    gathers = 5.0 * float(table.count.sum().item()) * 8.0 * B            # repeats x kept refs x 8 B, per launch set
+    entries = float(sum(b * (b + 1) // 2 for b in bins)) * B              # run evaluations (upper bound: no bin dropped)
+    hbm = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            hbm = float(json.load(fh)["hbm_gbs"])
+    except Exception:
+        pass
+    return {
+        "metric": "test_samples_per_s", "value": world * B / (dev_ms * 1e-3), "unit": "samples/s",
+        "samples_per_gpu": B, "n_gpus": world, "bins": n, "refsize": k, "repeats": 5, "ms_per_batch": dev_ms,
+        "phases_ms": {"prep": float(np.mean(pr)), "zscore": zms, "segment": sms}, "calls_in_batch": ncalls,
+        "zscore_gather_gbs": gathers / (zms * 1e-3) / 1e9, "hbm_peak_gbs_measured": hbm,
+        "zscore_note": "gathered operand bytes (5 passes x kept refs x 8 B x samples) per second; the sample tile stays "
+                       "in L2, so this may exceed the HBM copy peak",
+        "segment_run_evals_per_s": entries / (sms * 1e-3),
+        "e2e": {"value": world * B / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * n * 4, "d2h_bytes_per_step": B * n * 20,
+                "api": "device.test_prep + zscore_batch + segment_batch from pinned host counts, results copied back"},
+        "parallelism": "samples sharded over %d GPU(s), no communication" % world,
+    }
+
+
+# --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
 def main():
@@ -241,6 +341,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work in the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-test", action="store_true", help="skip the batched test (z-score + segmentation) section")
+    ap.add_argument("--test-batch", type=int, default=256, help="test samples per GPU in the test section")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -266,21 +368,23 @@ def main():
     X_host_np = synth.corrected_like(bins, S, seed=4)
     X_pinned = torch.from_numpy(X_host_np).pin_memory()
     X = X_pinned.to(dev, non_blocking=False)
-    r0, r1 = get_part(rank, world, n)
+    from wisecondor_b200 import shard
+    r0, r1 = shard.row_shard(rank, world, n)        # = the reference's getPart(rank, world, N)
     rows = r1 - r0
-    rows_max = max(get_part(p, world, n)[1] - get_part(p, world, n)[0] for p in range(world))
+    rows_max = shard.max_shard_rows(world, n)
     out_idx = torch.empty((rows_max, k), dtype=torch.int32, device=dev)
     out_dist = torch.empty((rows_max, k), dtype=torch.float64, device=dev)
     if world > 1:
-        all_idx = torch.empty((world * rows_max, k), dtype=torch.int32, device=dev)
-        all_dist = torch.empty((world * rows_max, k), dtype=torch.float64, device=dev)
+        scratch = (out_idx, out_dist, torch.empty((world * rows_max, k), dtype=torch.int32, device=dev),
+                   torch.empty((world * rows_max, k), dtype=torch.float64, device=dev))
+        full_idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+        full_dist = torch.empty((n, k), dtype=torch.float64, device=dev)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # 512 MiB > 126 MB L2
 
     def step():
         device.newref_topk(X, bins, r0, r1, k, out_idx[:rows], out_dist[:rows])
-        if world > 1:
-            dist.all_gather_into_tensor(all_idx, out_idx)
-            dist.all_gather_into_tensor(all_dist, out_dist)
+        if world > 1:       # NCCL all-gather of the row shards over NVLink: every rank ends with the whole table
+            shard.allgather_rows(out_idx[:rows], out_dist[:rows], n, out_idx=full_idx, out_dist=full_dist, scratch=scratch)
 
     def barrier():
         if world > 1:
@@ -344,9 +448,15 @@ def main():
         achieved = flops / (k5 * 1e-3) / 1e12
         # a kernel timed inside a long step under the power cap -> the sustained figure; short steps -> burst
         use_peak = sustained if ms_per_step > 50.0 else peak
+        traffic = None
+        try:      # dram__bytes_read.sum + dram__bytes_write.sum of one K5 launch, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "k5_traffic.json")) as fh:
+                traffic = json.load(fh).get(args.workload if world == 1 else "", None)
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": "wc_dist_topk_kernel (K5, fp64 DMMA.8x8x4 + TMA)",
                     "achieved": achieved, "peak": use_peak, "unit": "TFLOP/s", "frac": achieved / use_peak,
-                    "traffic": None, "flops_per_launch": flops, "kernel_ms": k5,
+                    "traffic": traffic, "flops_per_launch": flops, "kernel_ms": k5,
                     "peak_source": "measured FP64 tensor (DMMA) peak of this pool, %s (%s figure); "
                                    "MEASURED_PEAKS.json has no FP64 entry" %
                                    (peak_src, "sustained" if use_peak == sustained else "burst"),
@@ -371,6 +481,13 @@ def main():
             line["cpu_baseline"] = desc
         else:
             line["cpu_baseline"] = None
+    # ---- the test half of the path (BASELINE metric "test samples/s"): batched z-scores + segmentation ----------
+    test_line = None
+    if not args.no_test:
+        test_line = bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins, k, out_idx[:rows] if world == 1 else full_idx,
+                                    out_dist[:rows] if world == 1 else full_dist)
+    if rank == 0:
+        line["test"] = test_line
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
