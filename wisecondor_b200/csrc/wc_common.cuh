@@ -60,6 +60,7 @@ struct wc_ctx {
     unsigned timed_mask = 0;        // phases whose event pair is recorded but not yet read (asynchronous calls)
     int k5_dbg = 0;                 // timing experiments only (results invalid when non-zero)
     int k5_stages = 0;              // 0 = automatic TMA ring depth
+    int k5_group = 0;               // CTAs sharing a row block per scheduling round of K5 (0 = automatic)
     int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones
     int debug_profile = 0;          // K5 writes per-CTA cycle counters when set (wc_debug_profile)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)

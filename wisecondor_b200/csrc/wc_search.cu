@@ -66,12 +66,11 @@ struct TopkArgs {
     int nkc;                 // k chunks of BK, the last one holding the two extra samples
     int nd_last;             // data double-steps (8 samples each) in the last chunk: 0 or 1
     int extra_h;             // 8-sample block of the last chunk that holds (1, -n/2)
-    const int* rb_tile_prefix;   // [nrb+1] valid tiles before row block rb
     const int* rb_skip_lo;       // [nrb] first skipped column tile (own chromosome interior)
     const int* rb_skip_n;        // [nrb] number of skipped column tiles
     int nrb;
-    int total_tiles;
-    const int* cta_seg_base;     // [grid] first segment id of each CTA
+    const int* cta_piece_begin;  // [grid+1] this CTA's pieces are [begin, end)
+    const int* pieces;           // [npieces][5]: row block, first valid-tile index, end, step, segment id
     u64* cand_key;               // [nseg][BM][cap] score bit patterns
     int* cand_j;
     int* seg_cnt;                // [nseg][BM]
@@ -221,20 +220,9 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     }
     __syncthreads();
 
-    // this CTA's contiguous range of the (row block, column tile) work list
-    const long long T = a.total_tiles;
-    const int lin0 = (int)(T * blockIdx.x / gridDim.x);
-    const int lin1 = (int)(T * (blockIdx.x + 1) / gridDim.x);
-    if (lin0 >= lin1) return;
-    int rb = 0;
-    {
-        int lo = 0, hi = a.nrb;   // largest rb with prefix[rb] <= lin0
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (a.rb_tile_prefix[mid] <= lin0) lo = mid; else hi = mid;
-        }
-        rb = lo;
-    }
+    // this CTA's work: a list of pieces (row block, arithmetic progression of its valid column tiles), see the host side
+    const int pb = a.cta_piece_begin[blockIdx.x], pe = a.cta_piece_begin[blockIdx.x + 1];
+    if (pb >= pe) return;
 
     if (warp_all < PRODUCER_WARPS) {
         // ===== TMA producer: one elected lane streams the A (target rows) and B (candidate rows) k-slices =====
@@ -242,19 +230,21 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
         if (warp_all == 0 && lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int rbp = rb;
-            for (int lin = lin0; lin < lin1; ++lin) {
-                while (lin >= a.rb_tile_prefix[rbp + 1]) ++rbp;
-                int q = lin - a.rb_tile_prefix[rbp];
-                int t = q < a.rb_skip_lo[rbp] ? q : q + a.rb_skip_n[rbp];
-                int row0 = a.row_begin + rbp * BM;
-                int col0 = t * BN;
-                for (int kc = 0; kc < a.nkc; ++kc) {
-                    mbar_wait(&sm.empty[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&sm.full[stage], STAGE_BYTES);
-                    tma_load_2d(tiles + (size_t)stage * STAGE_BYTES, &tmap, kc * BK, row0, &sm.full[stage]);
-                    tma_load_2d(tiles + (size_t)stage * STAGE_BYTES + TILE_BYTES, &tmap, kc * BK, col0, &sm.full[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            for (int pi = pb; pi < pe; ++pi) {
+                const int* pc = a.pieces + (size_t)pi * 5;
+                const int rbp = pc[0], q1 = pc[2], qs = pc[3];
+                const int skip_lo = a.rb_skip_lo[rbp], skip_n = a.rb_skip_n[rbp];
+                const int row0 = a.row_begin + rbp * BM;
+                for (int q = pc[1]; q < q1; q += qs) {
+                    const int t = q < skip_lo ? q : q + skip_n;
+                    const int col0 = t * BN;
+                    for (int kc = 0; kc < a.nkc; ++kc) {
+                        mbar_wait(&sm.empty[stage], phase ^ 1u);
+                        mbar_arrive_expect_tx(&sm.full[stage], STAGE_BYTES);
+                        tma_load_2d(tiles + (size_t)stage * STAGE_BYTES, &tmap, kc * BK, row0, &sm.full[stage]);
+                        tma_load_2d(tiles + (size_t)stage * STAGE_BYTES + TILE_BYTES, &tmap, kc * BK, col0, &sm.full[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
                 }
             }
         }
@@ -293,8 +283,6 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     int my_cs[2] = {0, 0}, my_ce[2] = {0, 0};   // excluded column range [cs, ce) of this lane's two rows
     int stage = 0;
     uint32_t phase = 0;
-    int seg = a.cta_seg_base[blockIdx.x];
-    int cur_rb = -1;
     const size_t seg_stride = (size_t)BM * a.cap;
     bool ready = false;
 
@@ -305,16 +293,31 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
 
     long long pf_wait = 0, pf_epi = 0, pf_prune = 0, pf_nprune = 0, pf_emit = 0;
     const long long pf_t0 = clock64();
-    for (int lin = lin0; lin < lin1; ++lin) {
-        while (lin >= a.rb_tile_prefix[rb + 1]) ++rb;
-        if (rb != cur_rb) {
-            // segment boundary: flush this warp's rows of the previous row block, load the new block's
+    int pi = pb;
+    const int* pc = a.pieces + (size_t)pi * 5;
+    int rb = pc[0], q = pc[1], q1 = pc[2], qs = pc[3], seg = pc[4];
+    int skip_lo = a.rb_skip_lo[rb], skip_n = a.rb_skip_n[rb];
+    bool new_piece = true;
+    int tcount = 0;                             // tiles done by this CTA (debug timeline index)
+    while (true) {
+        if (q >= q1) {
+            // piece finished: flush this warp's rows of its segment, move to the next piece
             __syncwarp();
             if (lane < WROWS) {
-                if (cur_rb >= 0) {
-                    a.seg_cnt[(size_t)seg * BM + r0w + lane] = w_cnt[lane];
-                    a.seg_flag[(size_t)seg * BM + r0w + lane] = w_flag[lane];
-                }
+                a.seg_cnt[(size_t)seg * BM + r0w + lane] = w_cnt[lane] > a.cap ? a.cap : w_cnt[lane];
+                a.seg_flag[(size_t)seg * BM + r0w + lane] = w_flag[lane];
+            }
+            if (++pi >= pe) break;
+            pc = a.pieces + (size_t)pi * 5;
+            rb = pc[0]; q = pc[1]; q1 = pc[2]; qs = pc[3]; seg = pc[4];
+            skip_lo = a.rb_skip_lo[rb]; skip_n = a.rb_skip_n[rb];
+            new_piece = true;
+            continue;
+        }
+        if (new_piece) {
+            new_piece = false;
+            __syncwarp();
+            if (lane < WROWS) {
                 const int row = a.row_begin + rb * BM + r0w + lane;
                 const bool valid = row < a.row_end;
                 w_nrm[lane] = valid ? a.norms[row] : 0.0;
@@ -322,8 +325,6 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                 w_cnt[lane] = 0;
                 w_flag[lane] = 0;
             }
-            if (cur_rb >= 0) ++seg;
-            cur_rb = rb;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 const int row = a.row_begin + rb * BM + r0w + mt * 8 + pg;
@@ -333,11 +334,12 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             }
             __syncwarp();
         }
-        const int q = lin - a.rb_tile_prefix[rb];
-        const int t = q < a.rb_skip_lo[rb] ? q : q + a.rb_skip_n[rb];
+        const int t = q < skip_lo ? q : q + skip_n;
         const int col0 = t * BN;
-        const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && (lin - lin0) < 64;
-        long long* tr = tr_on ? a.trace + ((size_t)(warp >> 2) * 64 + (lin - lin0)) * 4 : nullptr;
+        q += qs;
+        const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && tcount < 64;
+        long long* tr = tr_on ? a.trace + ((size_t)(warp >> 2) * 64 + tcount) * 4 : nullptr;
+        ++tcount;
         if (tr_on) tr[0] = clock64();
 
         double acc[2][16][2];
@@ -511,11 +513,7 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     if (a.prof != nullptr && warp == 0 && lane == 0) {
         long long* o = a.prof + (size_t)blockIdx.x * 8;
         o[0] = clock64() - pf_t0; o[1] = pf_wait; o[2] = pf_epi; o[3] = pf_prune;
-        o[4] = lin1 - lin0; o[5] = pf_nprune; o[6] = pf_emit; o[7] = 0;
-    }
-    if (lane < WROWS && cur_rb >= 0) {
-        a.seg_cnt[(size_t)seg * BM + r0w + lane] = w_cnt[lane] > a.cap ? a.cap : w_cnt[lane];
-        a.seg_flag[(size_t)seg * BM + r0w + lane] = w_flag[lane];
+        o[4] = tcount; o[5] = pf_nprune; o[6] = pf_emit; o[7] = 0;
     }
 }
 
@@ -942,29 +940,90 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     int grid = ctx->sm_count;
     if (grid > (total_tiles + 7) / 8) grid = (total_tiles + 7) / 8;
     if (grid < 1) grid = 1;
-    std::vector<int> cta_seg_base(grid), rb_seg_first(nrb, -1), rb_seg_count(nrb, 0);
-    int nseg = 0;
+
+    // ---- schedule: which CTA computes which tiles, in which order ----------------------------------------------
+    // The centred matrix (Npad x ld doubles; 288 MB at 600 x 50 kb) does not fit the 126 MB L2, and every tile needs
+    // a 128-row A panel and a 128-row B panel of it.  With CTAs spread over unrelated columns every panel comes from
+    // DRAM for every tile (measured: 188 GB per launch at 600 x 50 kb).  So work is handed out in *rounds*: in a
+    // round a group of G CTAs shares one row block and walks its valid column tiles interleaved (CTA j takes tiles
+    // j, j+G, ...), all groups starting at column 0 together.  The CTAs then sit on (nearly) the same B panel at the
+    // same time - it is read from DRAM once per round - and the live A panels (grid/G of them) stay L2-resident.
+    // Row blocks left after the last full round are cut into contiguous column ranges that level the CTAs' tile
+    // counts (water-filling), so the balance of the plain equal split is kept.
+    struct Piece { int cta, rb, q0, q1, step, seg; };
+    std::vector<Piece> pieces;
+    std::vector<long long> load(grid, 0);
     {
-        int rb = 0;
-        for (int c = 0; c < grid; ++c) {
-            int lin0 = (int)((long long)total_tiles * c / grid);
-            int lin1 = (int)((long long)total_tiles * (c + 1) / grid);
-            cta_seg_base[c] = nseg;
-            int cur = -1;
-            for (int lin = lin0; lin < lin1;) {
-                while (lin >= prefix[rb + 1]) ++rb;
-                if (rb != cur) {
-                    if (rb_seg_first[rb] < 0) rb_seg_first[rb] = nseg;
-                    rb_seg_count[rb]++;
-                    ++nseg;
-                    cur = rb;
+        const double tile_bytes = (double)BM * ld * sizeof(double);
+        const double matrix_bytes = (double)Npad * ld * sizeof(double);
+        int G = ctx->k5_group;
+        if (G <= 0) {
+            G = 1;
+            if (matrix_bytes > 64e6)
+                while (G < 8 && (double)(grid / G) * tile_bytes > 48e6) G *= 2;
+        }
+        if (G > grid) G = grid;
+        const int groups = grid / G;
+        const int rounds = (matrix_bytes > 64e6 || ctx->k5_group > 0) ? nrb / groups : 0;
+        for (int r = 0; r < rounds; ++r)
+            for (int g = 0; g < groups; ++g) {
+                const int rb = r * groups + g;
+                const int nv = prefix[rb + 1] - prefix[rb];
+                for (int j = 0; j < G && j < nv; ++j) {
+                    pieces.push_back({g * G + j, rb, j, nv, G, 0});
+                    load[g * G + j] += (nv - j + G - 1) / G;
                 }
-                lin = std::min(lin1, prefix[rb + 1]);   // jump to the end of this row block's share
+            }
+        const int rb_left = rounds * groups;
+        long long left = prefix[nrb] - prefix[rb_left];
+        if (left > 0) {
+            long long lo = 0, hi = 0;
+            for (int c = 0; c < grid; ++c) hi = std::max(hi, load[c]);
+            hi += left;                                       // level with sum(max(0, level - load)) >= left
+            while (lo < hi) {
+                const long long mid = (lo + hi) / 2;
+                long long cap_sum = 0;
+                for (int c = 0; c < grid; ++c) cap_sum += std::max(0ll, mid - load[c]);
+                if (cap_sum >= left) hi = mid; else lo = mid + 1;
+            }
+            int rb = rb_left, q = 0;
+            for (int c = 0; c < grid && left > 0; ++c) {
+                long long want = std::min(left, std::max(0ll, lo - load[c]));
+                while (want > 0) {
+                    const int nv = prefix[rb + 1] - prefix[rb];
+                    if (q >= nv) { ++rb; q = 0; continue; }
+                    const int take = (int)std::min<long long>(want, nv - q);
+                    pieces.push_back({c, rb, q, q + take, 1, 0});
+                    load[c] += take;
+                    q += take;
+                    want -= take;
+                    left -= take;
+                }
             }
         }
     }
-    for (int rb = 0; rb < nrb; ++rb)
-        if (rb_seg_first[rb] < 0) { rb_seg_first[rb] = 0; rb_seg_count[rb] = 0; }
+    // segments (one candidate buffer set per piece) are numbered row-block-major so that K6 finds a row's pieces side by side
+    std::vector<int> rb_seg_first(nrb, 0), rb_seg_count(nrb, 0), cta_piece_begin(grid + 1, 0), piece_tab;
+    const int nseg = (int)pieces.size();
+    {
+        for (const Piece& pc : pieces) rb_seg_count[pc.rb]++;
+        int run = 0;
+        for (int rb = 0; rb < nrb; ++rb) { rb_seg_first[rb] = run; run += rb_seg_count[rb]; }
+        std::vector<int> next(rb_seg_first);
+        for (Piece& pc : pieces) pc.seg = next[pc.rb]++;
+        std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.cta < y.cta; });
+        piece_tab.resize((size_t)std::max(nseg, 1) * 5);
+        for (int i = 0; i < nseg; ++i) {
+            const Piece& pc = pieces[i];
+            cta_piece_begin[pc.cta + 1]++;
+            piece_tab[(size_t)i * 5 + 0] = pc.rb;
+            piece_tab[(size_t)i * 5 + 1] = pc.q0;
+            piece_tab[(size_t)i * 5 + 2] = pc.q1;
+            piece_tab[(size_t)i * 5 + 3] = pc.step;
+            piece_tab[(size_t)i * 5 + 4] = pc.seg;
+        }
+        for (int c = 0; c < grid; ++c) cta_piece_begin[c + 1] += cta_piece_begin[c];
+    }
 
     // ---- workspace ----------------------------------------------------------------------------------------
     double* Xc; double* norms; int* d_row_cs; int* d_row_ce; int* d_meta;
@@ -974,7 +1033,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     if ((rc = wc_reserve(ctx, SLOT_NORMS, Npad * sizeof(double), (void**)&norms))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_ROWCS, (size_t)N * sizeof(int), (void**)&d_row_cs))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_ROWCE, (size_t)N * sizeof(int), (void**)&d_row_ce))) return rc;
-    const size_t meta_ints = (size_t)(nrb + 1) + 4 * (size_t)nrb + grid;
+    const size_t meta_ints = 4 * (size_t)nrb + (size_t)grid + 1 + piece_tab.size();
     if ((rc = wc_reserve(ctx, SLOT_RBMETA, meta_ints * sizeof(int), (void**)&d_meta))) return rc;
     const size_t cand_n = (size_t)std::max(nseg, 1) * BM * cap;
     if ((rc = wc_reserve(ctx, SLOT_CAND_D, cand_n * sizeof(u64), (void**)&cand_key))) return rc;
@@ -982,21 +1041,21 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     if ((rc = wc_reserve(ctx, SLOT_SEGCNT, (size_t)std::max(nseg, 1) * BM * sizeof(int), (void**)&seg_cnt))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_SEGFLAG, (size_t)std::max(nseg, 1) * BM * sizeof(int), (void**)&seg_flag))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_SLOW, ((size_t)rows + 1) * sizeof(int), (void**)&slow))) return rc;
-    int* d_prefix = d_meta;
-    int* d_skip_lo = d_prefix + (nrb + 1);
+    int* d_skip_lo = d_meta;
     int* d_skip_n = d_skip_lo + nrb;
     int* d_seg_first = d_skip_n + nrb;
     int* d_seg_count = d_seg_first + nrb;
-    int* d_cta_seg = d_seg_count + nrb;
+    int* d_cta_piece = d_seg_count + nrb;
+    int* d_pieces = d_cta_piece + grid + 1;
 
     WC_CUDA(cudaMemcpyAsync(d_row_cs, row_cs.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, stream));
     WC_CUDA(cudaMemcpyAsync(d_row_ce, row_ce.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, stream));
-    WC_CUDA(cudaMemcpyAsync(d_prefix, prefix.data(), (size_t)(nrb + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
     WC_CUDA(cudaMemcpyAsync(d_skip_lo, skip_lo.data(), (size_t)nrb * sizeof(int), cudaMemcpyHostToDevice, stream));
     WC_CUDA(cudaMemcpyAsync(d_skip_n, skip_n.data(), (size_t)nrb * sizeof(int), cudaMemcpyHostToDevice, stream));
     WC_CUDA(cudaMemcpyAsync(d_seg_first, rb_seg_first.data(), (size_t)nrb * sizeof(int), cudaMemcpyHostToDevice, stream));
     WC_CUDA(cudaMemcpyAsync(d_seg_count, rb_seg_count.data(), (size_t)nrb * sizeof(int), cudaMemcpyHostToDevice, stream));
-    WC_CUDA(cudaMemcpyAsync(d_cta_seg, cta_seg_base.data(), (size_t)grid * sizeof(int), cudaMemcpyHostToDevice, stream));
+    WC_CUDA(cudaMemcpyAsync(d_cta_piece, cta_piece_begin.data(), (size_t)(grid + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    WC_CUDA(cudaMemcpyAsync(d_pieces, piece_tab.data(), piece_tab.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     WC_CUDA(cudaMemsetAsync(slow, 0, sizeof(int), stream));
     WC_CUDA(cudaMemsetAsync(seg_cnt, 0, (size_t)std::max(nseg, 1) * BM * sizeof(int), stream));
     WC_CUDA(cudaMemsetAsync(seg_flag, 0, (size_t)std::max(nseg, 1) * BM * sizeof(int), stream));
@@ -1032,8 +1091,8 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     TopkArgs ta;
     ta.norms = norms; ta.row_cs = d_row_cs; ta.row_ce = d_row_ce; ta.N = N;
     ta.row_begin = row_begin; ta.row_end = row_end; ta.nkc = nkc; ta.nd_last = nd_last; ta.extra_h = extra_h;
-    ta.rb_tile_prefix = d_prefix; ta.rb_skip_lo = d_skip_lo; ta.rb_skip_n = d_skip_n; ta.nrb = nrb;
-    ta.total_tiles = total_tiles; ta.cta_seg_base = d_cta_seg;
+    ta.rb_skip_lo = d_skip_lo; ta.rb_skip_n = d_skip_n; ta.nrb = nrb;
+    ta.cta_piece_begin = d_cta_piece; ta.pieces = d_pieces;
     ta.cand_key = cand_key; ta.cand_j = cand_j; ta.seg_cnt = seg_cnt; ta.seg_flag = seg_flag;
     ta.cap = cap; ta.k = k; ta.mcoef = mcoef; ta.tau_init = 1e10 * (1.0 + 1e-6);
     ta.lag = ctx->k5_lag;
@@ -1150,6 +1209,11 @@ extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
     if (strcmp(key, "k5_lag") == 0) {
         WC_CHECK_ARG(value >= 0 && value <= MAX_STAGES - 2);
         ctx->k5_lag = (int)value;
+        return WC_OK;
+    }
+    if (strcmp(key, "k5_group") == 0) {      // CTAs sharing a row block per round (0 = automatic; 1, 2, 4, 8)
+        WC_CHECK_ARG(value >= 0 && value <= 64);
+        ctx->k5_group = (int)value;
         return WC_OK;
     }
     if (strcmp(key, "k5_stages") == 0) {
