@@ -123,8 +123,10 @@ int wc_pca_apply(wc_ctx* ctx, const double* masked_d, int N, int S, const double
  * concatenation trySample rebuilds per chromosome (wisetools.py:420-424).
  *   indexes_d/distances_d DEVICE N x k: the reference npz's `indexes`, `distances` (wisecondor.py:164-165)
  *   cutoff                getOptimalCutoff's value (wisetools.py:328-336; sample independent, host numpy)
- *   table_d  DEVICE N x k int32: table[i][0..count[i]) = GLOBAL masked-bin ids of bin i's usable reference bins
+ *   table_d  DEVICE N x wc_table_stride(k) int32: table[i][0..count[i]) = GLOBAL masked-bin ids of bin i's usable
+ *            reference bins, in stored order (rows are padded to a multiple of 4 entries for 16-byte loads)
  *   count_d  DEVICE N int32 */
+int wc_table_stride(int k);
 int wc_test_table(wc_ctx* ctx, const int32_t* indexes_d, const double* distances_d, int N, int k,
                   const int* chrom_bins_h, int nchrom, double cutoff, int32_t* table_d, int32_t* count_d,
                   void* stream);

@@ -14,7 +14,7 @@ SYMBOLS = [
     "wc_create", "wc_destroy", "wc_last_error", "wc_version", "wc_sm_count", "wc_last_phase_ms",
     "wc_last_counter", "wc_newref_topk", "wc_newref_topk_host", "wc_debug_profile", "wc_set_option",
     "wc_newref_mask", "wc_newref_normalize", "wc_pca_gram", "wc_pca_apply",
-    "wc_test_table", "wc_test_prep", "wc_apply_pca", "wc_zscore_batch", "wc_segment_batch",
+    "wc_table_stride", "wc_test_table", "wc_test_prep", "wc_apply_pca", "wc_zscore_batch", "wc_segment_batch",
 ]
 
 
@@ -66,6 +66,8 @@ def lib():
     L.wc_pca_gram.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.wc_pca_apply.restype = ci
     L.wc_pca_apply.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, vp, vp, vp]
+    L.wc_table_stride.restype = ci
+    L.wc_table_stride.argtypes = [ci]
     L.wc_test_table.restype = ci
     L.wc_test_table.argtypes = [vp, vp, vp, i32, i32, vp, i32, cd, vp, vp, vp]
     L.wc_test_prep.restype = ci

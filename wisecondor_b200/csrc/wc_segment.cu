@@ -5,14 +5,16 @@
 // chromosome) the z-scores of the kept bins are compacted, every contiguous run [x..y] is scored
 // sum(z[x..y]) / sqrt(y-x+1), the most significant run above the threshold is called and the search recurses to its
 // left and right.  The reference materialises the n(n+1)/2 run values (99 MB for chr1 at 50 kb) with an O(n) numpy sum
-// each; here one CTA keeps the chromosome's prefix sums in shared memory and sweeps the triangle in registers.
+// each; here one CTA keeps the chromosome's prefix sums in shared memory and sweeps the triangle by diagonals (run lengths)
+// with the 1/sqrt(len) factors in registers.
 //
-// Exactness.  The sweep scores runs from prefix-sum differences times a reciprocal-sqrt table - not numpy's summation
-// order - so it is used only to *locate*: every run whose score lies within a rigorous error window `delta` of the sweep's
-// maximum (minimum) is re-scored in numpy's own pairwise order (wc_numpy_order.cuh) and divided by sqrt(len) exactly
-// as the reference does; champion and tie-breaking (first occurrence in the reference's row-major triangle order:
-// smallest x, then smallest y, triarray.py:62-66 argmax/argmin) are decided on those exact values.  Calls and their z
-// are therefore identical to the reference's, not merely close.
+// Exactness.  The sweep scores runs from prefix-sum differences times 1/sqrt(len) - not numpy's summation order - so it
+// is used only to *locate*, and it tracks one number: M = max |score|.  (The reference takes the maximum, then the
+// minimum, and prefers the minimum iff abs(min) > max, triarray.py:62-70: that is always the run of largest |score|,
+// the positive one on an exact tie.)  Every run whose |score| lies within a rigorous error window `delta` of M is
+// re-scored in numpy's own pairwise order (wc_numpy_order.cuh) and divided by sqrt(len) exactly as the reference does;
+// the max / min / abs rule and first-occurrence tie-breaking (the reference's row-major triangle order: smallest x,
+// then smallest y) are decided on those exact values.  Calls and their z are identical to the reference's.
 //
 // K9 wc_segment_kernel   one CTA per (sample, chromosome): compaction -> prefix sums -> [sweep -> exact re-score of the
 //                        windowed rows -> call -> push left/right ranges]*                       (FP64 ALU / shared memory)
@@ -23,11 +25,10 @@ namespace {
 
 constexpr int SEG_THREADS = 256;
 constexpr int SEG_WARPS = SEG_THREADS / 32;
-constexpr int SEG_R = 5;                      // rows per lane in the sweep (odd: conflict-free table reads)
-constexpr int SEG_TILE = 32 * SEG_R;          // rows per warp tile
-constexpr int SEG_PAD = SEG_TILE;             // NaN entries in front of the reciprocal-sqrt table
+constexpr int SEG_R = 5;                      // run lengths per lane in the sweep (odd: conflict-free prefix reads)
+constexpr int SEG_TILE = 32 * SEG_R;          // run lengths per warp tile
 constexpr int SEG_STACK = 128;                // pending ranges per chromosome
-constexpr int SEG_ROWCAP = 1024;              // rows re-scored exactly per search before falling back to all rows
+constexpr int SEG_ROWCAP = 1024;              // diagonals re-scored exactly per search before falling back to all of them
 constexpr double SEG_EPS = 1.1102230246251565e-16;
 
 struct SegArgs {
@@ -41,14 +42,14 @@ struct SegArgs {
     int minrefbins;
     double thr;
     int min_search;
-    const double* isq;       // [SEG_PAD + maxlen]: isq[SEG_PAD + L - 1] = 1/sqrt(L); NaN in the pad
+    double* zc;              // [B][N] scratch: kept z-scores of (sample, chromosome) compacted at the chromosome's offset
     double* cwz;             // [B][nsel]
     int* cleaned;            // [B][nsel]
     wc_call* calls;          // [B][max_calls]
     int* ncalls;             // [B]
     int max_calls;
+    int pcap;                // capacity of the shared arrays (>= longest chromosome + 1)
     int* status;             // [0] |= 1 call overflow, 2 range-stack overflow, 4 non-finite z in a kept bin
-    int zcap;                // capacity (doubles) of each shared array
 };
 
 struct Best {                // lexicographic champion: value, then first occurrence (x, then y)
@@ -69,16 +70,10 @@ __device__ __forceinline__ Best shfl_best(const Best& b, int o) {
     return r;
 }
 
-__global__ void wc_isq_kernel(double* isq, int maxlen) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < SEG_PAD) isq[i] = __longlong_as_double(0x7ff8000000000000ll);
-    if (i < maxlen) isq[SEG_PAD + i] = __ddiv_rn(1.0, sqrt((double)(i + 1)));
-}
-
 __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a) {
     extern __shared__ __align__(16) unsigned char seg_raw[];
-    double* zc = reinterpret_cast<double*>(seg_raw);              // [zcap] kept z-scores of this chromosome
-    double* P = zc + a.zcap;                                      // [zcap + 8] prefix sums, P[i] = sum zc[0..i)
+    double* P = reinterpret_cast<double*>(seg_raw);               // [pcap] prefix sums, P[i] = sum zc[0..i)
+    unsigned* dh = reinterpret_cast<unsigned*>(P + a.pcap);       // [pcap] per run length: max hi32(|score|) of the sweep
     __shared__ double s_red[2][SEG_WARPS];
     __shared__ Best s_best[2][SEG_WARPS];
     __shared__ int s_scan[SEG_WARPS];
@@ -92,6 +87,7 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     const int cstart = a.sel_start[sel], clen = a.sel_len[sel], slot = a.sel_slot[sel];
     const double* zrow = a.z + (size_t)b * a.N + cstart;
     const int* nrow = a.refsz + (size_t)b * a.N + cstart;
+    double* zc = a.zc + (size_t)b * a.N + cstart;                 // kept z-scores of this chromosome (global scratch)
 
     // ---- 1. compaction of the kept bins (wisecondor.py:215-218: refSizes >= minrefbins) -------------------------
     if (tid == 0) { s_n = 0; s_bad = 0; }
@@ -117,7 +113,7 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         }
         __syncthreads();
     }
-    const int n = s_n;
+    const int n = s_n;                              // (the __syncthreads above also orders the global zc writes)
     if (tid == 0) a.cleaned[(size_t)b * a.nsel + slot] = n;
     if (n == 0) {                                   // the reference raises on an empty chromosome (triarray.py:29)
         if (tid == 0) a.cwz[(size_t)b * a.nsel + slot] = __longlong_as_double(0x7ff8000000000000ll);
@@ -174,9 +170,6 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         a.cwz[(size_t)b * a.nsel + slot] = __ddiv_rn(tot, sqrt((double)n));
     }
 
-    const double* isq0 = a.isq + SEG_PAD;           // isq0[L - 1] = 1/sqrt(L); isq0[-1 .. -SEG_PAD] = NaN
-    const double NaN = __longlong_as_double(0x7ff8000000000000ll);
-
     // ---- 3. iterative most-significant-run search (triarray.py:59-84) --------------------------------------------------
     while (true) {
         __syncthreads();
@@ -187,75 +180,72 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         if (tid == 0) s_sp = sp - 1;
         const int m = hi - lo;
 
-        // -- sweep: per-thread max / min of (P[y+1] - P[x]) * isq[y - x] over its rows --
-        double vmax = -INFINITY, vmin = INFINITY;
+        // -- sweep by diagonals: lane owns the run lengths L0 .. L0+4 (their 1/sqrt in registers) and walks the start x;
+        //    P[x] is one broadcast read per step, P[x+L0+r] a 5-deep register window fed by one conflict-free read.
+        //    Per run: DADD, DMUL, and an integer max on the high word of |score| (20 mantissa bits: enough to locate) --
+        unsigned best = 0;                            // max over this thread's runs of hi32(|score|)
         const int ntiles = (m + SEG_TILE - 1) / SEG_TILE;
-        for (int round = 0; round * SEG_WARPS < ntiles; ++round) {
-            const int t = round * SEG_WARPS + ((round & 1) ? SEG_WARPS - 1 - warp : warp);   // boustrophedon: balance
-            if (t >= ntiles) continue;
-            const int xb = lo + t * SEG_TILE;
-            const int x0 = xb + lane * SEG_R;
-            double px[SEG_R];
+        {
+            for (int round = 0; round * SEG_WARPS < ntiles; ++round) {
+                const int t = round * SEG_WARPS + ((round & 1) ? SEG_WARPS - 1 - warp : warp);   // boustrophedon: balance
+                if (t >= ntiles) continue;
+                const int L0 = 1 + t * SEG_TILE + lane * SEG_R;
+                double isq[SEG_R];
+                unsigned bh[SEG_R];
 #pragma unroll
-            for (int r = 0; r < SEG_R; ++r) px[r] = (x0 + r < hi) ? P[x0 + r] : NaN;
-            // window of reciprocal square roots: slot (t mod 5) holds isq0[q0 + t], q = y - x0
-            double ww[SEG_R];
-            int q0 = xb - x0;                         // <= 0
+                for (int r = 0; r < SEG_R; ++r) { isq[r] = __ddiv_rn(1.0, sqrt((double)(L0 + r))); bh[r] = 0; }
+                int x = lo;
+                if (L0 + SEG_R - 1 <= m) {
+                    const int xfull = hi - (L0 + SEG_R - 1);       // starts x <= xfull have all five lengths inside [lo, hi)
+                    const double* Pq = P + L0;                     // Pq[x + r] = P[x + L0 + r]
+                    double ww[SEG_R];                               // slot (j + r) % 5 holds Pq[x + j + r]
 #pragma unroll
-            for (int r = 1; r < SEG_R; ++r) ww[SEG_R - r] = isq0[q0 - r];
-            int y = xb;
-            for (; y + SEG_R <= hi; y += SEG_R, q0 += SEG_R) {
+                    for (int r = 0; r < SEG_R - 1; ++r) ww[r] = Pq[x + r];
+                    for (; x + SEG_R - 1 <= xfull; x += SEG_R) {
 #pragma unroll
-                for (int j = 0; j < SEG_R; ++j) {
-                    ww[j] = isq0[q0 + j];
-                    const double py = P[y + j + 1];
+                        for (int j = 0; j < SEG_R; ++j) {
+                            ww[(j + SEG_R - 1) % SEG_R] = Pq[x + j + SEG_R - 1];
+                            const double px = P[x + j];
 #pragma unroll
-                    for (int r = 0; r < SEG_R; ++r) {
-                        const double v = __dmul_rn(__dsub_rn(py, px[r]), ww[(j - r + SEG_R) % SEG_R]);
-                        vmax = fmax(vmax, v);
-                        vmin = fmin(vmin, v);
+                            for (int r = 0; r < SEG_R; ++r) {
+                                const double v = __dmul_rn(__dsub_rn(ww[(j + r) % SEG_R], px), isq[r]);
+                                bh[r] = max(bh[r], (unsigned)__double2hiint(v) & 0x7fffffffu);
+                            }
+                        }
                     }
                 }
-            }
-            for (; y < hi; ++y) {
-                const double py = P[y + 1];
 #pragma unroll
-                for (int r = 0; r < SEG_R; ++r) {
-                    const double v = __dmul_rn(__dsub_rn(py, px[r]), isq0[y - x0 - r]);
-                    vmax = fmax(vmax, v);
-                    vmin = fmin(vmin, v);
+                for (int r = 0; r < SEG_R; ++r) {                  // ragged end: the remaining starts of each length
+                    const int L = L0 + r;
+                    for (int xx = x; xx + L <= hi; ++xx) {
+                        const double v = __dmul_rn(__dsub_rn(P[xx + L], P[xx]), isq[r]);
+                        bh[r] = max(bh[r], (unsigned)__double2hiint(v) & 0x7fffffffu);
+                    }
+                    if (L <= m) { dh[L] = bh[r]; best = max(best, bh[r]); }
                 }
             }
         }
-        // -- block-wide extremes --
-        double bmax = vmax, bmin = vmin;
+        // -- block-wide extreme --
+        unsigned bigh = best;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-            bmin = fmin(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
-        }
-        if (lane == 0) { s_red[0][warp] = bmax; s_red[1][warp] = bmin; }
+        for (int o = 16; o > 0; o >>= 1) bigh = max(bigh, __shfl_xor_sync(0xffffffffu, bigh, o));
+        if (lane == 0) s_scan[warp] = (int)bigh;
         if (tid == 0) s_nrows = 0;
         __syncthreads();
 #pragma unroll
-        for (int w = 0; w < SEG_WARPS; ++w) { bmax = fmax(bmax, s_red[0][w]); bmin = fmin(bmin, s_red[1][w]); }
-        const double big = fmax(fabs(bmax), fabs(bmin));
-        const double delta = delta_A + 16.0 * SEG_EPS * big;
-        if (big + delta < a.thr) continue;            // abs(champVal) < threshold for certain (triarray.py:72-73)
+        for (int w = 0; w < SEG_WARPS; ++w) bigh = max(bigh, (unsigned)s_scan[w]);
+        if (bigh >= 0x7fefffffu) bigh = 0x7feffffeu;                   // (finite data: cannot happen) keep bigh + 1 finite
+        // M = max |score| lies in [value(bigh), value(bigh + 1)); every run within delta of M has hi32 >= bigh - 1
+        const double m_up = __hiloint2double((int)(bigh + 1), 0);
+        const double delta = delta_A + 16.0 * SEG_EPS * m_up;
+        if (m_up + delta < a.thr) continue;           // abs(champVal) < threshold for certain (triarray.py:72-73)
+        const double vlow = __hiloint2double((int)(bigh > 0 ? bigh - 1 : 0), 0) - delta;   // window floor on |score|
 
-        // -- rows that can hold the exact champion: those of the threads whose own extreme lies in the window --
-        const bool cand = vmax >= bmax - delta || vmin <= bmin + delta;
-        if (cand) {
-            for (int round = 0; round * SEG_WARPS < ntiles; ++round) {
-                const int t = round * SEG_WARPS + ((round & 1) ? SEG_WARPS - 1 - warp : warp);
-                if (t >= ntiles) continue;
-                const int x0 = lo + t * SEG_TILE + lane * SEG_R;
-                for (int r = 0; r < SEG_R; ++r) {
-                    if (x0 + r < hi) {
-                        const int pos = atomicAdd(&s_nrows, 1);
-                        if (pos < SEG_ROWCAP) s_rows[pos] = x0 + r;
-                    }
-                }
+        // -- diagonals that can hold the exact champion: those whose own extreme reaches the window --
+        for (int L = 1 + tid; L <= m; L += SEG_THREADS) {
+            if (__hiloint2double((int)(dh[L] + 1), 0) >= vlow) {
+                const int pos = atomicAdd(&s_nrows, 1);
+                if (pos < SEG_ROWCAP) s_rows[pos] = L;
             }
         }
         __syncthreads();
@@ -263,20 +253,19 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         const bool all_rows = nrows_raw > SEG_ROWCAP;
         const int nrows = all_rows ? m : nrows_raw;
 
-        // -- exact re-score (numpy order) of every windowed run of those rows --
+        // -- exact re-score (numpy order) of every windowed run on those diagonals --
         Best cmax = {-INFINITY, 0x7fffffff, 0x7fffffff}, cmin = {INFINITY, 0x7fffffff, 0x7fffffff};
         for (int ri = 0; ri < nrows; ++ri) {
-            const int x = all_rows ? lo + ri : s_rows[ri];
-            const double pxv = P[x];
-            for (int y = x + tid; y < hi; y += SEG_THREADS) {
-                const double v = __dmul_rn(__dsub_rn(P[y + 1], pxv), isq0[y - x]);
-                const bool wmax = v >= bmax - delta, wmin = v <= bmin + delta;
-                if (wmax || wmin) {
-                    const int len = y - x + 1;
-                    const double sum = np_sum_thread([&](int i) { return zc[x + i]; }, len);   // np_sum(region[x:y+1])
-                    Best e = {__ddiv_rn(sum, sqrt((double)len)), x, y};                          // / np_sqrt(y-x+1)
-                    if (wmax && better_max(e, cmax)) cmax = e;
-                    if (wmin && better_min(e, cmin)) cmin = e;
+            const int L = all_rows ? ri + 1 : s_rows[ri];
+            const double sq = sqrt((double)L);
+            const double isqL = __ddiv_rn(1.0, sq);
+            for (int x = lo + tid; x + L <= hi; x += SEG_THREADS) {
+                const double av = fabs(__dmul_rn(__dsub_rn(P[x + L], P[x]), isqL));
+                if (av >= vlow) {
+                    const double sum = np_sum_thread([&](int i) { return zc[x + i]; }, L);     // np_sum(region[x:y+1])
+                    Best e = {__ddiv_rn(sum, sq), x, x + L - 1};                                 // / np_sqrt(y-x+1)
+                    if (better_max(e, cmax)) cmax = e;
+                    if (better_min(e, cmin)) cmin = e;
                 }
             }
         }
@@ -352,13 +341,13 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* r
         meta[nsel + i] = chrom_bins_h[c];
         meta[2 * nsel + i] = order[i];
     }
-    double* isq; int* meta_d; int* status_d;
+    double* zc; int* meta_d; int* status_d;
     int rc;
-    if ((rc = wc_reserve(ctx, SLOT_S_ISQ, (size_t)(SEG_PAD + maxlen + 8) * sizeof(double), (void**)&isq))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_S_ISQ, (size_t)B * N * sizeof(double), (void**)&zc))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_S_META, (size_t)3 * nsel * sizeof(int), (void**)&meta_d))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_S_STATUS, 4 * sizeof(int), (void**)&status_d))) return rc;
-    const int zcap = (maxlen + 8 + 1) & ~1;
-    const size_t smem = (size_t)(2 * zcap + 8) * sizeof(double);
+    const int pcap = (maxlen + 8) & ~1;
+    const size_t smem = (size_t)pcap * (sizeof(double) + sizeof(unsigned));
     if (smem > 220 * 1024) {
         wc_set_error("segmentation: a chromosome of %d bins needs %zu bytes of shared memory (limit 220 KiB)", maxlen, smem);
         return WC_ERR_ARG;
@@ -367,12 +356,11 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* r
     WC_CUDA(cudaMemcpyAsync(meta_d, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     WC_CUDA(cudaMemsetAsync(status_d, 0, 4 * sizeof(int), stream));
     WC_CUDA(cudaMemsetAsync(ncalls_d, 0, (size_t)B * sizeof(int), stream));
-    wc_isq_kernel<<<(SEG_PAD + maxlen + 255) / 256, 256, 0, stream>>>(isq, maxlen);
     SegArgs a;
     a.z = z_d; a.refsz = refsizes_d; a.N = N; a.B = B; a.sel_start = meta_d; a.sel_len = meta_d + nsel;
     a.sel_slot = meta_d + 2 * nsel; a.nsel = nsel; a.minrefbins = minrefbins; a.thr = z_threshold;
-    a.min_search = min_search; a.isq = isq; a.cwz = cwz_d; a.cleaned = cleaned_bins_d; a.calls = calls_d;
-    a.ncalls = ncalls_d; a.max_calls = max_calls; a.status = status_d; a.zcap = zcap;
+    a.min_search = min_search; a.zc = zc; a.cwz = cwz_d; a.cleaned = cleaned_bins_d; a.calls = calls_d;
+    a.ncalls = ncalls_d; a.max_calls = max_calls; a.status = status_d; a.pcap = pcap;
     WC_CUDA(cudaFuncSetAttribute(wc_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wc_segment_kernel<<<(unsigned)((size_t)nsel * B), SEG_THREADS, smem, stream>>>(a);
     WC_CUDA(cudaGetLastError());
@@ -381,7 +369,7 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* r
     WC_CUDA(cudaMemcpyAsync(&status, status_d, sizeof(int), cudaMemcpyDeviceToHost, stream));
     WC_CUDA(cudaStreamSynchronize(stream));       // meta/status host buffers; the call is documented as synchronous
     ctx->timed_mask |= 1u << 5;
-    ctx->counter[6] = 2;
+    ctx->counter[6] = 1;
     if (status & 4) {
         wc_set_error("segmentation: a kept bin has a non-finite z-score (reference sigma 0); not supported yet");
         return WC_ERR_ARG;

@@ -24,7 +24,7 @@ constexpr int ZS_BINS_PER_CTA = 64;
 // gather table: table[i][0..count[i]) = global masked-bin ids of bin i's usable reference bins, in stored order
 // ---------------------------------------------------------------------------------------------------------
 __global__ void wc_table_kernel(const int* __restrict__ indexes, const double* __restrict__ distances, int N, int k,
-                                const int* __restrict__ row_cs, const int* __restrict__ row_ce, double cutoff,
+                                int ldk, const int* __restrict__ row_cs, const int* __restrict__ row_ce, double cutoff,
                                 int* __restrict__ table, int* __restrict__ count) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= N) return;
@@ -43,9 +43,10 @@ __global__ void wc_table_kernel(const int* __restrict__ indexes, const double* _
             if (j < 0 || j >= nother) keep = false;                    // numpy would raise IndexError; never stored
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) table[(size_t)warp * k + w + __popc(bal & ((1u << lane) - 1u))] = g;
+        if (keep) table[(size_t)warp * ldk + w + __popc(bal & ((1u << lane) - 1u))] = g;
         w += __popc(bal);
     }
+    for (int m = w + lane; m < ldk; m += 32) table[(size_t)warp * ldk + m] = 0;     // defined padding
     if (lane == 0) count[warp] = w;
 }
 
@@ -136,7 +137,7 @@ struct ZArgs {
     const double* copy;      // [N][ldb] working copy: marked bins hold -1
     const int* table;        // [N][k]
     const int* count;        // [N]
-    int N, B, ldb, k;
+    int N, B, ldb, k;        // k = row stride of the table (wc_table_stride(refsize))
     double* z;               // [N][ldb]
     double* r;
     int* refsz;
@@ -144,29 +145,121 @@ struct ZArgs {
     const int* tile_active;  // [ntiles] 0 = nothing changed for these 32 samples since the previous pass: skip
 };
 
+// ---- K8 building blocks ----------------------------------------------------------------------------------------
+// Fast path (no marked / non-finite reference value for this lane): the lane streams its reference values straight from
+// L2 into eight register accumulators - numpy's leaf order needs no storage when nothing is dropped - once for the mean
+// and once more for sum((x - mean)^2).  DEV selects the second form.  `worst` collects the largest high word seen
+// (sign set or exponent all ones <=> the value is not a finite number >= +0).  n <= 128.
 template <bool DEV>
-__device__ __forceinline__ double zs_leaf(const double* p, int n, double mean) {
-    return np_sum_leaf([&](int i) {
-        const double v = p[i * 32];
-        if (!DEV) return v;
+__device__ __forceinline__ double zs_stream_leaf(const double* cp, const int* tab, int n, size_t ldb, double mean,
+                                                 unsigned& worst) {
+    auto term = [&](double v) {
+        if (!DEV) { worst = max(worst, (unsigned)__double2hiint(v)); return v; }
         const double d = __dsub_rn(v, mean);
         return __dmul_rn(d, d);
-    }, n);
+    };
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, term(cp[(size_t)tab[i] * ldb]));
+        return res;
+    }
+    double r[8];
+    {
+        const int4 i0 = *reinterpret_cast<const int4*>(tab), i1 = *reinterpret_cast<const int4*>(tab + 4);
+        r[0] = term(cp[(size_t)i0.x * ldb]); r[1] = term(cp[(size_t)i0.y * ldb]);
+        r[2] = term(cp[(size_t)i0.z * ldb]); r[3] = term(cp[(size_t)i0.w * ldb]);
+        r[4] = term(cp[(size_t)i1.x * ldb]); r[5] = term(cp[(size_t)i1.y * ldb]);
+        r[6] = term(cp[(size_t)i1.z * ldb]); r[7] = term(cp[(size_t)i1.w * ldb]);
+    }
+    const int full = n - (n & 7);
+    int i = 8;
+    for (; i < full; i += 8) {
+        const int4 i0 = *reinterpret_cast<const int4*>(tab + i), i1 = *reinterpret_cast<const int4*>(tab + i + 4);
+        double v[8];
+        v[0] = cp[(size_t)i0.x * ldb]; v[1] = cp[(size_t)i0.y * ldb]; v[2] = cp[(size_t)i0.z * ldb]; v[3] = cp[(size_t)i0.w * ldb];
+        v[4] = cp[(size_t)i1.x * ldb]; v[5] = cp[(size_t)i1.y * ldb]; v[6] = cp[(size_t)i1.z * ldb]; v[7] = cp[(size_t)i1.w * ldb];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], term(v[j]));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, term(cp[(size_t)tab[i] * ldb]));
+    return res;
 }
-// n <= 512: numpy splits at most twice
+// any n: numpy's halving above 128 elements (two levels cover n <= 512)
 template <bool DEV>
-__device__ __noinline__ double zs_sum_large(const double* p, int n, double mean) {
-    auto half = [&](const double* q, int len) {
-        if (len <= 128) return zs_leaf<DEV>(q, len, mean);
+__device__ __forceinline__ double zs_stream_sum(const double* cp, const int* tab, int n, size_t ldb, double mean,
+                                                unsigned& worst) {
+    if (n <= 128) return zs_stream_leaf<DEV>(cp, tab, n, ldb, mean, worst);
+    auto half = [&](const int* t, int len) {
+        if (len <= 128) return zs_stream_leaf<DEV>(cp, t, len, ldb, mean, worst);
         int h = len / 2;
         h -= h & 7;
-        return __dadd_rn(zs_leaf<DEV>(q, h, mean), zs_leaf<DEV>(q + (size_t)h * 32, len - h, mean));
+        const double a0 = zs_stream_leaf<DEV>(cp, t, h, ldb, mean, worst);
+        return __dadd_rn(a0, zs_stream_leaf<DEV>(cp, t + h, len - h, ldb, mean, worst));
     };
     int h = n / 2;
     h -= h & 7;
-    return __dadd_rn(half(p, h), half(p + (size_t)h * 32, n - h));
+    const double a0 = half(tab, h);
+    return __dadd_rn(a0, half(tab + h, n - h));
 }
 
+// Slow path, warp-cooperative, for one lane whose reference values contain marked (-1) / negative / non-finite entries:
+// all 32 lanes fetch that sample's values, the kept ones (refData[refData >= 0], wisetools.py:425) are compacted in
+// order into the warp's small shared buffer, and lanes 0..7 act as numpy's eight accumulators.
+__device__ __forceinline__ double zs_coop_sum(const double* buf, int n, double mean, bool dev, int lane) {
+    auto term = [&](int i) {
+        const double v = buf[i];
+        if (!dev) return v;
+        const double d = __dsub_rn(v, mean);
+        return __dmul_rn(d, d);
+    };
+    double res = 0.0;
+    if (n <= 128) {
+        if (n < 8) {
+            for (int i = 0; i < n; ++i) res = __dadd_rn(res, term(i));
+        } else {
+            const int full = n - (n & 7);
+            double r = 0.0;
+            if (lane < 8) {
+                r = term(lane);
+                for (int i = 8 + lane; i < full; i += 8) r = __dadd_rn(r, term(i));
+            }
+            r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+            r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+            r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+            res = __shfl_sync(0xffffffffu, r, 0);
+            for (int i = full; i < n; ++i) res = __dadd_rn(res, term(i));
+        }
+    } else {
+        res = np_sum_thread(term, n);          // refsize > 128: every lane redundantly, numpy's recursion
+    }
+    return res;
+}
+
+struct ZsSlow { double mean, sd; int n; };
+__device__ __forceinline__ ZsSlow zs_slow_lane(const double* copy_col, const int* tab, int cnt, size_t ldb, double* buf,
+                                               int lane) {
+    int n = 0;
+    __syncwarp();
+    for (int base = 0; base < cnt; base += 32) {
+        const int m = base + lane;
+        const double v = m < cnt ? copy_col[(size_t)tab[m] * ldb] : -1.0;
+        const bool keep = m < cnt && v >= 0.0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) buf[n + __popc(bal & ((1u << lane) - 1u))] = v;
+        n += __popc(bal);
+    }
+    __syncwarp();
+    ZsSlow o;
+    o.n = n;
+    o.mean = __ddiv_rn(zs_coop_sum(buf, n, 0.0, false, lane), (double)n);
+    o.sd = sqrt(__ddiv_rn(zs_coop_sum(buf, n, o.mean, true, lane), (double)n));
+    return o;
+}
+
+// One warp = 32 consecutive samples of one target bin at a time; no shared-memory staging on the fast path, so
+// occupancy (and with it the latency hiding of the L2 gathers) is bounded by registers only.
 __global__ void __launch_bounds__(ZS_WARPS * 32) wc_zscore_kernel(const ZArgs a) {
     extern __shared__ __align__(16) unsigned char zs_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,39 +267,32 @@ __global__ void __launch_bounds__(ZS_WARPS * 32) wc_zscore_kernel(const ZArgs a)
     const int tile = blockIdx.y;
     if (a.tile_active != nullptr && a.tile_active[tile] == 0) return;
     const int s = tile * 32 + lane;                      // < ldb by construction
-    double* buf = reinterpret_cast<double*>(zs_raw) + (size_t)warp * a.k * 32 + lane;   // entry p at buf[p * 32]
-    int* sidx = reinterpret_cast<int*>(reinterpret_cast<double*>(zs_raw) + (size_t)nwarps * a.k * 32) + warp * a.k;
+    double* buf = reinterpret_cast<double*>(zs_raw) + (size_t)warp * a.k;      // slow-path scratch, k doubles per warp
     const double* cp = a.copy + s;
+    const size_t ldb = (size_t)a.ldb;
     const int bin_end = min(a.N, (int)(blockIdx.x + 1) * ZS_BINS_PER_CTA);
     for (int i = blockIdx.x * ZS_BINS_PER_CTA + warp; i < bin_end; i += nwarps) {
         const int cnt = a.count[i];
-        __syncwarp();
-        for (int m = lane; m < cnt; m += 32) sidx[m] = a.table[(size_t)i * a.k + m];
-        __syncwarp();
-        // gather the reference values of this bin from the same sample, dropping marked (negative) ones
-        int p = 0;
-        for (int m0 = 0; m0 < cnt; m0 += 8) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int m = min(m0 + u, cnt - 1);
-                v[u] = cp[(size_t)sidx[m] * a.ldb];
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (m0 + u < cnt && v[u] >= 0.0) {       // wisetools.py:425
-                    buf[p * 32] = v[u];
-                    ++p;
-                }
-            }
+        const int* tab = a.table + (size_t)i * a.k;      // every lane reads the same entries: one broadcast sector
+        unsigned worst = 0;
+        int n = cnt;
+        const double sum = zs_stream_sum<false>(cp, tab, cnt, ldb, 0.0, worst);
+        double mean = __ddiv_rn(sum, (double)cnt);                          // np_mean (wisetools.py:426)
+        double sd = 0.0;
+        const bool bad = worst >= 0x7ff00000u;
+        if (!bad) {
+            unsigned unused = 0;
+            sd = sqrt(__ddiv_rn(zs_stream_sum<true>(cp, tab, cnt, ldb, mean, unused), (double)cnt));   // np_std (:427)
         }
-        const int n = p;
-        const double sum = n <= 128 ? zs_leaf<false>(buf, n, 0.0) : zs_sum_large<false>(buf, n, 0.0);
-        const double mean = __ddiv_rn(sum, (double)n);                       // np_mean (wisetools.py:426)
-        const double ssq = n <= 128 ? zs_leaf<true>(buf, n, mean) : zs_sum_large<true>(buf, n, mean);
-        const double sd = sqrt(__ddiv_rn(ssq, (double)n));                   // np_std, ddof 0 (wisetools.py:427)
-        const double x = a.test[(size_t)i * a.ldb + s];
-        const size_t o = (size_t)i * a.ldb + s;
+        unsigned todo = __ballot_sync(0xffffffffu, bad);
+        while (todo) {                                    // warp-uniform loop over the lanes that need the exact compaction
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const ZsSlow o = zs_slow_lane(a.copy + tile * 32 + src, tab, cnt, ldb, buf, lane);
+            if (lane == src) { mean = o.mean; sd = o.sd; n = o.n; }
+        }
+        const double x = a.test[(size_t)i * ldb + s];
+        const size_t o = (size_t)i * ldb + s;
         a.z[o] = __ddiv_rn(__dsub_rn(x, mean), sd);                          // wisetools.py:431
         a.r[o] = __ddiv_rn(x, mean);                                         // wisetools.py:432
         a.refsz[o] = n;
@@ -286,6 +372,8 @@ int upload_row_ranges(wc_ctx* ctx, int N, const int* chrom_bins_h, int nchrom, i
 
 }  // namespace
 
+extern "C" int wc_table_stride(int k) { return (k + 3) & ~3; }
+
 extern "C" int wc_test_table(wc_ctx* ctx, const int32_t* indexes_d, const double* distances_d, int N, int k,
                              const int* chrom_bins_h, int nchrom, double cutoff, int32_t* table_d, int32_t* count_d,
                              void* stream_v) {
@@ -301,7 +389,8 @@ extern "C" int wc_test_table(wc_ctx* ctx, const int32_t* indexes_d, const double
     int rc;
     if ((rc = upload_row_ranges(ctx, N, chrom_bins_h, nchrom, SLOT_ROWCS, SLOT_ROWCE, &cs_d, &ce_d, stream))) return rc;
     const int blocks = (int)(((size_t)N * 32 + 255) / 256);
-    wc_table_kernel<<<blocks, 256, 0, stream>>>(indexes_d, distances_d, N, k, cs_d, ce_d, cutoff, table_d, count_d);
+    wc_table_kernel<<<blocks, 256, 0, stream>>>(indexes_d, distances_d, N, k, wc_table_stride(k), cs_d, ce_d, cutoff, table_d,
+                                                count_d);
     WC_CUDA(cudaGetLastError());
     return WC_OK;
 }
@@ -371,14 +460,12 @@ extern "C" int wc_zscore_batch(wc_ctx* ctx, const double* test_d, const double* 
     WC_CUDA(cudaMemcpyAsync(copy, copy_init_d ? copy_init_d : test_d, elems * sizeof(double), cudaMemcpyDeviceToDevice,
                             stream));                                                                   // wisetools.py:442
     WC_CUDA(cudaMemsetAsync(flags, 0, (size_t)(repeats + 1) * ntiles * sizeof(int), stream));
-    const size_t per_warp = (size_t)k * 32 * sizeof(double) + (size_t)k * sizeof(int);
-    int warps = (int)std::min<size_t>(ZS_WARPS, (size_t)(227 * 1024) / per_warp);
-    if (warps < 1) { wc_set_error("z-score kernel: refsize %d needs %zu bytes of shared memory per warp", k, per_warp); return WC_ERR_ARG; }
-    if (warps == 3) warps = 2;
-    const size_t smem = (size_t)warps * per_warp;
+    const int warps = ZS_WARPS;
+    const int ldk = wc_table_stride(k);
+    const size_t smem = (size_t)warps * ldk * sizeof(double);     // slow-path scratch only
     WC_CUDA(cudaFuncSetAttribute(wc_zscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ZArgs a;
-    a.test = test_d; a.copy = copy; a.table = table_d; a.count = count_d; a.N = N; a.B = B; a.ldb = ldb; a.k = k;
+    a.test = test_d; a.copy = copy; a.table = table_d; a.count = count_d; a.N = N; a.B = B; a.ldb = ldb; a.k = ldk;
     a.z = zt; a.r = rt; a.refsz = nt; a.sd = sd;
     long long launches = 0;
     for (int rep = 0; rep < repeats; ++rep) {

@@ -106,7 +106,7 @@ class ReferenceTable(object):
         self.cutoff = float(cutoff)
         idx = torch.as_tensor(np.ascontiguousarray(indexes, dtype=np.int32), device=dev)
         dst = torch.as_tensor(np.ascontiguousarray(distances, dtype=np.float64), device=dev)
-        self.table = torch.empty((self.n, self.k), dtype=torch.int32, device=dev)
+        self.table = torch.empty((self.n, _cabi.lib().wc_table_stride(self.k)), dtype=torch.int32, device=dev)
         self.count = torch.empty((self.n,), dtype=torch.int32, device=dev)
         cb, cbp = _ints(self.masked_sizes)
         ctx = _cabi.context(_dev_index(dev))
