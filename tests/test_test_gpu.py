@@ -171,6 +171,41 @@ def test_segmentation_vs_oracle(n, seed):
             assert v == np.sum(z[x:y + 1]) / np.sqrt(y - x + 1)
 
 
+@pytest.mark.parametrize("case", ["posinf", "neginf", "nan", "both", "many", "edge"])
+def test_segmentation_non_finite_z_matches_numpy_argmax(case):
+    """A kept bin whose reference sigma is 0 has z = +-inf or NaN (wisetools.py:431).  The reference's triangle then
+    holds inf / NaN run values and numpy's argmax/argmin pick the first NaN, else the first +inf, else (abs(min) > max)
+    the first -inf entry (triarray.py:62-70); the search recurses to the right of that run."""
+    rng = np.random.default_rng(5)
+    n = 90
+    z = rng.normal(0, 1, size=n)
+    z[60:70] += 2.5                                   # a finite call to the right, found by the recursion
+    if case == "posinf":
+        z[20] = np.inf
+    elif case == "neginf":
+        z[33] = -np.inf
+    elif case == "nan":
+        z[41] = np.nan
+    elif case == "both":
+        z[10] = np.inf
+        z[25] = -np.inf
+    elif case == "many":
+        z[5] = -np.inf
+        z[6] = np.nan
+        z[50] = np.inf
+        z[80] = np.inf
+    else:
+        z[0] = np.inf
+        z[n - 1] = np.nan
+    (cw, m, segs), = _segment([z], 4.0)
+    with np.errstate(all="ignore"):
+        wcw, wsegs = wc_oracle.segment_region(z, 4.0, 3)
+    assert np.array_equal(np.array([cw]), np.array([wcw]), equal_nan=True)
+    assert [s[1] for s in segs] == [s[1] for s in wsegs]
+    assert np.array_equal(np.array([s[0] for s in segs]), np.array([s[0] for s in wsegs]), equal_nan=True)
+    assert len(segs) >= (1 if case == "edge" else 2)
+
+
 def test_segmentation_batch_keep_mask_and_chromosome_list():
     """Several samples, several chromosomes, bins dropped by minrefbins, a chromosome subset (-chromosomes)."""
     from wisecondor_b200 import wisetools

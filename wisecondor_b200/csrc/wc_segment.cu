@@ -49,7 +49,7 @@ struct SegArgs {
     int* ncalls;             // [B]
     int max_calls;
     int pcap;                // capacity of the shared arrays (>= longest chromosome + 1)
-    int* status;             // [0] |= 1 call overflow, 2 range-stack overflow, 4 non-finite z in a kept bin
+    int* status;             // [0] |= 1 call overflow, 2 range-stack overflow
 };
 
 struct Best {                // lexicographic champion: value, then first occurrence (x, then y)
@@ -119,20 +119,19 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         if (tid == 0) a.cwz[(size_t)b * a.nsel + slot] = __longlong_as_double(0x7ff8000000000000ll);
         return;
     }
-    if (s_bad) {                                    // +-inf / NaN z (a kept bin whose reference sigma is 0)
-        if (tid == 0) {
-            atomicOr(a.status, 4);
-            a.cwz[(size_t)b * a.nsel + slot] = __longlong_as_double(0x7ff8000000000000ll);
-        }
-        return;
-    }
+    // +-inf / NaN z (a kept bin whose reference sigma is 0, wisetools.py:431 under np.seterr('ignore')): the reference's
+    // argmax/argmin then see inf / NaN run values; handled per range below.  Prefix sums skip the non-finite bins.
+    const bool has_bad = s_bad != 0;
 
     // ---- 2. prefix sums and A = sum |z| (the scale of the error window) ---------------------------------------------
     {
         const int per = (n + SEG_THREADS - 1) / SEG_THREADS;
         const int i0 = min(n, tid * per), i1 = min(n, i0 + per);
         double loc = 0.0, la = 0.0;
-        for (int i = i0; i < i1; ++i) { loc += zc[i]; la += fabs(zc[i]); }
+        for (int i = i0; i < i1; ++i) {
+            const double v = zc[i];
+            if (isfinite(v)) { loc += v; la += fabs(v); }
+        }
         double inc = loc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -147,7 +146,11 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         double base = 0.0;
         for (int w = 0; w < warp; ++w) base += s_red[0][w];
         double run = base + (inc - loc);
-        for (int i = i0; i < i1; ++i) { P[i] = run; run += zc[i]; }
+        for (int i = i0; i < i1; ++i) {
+            const double v = zc[i];
+            P[i] = run;
+            if (isfinite(v)) run += v;
+        }
         if (i1 == n && i0 < n) P[n] = run;
         if (tid == 0) {
             double t = 0.0;
@@ -164,11 +167,13 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     // scan, warp bases) on both ends of the run, numpy's own pairwise rounding, the reciprocal multiply.  delta = 2 x that.
     const double delta_A = (4.0 * ((n + SEG_THREADS - 1) / SEG_THREADS) + 160.0) * SEG_EPS * A;
 
-    // chromosome-wide value: entry (0, n-1) of the triangle (wisecondor.py:237), numpy order, by one thread
+    // chromosome-wide value: entry (0, n-1) of the triangle (wisecondor.py:237), numpy order, by one thread (a non-finite
+    // bin propagates through the same additions: inf, or NaN for inf - inf)
     if (tid == SEG_THREADS - 1) {
         const double tot = np_sum_thread([&](int i) { return zc[i]; }, n);
         a.cwz[(size_t)b * a.nsel + slot] = __ddiv_rn(tot, sqrt((double)n));
     }
+    __shared__ int s_first[3];                      // first NaN / +inf / -inf position of the current range
 
     // ---- 3. iterative most-significant-run search (triarray.py:59-84) --------------------------------------------------
     while (true) {
@@ -179,6 +184,42 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         __syncthreads();
         if (tid == 0) s_sp = sp - 1;
         const int m = hi - lo;
+
+        if (has_bad) {
+            // Run values that contain a NaN, or both +inf and -inf, are NaN; a run with only +inf (-inf) bins is +inf
+            // (-inf).  numpy's argmax/argmin return the first NaN entry if there is one (triarray.py:62-66), and a run
+            // [x..y] that is NaN makes [lo..y] NaN too, so the first NaN entry is (lo, first y at which [lo..y] turns NaN).
+            // Without NaN entries the first +inf entry is the maximum; with only -inf present abs(min) > max picks the
+            // first -inf entry (triarray.py:68-70).  Every such value passes `abs(champVal) < threshold` as False.
+            if (tid < 3) s_first[tid] = 0x7fffffff;
+            __syncthreads();
+            for (int i = lo + tid; i < hi; i += SEG_THREADS) {
+                const double v = zc[i];
+                if (!isfinite(v)) atomicMin(&s_first[isnan(v) ? 0 : (v > 0.0 ? 1 : 2)], i);
+            }
+            __syncthreads();
+            const int fnan = s_first[0], fpos = s_first[1], fneg = s_first[2];
+            if (fnan < hi || fpos < hi || fneg < hi) {
+                __syncthreads();                     // s_first is rewritten by the next range
+                if (tid == 0) {
+                    const int both = (fpos < hi && fneg < hi) ? max(fpos, fneg) : 0x7fffffff;
+                    const int ynan = min(fnan, both);
+                    wc_call c;
+                    c.sample = b; c.chrom = slot; c.x = lo;
+                    if (ynan < hi) { c.y = ynan; c.z = __longlong_as_double(0x7ff8000000000000ll); }
+                    else if (fpos < hi) { c.y = fpos; c.z = INFINITY; }
+                    else { c.y = fneg; c.z = -INFINITY; }
+                    const int slot_i = atomicAdd(&a.ncalls[b], 1);
+                    if (slot_i < a.max_calls) a.calls[(size_t)b * a.max_calls + slot_i] = c; else atomicOr(a.status, 1);
+                    if ((c.y - lo) + 1 < m - a.min_search) {            // triarray.py:79 (x == lo: never a left part)
+                        int spn = s_sp;
+                        if (spn < SEG_STACK) { s_lo[spn] = c.y + 1; s_hi[spn] = hi; ++spn; } else atomicOr(a.status, 2);
+                        s_sp = spn;
+                    }
+                }
+                continue;
+            }
+        }
 
         // -- sweep by diagonals: lane owns the run lengths L0 .. L0+4 (their 1/sqrt in registers) and walks the start x;
         //    P[x] is one broadcast read per step, P[x+L0+r] a 5-deep register window fed by one conflict-free read.
@@ -370,10 +411,6 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* r
     WC_CUDA(cudaStreamSynchronize(stream));       // meta/status host buffers; the call is documented as synchronous
     ctx->timed_mask |= 1u << 5;
     ctx->counter[6] = 1;
-    if (status & 4) {
-        wc_set_error("segmentation: a kept bin has a non-finite z-score (reference sigma 0); not supported yet");
-        return WC_ERR_ARG;
-    }
     if (status & 2) { wc_set_error("segmentation: more than %d pending ranges on one chromosome", SEG_STACK); return WC_ERR_INTERNAL; }
     if (status & 1) { wc_set_error("segmentation: more than max_calls=%d calls for one sample", max_calls); return WC_ERR_ARG; }
     return WC_OK;

@@ -92,3 +92,24 @@ def corrected_like(nbins_per_chrom, nsamples, seed=5, sigma=0.05, dtype=np.float
     fam_profile = rng.normal(0.0, sigma, size=(nfam, nsamples))
     x = 1.0 + fam_profile[fam] * rng.uniform(0.3, 1.0, size=(n, 1)) + rng.normal(0.0, sigma, size=(n, nsamples))
     return np.ascontiguousarray(x.astype(dtype))
+
+
+def corrected_like_device(nbins_per_chrom, nsamples, seed=5, sigma=0.05, device=None, chunk=8192):
+    """Device-side counterpart of corrected_like for matrices too large to build on the host (2000 x 10 kb = 4.6 GB):
+    same structure (bin families + independent noise), generated in row chunks with a seeded torch generator, so
+    every rank of one job - same GPU model, same seed - holds the same matrix.  Not bit-equal to corrected_like."""
+    import torch
+    n = int(sum(nbins_per_chrom))
+    dev = torch.device("cuda") if device is None else device
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    nfam = max(8, n // 64)
+    fam_profile = torch.randn((nfam, nsamples), generator=g, device=dev, dtype=torch.float64) * sigma
+    out = torch.empty((n, nsamples), dtype=torch.float64, device=dev)
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        fam = torch.randint(0, nfam, (b - a,), generator=g, device=dev)
+        scale = torch.rand((b - a, 1), generator=g, device=dev, dtype=torch.float64) * 0.7 + 0.3
+        noise = torch.randn((b - a, nsamples), generator=g, device=dev, dtype=torch.float64) * sigma
+        out[a:b] = 1.0 + fam_profile[fam] * scale + noise
+    return out
