@@ -154,7 +154,7 @@ def test_test_tool_matches_reference(workdir, tiny):
 def test_testbatch_equals_single_runs(workdir, tiny):
     outdir = str(workdir / "batch")
     tests = [str(workdir / ("t%d.npz" % t)) for t in (0, 1, 3)]
-    _run(["testbatch"] + tests + [outdir, str(workdir / "goldref.npz"), "-minrefbins", "10"])
+    _run(["testbatch"] + tests + [outdir, str(workdir / "goldref.npz"), "-minrefbins", "10", "-batch", "2"])
     for t in (0, 1, 3):
         res = np.load(os.path.join(outdir, "t%d.npz" % t), allow_pickle=True)
         _check_result(res, tiny, t)

@@ -48,14 +48,18 @@ def newref_topk(corrected, chrom_bins, row_begin, row_end, refsize, out_idx=None
     return out_idx, out_dist
 
 
-def newref_topk_host(corrected, chrom_bins, row_begin, row_end, refsize, device=0):
-    """Same search with HOST numpy buffers: copies in and out inside the C call (wc_newref_topk_host)."""
+def newref_topk_host(corrected, chrom_bins, row_begin, row_end, refsize, device=0, out_idx=None, out_dist=None):
+    """Same search with HOST numpy buffers: copies in and out inside the C call (wc_newref_topk_host).  out_idx /
+    out_dist may be preallocated (e.g. views of pinned memory: faster device-to-host copies)."""
     X = np.ascontiguousarray(corrected, dtype=np.float64)
     n, s = X.shape
     cb = np.ascontiguousarray(chrom_bins, dtype=np.int32)
     rows = int(row_end) - int(row_begin)
-    idx = np.empty((max(rows, 0), refsize), dtype=np.int32)
-    dist = np.empty((max(rows, 0), refsize), dtype=np.float64)
+    idx = np.empty((max(rows, 0), refsize), dtype=np.int32) if out_idx is None else out_idx
+    dist = np.empty((max(rows, 0), refsize), dtype=np.float64) if out_dist is None else out_dist
+    if idx.shape != (max(rows, 0), refsize) or idx.dtype != np.int32 or not idx.flags.c_contiguous or \
+            dist.shape != idx.shape or dist.dtype != np.float64 or not dist.flags.c_contiguous:
+        raise _cabi.WisecondorError("out_idx / out_dist must be C-contiguous int32 / float64 arrays of shape rows x refsize")
     ctx = _cabi.context(device)
     rc = _cabi.lib().wc_newref_topk_host(ctx.handle, X.ctypes.data_as(ctypes.c_void_p), n, s,
                                          cb.ctypes.data_as(ctypes.c_void_p), len(cb), int(row_begin), int(row_end),
