@@ -156,18 +156,20 @@ int wc_zscore_batch(wc_ctx* ctx, const double* test_d, const double* copy_init_d
                     const int32_t* count_d, int k, double z_threshold, int repeats, double* z_d, double* r_d,
                     int32_t* refsizes_d, double* asdef_d, void* stream);
 
-/* Replaces the chromosome loop of toolTest (wisecondor.py:233-238): fillTri (wisetools.py:466-472) +
+/* Replaces the chromosome loop of toolTest (wisecondor.py:233-238): fillTriMin / fillTri (wisetools.py:466-487) +
  * TriArr.segmentTri (triarray.py:59-84) on the bins with refsizes >= minrefbins (wisecondor.py:215-218), for the
  * chromosomes listed (0-based) in chromosomes_h.
+ *   r_d, mineffectsize  -mineffectsize (wisecondor.py:460): when > 0, a run only counts if abs(median(R) - 1) >=
+ *                  mineffectsize (r_d = DEVICE B x N resultsR); 0 = plain fillTri, r_d may be NULL
  *   cwz_d          DEVICE B x nsel float64: zTriangle.getValue(0, n-1) (wisecondor.py:237)
  *   cleaned_bins_d DEVICE B x nsel int32: kept bins of each listed chromosome (`cleanedBins`, wisecondor.py:220-222)
  *   calls_d        DEVICE B x max_calls wc_call, ncalls_d DEVICE B int32: unordered; sort by (chrom, x)
  * Non-finite z of a kept bin (reference sigma 0) gives the NaN / inf calls numpy's argmax/argmin give the reference.
- * mineffectsize != 0 (fillTriMin, wisetools.py:475-487) is not implemented here.  Synchronous. */
-int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* refsizes_d, int N, int B,
+ * Synchronous. */
+int wc_segment_batch(wc_ctx* ctx, const double* z_d, const double* r_d, const int32_t* refsizes_d, int N, int B,
                      const int* chrom_bins_h, int nchrom, const int* chromosomes_h, int nsel, int minrefbins,
-                     double z_threshold, int min_search, double* cwz_d, int32_t* cleaned_bins_d, wc_call* calls_d,
-                     int32_t* ncalls_d, int max_calls, void* stream);
+                     double z_threshold, double mineffectsize, int min_search, double* cwz_d,
+                     int32_t* cleaned_bins_d, wc_call* calls_d, int32_t* ncalls_d, int max_calls, void* stream);
 
 #ifdef __cplusplus
 }

@@ -206,6 +206,38 @@ def test_segmentation_non_finite_z_matches_numpy_argmax(case):
     assert len(segs) >= (1 if case == "edge" else 2)
 
 
+def test_segmentation_min_effect_golden_and_random(fn):
+    """fillTriMin (wisetools.py:475-487): runs whose median ratio is within mineffectsize of 1 are zeroed."""
+    from wisecondor_b200 import wisetools
+
+    def run(z, r, t, thr):
+        n = len(z)
+        cwz, cleaned, calls = wisetools.segmentChromosomes(z[None, :], np.full((1, n), 100), [n], [1], 25, thr, 3,
+                                                           resultsR=r[None, :], mineffectsize=t)
+        return cwz[0, 0], [(float(c['z']), (int(c['x']), int(c['y']))) for c in calls]
+
+    cw, segs = run(fn['segmin_z'], fn['segmin_r'], 0.05, 3.5)         # the reference's own output
+    assert cw == float(fn['segmin_cw'])
+    assert np.array_equal(np.array([[s[1][0], s[1][1], s[0]] for s in segs], dtype=float).reshape(-1, 3),
+                          fn['segmin_calls'].reshape(-1, 3))
+    rng = np.random.default_rng(21)
+    for trial in range(6):
+        n = int(rng.integers(8, 220))
+        z = rng.normal(0, 1, size=n)
+        r = 1.0 + rng.normal(0, 0.01, size=n)
+        a = int(rng.integers(0, n - 6))
+        w = int(rng.integers(3, max(4, n // 3)))
+        z[a:a + w] += rng.choice([-2.5, 2.5])
+        r[a:a + w] += rng.choice([-0.06, 0.06, 0.02])                 # sometimes below the effect threshold
+        if trial % 2:
+            r = np.round(r, 2)                                         # ties at the boundaries, exact halves
+        t = float(rng.choice([0.03, 0.05]))
+        cw, segs = run(z, r, t, 3.0)
+        wcw, wsegs = wc_oracle.segment_region(z, 3.0, 3, r, t)
+        assert cw == wcw, trial
+        assert segs == [(float(v), xy) for v, xy in wsegs], trial
+
+
 def test_segmentation_batch_keep_mask_and_chromosome_list():
     """Several samples, several chromosomes, bins dropped by minrefbins, a chromosome subset (-chromosomes)."""
     from wisecondor_b200 import wisetools

@@ -77,7 +77,7 @@ def lib():
     L.wc_zscore_batch.restype = ci
     L.wc_zscore_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, cd, i32, vp, vp, vp, vp, vp]
     L.wc_segment_batch.restype = ci
-    L.wc_segment_batch.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, i32, i32, cd, i32, vp, vp, vp, vp, i32, vp]
+    L.wc_segment_batch.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, vp, i32, i32, cd, cd, i32, vp, vp, vp, vp, i32, vp]
     _LIB = L
     return L
 

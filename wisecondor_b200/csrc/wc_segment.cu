@@ -43,13 +43,16 @@ struct SegArgs {
     double thr;
     int min_search;
     double* zc;              // [B][N] scratch: kept z-scores of (sample, chromosome) compacted at the chromosome's offset
+    const double* r;         // [B][N] ratios (resultsR); only for the effect-size filter
+    double* rc;              // [B][N] scratch: kept ratios, compacted like zc
+    double c_hi, c_lo;       // fillTriMin keeps a run iff median(R) >= c_hi or median(R) <= c_lo (= abs(median - 1) >= t)
     double* cwz;             // [B][nsel]
     int* cleaned;            // [B][nsel]
     wc_call* calls;          // [B][max_calls]
     int* ncalls;             // [B]
     int max_calls;
     int pcap;                // capacity of the shared arrays (>= longest chromosome + 1)
-    int* status;             // [0] |= 1 call overflow, 2 range-stack overflow
+    int* status;             // [0] |= 1 call overflow, 2 range-stack overflow, 4 non-finite z with the effect-size filter
 };
 
 struct Best {                // lexicographic champion: value, then first occurrence (x, then y)
@@ -70,10 +73,15 @@ __device__ __forceinline__ Best shfl_best(const Best& b, int o) {
     return r;
 }
 
+// MINEFF: fillTriMin's effect-size filter (wisetools.py:475-487): a run only counts if abs(median(R[x..y]) - 1) >=
+// mineffectsize, otherwise its triangle entry is 0 (and 0 never wins against a positive threshold).
+template <bool MINEFF>
 __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a) {
     extern __shared__ __align__(16) unsigned char seg_raw[];
     double* P = reinterpret_cast<double*>(seg_raw);               // [pcap] prefix sums, P[i] = sum zc[0..i)
     unsigned* dh = reinterpret_cast<unsigned*>(P + a.pcap);       // [pcap] per run length: max hi32(|score|) of the sweep
+    int* CH = reinterpret_cast<int*>(dh + a.pcap);                // [pcap] MINEFF: #{j < i : rc[j] >= c_hi}
+    int* CL = CH + a.pcap;                                        // [pcap] MINEFF: #{j < i : rc[j] <= c_lo}
     __shared__ double s_red[2][SEG_WARPS];
     __shared__ Best s_best[2][SEG_WARPS];
     __shared__ int s_scan[SEG_WARPS];
@@ -88,6 +96,8 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     const double* zrow = a.z + (size_t)b * a.N + cstart;
     const int* nrow = a.refsz + (size_t)b * a.N + cstart;
     double* zc = a.zc + (size_t)b * a.N + cstart;                 // kept z-scores of this chromosome (global scratch)
+    double* rc = MINEFF ? a.rc + (size_t)b * a.N + cstart : nullptr;
+    const double* rrow = MINEFF ? a.r + (size_t)b * a.N + cstart : nullptr;
 
     // ---- 1. compaction of the kept bins (wisecondor.py:215-218: refSizes >= minrefbins) -------------------------
     if (tid == 0) { s_n = 0; s_bad = 0; }
@@ -103,6 +113,7 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         for (int w = 0; w < warp; ++w) off += s_scan[w];
         if (keep) {
             zc[off + __popc(bal & ((1u << lane) - 1u))] = v;
+            if (MINEFF) rc[off + __popc(bal & ((1u << lane) - 1u))] = rrow[i];
             if (!isfinite(v)) s_bad = 1;
         }
         __syncthreads();
@@ -122,6 +133,13 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     // +-inf / NaN z (a kept bin whose reference sigma is 0, wisetools.py:431 under np.seterr('ignore')): the reference's
     // argmax/argmin then see inf / NaN run values; handled per range below.  Prefix sums skip the non-finite bins.
     const bool has_bad = s_bad != 0;
+    if (MINEFF && has_bad) {                        // the effect-size filter on inf / NaN runs is not implemented
+        if (tid == 0) {
+            atomicOr(a.status, 4);
+            a.cwz[(size_t)b * a.nsel + slot] = __longlong_as_double(0x7ff8000000000000ll);
+        }
+        return;
+    }
 
     // ---- 2. prefix sums and A = sum |z| (the scale of the error window) ---------------------------------------------
     {
@@ -167,11 +185,53 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     // scan, warp bases) on both ends of the run, numpy's own pairwise rounding, the reciprocal multiply.  delta = 2 x that.
     const double delta_A = (4.0 * ((n + SEG_THREADS - 1) / SEG_THREADS) + 160.0) * SEG_EPS * A;
 
+    // MINEFF: prefix counts of the ratios above c_hi / below c_lo decide the median test in O(1) for all odd lengths and
+    // for even lengths unless exactly half of the run lies on the far side; then the two middle order statistics are
+    // the largest value on the near side and the smallest on the far side (one scan of the run).
+    if (MINEFF) {
+        if (tid == 0) {
+            int ch = 0, cl = 0;
+            for (int i = 0; i < n; ++i) {
+                CH[i] = ch; CL[i] = cl;
+                const double rv = rc[i];
+                ch += rv >= a.c_hi ? 1 : 0;
+                cl += rv <= a.c_lo ? 1 : 0;
+            }
+            CH[n] = ch; CL[n] = cl;
+        }
+        __syncthreads();
+    }
+    auto passes = [&](int x, int L) -> bool {          // abs(np_median(regionR[x:y+1]) - 1) >= threshold (wisetools.py:483)
+        if (!MINEFF) return true;
+        const int mid = L >> 1;
+        const int nh = CH[x + L] - CH[x], nl = CL[x + L] - CL[x];
+        if (L & 1) return nh >= mid + 1 || nl >= mid + 1;            // the median is the middle element
+        if (nh >= mid + 1 || nl >= mid + 1) return true;             // both middle elements on the far side
+        bool ok = false;
+        if (nh == mid) {                              // a_mid < c_hi <= a_mid+1: median = (a_mid + a_mid+1) / 2
+            double below = -INFINITY, above = INFINITY;
+            for (int i = x; i < x + L; ++i) {
+                const double rv = rc[i];
+                if (rv >= a.c_hi) above = fmin(above, rv); else below = fmax(below, rv);
+            }
+            ok = __ddiv_rn(__dadd_rn(below, above), 2.0) >= a.c_hi;
+        }
+        if (!ok && nl == mid) {
+            double below = -INFINITY, above = INFINITY;
+            for (int i = x; i < x + L; ++i) {
+                const double rv = rc[i];
+                if (rv <= a.c_lo) below = fmax(below, rv); else above = fmin(above, rv);
+            }
+            ok = __ddiv_rn(__dadd_rn(below, above), 2.0) <= a.c_lo;
+        }
+        return ok;
+    };
+
     // chromosome-wide value: entry (0, n-1) of the triangle (wisecondor.py:237), numpy order, by one thread (a non-finite
     // bin propagates through the same additions: inf, or NaN for inf - inf)
     if (tid == SEG_THREADS - 1) {
         const double tot = np_sum_thread([&](int i) { return zc[i]; }, n);
-        a.cwz[(size_t)b * a.nsel + slot] = __ddiv_rn(tot, sqrt((double)n));
+        a.cwz[(size_t)b * a.nsel + slot] = passes(0, n) ? __ddiv_rn(tot, sqrt((double)n)) : 0.0;
     }
     __shared__ int s_first[3];                      // first NaN / +inf / -inf position of the current range
 
@@ -250,7 +310,9 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
 #pragma unroll
                             for (int r = 0; r < SEG_R; ++r) {
                                 const double v = __dmul_rn(__dsub_rn(ww[(j + r) % SEG_R], px), isq[r]);
-                                bh[r] = max(bh[r], (unsigned)__double2hiint(v) & 0x7fffffffu);
+                                const unsigned h = (unsigned)__double2hiint(v) & 0x7fffffffu;
+                                if (!MINEFF) bh[r] = max(bh[r], h);
+                                else if (h > bh[r] && passes(x + j, L0 + r)) bh[r] = h;   // only record attempts pay
                             }
                         }
                     }
@@ -260,7 +322,9 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
                     const int L = L0 + r;
                     for (int xx = x; xx + L <= hi; ++xx) {
                         const double v = __dmul_rn(__dsub_rn(P[xx + L], P[xx]), isq[r]);
-                        bh[r] = max(bh[r], (unsigned)__double2hiint(v) & 0x7fffffffu);
+                        const unsigned h = (unsigned)__double2hiint(v) & 0x7fffffffu;
+                        if (!MINEFF) bh[r] = max(bh[r], h);
+                        else if (h > bh[r] && passes(xx, L)) bh[r] = h;
                     }
                     if (L <= m) { dh[L] = bh[r]; best = max(best, bh[r]); }
                 }
@@ -302,7 +366,7 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
             const double isqL = __ddiv_rn(1.0, sq);
             for (int x = lo + tid; x + L <= hi; x += SEG_THREADS) {
                 const double av = fabs(__dmul_rn(__dsub_rn(P[x + L], P[x]), isqL));
-                if (av >= vlow) {
+                if (av >= vlow && passes(x, L)) {
                     const double sum = np_sum_thread([&](int i) { return zc[x + i]; }, L);     // np_sum(region[x:y+1])
                     Best e = {__ddiv_rn(sum, sq), x, x + L - 1};                                 // / np_sqrt(y-x+1)
                     if (better_max(e, cmax)) cmax = e;
@@ -350,16 +414,37 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
 
 }  // namespace
 
-extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* refsizes_d, int N, int B,
+extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const double* r_d, const int32_t* refsizes_d, int N, int B,
                                 const int* chrom_bins_h, int nchrom, const int* chromosomes_h, int nsel, int minrefbins,
-                                double z_threshold, int min_search, double* cwz_d, int32_t* cleaned_bins_d,
-                                wc_call* calls_d, int32_t* ncalls_d, int max_calls, void* stream_v) {
+                                double z_threshold, double mineffectsize, int min_search, double* cwz_d,
+                                int32_t* cleaned_bins_d, wc_call* calls_d, int32_t* ncalls_d, int max_calls,
+                                void* stream_v) {
     WC_CHECK_ARG(ctx != nullptr && z_d != nullptr && refsizes_d != nullptr && chrom_bins_h != nullptr);
     WC_CHECK_ARG(chromosomes_h != nullptr && cwz_d != nullptr && cleaned_bins_d != nullptr);
     WC_CHECK_ARG(calls_d != nullptr && ncalls_d != nullptr && max_calls > 0);
     WC_CHECK_ARG(N > 0 && B > 0 && nchrom > 0 && nsel > 0 && min_search >= 0);
+    // fillTriMin (wisetools.py:475-487): threshold 0 is the plain triangle; a negative threshold keeps every run too
+    const bool mineff = mineffectsize > 0.0;
+    if (mineff) {
+        WC_CHECK_ARG(r_d != nullptr);
+        if (!(z_threshold > 0.0)) {
+            wc_set_error("segmentation with mineffectsize needs a positive z threshold (zeroed runs would be called)");
+            return WC_ERR_ARG;
+        }
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     WC_CUDA(cudaSetDevice(ctx->device));
+    // abs(m - 1) >= t  <=>  m >= c_hi or m <= c_lo, with c_hi / c_lo the exact double boundaries of the rounded test
+    double c_hi = INFINITY, c_lo = -INFINITY;
+    if (mineff) {
+        const double t = mineffectsize;
+        c_hi = 1.0 + t;
+        while (c_hi - 1.0 >= t) c_hi = nextafter(c_hi, -INFINITY);
+        while (!(c_hi - 1.0 >= t)) c_hi = nextafter(c_hi, INFINITY);
+        c_lo = 1.0 - t;
+        while (1.0 - c_lo >= t) c_lo = nextafter(c_lo, INFINITY);
+        while (!(1.0 - c_lo >= t)) c_lo = nextafter(c_lo, -INFINITY);
+    }
     std::vector<int> start(nchrom);
     long long tot = 0;
     for (int c = 0; c < nchrom; ++c) { WC_CHECK_ARG(chrom_bins_h[c] >= 0); start[c] = (int)tot; tot += chrom_bins_h[c]; }
@@ -382,13 +467,14 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* r
         meta[nsel + i] = chrom_bins_h[c];
         meta[2 * nsel + i] = order[i];
     }
-    double* zc; int* meta_d; int* status_d;
+    double* zc; double* rcomp = nullptr; int* meta_d; int* status_d;
     int rc;
     if ((rc = wc_reserve(ctx, SLOT_S_ISQ, (size_t)B * N * sizeof(double), (void**)&zc))) return rc;
+    if (mineff && (rc = wc_reserve(ctx, SLOT_S_RC, (size_t)B * N * sizeof(double), (void**)&rcomp))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_S_META, (size_t)3 * nsel * sizeof(int), (void**)&meta_d))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_S_STATUS, 4 * sizeof(int), (void**)&status_d))) return rc;
     const int pcap = (maxlen + 8) & ~1;
-    const size_t smem = (size_t)pcap * (sizeof(double) + sizeof(unsigned));
+    const size_t smem = (size_t)pcap * (sizeof(double) + sizeof(unsigned) + (mineff ? 2 * sizeof(int) : 0));
     if (smem > 220 * 1024) {
         wc_set_error("segmentation: a chromosome of %d bins needs %zu bytes of shared memory (limit 220 KiB)", maxlen, smem);
         return WC_ERR_ARG;
@@ -400,10 +486,15 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* r
     SegArgs a;
     a.z = z_d; a.refsz = refsizes_d; a.N = N; a.B = B; a.sel_start = meta_d; a.sel_len = meta_d + nsel;
     a.sel_slot = meta_d + 2 * nsel; a.nsel = nsel; a.minrefbins = minrefbins; a.thr = z_threshold;
-    a.min_search = min_search; a.zc = zc; a.cwz = cwz_d; a.cleaned = cleaned_bins_d; a.calls = calls_d;
+    a.min_search = min_search; a.zc = zc; a.r = r_d; a.rc = rcomp; a.c_hi = c_hi; a.c_lo = c_lo; a.cwz = cwz_d; a.cleaned = cleaned_bins_d; a.calls = calls_d;
     a.ncalls = ncalls_d; a.max_calls = max_calls; a.status = status_d; a.pcap = pcap;
-    WC_CUDA(cudaFuncSetAttribute(wc_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wc_segment_kernel<<<(unsigned)((size_t)nsel * B), SEG_THREADS, smem, stream>>>(a);
+    if (mineff) {
+        WC_CUDA(cudaFuncSetAttribute(wc_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wc_segment_kernel<true><<<(unsigned)((size_t)nsel * B), SEG_THREADS, smem, stream>>>(a);
+    } else {
+        WC_CUDA(cudaFuncSetAttribute(wc_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wc_segment_kernel<false><<<(unsigned)((size_t)nsel * B), SEG_THREADS, smem, stream>>>(a);
+    }
     WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[11], stream));
     int status = 0;
@@ -411,6 +502,10 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const int32_t* r
     WC_CUDA(cudaStreamSynchronize(stream));       // meta/status host buffers; the call is documented as synchronous
     ctx->timed_mask |= 1u << 5;
     ctx->counter[6] = 1;
+    if (status & 4) {
+        wc_set_error("segmentation: non-finite z-scores in kept bins together with mineffectsize != 0 is not supported");
+        return WC_ERR_ARG;
+    }
     if (status & 2) { wc_set_error("segmentation: more than %d pending ranges on one chromosome", SEG_STACK); return WC_ERR_INTERNAL; }
     if (status & 1) { wc_set_error("segmentation: more than max_calls=%d calls for one sample", max_calls); return WC_ERR_ARG; }
     return WC_OK;

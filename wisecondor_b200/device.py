@@ -187,12 +187,18 @@ def zscore_batch(test, nsamples, table, z_threshold, repeats, copy_init=None):
     return z, r, sizes, asdef
 
 
-def segment_batch(z, refsizes, masked_sizes, chromosomes, minrefbins, z_threshold, min_search=3, max_calls=256):
+def segment_batch(z, refsizes, masked_sizes, chromosomes, minrefbins, z_threshold, min_search=3, max_calls=256, r=None,
+                  mineffectsize=0.0):
     """The chromosome loop of toolTest (wisecondor.py:233-238) for a batch.  z: CUDA f64 [B][N]; refsizes: CUDA
-    int32 [B][N]; chromosomes: 0-based indices.  Returns (cwz [B][nsel] CUDA, cleaned_bins int32 [B][nsel] CUDA,
+    int32 [B][N]; chromosomes: 0-based indices; r (CUDA f64 [B][N], resultsR) and mineffectsize select fillTriMin's
+    effect-size filter (wisetools.py:475-487).  Returns (cwz [B][nsel] CUDA, cleaned_bins int32 [B][nsel] CUDA,
     calls: numpy structured array (sample, chrom, x, y, z) sorted by (sample, chrom, x))."""
     _require_cuda(z, torch.float64, "z")
     _require_cuda(refsizes, torch.int32, "refsizes")
+    if mineffectsize != 0:
+        _require_cuda(r, torch.float64, "r")
+        if r.shape != z.shape:
+            raise _cabi.WisecondorError("r must have the shape of z")
     b, n = z.shape
     dev = z.device
     cb, cbp = _ints(masked_sizes)
@@ -203,8 +209,9 @@ def segment_batch(z, refsizes, masked_sizes, chromosomes, minrefbins, z_threshol
     while True:
         calls = torch.empty((b, max_calls * CALL_DTYPE.itemsize), dtype=torch.uint8, device=dev)
         ncalls = torch.empty((b,), dtype=torch.int32, device=dev)
-        rc = _cabi.lib().wc_segment_batch(ctx.handle, _ptr(z), _ptr(refsizes), n, b, cbp, len(cb), selp, len(sel),
-                                          int(minrefbins), float(z_threshold), int(min_search), _ptr(cwz), _ptr(cleaned),
+        rc = _cabi.lib().wc_segment_batch(ctx.handle, _ptr(z), _ptr(r) if r is not None else None, _ptr(refsizes), n, b,
+                                          cbp, len(cb), selp, len(sel), int(minrefbins), float(z_threshold),
+                                          float(mineffectsize), int(min_search), _ptr(cwz), _ptr(cleaned),
                                           _ptr(calls), _ptr(ncalls), int(max_calls), _stream_ptr(dev))
         if rc != 0 and b"max_calls" in _cabi.lib().wc_last_error() and max_calls < (1 << 16):
             max_calls *= 8

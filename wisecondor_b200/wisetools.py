@@ -245,16 +245,21 @@ def repeatTest(testData, indexes, distances, chromosomeBins, chromosomeBinSums, 
     return z[0], r[0], sizes[0], float(asdef[0])
 
 
-def segmentChromosomes(cleanedZ_or_z, refSizes, masked_sizes, chromosomes, minrefbins, z_threshold, min_search=3):
-    """fillTri + segmentTri for the listed chromosomes (1-based, as -chromosomes) of a batch (reference
-    wisecondor.py:233-238, wisetools.py:466-472, triarray.py:59-84).  z, refSizes: numpy [B][N].
+def segmentChromosomes(cleanedZ_or_z, refSizes, masked_sizes, chromosomes, minrefbins, z_threshold, min_search=3,
+                       resultsR=None, mineffectsize=0):
+    """fillTriMin + segmentTri for the listed chromosomes (1-based, as -chromosomes) of a batch (reference
+    wisecondor.py:233-238, wisetools.py:466-487, triarray.py:59-84).  z, refSizes (and resultsR when
+    mineffectsize != 0): numpy [B][N].
     Returns (chromWide [B][nsel], cleanedBins [B][nsel], calls structured array sorted by (sample, chrom, x))."""
     torch = _torch()
     dev = torch.device("cuda", DEVICE)
     z = torch.as_tensor(np.ascontiguousarray(cleanedZ_or_z, dtype=np.float64), device=dev)
     sizes = torch.as_tensor(np.ascontiguousarray(refSizes).astype(np.int32), device=dev)
+    r = None
+    if mineffectsize != 0:
+        r = torch.as_tensor(np.ascontiguousarray(resultsR, dtype=np.float64), device=dev)
     cwz, cleaned, calls = _dev.segment_batch(z, sizes, masked_sizes, [c - 1 for c in chromosomes], minrefbins,
-                                             z_threshold, min_search)
+                                             z_threshold, min_search, r=r, mineffectsize=mineffectsize)
     return cwz.cpu().numpy(), cleaned.cpu().numpy(), calls
 
 
@@ -264,11 +269,8 @@ def testSamples(samples, ref, z_threshold, chromosomes=tuple(range(1, 23)), mine
     the reference's binsize.  `ref` holds the reference-npz entries.  Returns one dict per sample with the
     result-npz entries results_r, results_z, results_cwz, results_calls, threshold_z, asdef, aasdef.
 
-    Device: prepSample (K7), repeatTest (K8), fillTri + segmentTri (K9).  Host: getOptimalCutoff (once per
+    Device: prepSample (K7), repeatTest (K8), fillTriMin + segmentTri (K9).  Host: getOptimalCutoff (once per
     reference), the cleaned->raw coordinate walk and the per-call median of R (wisecondor.py:241-257), inflate."""
-    if mineffectsize != 0:
-        raise NotImplementedError("-mineffectsize != 0 (fillTriMin's run-median filter, reference "
-                                  "wisetools.py:475-487) is not implemented on the device yet")
     torch = _torch()
     chromosome_sizes = [int(v) for v in ref['chromosome_sizes']]
     masked_sizes = [int(v) for v in ref['masked_sizes']]
@@ -286,7 +288,8 @@ def testSamples(samples, ref, z_threshold, chromosomes=tuple(range(1, 23)), mine
         nb = len(chunk)
         T = prepSamples(chunk, chromosome_sizes, mask, ref['pca_mean'], ref['pca_components'], as_device=True)
         z_d, r_d, sizes_d, asdef_d = _dev.zscore_batch(T, nb, table, z_threshold, repeats)
-        cwz_d, cleaned_d, calls = _dev.segment_batch(z_d, sizes_d, masked_sizes, sel, minrefbins, z_threshold, min_search)
+        cwz_d, cleaned_d, calls = _dev.segment_batch(z_d, sizes_d, masked_sizes, sel, minrefbins, z_threshold, min_search,
+                                                     r=r_d if mineffectsize != 0 else None, mineffectsize=mineffectsize)
         z_h, r_h, sizes_h = z_d.cpu().numpy(), r_d.cpu().numpy(), sizes_d.cpu().numpy()
         asdef_h, cwz_h = asdef_d.cpu().numpy(), cwz_d.cpu().numpy()
         call_lo = np.searchsorted(calls['sample'], np.arange(nb), side='left')
