@@ -43,7 +43,7 @@ enum { WC_NBUF = 48, WC_NPHASE = 8, WC_NCOUNTER = 8 };
 // Workspace slots (one grow-only device buffer each).
 enum {
     SLOT_XC = 0, SLOT_NORMS, SLOT_ROWCS, SLOT_ROWCE, SLOT_RBMETA, SLOT_CAND_D, SLOT_CAND_J, SLOT_SEGCNT,
-    SLOT_SEGFLAG, SLOT_SLOW, SLOT_SCRATCH, SLOT_IO_X, SLOT_IO_IDX, SLOT_IO_DIST,                       // search
+    SLOT_SEGFLAG, SLOT_SLOW, SLOT_SCRATCH, SLOT_IO_X, SLOT_IO_IDX, SLOT_IO_DIST, SLOT_ROWTHR,          // search
     SLOT_PROF = 20,
     SLOT_T_COPY = 24, SLOT_T_ZT, SLOT_T_RT, SLOT_T_NT, SLOT_T_SD, SLOT_T_FLAGS, SLOT_T_TOTALS, SLOT_T_PROJ,   // test
     SLOT_S_ISQ = 32, SLOT_S_META, SLOT_S_STATUS, SLOT_S_RC,                                                       // segmentation

@@ -81,6 +81,7 @@ struct TopkArgs {
     double tau_init;
     long long* prof;             // optional [grid][8] per-CTA cycle counters (consumer warp 0), or nullptr
     long long* trace;            // optional debug timeline of CTA 0: [2 warps (0 and 4)][64 tiles][4 stamps]
+    u64* row_thr;                // [rows] tightest threshold key any CTA has found for the row (shared between segments)
     int lag;                     // chunks by which warps 4-7 trail warps 0-3 (0 = all in phase)
     int nstages;                 // depth of the TMA ring (3..MAX_STAGES)
 };
@@ -118,6 +119,12 @@ __device__ __forceinline__ int bucket_of(double d, double mn, float scale) {
 // threshold key for "d~ <= tau": bits(-tau/2); tau is kept strictly positive so the key has its sign bit set and
 // every score >= +0 (d~ <= 0, rounding noise of duplicates) passes the unsigned compare.
 __device__ __forceinline__ u64 key_of_tau(double tau) { return (u64)__double_as_longlong(-0.5 * tau); }
+inline u64 host_key_of_tau(double tau) {
+    const double v = -0.5 * tau;
+    u64 bits;
+    memcpy(&bits, &v, sizeof(bits));
+    return bits;
+}
 __device__ __forceinline__ double dist_of_key(u64 key) { return -2.0 * __longlong_as_double((long long)key); }
 
 // Warp-collective prune of one row's candidate buffer, on score keys (unsigned order == distance order).  The
@@ -321,7 +328,8 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                 const int row = a.row_begin + rb * BM + r0w + lane;
                 const bool valid = row < a.row_end;
                 w_nrm[lane] = valid ? a.norms[row] : 0.0;
-                w_thr[lane] = valid ? key_of_tau(a.tau_init) : KEY_NEVER;
+                // a threshold found by any other CTA for this row (other columns) bounds the row's k-th distance too
+                w_thr[lane] = valid ? __ldcg(a.row_thr + (row - a.row_begin)) : KEY_NEVER;
                 w_cnt[lane] = 0;
                 w_flag[lane] = 0;
             }
@@ -337,6 +345,11 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
         const int t = q < skip_lo ? q : q + skip_n;
         const int col0 = t * BN;
         q += qs;
+        u64 shared_thr = ~0ull;                 // issued now, consumed after the tile's MMAs: latency fully hidden
+        if (lane < WROWS) {
+            const int row = a.row_begin + rb * BM + r0w + lane;
+            if (row < a.row_end) shared_thr = __ldcg(a.row_thr + (row - a.row_begin));
+        }
         const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && tcount < 64;
         long long* tr = tr_on ? a.trace + ((size_t)(warp >> 2) * 64 + tcount) * 4 : nullptr;
         ++tcount;
@@ -420,6 +433,8 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
         // accumulator (mt, nt, e) of lane (g, q) is row 16w + mt*8 + perm(g), column nt*8 + perm(2q+e) = nt*8 + 4e + q.
         const long long pf_e0 = clock64();
         if (tr_on) tr[1] = pf_e0;
+        if (lane < WROWS && shared_thr < w_thr[lane]) w_thr[lane] = shared_thr;
+        __syncwarp();
         u64* ck = a.cand_key + (size_t)seg * seg_stride;
         int* cj = a.cand_j + (size_t)seg * seg_stride;
 #pragma unroll
@@ -498,7 +513,9 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                         w_thr[rw] = KEY_NEVER;
                         w_cnt[rw] = 0;
                     } else {
-                        w_thr[rw] = thr;
+                        const int row = a.row_begin + rb * BM + r0w + rw;
+                        const u64 other = atomicMin(a.row_thr + (row - a.row_begin), thr);   // publish; adopt a tighter one
+                        w_thr[rw] = other < thr ? other : thr;
                         w_cnt[rw] = kept;
                     }
                 }
@@ -515,6 +532,11 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
         o[0] = clock64() - pf_t0; o[1] = pf_wait; o[2] = pf_epi; o[3] = pf_prune;
         o[4] = tcount; o[5] = pf_nprune; o[6] = pf_emit; o[7] = 0;
     }
+}
+
+__global__ void wc_fill_u64_kernel(u64* p, size_t n, u64 v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1041,6 +1063,8 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     if ((rc = wc_reserve(ctx, SLOT_SEGCNT, (size_t)std::max(nseg, 1) * BM * sizeof(int), (void**)&seg_cnt))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_SEGFLAG, (size_t)std::max(nseg, 1) * BM * sizeof(int), (void**)&seg_flag))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_SLOW, ((size_t)rows + 1) * sizeof(int), (void**)&slow))) return rc;
+    u64* row_thr;
+    if ((rc = wc_reserve(ctx, SLOT_ROWTHR, (size_t)rows * sizeof(u64), (void**)&row_thr))) return rc;
     int* d_skip_lo = d_meta;
     int* d_skip_n = d_skip_lo + nrb;
     int* d_seg_first = d_skip_n + nrb;
@@ -1095,6 +1119,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     ta.cta_piece_begin = d_cta_piece; ta.pieces = d_pieces;
     ta.cand_key = cand_key; ta.cand_j = cand_j; ta.seg_cnt = seg_cnt; ta.seg_flag = seg_flag;
     ta.cap = cap; ta.k = k; ta.mcoef = mcoef; ta.tau_init = 1e10 * (1.0 + 1e-6);
+    ta.row_thr = row_thr;
     ta.lag = ctx->k5_lag;
     ta.nstages = cap <= 512 ? 5 : 3;
     if (ctx->k5_stages >= 3 && ctx->k5_stages <= MAX_STAGES) ta.nstages = ctx->k5_stages;
@@ -1109,6 +1134,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
                              (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192);
     if (topk_smem > 227 * 1024) { wc_set_error("K5 shared memory %zu exceeds 227 KiB", topk_smem); return WC_ERR_INTERNAL; }
     WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+    wc_fill_u64_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(row_thr, (size_t)rows, host_key_of_tau(ta.tau_init));
     WC_CUDA(cudaEventRecord(ctx->ev[2], stream));
     wc_dist_topk_kernel<<<grid, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
     WC_CUDA(cudaGetLastError());
@@ -1132,7 +1158,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     int nslow = 0;
     WC_CUDA(cudaMemcpyAsync(&nslow, slow, sizeof(int), cudaMemcpyDeviceToHost, stream));
     WC_CUDA(cudaStreamSynchronize(stream));
-    long long launches = 4;
+    long long launches = 5;
     if (nslow > 0) {
         const int batch = 64;
         double* scratch;
