@@ -43,6 +43,7 @@ constexpr int HIST_BINS = 256;
 constexpr int FIN_THREADS = 128;    // one thread per shortlisted candidate during the exact re-score
 constexpr int FIN_CHUNK = 32;       // samples staged per pipeline step of the re-score
 constexpr int FIN_LD = FIN_CHUNK + 1;   // padded tile row (bank-conflict free per-thread row walks)
+constexpr int FIN_LDB = FIN_CHUNK + 2;  // tile row of the bulk-copy path: 16-byte aligned rows (2-way conflicts, cheap)
 constexpr int EXH_THREADS = 256;
 constexpr u64 KEY_NEVER = 0ull;     // threshold key of an inactive row: no finite negative score passes
 
@@ -597,6 +598,7 @@ struct FinArgs {
     double* dist_out;
     int* slow_list;
     int* slow_count;
+    int bulk;               // 1: stage candidate rows with cp.async.bulk (needs 16-byte aligned rows: S even)
 };
 
 // One CTA per target row.
@@ -609,8 +611,8 @@ struct FinArgs {
 //  3. rank by (distance, index), write the first k with indices remapped to other-chromosome coordinates.
 __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs a) {
     extern __shared__ __align__(16) unsigned char fin_raw[];
-    double* tile0 = reinterpret_cast<double*>(fin_raw);                    // 2 x FIN_THREADS x FIN_LD
-    double* xi0 = tile0 + 2 * FIN_THREADS * FIN_LD;                        // 2 x FIN_CHUNK
+    double* tile0 = reinterpret_cast<double*>(fin_raw);                    // 2 x FIN_THREADS x FIN_LDB (or FIN_LD)
+    double* xi0 = tile0 + 2 * FIN_THREADS * FIN_LDB;                       // 2 x FIN_CHUNK
     double* ex_d = xi0 + 2 * FIN_CHUNK;                                    // shortcap
     int* ex_j = reinterpret_cast<int*>(ex_d + a.shortcap);                 // shortcap
     int* hist = ex_j + a.shortcap;                                         // HIST_BINS
@@ -731,6 +733,63 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     // ---- 2. exact re-score ----
     const double* xrow = a.X + (size_t)row * a.S;
     const int nchunks = (a.S + FIN_CHUNK - 1) / FIN_CHUNK;
+    if (a.bulk) {
+        // Every thread stages its own candidate's 32-sample slice with ONE bulk copy (cp.async.bulk, SASS UBLKCP)
+        // that completes on the stage's mbarrier - no per-element copy instructions, no address arithmetic.
+        __shared__ uint64_t s_bar[2];
+        if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+        __syncthreads();
+        uint32_t phase_bits = 0;                       // bit st = parity to wait for on stage st
+        for (int c0 = 0; c0 < p; c0 += FIN_THREADS) {
+            const int nc = (p - c0) < FIN_THREADS ? (p - c0) : FIN_THREADS;
+            const double* crow = tid < nc ? a.X + (size_t)ex_j[c0 + tid] * a.S : nullptr;
+            auto issue = [&](int chunk, int st) {
+                const int s0 = chunk * FIN_CHUNK;
+                const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
+                const uint32_t bytes = (uint32_t)ns * 8u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&s_bar[st], bytes * (uint32_t)(nc + 1));
+                    bulk_g2s(xi0 + st * FIN_CHUNK, xrow + s0, bytes, &s_bar[st]);
+                }
+                if (tid < nc) bulk_g2s(tile0 + ((size_t)st * FIN_THREADS + tid) * FIN_LDB, crow + s0, bytes, &s_bar[st]);
+            };
+            double accd = 0.0;
+            issue(0, 0);
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int st = ch & 1;
+                if (ch + 1 < nchunks) issue(ch + 1, st ^ 1);
+                mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
+                phase_bits ^= 1u << st;
+                const int s0 = ch * FIN_CHUNK;
+                const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
+                if (tid < nc) {
+                    const double* tr = tile0 + ((size_t)st * FIN_THREADS + tid) * FIN_LDB;
+                    const double* xi = xi0 + st * FIN_CHUNK;
+                    if (ns == FIN_CHUNK) {
+#pragma unroll
+                        for (int l = 0; l < FIN_CHUNK; ++l) {
+                            double v = __dsub_rn(tr[l], xi[l]);
+                            accd = __dadd_rn(accd, __dmul_rn(v, v));
+                        }
+                    } else {
+                        for (int l = 0; l < ns; ++l) {
+                            double v = __dsub_rn(tr[l], xi[l]);
+                            accd = __dadd_rn(accd, __dmul_rn(v, v));
+                        }
+                    }
+                }
+                __syncthreads();                       // stage st may be refilled by the next issue
+            }
+            if (tid < nc) {
+                const bool ok = accd < 1e10;     // wisetools.py:312-314: strict `<` against the 1e10 start value; NaN fails
+                const int j = ex_j[c0 + tid];
+                ex_d[c0 + tid] = ok ? accd : INFINITY;
+                ex_j[c0 + tid] = ok ? j : 0x7fffffff;
+            }
+            __syncthreads();
+        }
+    } else
     for (int c0 = 0; c0 < p; c0 += FIN_THREADS) {
         const int nc = (p - c0) < FIN_THREADS ? (p - c0) : FIN_THREADS;
         auto issue = [&](int chunk, int buf) {
@@ -1147,7 +1206,8 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     fa.cand_key = cand_key; fa.cand_j = cand_j; fa.seg_cnt = seg_cnt; fa.seg_flag = seg_flag; fa.cap = cap; fa.k = k;
     fa.shortcap = k <= 128 ? 256 : 512;
     fa.mcoef = mcoef; fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
-    const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LD + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 +
+    fa.bulk = (S % 2 == 0 && (reinterpret_cast<uintptr_t>(corrected_d) & 15) == 0) ? 1 : 0;
+    const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 +
                             HIST_BINS * 4;
     WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
