@@ -283,15 +283,14 @@ def testSamples(samples, ref, z_threshold, chromosomes=tuple(range(1, 23)), mine
     sel = [c - 1 for c in chromosomes]
     out = []
     timeStartTest = time.time()
-    for first in range(0, len(samples), batch):
-        chunk = samples[first:first + batch]
-        nb = len(chunk)
-        T = prepSamples(chunk, chromosome_sizes, mask, ref['pca_mean'], ref['pca_components'], as_device=True)
-        z_d, r_d, sizes_d, asdef_d = _dev.zscore_batch(T, nb, table, z_threshold, repeats)
-        cwz_d, cleaned_d, calls = _dev.segment_batch(z_d, sizes_d, masked_sizes, sel, minrefbins, z_threshold, min_search,
-                                                     r=r_d if mineffectsize != 0 else None, mineffectsize=mineffectsize)
-        z_h, r_h, sizes_h = z_d.cpu().numpy(), r_d.cpu().numpy(), sizes_d.cpu().numpy()
-        asdef_h, cwz_h = asdef_d.cpu().numpy(), cwz_d.cpu().numpy()
+    dev = torch.device("cuda", DEVICE)
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def assemble(pending):
+        """Host glue of one finished chunk (wisecondor.py:214-222, 241-268): keep mask, cleaned->raw walk, medians, inflate."""
+        nb, host, calls, done = pending
+        done.synchronize()
+        z_h, r_h, sizes_h, asdef_h, cwz_h = [t.numpy() for t in host]
         call_lo = np.searchsorted(calls['sample'], np.arange(nb), side='left')
         call_hi = np.searchsorted(calls['sample'], np.arange(nb), side='right')
         for b in range(nb):
@@ -319,6 +318,32 @@ def testSamples(samples, ref, z_threshold, chromosomes=tuple(range(1, 23)), mine
                 results_r=[inflatedR[raw_starts[i]:raw_starts[i + 1]] for i in range(len(chromosome_sizes))],
                 results_cwz=cwz_h[b].copy(), results_calls=np.array(stouffCalls), threshold_z=z_threshold,
                 asdef=asdef, aasdef=asdef * z_threshold))
+
+    # Pipeline over chunks: the z-score kernels of chunk i run while the host assembles chunk i-1, and the results of
+    # chunk i travel to (pinned) host memory on a second stream while chunk i+1 computes.
+    pending = None
+    for first in range(0, len(samples), batch):
+        chunk = samples[first:first + batch]
+        nb = len(chunk)
+        T = prepSamples(chunk, chromosome_sizes, mask, ref['pca_mean'], ref['pca_components'], as_device=True)
+        z_d, r_d, sizes_d, asdef_d = _dev.zscore_batch(T, nb, table, z_threshold, repeats)       # asynchronous
+        if pending is not None:
+            assemble(pending)
+        cwz_d, cleaned_d, calls = _dev.segment_batch(z_d, sizes_d, masked_sizes, sel, minrefbins, z_threshold, min_search,
+                                                     r=r_d if mineffectsize != 0 else None, mineffectsize=mineffectsize)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (z_d, r_d, sizes_d, asdef_d, cwz_d)]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            for h, t in zip(host, (z_d, r_d, sizes_d, asdef_d, cwz_d)):
+                h.copy_(t, non_blocking=True)
+                t.record_stream(copy_stream)
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        pending = (nb, host, calls, done)
+    if pending is not None:
+        assemble(pending)
     del masked_starts
     print('Time spent on obtaining z-scores and stouffers z-scores:', int(time.time() - timeStartTest), 'seconds')
     return out
