@@ -238,6 +238,21 @@ def test_segmentation_min_effect_golden_and_random(fn):
         assert segs == [(float(v), xy) for v, xy in wsegs], trial
 
 
+def test_segmentation_very_long_chromosome_uses_global_side_arrays():
+    """chr1 at 10 kb bins has 24 926 bins: the prefix sums alone fill shared memory, the side arrays move to global."""
+    rng = np.random.default_rng(8)
+    n = 20000
+    z = rng.normal(0, 1, size=n)
+    z[3000:3400] += 0.6
+    z[15000:15040] -= 2.0
+    (cw, m, segs), = _segment([z], 5.0)
+    wcw, wsegs = wc_oracle.segment_region_prefix(z, 5.0, 3)
+    assert m == n and [s[1] for s in segs] == [s[1] for s in wsegs] and len(segs) >= 2
+    assert cw == np.sum(z) / np.sqrt(n)
+    for v, (x, y) in segs:
+        assert v == np.sum(z[x:y + 1]) / np.sqrt(y - x + 1)
+
+
 def test_segmentation_batch_keep_mask_and_chromosome_list():
     """Several samples, several chromosomes, bins dropped by minrefbins, a chromosome subset (-chromosomes)."""
     from wisecondor_b200 import wisetools

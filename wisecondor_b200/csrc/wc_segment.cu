@@ -51,7 +51,8 @@ struct SegArgs {
     wc_call* calls;          // [B][max_calls]
     int* ncalls;             // [B]
     int max_calls;
-    int pcap;                // capacity of the shared arrays (>= longest chromosome + 1)
+    int pcap;                // capacity of the per-chromosome arrays (>= longest chromosome + 1)
+    unsigned* aux_g;         // when the side arrays do not fit in shared memory next to P: [blocks][pcap * aux_words] global
     int* status;             // [0] |= 1 call overflow, 2 range-stack overflow, 4 non-finite z with the effect-size filter
 };
 
@@ -79,7 +80,10 @@ template <bool MINEFF>
 __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a) {
     extern __shared__ __align__(16) unsigned char seg_raw[];
     double* P = reinterpret_cast<double*>(seg_raw);               // [pcap] prefix sums, P[i] = sum zc[0..i)
-    unsigned* dh = reinterpret_cast<unsigned*>(P + a.pcap);       // [pcap] per run length: max hi32(|score|) of the sweep
+    // side arrays: in shared memory after P when they fit, else a per-CTA slice of global scratch (10 kb bins: chr1 has
+    // 24 926 bins, P alone takes 199 KB)
+    unsigned* dh = a.aux_g ? a.aux_g + (size_t)blockIdx.x * a.pcap * (MINEFF ? 3 : 1)
+                           : reinterpret_cast<unsigned*>(P + a.pcap);   // [pcap] per run length: max hi32(|score|) of the sweep
     int* CH = reinterpret_cast<int*>(dh + a.pcap);                // [pcap] MINEFF: #{j < i : rc[j] >= c_hi}
     int* CL = CH + a.pcap;                                        // [pcap] MINEFF: #{j < i : rc[j] <= c_lo}
     __shared__ double s_red[2][SEG_WARPS];
@@ -474,10 +478,16 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const double* r_
     if ((rc = wc_reserve(ctx, SLOT_S_META, (size_t)3 * nsel * sizeof(int), (void**)&meta_d))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_S_STATUS, 4 * sizeof(int), (void**)&status_d))) return rc;
     const int pcap = (maxlen + 8) & ~1;
-    const size_t smem = (size_t)pcap * (sizeof(double) + sizeof(unsigned) + (mineff ? 2 * sizeof(int) : 0));
-    if (smem > 220 * 1024) {
-        wc_set_error("segmentation: a chromosome of %d bins needs %zu bytes of shared memory (limit 220 KiB)", maxlen, smem);
-        return WC_ERR_ARG;
+    const size_t aux_bytes = (size_t)pcap * (sizeof(unsigned) + (mineff ? 2 * sizeof(int) : 0));
+    size_t smem = (size_t)pcap * sizeof(double) + aux_bytes;
+    unsigned* aux_g = nullptr;
+    if (smem > 220 * 1024) {                      // keep only the prefix sums in shared memory
+        smem = (size_t)pcap * sizeof(double);
+        if (smem > 220 * 1024) {
+            wc_set_error("segmentation: a chromosome of %d bins needs %zu bytes of shared memory (limit 220 KiB)", maxlen, smem);
+            return WC_ERR_ARG;
+        }
+        if ((rc = wc_reserve(ctx, SLOT_S_AUX, (size_t)nsel * B * aux_bytes, (void**)&aux_g))) return rc;
     }
     WC_CUDA(cudaEventRecord(ctx->ev[10], stream));
     WC_CUDA(cudaMemcpyAsync(meta_d, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -487,7 +497,7 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const double* r_
     a.z = z_d; a.refsz = refsizes_d; a.N = N; a.B = B; a.sel_start = meta_d; a.sel_len = meta_d + nsel;
     a.sel_slot = meta_d + 2 * nsel; a.nsel = nsel; a.minrefbins = minrefbins; a.thr = z_threshold;
     a.min_search = min_search; a.zc = zc; a.r = r_d; a.rc = rcomp; a.c_hi = c_hi; a.c_lo = c_lo; a.cwz = cwz_d; a.cleaned = cleaned_bins_d; a.calls = calls_d;
-    a.ncalls = ncalls_d; a.max_calls = max_calls; a.status = status_d; a.pcap = pcap;
+    a.ncalls = ncalls_d; a.max_calls = max_calls; a.status = status_d; a.pcap = pcap; a.aux_g = aux_g;
     if (mineff) {
         WC_CUDA(cudaFuncSetAttribute(wc_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         wc_segment_kernel<true><<<(unsigned)((size_t)nsel * B), SEG_THREADS, smem, stream>>>(a);
