@@ -57,6 +57,7 @@ struct wc_ctx {
     cudaEvent_t ev[2 * WC_NPHASE];
     double phase_ms[WC_NPHASE];
     long long counter[WC_NCOUNTER];
+    unsigned long long sched_hash = 0;   // fingerprint of the K5 schedule metadata currently on the device
     unsigned timed_mask = 0;        // phases whose event pair is recorded but not yet read (asynchronous calls)
     int k5_dbg = 0;                 // timing experiments only (results invalid when non-zero)
     int k5_stages = 0;              // 0 = automatic TMA ring depth

@@ -362,6 +362,7 @@ int upload_row_ranges(wc_ctx* ctx, int N, const int* chrom_bins_h, int nchrom, i
         pos += chrom_bins_h[c];
     }
     int rc;
+    ctx->sched_hash = 0;                         // these slots are shared with the search: its cached metadata is gone
     if ((rc = wc_reserve(ctx, slot_cs, (size_t)N * sizeof(int), (void**)cs_d))) return rc;
     if ((rc = wc_reserve(ctx, slot_ce, (size_t)N * sizeof(int), (void**)ce_d))) return rc;
     WC_CUDA(cudaMemcpyAsync(*cs_d, row_cs.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, stream));

@@ -42,15 +42,16 @@ def allgather_rows(idx_local, dist_local, bincount, group=None, out_idx=None, ou
                    torch.empty((world * rmax, k), dtype=dist_local.dtype, device=dev))
     pad_idx, pad_dist, all_idx, all_dist = scratch
     rows = idx_local.shape[0]
-    pad_idx[:rows].copy_(idx_local)
-    pad_dist[:rows].copy_(dist_local)
+    if pad_idx.data_ptr() != idx_local.data_ptr():      # the caller may have let the search write into the scratch
+        pad_idx[:rows].copy_(idx_local)
+    if pad_dist.data_ptr() != dist_local.data_ptr():
+        pad_dist[:rows].copy_(dist_local)
     dist.all_gather_into_tensor(all_idx, pad_idx, group=group)
     dist.all_gather_into_tensor(all_dist, pad_dist, group=group)
     if out_idx is None:
         out_idx = torch.empty((bincount, k), dtype=idx_local.dtype, device=dev)
         out_dist = torch.empty((bincount, k), dtype=dist_local.dtype, device=dev)
-    for r in range(world):
-        a, b = row_shard(r, world, bincount)
-        out_idx[a:b].copy_(all_idx[r * rmax:r * rmax + (b - a)])
-        out_dist[a:b].copy_(all_dist[r * rmax:r * rmax + (b - a)])
+    lens = [row_shard(r, world, bincount)[1] - row_shard(r, world, bincount)[0] for r in range(world)]
+    torch.cat([all_idx[r * rmax:r * rmax + lens[r]] for r in range(world)], out=out_idx)      # drop the padding rows
+    torch.cat([all_dist[r * rmax:r * rmax + lens[r]] for r in range(world)], out=out_dist)
     return out_idx, out_dist
