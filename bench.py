@@ -266,21 +266,16 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
     host_r = torch.empty((B, n), dtype=torch.float64).pin_memory()
     host_n = torch.empty((B, n), dtype=torch.int32).pin_memory()
 
-    copy_out = torch.cuda.Stream(device=dev)
-
     def run(from_host):
         counts = counts_pinned.to(dev, non_blocking=True) if from_host else counts_dev
         T = device.test_prep(counts, masked_raw, mean, comps)
         z, r, sizes, asdef = device.zscore_batch(T, B, table, thr, 5)
         cwz, cleaned, calls = device.segment_batch(z, sizes, bins, list(range(22)), 25, thr, 3)
-        if from_host:       # results travel to pinned host memory on a second stream while the next batch computes
-            ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(copy_out):
-                copy_out.wait_event(ready)
-                for h, t in ((host_z, z), (host_r, r), (host_n, sizes)):
-                    h.copy_(t, non_blocking=True)
-                    t.record_stream(copy_out)
+        if from_host:
+            host_z.copy_(z, non_blocking=True)
+            host_r.copy_(r, non_blocking=True)
+            host_n.copy_(sizes, non_blocking=True)
+            torch.cuda.synchronize(dev)
         return len(calls)
 
     counts_dev = counts_pinned.to(dev)
@@ -334,7 +329,7 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
         "segment_run_evals_per_s": entries / (sms * 1e-3),
         "e2e": {"value": world * B / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * n * 4, "d2h_bytes_per_step": B * n * 20,
                 "api": "device.test_prep + zscore_batch + segment_batch from pinned host counts; z, r, refsizes copied back "
-                       "to pinned host memory on a second stream (overlaps the next batch), %d batches" % e2e_steps},
+                       "to pinned host memory, synchronous, %d batches" % e2e_steps},
         "parallelism": "samples sharded over %d GPU(s), no communication" % world,
     }
 

@@ -494,10 +494,14 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
         pf_epi += pf_p0 - pf_e0;
         if (tr_on) tr[2] = pf_p0;
         // ---- prune rows whose buffer could overflow during the next tile ----
-        for (int rw = 0; rw < WROWS; ++rw) {
+        // (one ballot finds them: the common case - nothing to prune - costs a single shared-memory read per lane)
+        unsigned need = __ballot_sync(0xffffffffu, lane < WROWS && w_cnt[lane] > a.cap - BN && !w_flag[lane]);
+        while (need) {
+            const int rw = __ffs(need) - 1;
+            need &= need - 1;
             int n = w_cnt[rw];
             if (n > a.cap) n = a.cap;
-            if (n > a.cap - BN && !w_flag[rw]) {
+            {
                 u64 thr;
                 int kept;
                 ++pf_nprune;
