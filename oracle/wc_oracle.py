@@ -85,7 +85,9 @@ def train_pca(masked, ncomp=3):
     ncomp x N, mean N).  Component signs follow sklearn's svd_flip (largest |entry| of each row of Vt
     positive); they do not affect `corrected`."""
     t = np.ascontiguousarray(masked.T)                 # S x N
-    mean = t.mean(axis=0)
+    # pca.mean_: scikit-learn reduces the Fortran-ordered view refData.T along its contiguous axis, i.e. each bin's S
+    # values with numpy's pairwise sum - the same additions as a row mean of the C-ordered bins x samples matrix
+    mean = np.ascontiguousarray(masked).mean(axis=1)
     tc = t - mean
     u, s, vt = np.linalg.svd(tc, full_matrices=False)
     vt = vt[:ncomp]

@@ -177,3 +177,53 @@ def test_host_only_tools_say_so(workdir):
         wisecondor.main(["convert", "x.bam", "x.npz"])
     assert e.value.code == 2
     assert wc_oracle is not None
+
+
+def test_config2_shape_prep_and_test_path_vs_oracle():
+    """BASELINE configs[1]/[3] shapes at 250 kb (N raw 11 537): normalise + PCA of 600 synthetic samples against the
+    oracle's full SVD, then the whole test tool for three samples against the oracle (prefix-sum segmentation oracle:
+    the exact triangle is out of reach of a Python double loop at chromosome sizes of ~1000 bins)."""
+    from wisecondor_b200 import wisetools
+    binsize = 250000
+    bins, lam, fac = synth.bin_model(binsize, bin_seed=1)
+    ref_counts = synth.sample_counts(600, lam, fac, seed=2)
+    test_counts = synth.sample_counts(3, lam, fac, seed=3)
+    synth.inject_aberration(test_counts[1], bins, 21, 0.0, 1.0, 1.04, seed=4)
+    synth.inject_aberration(test_counts[2], bins, 8, 0.4, 0.5, 0.8, seed=5)
+    samples = [synth.counts_to_sample_dict(ref_counts[i], bins, binsize) for i in range(600)]
+    masked, chrom_bins, mask = wisetools.toNumpyArray(samples, as_device=True)
+    omasked, ochrom_bins, omask = wc_oracle.to_numpy_array(samples)
+    assert np.array_equal(mask, omask) and chrom_bins == ochrom_bins
+    assert np.array_equal(masked.cpu().numpy(), omasked)
+    corrected, pca = wisetools.trainPCA(masked, as_device=True)
+    ocorrected, ocomps, omean = wc_oracle.train_pca(omasked)
+    assert np.array_equal(pca.mean_, omean)
+    _close(corrected.cpu().numpy(), ocorrected)
+    _components_close(pca.components_, ocomps)
+    # reference-bin search on the device-resident corrected matrix, sampled rows against the C oracle
+    import c_oracle
+    starts = np.concatenate(([0], np.cumsum(chrom_bins)))
+    masked_sizes = [int(mask[starts[i]:starts[i + 1]].sum()) for i in range(22)]
+    sums = [int(v) for v in np.cumsum(masked_sizes)]
+    idx, dist = wisetools.getReference(corrected, masked_sizes, sums, 100, 1, 1)
+    Xh = corrected.cpu().numpy()
+    n = Xh.shape[0]
+    for r0 in (0, 4000, n - 32):
+        oidx, odist = c_oracle.get_reference_rows(Xh, masked_sizes, r0, r0 + 32, 100)
+        assert np.array_equal(idx[r0:r0 + 32], oidx) and np.array_equal(dist[r0:r0 + 32], odist)
+    ref = dict(binsize=binsize, indexes=idx, distances=dist, chromosome_sizes=np.array(chrom_bins), mask=mask,
+               masked_sizes=np.array(masked_sizes), pca_mean=pca.mean_, pca_components=pca.components_)
+    tests = [synth.counts_to_sample_dict(test_counts[i], bins, binsize) for i in range(3)]
+    thr = 5.0961
+    got = wisetools.testSamples(tests, ref, thr, batch=2)
+    for t in range(3):
+        want = wc_oracle.test_sample(tests[t], binsize, ref, minzscore=thr, segmenter=wc_oracle.segment_region_prefix)
+        _close(np.concatenate(got[t]['results_z']), np.concatenate(want['results_z']))
+        _close(np.concatenate(got[t]['results_r']), np.concatenate(want['results_r']))
+        _close(got[t]['results_cwz'], want['results_cwz'])
+        gc = np.asarray(got[t]['results_calls'], dtype=float).reshape(-1, 5)
+        wc = np.asarray(want['results_calls'], dtype=float).reshape(-1, 5)
+        assert gc.shape == wc.shape and np.array_equal(gc[:, :3], wc[:, :3]), (t, gc, wc)
+        _close(gc[:, 3:], wc[:, 3:])
+        _close([got[t]['asdef']], [want['asdef']])
+    assert len(got[1]['results_calls']) >= 1

@@ -90,7 +90,7 @@ def test_ingest_bit_exact(fn):
 def test_pca_matches_full_svd_reference(fn, tiny):
     corrected, comps, mean = wc_oracle.train_pca(fn['ingest_masked'])
     _close(corrected, fn['ingest_corrected'])
-    _close(mean, fn['ingest_mean'], 1e-12)
+    assert np.array_equal(mean, fn['ingest_mean'])        # numpy's pairwise order over each bin's samples
     # components up to a per-row sign (svd_flip convention; does not affect any result)
     for a, b in zip(comps, fn['ingest_components']):
         s = np.sign(np.dot(a, b))
@@ -98,6 +98,7 @@ def test_pca_matches_full_svd_reference(fn, tiny):
     _close(wc_oracle.apply_pca(fn['ingest_tref'], fn['ingest_mean'], fn['ingest_components']), fn['ingest_applied'], 1e-12)
     corrected, comps, mean = wc_oracle.train_pca(tiny['prep_maskedData'])
     _close(corrected, tiny['prep_correctedData'])
+    assert np.array_equal(mean, tiny['ref_pca_mean'])
 
 
 # ---- z-scores ----------------------------------------------------------------------------------------------
