@@ -227,3 +227,17 @@ def test_config2_shape_prep_and_test_path_vs_oracle():
         _close(gc[:, 3:], wc[:, 3:])
         _close([got[t]['asdef']], [want['asdef']])
     assert len(got[1]['results_calls']) >= 1
+
+
+def test_newref_on_two_gpus_equals_reference(workdir, tiny):
+    """`newref -gpus 2`: the parts run on two devices from two host threads; same reference file."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    refs = [str(workdir / ("r%02d.npz" % i)) for i in range(tiny['ref_counts'].shape[0])]
+    out = str(workdir / "two.npz")
+    _run(["newref"] + refs + [out, "-refsize", "40", "-gpus", "2", "-parts", "5"])
+    r = np.load(out, allow_pickle=True)
+    assert np.array_equal(r['indexes'], tiny['ref_indexes'])
+    _close(r['distances'], tiny['ref_distances'])
+    assert not os.path.exists(str(workdir / "two_part_3.npz"))

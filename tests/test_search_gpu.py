@@ -113,3 +113,34 @@ def test_config2_shape_sampled_rows():
     for r0 in (0, 990, 5000, n - 64):
         oidx, odist = c_oracle.get_reference_rows(X, bins, r0, r0 + 64, 100)
         _assert_same(idx[r0:r0 + 64], dist[r0:r0 + 64], oidx, odist)
+
+
+def test_degenerate_genomes():
+    """One chromosome only (no candidate at all), empty chromosomes in the list, refsize 1, fewer bins than a tile."""
+    X = synth.corrected_like([25], 10, seed=1)
+    idx, dist = _gpu_search(X, [25], 0, 25, 5)
+    assert (idx == -1).all() and (dist == 1e10).all()                 # wisetools.py:305-306 fillers only
+    bins = [0, 9, 0, 0, 14, 3, 0]
+    X = synth.corrected_like(bins, 7, seed=2)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, 26, 1)
+    idx, dist = _gpu_search(X, bins, 0, 26, 1)
+    _assert_same(idx, dist, oidx, odist)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 3, 20, 6)
+    idx, dist = _gpu_search(X, bins, 3, 20, 6)
+    _assert_same(idx, dist, oidx, odist)
+
+
+def test_single_sample_and_wide_refsize():
+    bins = [40, 35, 30, 500]
+    X = synth.corrected_like(bins, 1, seed=3)                          # S = 1: distances are single squares
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, 605, 64)
+    idx, dist = _gpu_search(X, bins, 0, 605, 64)
+    _assert_same(idx, dist, oidx, odist)
+    X = synth.corrected_like(bins, 33, seed=4)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, 605, 384)     # the largest refsize the kernels accept
+    idx, dist = _gpu_search(X, bins, 0, 605, 384)
+    _assert_same(idx, dist, oidx, odist)
+    with pytest.raises(Exception):
+        _gpu_search(X, bins, 0, 605, 385)
+    with pytest.raises(Exception):
+        _gpu_search(X, [40, 35], 0, 75, 10)                            # chromosome sizes do not add up to N
