@@ -125,11 +125,14 @@ int wc_pca_apply(wc_ctx* ctx, const double* masked_d, int N, int S, const double
  *   cutoff                getOptimalCutoff's value (wisetools.py:328-336; sample independent, host numpy)
  *   table_d  DEVICE N x wc_table_stride(k) int32: table[i][0..count[i]) = GLOBAL masked-bin ids of bin i's usable
  *            reference bins, in stored order (rows are padded to a multiple of 4 entries for 16-byte loads)
- *   count_d  DEVICE N int32 */
+ *   count_d  DEVICE N int32
+ *   rev_off_d DEVICE N+1 int32, rev_idx_d DEVICE N x wc_table_stride(k) int32: the reverse table (CSR) - for every bin
+ *            the bins that use it as a reference bin; lets the later passes of wc_zscore_batch touch only what a
+ *            newly marked bin can change */
 int wc_table_stride(int k);
 int wc_test_table(wc_ctx* ctx, const int32_t* indexes_d, const double* distances_d, int N, int k,
                   const int* chrom_bins_h, int nchrom, double cutoff, int32_t* table_d, int32_t* count_d,
-                  void* stream);
+                  int32_t* rev_off_d, int32_t* rev_idx_d, void* stream);
 
 /* Replaces toNumpyRefFormat + applyPCA (wisetools.py:267-278, 104-113) for B samples.
  *   counts_d     DEVICE B x Nraw int32: per sample the autosomal read counts, each chromosome zero-padded /
@@ -152,9 +155,10 @@ int wc_apply_pca(wc_ctx* ctx, const double* x_d, int B, int N, const double* pca
  *   the last pass;  asdef_d DEVICE B float64: stdDevSum / stdDevNum.  Bit-identical to the reference (numpy's
  *   summation order).  copy_init_d (DEVICE N x ldb, or NULL = test_d) is trySample's `testCopy`: the values the
  *   reference bins are gathered from in the first pass, -1 where already marked.  Asynchronous. */
-int wc_zscore_batch(wc_ctx* ctx, const double* test_d, const double* copy_init_d, int N, int B, int ldb, const int32_t* table_d,
-                    const int32_t* count_d, int k, double z_threshold, int repeats, double* z_d, double* r_d,
-                    int32_t* refsizes_d, double* asdef_d, void* stream);
+int wc_zscore_batch(wc_ctx* ctx, const double* test_d, const double* copy_init_d, int N, int B, int ldb,
+                    const int32_t* table_d, const int32_t* count_d, const int32_t* rev_off_d, const int32_t* rev_idx_d,
+                    int k, double z_threshold, int repeats, double* z_d, double* r_d, int32_t* refsizes_d,
+                    double* asdef_d, void* stream);
 
 /* Replaces the chromosome loop of toolTest (wisecondor.py:233-238): fillTriMin / fillTri (wisetools.py:466-487) +
  * TriArr.segmentTri (triarray.py:59-84) on the bins with refsizes >= minrefbins (wisecondor.py:215-218), for the

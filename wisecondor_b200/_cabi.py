@@ -69,13 +69,13 @@ def lib():
     L.wc_table_stride.restype = ci
     L.wc_table_stride.argtypes = [ci]
     L.wc_test_table.restype = ci
-    L.wc_test_table.argtypes = [vp, vp, vp, i32, i32, vp, i32, cd, vp, vp, vp]
+    L.wc_test_table.argtypes = [vp, vp, vp, i32, i32, vp, i32, cd, vp, vp, vp, vp, vp]
     L.wc_test_prep.restype = ci
     L.wc_test_prep.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp, i32, vp, i32, vp]
     L.wc_apply_pca.restype = ci
     L.wc_apply_pca.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, i32, vp]
     L.wc_zscore_batch.restype = ci
-    L.wc_zscore_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, cd, i32, vp, vp, vp, vp, vp]
+    L.wc_zscore_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, cd, i32, vp, vp, vp, vp, vp]
     L.wc_segment_batch.restype = ci
     L.wc_segment_batch.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, vp, i32, i32, cd, cd, i32, vp, vp, vp, vp, i32, vp]
     _LIB = L

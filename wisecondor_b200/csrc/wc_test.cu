@@ -50,6 +50,40 @@ __global__ void wc_table_kernel(const int* __restrict__ indexes, const double* _
     if (lane == 0) count[warp] = w;
 }
 
+// reverse table: for every bin j the bins i that list j among their usable reference bins (CSR).  When j is marked
+// in a sample, exactly these bins' statistics change in the next pass.
+__global__ void wc_rev_count_kernel(const int* __restrict__ table, const int* __restrict__ count, int N, int ldk,
+                                    int* __restrict__ rev_cnt) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= N) return;
+    const int c = count[i];
+    for (int m = lane; m < c; m += 32) atomicAdd(&rev_cnt[table[(size_t)i * ldk + m]], 1);
+}
+__global__ void wc_rev_scan_kernel(const int* __restrict__ rev_cnt, int N, int* __restrict__ rev_off, int* __restrict__ cursor) {
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x, per = (N + 1023) / 1024;
+    const int i0 = min(N, tid * per), i1 = min(N, i0 + per);
+    int loc = 0;
+    for (int i = i0; i < i1; ++i) loc += rev_cnt[i];
+    s_part[tid] = loc;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int t = 0; t < 1024; ++t) { const int v = s_part[t]; s_part[t] = run; run += v; }
+        rev_off[N] = run;
+    }
+    __syncthreads();
+    int run = s_part[tid];
+    for (int i = i0; i < i1; ++i) { rev_off[i] = run; cursor[i] = run; run += rev_cnt[i]; }
+}
+__global__ void wc_rev_fill_kernel(const int* __restrict__ table, const int* __restrict__ count, int N, int ldk,
+                                   int* __restrict__ cursor, int* __restrict__ rev_idx) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= N) return;
+    const int c = count[i];
+    for (int m = lane; m < c; m += 32) rev_idx[atomicAdd(&cursor[table[(size_t)i * ldk + m]], 1)] = i;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K7: sample preparation
 // ---------------------------------------------------------------------------------------------------------
@@ -142,8 +176,13 @@ struct ZArgs {
     double* r;
     int* refsz;
     double* sd;
-    const int* tile_active;  // [ntiles] 0 = nothing changed for these 32 samples since the previous pass: skip
+    const int* npairs;       // later passes: size of the dirty-pair list; the full kernel runs iff it exceeds pair_limit
+    int pair_limit;
 };
+
+__device__ __forceinline__ void zs_cp_async_8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 
 // ---- K8 building blocks ----------------------------------------------------------------------------------------
 // Fast path (no marked / non-finite reference value for this lane): the lane streams its reference values straight from
@@ -265,7 +304,7 @@ __global__ void __launch_bounds__(ZS_WARPS * 32) wc_zscore_kernel(const ZArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
     const int tile = blockIdx.y;
-    if (a.tile_active != nullptr && a.tile_active[tile] == 0) return;
+    if (a.npairs != nullptr && *a.npairs <= a.pair_limit) return;       // the pair kernel handles this pass
     const int s = tile * 32 + lane;                      // < ldb by construction
     double* buf = reinterpret_cast<double*>(zs_raw) + (size_t)warp * a.k;      // slow-path scratch, k doubles per warp
     const double* cp = a.copy + s;
@@ -300,43 +339,125 @@ __global__ void __launch_bounds__(ZS_WARPS * 32) wc_zscore_kernel(const ZArgs a)
     }
 }
 
-// testCopy[abs(z) >= threshold] = -1 (wisetools.py:446), applied between passes; flags the sample tiles that changed
+// Later passes only touch what changed.  A (bin, sample) pair's statistics depend on the working copy at the bin's
+// reference bins only, so after a pass has marked some bins (testCopy[abs(z) >= threshold] = -1, wisetools.py:446) the
+// next pass differs from it exactly at the pairs (i, s) with a newly marked j among i's reference bins - everything
+// else would be recomputed to the same bits.  wc_mark_kernel applies the marks and raises a dirty flag on those pairs
+// through the reverse table; wc_compact_kernel turns the flags into a work list; wc_zscore_pairs_kernel recomputes the
+// listed pairs (one pair per lane; gathers are no longer coalesced, but the list is a few per cent of a full pass).
 __global__ void wc_mark_kernel(const double* __restrict__ z, double* __restrict__ copy, int N, int B, int ldb, double thr,
-                               int* __restrict__ next_active) {
+                               const int* __restrict__ rev_off, const int* __restrict__ rev_idx,
+                               unsigned char* __restrict__ dirty) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)N * ldb;
-    bool changed = false;
-    int s = 0;
-    if (idx < total) {
-        s = (int)(idx % ldb);
-        if (s < B && fabs(z[idx]) >= thr && copy[idx] != -1.0) {
-            copy[idx] = -1.0;
-            changed = true;
-        }
+    if (idx >= (size_t)N * ldb) return;
+    const int s = (int)(idx % ldb), j = (int)(idx / ldb);
+    if (s < B && fabs(z[idx]) >= thr && copy[idx] != -1.0) {      // NaN never marks
+        copy[idx] = -1.0;
+        for (int e = rev_off[j]; e < rev_off[j + 1]; ++e) dirty[(size_t)rev_idx[e] * ldb + s] = 1;
     }
-    if (__any_sync(0xffffffffu, changed) && (threadIdx.x & 31) == 0) next_active[s >> 5] = 1;
 }
 
-// stdDevSum / stdDevNum accumulated bin by bin like the reference's Python loop (wisetools.py:428-430, 435)
-__global__ void wc_sigma_kernel(const double* __restrict__ sd, int N, int B, int ldb, double* __restrict__ asdef) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= B) return;
+__global__ void wc_compact_kernel(unsigned char* __restrict__ dirty, size_t total, int* __restrict__ pairs,
+                                  int* __restrict__ npairs) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool d = idx < total && dirty[idx] != 0;
+    if (d) dirty[idx] = 0;                                        // clean for the next pass
+    const unsigned bal = __ballot_sync(0xffffffffu, d);
+    if (bal == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(npairs, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (d) pairs[base + __popc(bal & ((1u << lane) - 1u))] = (int)idx;
+}
+
+__global__ void __launch_bounds__(ZS_WARPS * 32) wc_zscore_pairs_kernel(const ZArgs a, const int* __restrict__ pairs,
+                                                                        const int* __restrict__ npairs) {
+    extern __shared__ __align__(16) unsigned char zs_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    double* buf = reinterpret_cast<double*>(zs_raw) + (size_t)warp * a.k;
+    const size_t ldb = (size_t)a.ldb;
+    const int n_pairs = *npairs;
+    if (n_pairs > a.pair_limit) return;                   // too many for scattered gathers: the full kernel runs instead
+    for (int base = (blockIdx.x * nwarps + warp) * 32; base < n_pairs; base += gridDim.x * nwarps * 32) {
+        const bool valid = base + lane < n_pairs;
+        const int code = valid ? pairs[base + lane] : 0;
+        const int i = code / a.ldb, s = code - i * a.ldb;
+        const int cnt = valid ? a.count[i] : 0;
+        const int* tab = a.table + (size_t)i * a.k;
+        const double* cp = a.copy + s;
+        unsigned worst = 0;
+        int n = cnt;
+        double mean = 0.0, sd = 0.0;
+        if (valid) {
+            mean = __ddiv_rn(zs_stream_sum<false>(cp, tab, cnt, ldb, 0.0, worst), (double)cnt);
+            if (worst < 0x7ff00000u) {
+                unsigned unused = 0;
+                sd = sqrt(__ddiv_rn(zs_stream_sum<true>(cp, tab, cnt, ldb, mean, unused), (double)cnt));
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, valid && worst >= 0x7ff00000u);
+        while (todo) {                                    // warp-cooperative exact compaction, one listed pair at a time
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int si = __shfl_sync(0xffffffffu, i, src), ss = __shfl_sync(0xffffffffu, s, src);
+            const ZsSlow o = zs_slow_lane(a.copy + ss, a.table + (size_t)si * a.k, a.count[si], ldb, buf, lane);
+            if (lane == src) { mean = o.mean; sd = o.sd; n = o.n; }
+        }
+        if (valid) {
+            const size_t o = (size_t)i * ldb + s;
+            const double x = a.test[o];
+            a.z[o] = __ddiv_rn(__dsub_rn(x, mean), sd);
+            a.r[o] = __ddiv_rn(x, mean);
+            a.refsz[o] = n;
+            a.sd[o] = sd;
+        }
+    }
+}
+
+// stdDevSum / stdDevNum accumulated bin by bin like the reference's Python loop (wisetools.py:428-430, 435): a strictly
+// sequential sum per sample, so the parallelism is across samples only.  A CTA owns 32 samples: all eight warps stream
+// the [64 bins][32 samples] tiles of the sigma array into shared memory (coalesced, cp.async, double buffered) and warp 0
+// - one lane per sample - walks each tile in bin order.
+constexpr int SG_BINS = 64;    // 2 x 64 x 32 doubles = 32 KB of static shared memory
+__global__ void __launch_bounds__(256) wc_sigma_kernel(const double* __restrict__ sd, int N, int B, int ldb,
+                                                       double* __restrict__ asdef) {
+    __shared__ double tile[2][SG_BINS][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s0 = blockIdx.x * 32;
+    auto issue = [&](int chunk, int buf) {
+        const int b0 = chunk * SG_BINS;
+        for (int e = tid; e < SG_BINS * 32; e += 256) {
+            const int bin = e >> 5, l = e & 31;
+            if (b0 + bin < N) zs_cp_async_8(&tile[buf][bin][l], sd + (size_t)(b0 + bin) * ldb + s0 + l);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nchunks = (N + SG_BINS - 1) / SG_BINS;
     double sum = 0.0;
     int num = 0;
-    int i = 0;
-    for (; i + 8 <= N; i += 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = sd[(size_t)(i + u) * ldb + s];
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (!isnan(v[u])) { sum = __dadd_rn(sum, v[u]); ++num; }
+    issue(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+            issue(c + 1, (c + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int nb = min(SG_BINS, N - c * SG_BINS);
+            const double* col = &tile[c & 1][0][lane];
+#pragma unroll 8
+            for (int bin = 0; bin < nb; ++bin) {
+                const double v = col[bin * 32];
+                if (!isnan(v)) { sum = __dadd_rn(sum, v); ++num; }
+            }
+        }
+        __syncthreads();
     }
-    for (; i < N; ++i) {
-        const double v = sd[(size_t)i * ldb + s];
-        if (!isnan(v)) { sum = __dadd_rn(sum, v); ++num; }
-    }
-    asdef[s] = __ddiv_rn(sum, (double)num);
+    if (warp == 0 && s0 + lane < B) asdef[s0 + lane] = __ddiv_rn(sum, (double)num);
 }
 
 // [N][ldb] sample-minor -> [B][N] sample-major (what the host copies out and what the segmentation reads)
@@ -377,9 +498,9 @@ extern "C" int wc_table_stride(int k) { return (k + 3) & ~3; }
 
 extern "C" int wc_test_table(wc_ctx* ctx, const int32_t* indexes_d, const double* distances_d, int N, int k,
                              const int* chrom_bins_h, int nchrom, double cutoff, int32_t* table_d, int32_t* count_d,
-                             void* stream_v) {
+                             int32_t* rev_off_d, int32_t* rev_idx_d, void* stream_v) {
     WC_CHECK_ARG(ctx != nullptr && indexes_d != nullptr && distances_d != nullptr && chrom_bins_h != nullptr);
-    WC_CHECK_ARG(table_d != nullptr && count_d != nullptr);
+    WC_CHECK_ARG(table_d != nullptr && count_d != nullptr && rev_off_d != nullptr && rev_idx_d != nullptr);
     WC_CHECK_ARG(N > 0 && k > 0 && nchrom > 0);
     long long tot = 0;
     for (int c = 0; c < nchrom; ++c) { WC_CHECK_ARG(chrom_bins_h[c] >= 0); tot += chrom_bins_h[c]; }
@@ -390,8 +511,16 @@ extern "C" int wc_test_table(wc_ctx* ctx, const int32_t* indexes_d, const double
     int rc;
     if ((rc = upload_row_ranges(ctx, N, chrom_bins_h, nchrom, SLOT_ROWCS, SLOT_ROWCE, &cs_d, &ce_d, stream))) return rc;
     const int blocks = (int)(((size_t)N * 32 + 255) / 256);
-    wc_table_kernel<<<blocks, 256, 0, stream>>>(indexes_d, distances_d, N, k, wc_table_stride(k), cs_d, ce_d, cutoff, table_d,
-                                                count_d);
+    const int ldk = wc_table_stride(k);
+    wc_table_kernel<<<blocks, 256, 0, stream>>>(indexes_d, distances_d, N, k, ldk, cs_d, ce_d, cutoff, table_d, count_d);
+    // reverse table (CSR): counting sort of the (bin -> reference bin) edges by reference bin
+    int* rev_cnt; int* cursor;
+    if ((rc = wc_reserve(ctx, SLOT_T_REVCNT, (size_t)N * sizeof(int), (void**)&rev_cnt))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_T_REVCUR, (size_t)N * sizeof(int), (void**)&cursor))) return rc;
+    WC_CUDA(cudaMemsetAsync(rev_cnt, 0, (size_t)N * sizeof(int), stream));
+    wc_rev_count_kernel<<<blocks, 256, 0, stream>>>(table_d, count_d, N, ldk, rev_cnt);
+    wc_rev_scan_kernel<<<1, 1024, 0, stream>>>(rev_cnt, N, rev_off_d, cursor);
+    wc_rev_fill_kernel<<<blocks, 256, 0, stream>>>(table_d, count_d, N, ldk, cursor, rev_idx_d);
     WC_CUDA(cudaGetLastError());
     return WC_OK;
 }
@@ -439,48 +568,60 @@ extern "C" int wc_apply_pca(wc_ctx* ctx, const double* x_d, int B, int N, const 
                                static_cast<cudaStream_t>(stream_v));
 }
 
-extern "C" int wc_zscore_batch(wc_ctx* ctx, const double* test_d, const double* copy_init_d, int N, int B, int ldb, const int32_t* table_d,
-                               const int32_t* count_d, int k, double z_threshold, int repeats, double* z_d, double* r_d,
+extern "C" int wc_zscore_batch(wc_ctx* ctx, const double* test_d, const double* copy_init_d, int N, int B, int ldb,
+                               const int32_t* table_d, const int32_t* count_d, const int32_t* rev_off_d,
+                               const int32_t* rev_idx_d, int k, double z_threshold, int repeats, double* z_d, double* r_d,
                                int32_t* refsizes_d, double* asdef_d, void* stream_v) {
     WC_CHECK_ARG(ctx != nullptr && test_d != nullptr && table_d != nullptr && count_d != nullptr);
     WC_CHECK_ARG(z_d != nullptr && r_d != nullptr && refsizes_d != nullptr && asdef_d != nullptr);
     WC_CHECK_ARG(N > 0 && B > 0 && ldb >= B && ldb % 32 == 0 && k >= 1 && k <= 512 && repeats >= 1);
+    WC_CHECK_ARG(repeats == 1 || (rev_off_d != nullptr && rev_idx_d != nullptr));
+    WC_CHECK_ARG((size_t)N * ldb < ((size_t)1 << 31));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     WC_CUDA(cudaSetDevice(ctx->device));
-    const int ntiles = ldb / 32;
     const size_t elems = (size_t)N * ldb;
-    double* copy; double* zt; double* rt; int* nt; double* sd; int* flags;
+    double* copy; double* zt; double* rt; int* nt; double* sd; unsigned char* dirty; int* pairs; int* npairs;
     int rc;
     if ((rc = wc_reserve(ctx, SLOT_T_COPY, elems * sizeof(double), (void**)&copy))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_T_ZT, elems * sizeof(double), (void**)&zt))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_T_RT, elems * sizeof(double), (void**)&rt))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_T_NT, elems * sizeof(int), (void**)&nt))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_T_SD, elems * sizeof(double), (void**)&sd))) return rc;
-    if ((rc = wc_reserve(ctx, SLOT_T_FLAGS, (size_t)(repeats + 1) * ntiles * sizeof(int), (void**)&flags))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_T_FLAGS, (size_t)(repeats + 1) * sizeof(int), (void**)&npairs))) return rc;
     WC_CUDA(cudaEventRecord(ctx->ev[8], stream));
     WC_CUDA(cudaMemcpyAsync(copy, copy_init_d ? copy_init_d : test_d, elems * sizeof(double), cudaMemcpyDeviceToDevice,
                             stream));                                                                   // wisetools.py:442
-    WC_CUDA(cudaMemsetAsync(flags, 0, (size_t)(repeats + 1) * ntiles * sizeof(int), stream));
     const int warps = ZS_WARPS;
     const int ldk = wc_table_stride(k);
     const size_t smem = (size_t)warps * ldk * sizeof(double);     // slow-path scratch only
     WC_CUDA(cudaFuncSetAttribute(wc_zscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WC_CUDA(cudaFuncSetAttribute(wc_zscore_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ZArgs a;
     a.test = test_d; a.copy = copy; a.table = table_d; a.count = count_d; a.N = N; a.B = B; a.ldb = ldb; a.k = ldk;
-    a.z = zt; a.r = rt; a.refsz = nt; a.sd = sd;
+    a.z = zt; a.r = rt; a.refsz = nt; a.sd = sd; a.npairs = nullptr;
+    // a listed pair gathers with 32-byte sectors for 8 useful bytes and shares nothing with its warp: past ~1/8 of all
+    // pairs a full coalesced pass is cheaper
+    a.pair_limit = (int)std::min<size_t>((size_t)N * B / 8, (size_t)0x7fffffff);
     long long launches = 0;
-    for (int rep = 0; rep < repeats; ++rep) {
-        a.tile_active = rep == 0 ? nullptr : flags + (size_t)rep * ntiles;
-        dim3 grid((N + ZS_BINS_PER_CTA - 1) / ZS_BINS_PER_CTA, ntiles);
-        wc_zscore_kernel<<<grid, warps * 32, smem, stream>>>(a);
-        ++launches;
-        if (rep + 1 < repeats) {     // the marks of the last pass are never read (wisetools.py:443-448)
-            wc_mark_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, stream>>>(zt, copy, N, B, ldb, z_threshold,
-                                                                                  flags + (size_t)(rep + 1) * ntiles);
-            ++launches;
+    const dim3 zgrid((N + ZS_BINS_PER_CTA - 1) / ZS_BINS_PER_CTA, ldb / 32);
+    wc_zscore_kernel<<<zgrid, warps * 32, smem, stream>>>(a);       // first pass: every (bin, sample) pair
+    ++launches;
+    if (repeats > 1) {
+        if ((rc = wc_reserve(ctx, SLOT_T_DIRTY, elems, (void**)&dirty))) return rc;
+        if ((rc = wc_reserve(ctx, SLOT_T_PAIRS, elems * sizeof(int), (void**)&pairs))) return rc;
+        WC_CUDA(cudaMemsetAsync(dirty, 0, elems, stream));
+        WC_CUDA(cudaMemsetAsync(npairs, 0, (size_t)(repeats + 1) * sizeof(int), stream));
+        const unsigned eblocks = (unsigned)((elems + 255) / 256);
+        for (int rep = 1; rep < repeats; ++rep) {     // the marks of the last pass are never read (wisetools.py:443-448)
+            wc_mark_kernel<<<eblocks, 256, 0, stream>>>(zt, copy, N, B, ldb, z_threshold, rev_off_d, rev_idx_d, dirty);
+            wc_compact_kernel<<<eblocks, 256, 0, stream>>>(dirty, elems, pairs, npairs + rep);
+            a.npairs = npairs + rep;                   // exactly one of the next two kernels does the pass
+            wc_zscore_pairs_kernel<<<4 * ctx->sm_count, warps * 32, smem, stream>>>(a, pairs, npairs + rep);
+            wc_zscore_kernel<<<zgrid, warps * 32, smem, stream>>>(a);
+            launches += 4;
         }
     }
-    wc_sigma_kernel<<<(B + 63) / 64, 64, 0, stream>>>(sd, N, B, ldb, asdef_d);
+    wc_sigma_kernel<<<ldb / 32, 256, 0, stream>>>(sd, N, B, ldb, asdef_d);
     dim3 tgrid((N + 31) / 32, ldb / 32);
     wc_transpose_kernel<double><<<tgrid, dim3(32, 32), 0, stream>>>(zt, N, B, ldb, z_d);
     wc_transpose_kernel<double><<<tgrid, dim3(32, 32), 0, stream>>>(rt, N, B, ldb, r_d);

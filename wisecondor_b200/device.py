@@ -112,10 +112,14 @@ class ReferenceTable(object):
         dst = torch.as_tensor(np.ascontiguousarray(distances, dtype=np.float64), device=dev)
         self.table = torch.empty((self.n, _cabi.lib().wc_table_stride(self.k)), dtype=torch.int32, device=dev)
         self.count = torch.empty((self.n,), dtype=torch.int32, device=dev)
+        # reverse table (CSR): which bins use bin j as a reference bin
+        self.rev_off = torch.empty((self.n + 1,), dtype=torch.int32, device=dev)
+        self.rev_idx = torch.empty((self.n, self.table.shape[1]), dtype=torch.int32, device=dev)
         cb, cbp = _ints(self.masked_sizes)
         ctx = _cabi.context(_dev_index(dev))
         rc = _cabi.lib().wc_test_table(ctx.handle, _ptr(idx), _ptr(dst), self.n, self.k, cbp, len(cb), self.cutoff,
-                                       _ptr(self.table), _ptr(self.count), _stream_ptr(dev))
+                                       _ptr(self.table), _ptr(self.count), _ptr(self.rev_off), _ptr(self.rev_idx),
+                                       _stream_ptr(dev))
         _cabi.check(rc)
         torch.cuda.current_stream(dev).synchronize()
 
@@ -180,7 +184,8 @@ def zscore_batch(test, nsamples, table, z_threshold, repeats, copy_init=None):
     sizes = torch.empty((b, n), dtype=torch.int32, device=dev)
     asdef = torch.empty((b,), dtype=torch.float64, device=dev)
     ctx = _cabi.context(_dev_index(dev))
-    rc = _cabi.lib().wc_zscore_batch(ctx.handle, _ptr(test), _ptr(copy_init) if copy_init is not None else None, n, b, ldb, _ptr(table.table), _ptr(table.count), table.k,
+    rc = _cabi.lib().wc_zscore_batch(ctx.handle, _ptr(test), _ptr(copy_init) if copy_init is not None else None, n, b, ldb,
+                                     _ptr(table.table), _ptr(table.count), _ptr(table.rev_off), _ptr(table.rev_idx), table.k,
                                      float(z_threshold), int(repeats), _ptr(z), _ptr(r), _ptr(sizes), _ptr(asdef),
                                      _stream_ptr(dev))
     _cabi.check(rc)
