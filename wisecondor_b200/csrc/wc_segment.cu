@@ -79,11 +79,10 @@ __device__ __forceinline__ Best shfl_best(const Best& b, int o) {
 template <bool MINEFF>
 __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a) {
     extern __shared__ __align__(16) unsigned char seg_raw[];
-    double* P = reinterpret_cast<double*>(seg_raw);               // [pcap] prefix sums, P[i] = sum zc[0..i)
-    // side arrays: in shared memory after P when they fit, else a per-CTA slice of global scratch (10 kb bins: chr1 has
-    // 24 926 bins, P alone takes 199 KB)
-    unsigned* dh = a.aux_g ? a.aux_g + (size_t)blockIdx.x * a.pcap * (MINEFF ? 3 : 1)
-                           : reinterpret_cast<unsigned*>(P + a.pcap);   // [pcap] per run length: max hi32(|score|) of the sweep
+    float* P = reinterpret_cast<float*>(seg_raw);                 // [pcap] prefix sums (fp32 copy), P[i] = sum zc[0..i)
+    // side arrays: in shared memory after P when they fit, else a per-CTA slice of global scratch
+    float* dh = a.aux_g ? reinterpret_cast<float*>(a.aux_g + (size_t)blockIdx.x * a.pcap * (MINEFF ? 3 : 1))
+                        : P + a.pcap;                             // [pcap] per run length: max |score| of the sweep
     int* CH = reinterpret_cast<int*>(dh + a.pcap);                // [pcap] MINEFF: #{j < i : rc[j] >= c_hi}
     int* CL = CH + a.pcap;                                        // [pcap] MINEFF: #{j < i : rc[j] <= c_lo}
     __shared__ double s_red[2][SEG_WARPS];
@@ -92,7 +91,7 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     __shared__ int s_lo[SEG_STACK], s_hi[SEG_STACK];
     __shared__ int s_rows[SEG_ROWCAP];
     __shared__ int s_nrows, s_sp, s_n, s_bad;
-    __shared__ double s_A;
+    __shared__ double s_A, s_Pm;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sel = blockIdx.x / a.B, b = blockIdx.x % a.B;     // long chromosomes first
@@ -168,16 +167,24 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         double base = 0.0;
         for (int w = 0; w < warp; ++w) base += s_red[0][w];
         double run = base + (inc - loc);
+        double pm = 0.0;                              // largest |prefix sum|: the scale of the fp32 rounding
         for (int i = i0; i < i1; ++i) {
             const double v = zc[i];
-            P[i] = run;
+            P[i] = (float)run;
+            pm = fmax(pm, fabs(run));
             if (isfinite(v)) run += v;
         }
-        if (i1 == n && i0 < n) P[n] = run;
+        if (i1 == n && i0 < n) { P[n] = (float)run; pm = fmax(pm, fabs(run)); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+        __syncthreads();                              // s_red[0] (warp totals) has been consumed
+        if (lane == 0) s_red[0][warp] = pm;
+        __syncthreads();
         if (tid == 0) {
-            double t = 0.0;
-            for (int w = 0; w < SEG_WARPS; ++w) t += s_red[1][w];
+            double t = 0.0, m = 0.0;
+            for (int w = 0; w < SEG_WARPS; ++w) { t += s_red[1][w]; m = fmax(m, s_red[0][w]); }
             s_A = t;
+            s_Pm = m;
             s_sp = 1;
             s_lo[0] = 0;
             s_hi[0] = n;
@@ -187,7 +194,9 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     const double A = s_A;
     // |sweep value - numpy value| <= (2 (per + 16) + 40) eps A + 3 eps |v|: prefix sums (sequential chunk of `per`, warp
     // scan, warp bases) on both ends of the run, numpy's own pairwise rounding, the reciprocal multiply.  delta = 2 x that.
-    const double delta_A = (4.0 * ((n + SEG_THREADS - 1) / SEG_THREADS) + 160.0) * SEG_EPS * A;
+    // The sweep itself runs in fp32 on an fp32 copy of the prefix sums: |fp32 score - fp64 score| <= 2^-23 Pm + 2^-21 |v|
+    // (rounding of the two prefix sums, of their difference, of 1/sqrt(len) and of the product), Pm = max |prefix sum|.
+    const double delta_A = (4.0 * ((n + SEG_THREADS - 1) / SEG_THREADS) + 160.0) * SEG_EPS * A + 2.0 * 1.1920929e-07 * s_Pm;
 
     // MINEFF: prefix counts of the ratios above c_hi / below c_lo decide the median test in O(1) for all odd lengths and
     // for even lengths unless exactly half of the run lies on the far side; then the two middle order statistics are
@@ -285,38 +294,36 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
             }
         }
 
-        // -- sweep by diagonals: lane owns the run lengths L0 .. L0+4 (their 1/sqrt in registers) and walks the start x;
-        //    P[x] is one broadcast read per step, P[x+L0+r] a 5-deep register window fed by one conflict-free read.
-        //    Per run: DADD, DMUL, and an integer max on the high word of |score| (20 mantissa bits: enough to locate) --
-        unsigned best = 0;                            // max over this thread's runs of hi32(|score|)
+        // -- sweep by diagonals, in fp32 (it only locates): lane owns the run lengths L0 .. L0+4 (their 1/sqrt in
+        //    registers) and walks the start x; P[x] is one broadcast read per step, P[x+L0+r] a 5-deep register window
+        //    fed by one conflict-free read.  Per run: FADD, FMUL, FMNMX(|.|) --
+        float best = 0.f;                             // max over this thread's runs of |score|
         const int ntiles = (m + SEG_TILE - 1) / SEG_TILE;
         {
             for (int round = 0; round * SEG_WARPS < ntiles; ++round) {
                 const int t = round * SEG_WARPS + ((round & 1) ? SEG_WARPS - 1 - warp : warp);   // boustrophedon: balance
                 if (t >= ntiles) continue;
                 const int L0 = 1 + t * SEG_TILE + lane * SEG_R;
-                double isq[SEG_R];
-                unsigned bh[SEG_R];
+                float isq[SEG_R], bh[SEG_R];
 #pragma unroll
-                for (int r = 0; r < SEG_R; ++r) { isq[r] = __ddiv_rn(1.0, sqrt((double)(L0 + r))); bh[r] = 0; }
+                for (int r = 0; r < SEG_R; ++r) { isq[r] = (float)__ddiv_rn(1.0, sqrt((double)(L0 + r))); bh[r] = 0.f; }
                 int x = lo;
                 if (L0 + SEG_R - 1 <= m) {
                     const int xfull = hi - (L0 + SEG_R - 1);       // starts x <= xfull have all five lengths inside [lo, hi)
-                    const double* Pq = P + L0;                     // Pq[x + r] = P[x + L0 + r]
-                    double ww[SEG_R];                               // slot (j + r) % 5 holds Pq[x + j + r]
+                    const float* Pq = P + L0;                      // Pq[x + r] = P[x + L0 + r]
+                    float ww[SEG_R];                                // slot (j + r) % 5 holds Pq[x + j + r]
 #pragma unroll
                     for (int r = 0; r < SEG_R - 1; ++r) ww[r] = Pq[x + r];
                     for (; x + SEG_R - 1 <= xfull; x += SEG_R) {
 #pragma unroll
                         for (int j = 0; j < SEG_R; ++j) {
                             ww[(j + SEG_R - 1) % SEG_R] = Pq[x + j + SEG_R - 1];
-                            const double px = P[x + j];
+                            const float px = P[x + j];
 #pragma unroll
                             for (int r = 0; r < SEG_R; ++r) {
-                                const double v = __dmul_rn(__dsub_rn(ww[(j + r) % SEG_R], px), isq[r]);
-                                const unsigned h = (unsigned)__double2hiint(v) & 0x7fffffffu;
-                                if (!MINEFF) bh[r] = max(bh[r], h);
-                                else if (h > bh[r] && passes(x + j, L0 + r)) bh[r] = h;   // only record attempts pay
+                                const float v = __fmul_rn(__fsub_rn(ww[(j + r) % SEG_R], px), isq[r]);
+                                if (!MINEFF) bh[r] = fmaxf(bh[r], fabsf(v));
+                                else if (fabsf(v) > bh[r] && passes(x + j, L0 + r)) bh[r] = fabsf(v);   // only record attempts pay
                             }
                         }
                     }
@@ -325,34 +332,32 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
                 for (int r = 0; r < SEG_R; ++r) {                  // ragged end: the remaining starts of each length
                     const int L = L0 + r;
                     for (int xx = x; xx + L <= hi; ++xx) {
-                        const double v = __dmul_rn(__dsub_rn(P[xx + L], P[xx]), isq[r]);
-                        const unsigned h = (unsigned)__double2hiint(v) & 0x7fffffffu;
-                        if (!MINEFF) bh[r] = max(bh[r], h);
-                        else if (h > bh[r] && passes(xx, L)) bh[r] = h;
+                        const float v = __fmul_rn(__fsub_rn(P[xx + L], P[xx]), isq[r]);
+                        if (!MINEFF) bh[r] = fmaxf(bh[r], fabsf(v));
+                        else if (fabsf(v) > bh[r] && passes(xx, L)) bh[r] = fabsf(v);
                     }
-                    if (L <= m) { dh[L] = bh[r]; best = max(best, bh[r]); }
+                    if (L <= m) { dh[L] = bh[r]; best = fmaxf(best, bh[r]); }
                 }
             }
         }
         // -- block-wide extreme --
-        unsigned bigh = best;
+        float bigf = best;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) bigh = max(bigh, __shfl_xor_sync(0xffffffffu, bigh, o));
-        if (lane == 0) s_scan[warp] = (int)bigh;
+        for (int o = 16; o > 0; o >>= 1) bigf = fmaxf(bigf, __shfl_xor_sync(0xffffffffu, bigf, o));
+        if (lane == 0) s_scan[warp] = __float_as_int(bigf);
         if (tid == 0) s_nrows = 0;
         __syncthreads();
 #pragma unroll
-        for (int w = 0; w < SEG_WARPS; ++w) bigh = max(bigh, (unsigned)s_scan[w]);
-        if (bigh >= 0x7fefffffu) bigh = 0x7feffffeu;                   // (finite data: cannot happen) keep bigh + 1 finite
-        // M = max |score| lies in [value(bigh), value(bigh + 1)); every run within delta of M has hi32 >= bigh - 1
-        const double m_up = __hiloint2double((int)(bigh + 1), 0);
-        const double delta = delta_A + 16.0 * SEG_EPS * m_up;
-        if (m_up + delta < a.thr) continue;           // abs(champVal) < threshold for certain (triarray.py:72-73)
-        const double vlow = __hiloint2double((int)(bigh > 0 ? bigh - 1 : 0), 0) - delta;   // window floor on |score|
+        for (int w = 0; w < SEG_WARPS; ++w) bigf = fmaxf(bigf, __int_as_float(s_scan[w]));
+        // every run within delta of the true maximum M has an fp32 score >= vlow
+        const double big = (double)bigf;
+        const double delta = delta_A + 4.0 * 1.1920929e-07 * big;
+        if (big + delta < a.thr) continue;            // abs(champVal) < threshold for certain (triarray.py:72-73)
+        const float vlow = (float)(big - 2.0 * delta);                  // window floor on the fp32 |score|
 
         // -- diagonals that can hold the exact champion: those whose own extreme reaches the window --
         for (int L = 1 + tid; L <= m; L += SEG_THREADS) {
-            if (__hiloint2double((int)(dh[L] + 1), 0) >= vlow) {
+            if (dh[L] >= vlow) {
                 const int pos = atomicAdd(&s_nrows, 1);
                 if (pos < SEG_ROWCAP) s_rows[pos] = L;
             }
@@ -367,9 +372,9 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         for (int ri = 0; ri < nrows; ++ri) {
             const int L = all_rows ? ri + 1 : s_rows[ri];
             const double sq = sqrt((double)L);
-            const double isqL = __ddiv_rn(1.0, sq);
+            const float isqL = (float)__ddiv_rn(1.0, sq);
             for (int x = lo + tid; x + L <= hi; x += SEG_THREADS) {
-                const double av = fabs(__dmul_rn(__dsub_rn(P[x + L], P[x]), isqL));
+                const float av = fabsf(__fmul_rn(__fsub_rn(P[x + L], P[x]), isqL));
                 if (av >= vlow && passes(x, L)) {
                     const double sum = np_sum_thread([&](int i) { return zc[x + i]; }, L);     // np_sum(region[x:y+1])
                     Best e = {__ddiv_rn(sum, sq), x, x + L - 1};                                 // / np_sqrt(y-x+1)
@@ -479,10 +484,10 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const double* r_
     if ((rc = wc_reserve(ctx, SLOT_S_STATUS, 4 * sizeof(int), (void**)&status_d))) return rc;
     const int pcap = (maxlen + 8) & ~1;
     const size_t aux_bytes = (size_t)pcap * (sizeof(unsigned) + (mineff ? 2 * sizeof(int) : 0));
-    size_t smem = (size_t)pcap * sizeof(double) + aux_bytes;
+    size_t smem = (size_t)pcap * sizeof(float) + aux_bytes;
     unsigned* aux_g = nullptr;
     if (smem > 220 * 1024) {                      // keep only the prefix sums in shared memory
-        smem = (size_t)pcap * sizeof(double);
+        smem = (size_t)pcap * sizeof(float);
         if (smem > 220 * 1024) {
             wc_set_error("segmentation: a chromosome of %d bins needs %zu bytes of shared memory (limit 220 KiB)", maxlen, smem);
             return WC_ERR_ARG;
