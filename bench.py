@@ -266,16 +266,27 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
     host_r = torch.empty((B, n), dtype=torch.float64).pin_memory()
     host_n = torch.empty((B, n), dtype=torch.int32).pin_memory()
 
+    copy_out = torch.cuda.Stream(device=dev)
+    in_flight = []          # (device tensors, copy-finished event) of the batches whose results are still travelling
+
     def run(from_host):
         counts = counts_pinned.to(dev, non_blocking=True) if from_host else counts_dev
         T = device.test_prep(counts, masked_raw, mean, comps)
         z, r, sizes, asdef = device.zscore_batch(T, B, table, thr, 5)
         cwz, cleaned, calls = device.segment_batch(z, sizes, bins, list(range(22)), 25, thr, 3)
-        if from_host:
-            host_z.copy_(z, non_blocking=True)
-            host_r.copy_(r, non_blocking=True)
-            host_n.copy_(sizes, non_blocking=True)
-            torch.cuda.synchronize(dev)
+        if from_host:       # results go to pinned host memory on a second stream while the next batch computes
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(ready)
+                host_z.copy_(z, non_blocking=True)
+                host_r.copy_(r, non_blocking=True)
+                host_n.copy_(sizes, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(copy_out)
+            in_flight.append(((z, r, sizes), done))     # keep the device buffers alive until their copy has finished
+            while len(in_flight) > 1:
+                in_flight.pop(0)[1].synchronize()
         return len(calls)
 
     counts_dev = counts_pinned.to(dev)
@@ -329,7 +340,7 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
         "segment_run_evals_per_s": entries / (sms * 1e-3),
         "e2e": {"value": world * B / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * n * 4, "d2h_bytes_per_step": B * n * 20,
                 "api": "device.test_prep + zscore_batch + segment_batch from pinned host counts; z, r, refsizes copied back "
-                       "to pinned host memory, synchronous, %d batches" % e2e_steps},
+                       "to pinned host memory on a second stream overlapping the next batch, %d batches" % e2e_steps},
         "parallelism": "samples sharded over %d GPU(s), no communication" % world,
     }
 
@@ -347,7 +358,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work in the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-test", action="store_true", help="skip the batched test (z-score + segmentation) section")
-    ap.add_argument("--test-batch", type=int, default=256, help="test samples per GPU in the test section")
+    ap.add_argument("--test-batch", type=int, default=512, help="test samples per GPU in the test section")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
