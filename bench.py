@@ -294,7 +294,7 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
         ncalls = run(False)
     torch.cuda.synchronize(dev)
     steps = max(2, min(args.steps, 5))
-    zs, sg, pr = [], [], []
+    zs, sg, pr, executed = [], [], [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
@@ -304,6 +304,7 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
         run(False)
         st = device.last_test_stats(local)
         zs.append(st["zscore_ms"]); sg.append(st["segment_ms"]); pr.append(st["prep_ms"])
+        executed.append(st["zscore_pairs_per_pass"])
     e1.record()
     torch.cuda.synchronize(dev)
     dev_ms = e0.elapsed_time(e1) / steps
@@ -322,7 +323,11 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
     if rank != 0:
         return None
     zms, sms = float(np.mean(zs)), float(np.mean(sg))
-    gathers = 5.0 * float(table.count.sum().item()) * 8.0 * B            # repeats x kept refs x 8 B, per launch set
+    # gathered operand bytes actually executed: every pass's computed (bin, sample) pairs x mean kept refs x 8 B, twice
+    # (mean pass and sum-of-squares pass); later passes only recompute what a newly marked bin can change
+    mean_refs = float(table.count.float().mean().item())
+    pairs_per_pass = [float(np.mean([e[p] for e in executed])) for p in range(len(executed[0]))]
+    gathers = 2.0 * sum(pairs_per_pass) * mean_refs * 8.0
     entries = float(sum(b * (b + 1) // 2 for b in bins)) * B              # run evaluations (upper bound: no bin dropped)
     hbm = None
     try:
@@ -335,8 +340,10 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
         "samples_per_gpu": B, "n_gpus": world, "bins": n, "refsize": k, "repeats": 5, "ms_per_batch": dev_ms,
         "phases_ms": {"prep": float(np.mean(pr)), "zscore": zms, "segment": sms}, "calls_in_batch": ncalls,
         "zscore_gather_gbs": gathers / (zms * 1e-3) / 1e9, "hbm_peak_gbs_measured": hbm,
-        "zscore_note": "gathered operand bytes (5 passes x kept refs x 8 B x samples) per second; the sample tile stays "
-                       "in L2, so this may exceed the HBM copy peak",
+        "zscore_pairs_per_pass": pairs_per_pass,
+        "zscore_note": "executed gathers (computed pairs per pass x kept refs x 8 B x 2 reductions) per second of the "
+                       "whole z-score phase (marks, work lists, sigma average and transposes included); operands come "
+                       "from L2, not HBM",
         "segment_run_evals_per_s": entries / (sms * 1e-3),
         "e2e": {"value": world * B / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * n * 4, "d2h_bytes_per_step": B * n * 20,
                 "api": "device.test_prep + zscore_batch + segment_batch from pinned host counts; z, r, refsizes copied back "

@@ -59,7 +59,8 @@ int wc_sm_count(const wc_ctx* ctx);
 double wc_last_phase_ms(wc_ctx* ctx, int which);
 /* Counters of the most recent calls: which: 0 = kernel launches of wc_newref_topk, 1 = its rows sent to the exhaustive
  * fallback, 2 = candidate entries emitted by K5, 3 = tiles computed, 4 = CTAs launched for K5, 5 = kernel launches of
- * the last wc_zscore_batch, 6 = of the last wc_segment_batch, 7 = of the last wc_newref_prep. */
+ * the last wc_zscore_batch, 6 = of the last wc_segment_batch, 7 = of the last wc_newref_prep;
+ * 16 + p = (bin, sample) pairs that z-score pass p of the last wc_zscore_batch computed (synchronises). */
 long long wc_last_counter(const wc_ctx* ctx, int which);
 
 /* Debug aid: enable (1) / disable (0) per-CTA cycle counters in the distance kernel and copy the counters of the

@@ -83,7 +83,18 @@ extern "C" double wc_last_phase_ms(wc_ctx* ctx, int which) {
 }
 
 extern "C" long long wc_last_counter(const wc_ctx* ctx, int which) {
-    if (!ctx || which < 0 || which >= WC_NCOUNTER) return -1;
+    if (!ctx || which < 0) return -1;
+    if (which >= 16 && which < 16 + 64) {
+        // (bin, sample) pairs the z-score pass `which - 16` of the last wc_zscore_batch computed (waits for the stream)
+        const int pass = which - 16;
+        if (pass >= ctx->zs_repeats) return -1;
+        if (pass == 0 || ctx->zs_npairs_d == nullptr) return ctx->zs_all_pairs;
+        int n = 0;
+        cudaSetDevice(ctx->device);
+        if (cudaMemcpy(&n, ctx->zs_npairs_d + pass, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return n > ctx->zs_pair_limit ? ctx->zs_all_pairs : n;      // long lists run as a full pass
+    }
+    if (which >= WC_NCOUNTER) return -1;
     return ctx->counter[which];
 }
 

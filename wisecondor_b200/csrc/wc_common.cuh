@@ -58,6 +58,9 @@ struct wc_ctx {
     cudaEvent_t ev[2 * WC_NPHASE];
     double phase_ms[WC_NPHASE];
     long long counter[WC_NCOUNTER];
+    const int* zs_npairs_d = nullptr;    // device counters of the last wc_zscore_batch: listed pairs of pass 1..repeats-1
+    int zs_repeats = 0;
+    long long zs_pair_limit = 0, zs_all_pairs = 0;
     unsigned long long sched_hash = 0;   // fingerprint of the K5 schedule metadata currently on the device
     unsigned timed_mask = 0;        // phases whose event pair is recorded but not yet read (asynchronous calls)
     int k5_dbg = 0;                 // timing experiments only (results invalid when non-zero)

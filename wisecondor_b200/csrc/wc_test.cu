@@ -631,5 +631,9 @@ extern "C" int wc_zscore_batch(wc_ctx* ctx, const double* test_d, const double* 
     WC_CUDA(cudaEventRecord(ctx->ev[9], stream));
     ctx->timed_mask |= 1u << 4;
     ctx->counter[5] = launches;
+    ctx->zs_npairs_d = repeats > 1 ? npairs : nullptr;
+    ctx->zs_repeats = repeats;
+    ctx->zs_pair_limit = a.pair_limit;
+    ctx->zs_all_pairs = (long long)N * B;
     return WC_OK;
 }

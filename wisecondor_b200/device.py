@@ -234,8 +234,14 @@ def segment_batch(z, refsizes, masked_sizes, chromosomes, minrefbins, z_threshol
 def last_test_stats(device=0):
     """Device timings (ms) of the most recent prep / z-score / segmentation calls on `device`."""
     ctx = _cabi.context(device)
+    pairs = []
+    while len(pairs) < 64:
+        n = ctx.counter(16 + len(pairs))
+        if n < 0:
+            break
+        pairs.append(int(n))
     return {"prep_ms": ctx.phase_ms(6), "zscore_ms": ctx.phase_ms(4), "segment_ms": ctx.phase_ms(5),
-            "zscore_launches": ctx.counter(5), "segment_launches": ctx.counter(6)}
+            "zscore_launches": ctx.counter(5), "segment_launches": ctx.counter(6), "zscore_pairs_per_pass": pairs}
 
 
 # ------------------------------------------------------------------------------------------------------------
