@@ -136,30 +136,27 @@ __device__ __forceinline__ double dist_of_key(u64 key) { return -2.0 * __longlon
 template <int PER_LANE>   // cap / 32: every load of the buffer is issued before the first one is consumed
 __device__ __noinline__ void prune_row(u64* ck, int* cj, int n, int k, double nrm, double mcoef, int lane, u64* sk,
                                        int* sj, u64* thr_out, int* n_out) {
+    // The row's buffer lives in registers for the whole prune (16 or 32 keys + column ids per lane; the accumulators
+    // are dead between tiles): the bisection counts, the v* search and the compaction never touch memory again.
+    (void)sk; (void)sj;
+    u64 d[PER_LANE];
+    int j[PER_LANE];
+#pragma unroll
+    for (int t = 0; t < PER_LANE; ++t) {
+        const int i = t * 32 + lane;
+        d[t] = i < n ? __ldcg(ck + i) : ~0ull;       // padding never counts (keys <= mid < ~0) and is never kept
+        j[t] = i < n ? __ldcg(cj + i) : 0;
+    }
     u64 lo = ~0ull, hi = 0ull;
-    {
-        u64 d[PER_LANE];
-        int j[PER_LANE];
 #pragma unroll
-        for (int t = 0; t < PER_LANE; ++t) {
-            const int i = t * 32 + lane;
-            d[t] = i < n ? __ldcg(ck + i) : ~0ull;
-            j[t] = i < n ? __ldcg(cj + i) : 0;
-        }
-#pragma unroll
-        for (int t = 0; t < PER_LANE; ++t) {
-            const int i = t * 32 + lane;
-            if (i < n) {
-                sk[i] = d[t];
-                sj[i] = j[t];
-                lo = d[t] < lo ? d[t] : lo;
-                hi = d[t] > hi ? d[t] : hi;
-            }
+    for (int t = 0; t < PER_LANE; ++t) {
+        if (t * 32 + lane < n) {
+            lo = d[t] < lo ? d[t] : lo;
+            hi = d[t] > hi ? d[t] : hi;
         }
     }
     lo = warp_min_u64(lo);
     hi = warp_max_u64(hi);
-    __syncwarp();
     const int k_hi = k + 24;
     u64 blo = lo, bhi = hi, cut = hi;           // count(<= cut) >= k throughout
     int c_hi = n;
@@ -167,18 +164,16 @@ __device__ __noinline__ void prune_row(u64* ck, int* cj, int n, int k, double nr
         if (bhi - blo < 2) break;               // bracket exhausted (ties): keep the current cut
         const u64 mid = blo + ((bhi - blo) >> 1);
         int c = 0;
-#pragma unroll 4
-        for (int i = lane; i < n; i += 32) c += sk[i] <= mid ? 1 : 0;
+#pragma unroll
+        for (int t = 0; t < PER_LANE; ++t) c += d[t] <= mid ? 1 : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (c >= k) { bhi = mid; c_hi = c; cut = mid; } else { blo = mid; }
     }
     u64 vstar = 0ull;
-#pragma unroll 4
-    for (int i = lane; i < n; i += 32) {
-        const u64 d = sk[i];
-        if (d <= cut && d > vstar) vstar = d;
-    }
+#pragma unroll
+    for (int t = 0; t < PER_LANE; ++t)
+        if (d[t] <= cut && d[t] > vstar) vstar = d[t];
     vstar = warp_max_u64(vstar);
     const double dv = dist_of_key(vstar);
     double tau = dv + mcoef * (nrm + fabs(dv));
@@ -186,14 +181,14 @@ __device__ __noinline__ void prune_row(u64* ck, int* cj, int n, int k, double nr
     if (!(tau > tiny)) tau = tiny;
     const u64 thr = key_of_tau(tau);
     int w = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const bool keep = i < n && sk[i] <= thr;
+#pragma unroll
+    for (int t = 0; t < PER_LANE; ++t) {
+        const bool keep = d[t] <= thr && t * 32 + lane < n;
         const unsigned km = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int pos = w + __popc(km & ((1u << lane) - 1u));
-            ck[pos] = sk[i];
-            cj[pos] = sj[i];
+            ck[pos] = d[t];
+            cj[pos] = j[t];
         }
         w += __popc(km);
     }
