@@ -244,6 +244,53 @@ def synthetic_test_counts(nsamples, nraw, seed):
     return out
 
 
+def cpu_reference_test(bins, idx_h, dist_h, cutoff, thr, budget_s=15.0):
+    """The reference's own test path on ONE host core (it has no multi-CPU option for `test`; run.sh loops over samples):
+    repeatTest on one synthetic sample, and fillTri + segmentTri on one small chromosome, extrapolated to all
+    chromosomes by triangle entries (the reference's cost is per entry).  Returns (samples/s, description)."""
+    import contextlib
+    import io
+    n = int(sum(bins))
+    sums = [int(v) for v in np.cumsum(bins)]
+    rng = np.random.default_rng(7)
+    test = 1.0 + rng.normal(0, 0.03, size=n)
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    have_ref = os.path.isfile(os.path.join(ref_dir, "wisetools.py"))
+    sys.path.insert(0, ref_dir if have_ref else os.path.join(ROOT, "oracle"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        if have_ref:
+            import wisetools as ref_wt
+            t0 = time.time()
+            z, r, sizes, sd = ref_wt.repeatTest(np.copy(test), idx_h, dist_h, bins, sums, cutoff, thr, 5)
+            tz = time.time() - t0
+        else:
+            import wc_oracle
+            t0 = time.time()
+            z, r, sizes, sd = wc_oracle.repeat_test(np.copy(test), idx_h, dist_h, bins, sums, cutoff, thr, 5)
+            tz = time.time() - t0
+        # smallest chromosome whose triangle still takes a measurable time; cost model: seconds per triangle entry
+        c = int(np.argmin(bins))
+        zc = z[sums[c] - bins[c]:sums[c]]
+        zc = zc[np.isfinite(zc)][:max(50, int((budget_s * 2 / 6e-6) ** 0.5))]
+        t0 = time.time()
+        if have_ref:
+            ref_wt.fillTri(zc).segmentTri(thr, 3)
+        else:
+            wc_oracle.segment_region(zc, thr, 3)
+        tseg = time.time() - t0
+    entries_c = len(zc) * (len(zc) + 1) / 2.0
+    entries_all = float(sum(b * (b + 1) // 2 for b in bins))
+    tseg_all = tseg * entries_all / entries_c
+    desc = {"kind": "reference" if have_ref else "port", "cores": 1, "unit": "samples/s",
+            "zscore_s_per_sample": tz, "segmentation_s_per_sample_extrapolated": tseg_all,
+            "sample": "%s repeatTest (5 passes) on 1 sample, %d bins: %.1f s; fillTri + segmentTri on %d bins of the smallest "
+                      "chromosome: %.2f s for %.3g triangle entries, extrapolated to the %.3g entries of all chromosomes; one "
+                      "host core (the reference tests samples one by one)" %
+                      ("oracle/_ref wisetools" if have_ref else "oracle/wc_oracle.py", n, tz, len(zc), tseg, entries_c, entries_all)}
+    desc["value"] = 1.0 / (tz + tseg_all)
+    return desc
+
+
 def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins, k, idx_full, dist_full):
     n = int(sum(bins))
     B = int(args.test_batch)
@@ -335,7 +382,11 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
             hbm = float(json.load(fh)["hbm_gbs"])
     except Exception:
         pass
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_test(bins, idx_full.cpu().numpy(), dist_h, cut, thr)
     return {
+        "cpu_baseline": cpu,
         "metric": "test_samples_per_s", "value": world * B / (dev_ms * 1e-3), "unit": "samples/s",
         "samples_per_gpu": B, "n_gpus": world, "bins": n, "refsize": k, "repeats": 5, "ms_per_batch": dev_ms,
         "phases_ms": {"prep": float(np.mean(pr)), "zscore": zms, "segment": sms}, "calls_in_batch": ncalls,

@@ -63,7 +63,6 @@ struct wc_ctx {
     long long zs_pair_limit = 0, zs_all_pairs = 0;
     unsigned long long sched_hash = 0;   // fingerprint of the K5 schedule metadata currently on the device
     unsigned timed_mask = 0;        // phases whose event pair is recorded but not yet read (asynchronous calls)
-    int k5_dbg = 0;                 // timing experiments only (results invalid when non-zero)
     int k5_stages = 0;              // 0 = automatic TMA ring depth
     int k5_group = 0;               // CTAs sharing a row block per scheduling round of K5 (0 = automatic)
     int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones
