@@ -43,7 +43,7 @@ constexpr int HIST_BINS = 256;
 constexpr int FIN_THREADS = 128;    // one thread per shortlisted candidate during the exact re-score
 constexpr int FIN_CHUNK = 32;       // samples staged per pipeline step of the re-score
 constexpr int FIN_LD = FIN_CHUNK + 1;   // padded tile row (bank-conflict free per-thread row walks)
-constexpr int FIN_LDB = FIN_CHUNK + 2;  // tile row of the bulk-copy path: 16-byte aligned rows (2-way conflicts, cheap)
+constexpr int FIN_LDB = FIN_CHUNK + 2;  // tile row of the 16-byte copy path: 16-byte aligned rows (2-way conflicts, cheap)
 constexpr int EXH_THREADS = 256;
 constexpr u64 KEY_NEVER = 0ull;     // threshold key of an inactive row: no finite negative score passes
 
@@ -109,6 +109,9 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v) {
 }
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -597,7 +600,7 @@ struct FinArgs {
     double* dist_out;
     int* slow_list;
     int* slow_count;
-    int bulk;               // 1: stage candidate rows with cp.async.bulk (needs 16-byte aligned rows: S even)
+    int bulk;               // 1: rows are 16-byte aligned (S even): stage candidate rows with 16-byte cp.async
 };
 
 // One CTA per target row.
@@ -733,38 +736,42 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     const double* xrow = a.X + (size_t)row * a.S;
     const int nchunks = (a.S + FIN_CHUNK - 1) / FIN_CHUNK;
     if (a.bulk) {
-        // Every thread stages its own candidate's 32-sample slice with ONE bulk copy (cp.async.bulk, SASS UBLKCP)
-        // that completes on the stage's mbarrier - no per-element copy instructions, no address arithmetic.
-        __shared__ uint64_t s_bar[2];
-        if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
-        __syncthreads();
-        uint32_t phase_bits = 0;                       // bit st = parity to wait for on stage st
+        // Rows are 16-byte aligned (S even): 16-byte cp.async, one warp instruction stages the 32-sample slices of two
+        // candidates (lanes 0-15 / 16-31); the candidates' row pointers are computed once per round into shared memory.
+        // (cp.async.bulk - one copy per thread - was tried: UBLKCP takes warp-uniform operands, so the compiler
+        // serialises it into a 32-iteration loop per warp and the copies alone were 40 % of the kernel's instructions.)
+        unsigned long long* rowp = reinterpret_cast<unsigned long long*>(hist);    // the histogram is dead by now
         for (int c0 = 0; c0 < p; c0 += FIN_THREADS) {
             const int nc = (p - c0) < FIN_THREADS ? (p - c0) : FIN_THREADS;
-            const double* crow = tid < nc ? a.X + (size_t)ex_j[c0 + tid] * a.S : nullptr;
-            auto issue = [&](int chunk, int st) {
+            __syncthreads();
+            if (tid < nc) rowp[tid] = (unsigned long long)(a.X + (size_t)ex_j[c0 + tid] * a.S);
+            __syncthreads();
+            const int half = lane >> 4, l2 = (lane & 15) * 2;
+            auto issue = [&](int chunk, int buf) {
                 const int s0 = chunk * FIN_CHUNK;
-                const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
-                const uint32_t bytes = (uint32_t)ns * 8u;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if (tid == 0) {
-                    mbar_arrive_expect_tx(&s_bar[st], bytes * (uint32_t)(nc + 1));
-                    bulk_g2s(xi0 + st * FIN_CHUNK, xrow + s0, bytes, &s_bar[st]);
-                }
-                if (tid < nc) bulk_g2s(tile0 + ((size_t)st * FIN_THREADS + tid) * FIN_LDB, crow + s0, bytes, &s_bar[st]);
+                const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;       // even
+                double* tile = tile0 + (size_t)buf * FIN_THREADS * FIN_LDB;
+                if (l2 < ns)
+                    for (int c = warp * 2 + half; c < nc; c += (FIN_THREADS / 32) * 2)
+                        cp_async_16(tile + c * FIN_LDB + l2, reinterpret_cast<const double*>(rowp[c]) + s0 + l2);
+                if (tid * 2 < ns) cp_async_16(xi0 + buf * FIN_CHUNK + tid * 2, xrow + s0 + tid * 2);
+                cp_async_commit();
             };
             double accd = 0.0;
             issue(0, 0);
             for (int ch = 0; ch < nchunks; ++ch) {
-                const int st = ch & 1;
-                if (ch + 1 < nchunks) issue(ch + 1, st ^ 1);
-                mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
-                phase_bits ^= 1u << st;
+                if (ch + 1 < nchunks) {
+                    issue(ch + 1, (ch + 1) & 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
                 const int s0 = ch * FIN_CHUNK;
                 const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
                 if (tid < nc) {
-                    const double* tr = tile0 + ((size_t)st * FIN_THREADS + tid) * FIN_LDB;
-                    const double* xi = xi0 + st * FIN_CHUNK;
+                    const double* tr = tile0 + ((size_t)(ch & 1) * FIN_THREADS + tid) * FIN_LDB;
+                    const double* xi = xi0 + (ch & 1) * FIN_CHUNK;
                     if (ns == FIN_CHUNK) {
 #pragma unroll
                         for (int l = 0; l < FIN_CHUNK; ++l) {
@@ -778,7 +785,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
                         }
                     }
                 }
-                __syncthreads();                       // stage st may be refilled by the next issue
+                __syncthreads();
             }
             if (tid < nc) {
                 const bool ok = accd < 1e10;     // wisetools.py:312-314: strict `<` against the 1e10 start value; NaN fails
