@@ -277,3 +277,59 @@ def test_segmentation_batch_keep_mask_and_chromosome_list():
             assert cwz[b, slot] == wcw
             mine = calls[(calls['sample'] == b) & (calls['chrom'] == slot)]
             assert [(float(m['z']), (int(m['x']), int(m['y']))) for m in mine] == [(float(v), xy) for v, xy in wsegs]
+
+
+def test_full_size_properties_50kb():
+    """BASELINE configs[3] shape (57 633 bins, refsize 100): properties that hold at any size - results do not depend on
+    how samples are batched or ordered, called runs are disjoint, above threshold and exactly numpy's values."""
+    import torch
+    from wisecondor_b200 import device
+    bins = synth.chrom_bins(50000)
+    n = int(sum(bins))
+    X = torch.from_numpy(synth.corrected_like(bins, 64, seed=4)).cuda()
+    idx, dist = device.newref_topk(X, bins, 0, n, 100)
+    dist_h = dist.cpu().numpy()
+    cutoff = wc_oracle.get_optimal_cutoff(dist_h, 3)
+    table = device.ReferenceTable(idx.cpu().numpy(), dist_h, bins, cutoff)
+    rng = np.random.default_rng(2)
+    B = 48
+    host = 1.0 + rng.normal(0, 0.03, size=(B, n))
+    for b in range(B):
+        a = int(rng.integers(0, n - 500))
+        host[b, a:a + int(rng.integers(20, 400))] *= rng.choice([0.85, 1.15])
+    thr = 5.4
+
+    def run(rows):
+        m = len(rows)
+        T = torch.ones((n, device.pad32(m)), dtype=torch.float64, device="cuda")
+        T[:, :m] = torch.from_numpy(np.ascontiguousarray(host[rows].T)).cuda()
+        z, r, sizes, asdef = device.zscore_batch(T, m, table, thr, 5)
+        cwz, cleaned, calls = device.segment_batch(z, sizes, bins, list(range(22)), 25, thr, 3)
+        return z.cpu().numpy(), r.cpu().numpy(), sizes.cpu().numpy(), asdef.cpu().numpy(), cwz.cpu().numpy(), calls
+
+    whole = run(list(range(B)))
+    perm = list(rng.permutation(B))
+    shuffled = run(perm)
+    first, second = run(list(range(20))), run(list(range(20, B)))
+    for k in range(5):
+        assert np.array_equal(shuffled[k], whole[k][perm], equal_nan=True)
+        assert np.array_equal(np.concatenate([first[k], second[k]]), whole[k], equal_nan=True)
+    calls = whole[5]
+    assert len(calls) >= B // 2                                       # the injected stretches are found
+    starts = np.concatenate(([0], np.cumsum(bins)))
+    z, sizes = whole[0], whole[2]
+    for c in calls[:: max(1, len(calls) // 40)]:
+        b, ch = int(c['sample']), int(c['chrom'])
+        keep = sizes[b, starts[ch]:starts[ch + 1]] >= 25
+        zc = z[b, starts[ch]:starts[ch + 1]][keep]
+        x, y = int(c['x']), int(c['y'])
+        assert abs(c['z']) >= thr and c['z'] == np.sum(zc[x:y + 1]) / np.sqrt(y - x + 1)
+    for b in range(0, B, 7):
+        mine = calls[calls['sample'] == b]
+        for ch in np.unique(mine['chrom']):
+            seg = mine[mine['chrom'] == ch]
+            assert (seg['x'][1:] > seg['y'][:-1]).all()                  # disjoint, ordered
+        ch = 3
+        keep = sizes[b, starts[ch]:starts[ch + 1]] >= 25
+        zc = z[b, starts[ch]:starts[ch + 1]][keep]
+        assert whole[4][b, ch] == np.sum(zc) / np.sqrt(len(zc))
