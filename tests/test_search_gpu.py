@@ -144,3 +144,28 @@ def test_single_sample_and_wide_refsize():
         _gpu_search(X, bins, 0, 605, 385)
     with pytest.raises(Exception):
         _gpu_search(X, [40, 35], 0, 75, 10)                            # chromosome sizes do not add up to N
+
+
+def test_config3_shape_parts_and_sampled_rows():
+    """BASELINE configs[2] shape (N = 57 633, S = 600, refsize 100), device-resident: the 8 getPart shards concatenate
+    to the single-part result bit for bit, rows are sorted with valid indices, sampled rows equal the C oracle."""
+    import torch
+    from wisecondor_b200 import device, shard
+    bins = synth.chrom_bins(50000)
+    Xh = synth.corrected_like(bins, 600, seed=4)
+    X = torch.from_numpy(Xh).cuda()
+    n = Xh.shape[0]
+    idx, dist = device.newref_topk(X, bins, 0, n, 100)
+    idx_h, dist_h = idx.cpu().numpy(), dist.cpu().numpy()
+    parts_i, parts_d = [], []
+    for r in range(8):
+        a, b = shard.row_shard(r, 8, n)
+        pi, pd = device.newref_topk(X, bins, a, b, 100)
+        parts_i.append(pi.cpu().numpy())
+        parts_d.append(pd.cpu().numpy())
+    assert np.array_equal(np.concatenate(parts_i), idx_h) and np.array_equal(np.concatenate(parts_d), dist_h)
+    assert (np.diff(dist_h, axis=1) >= 0).all()
+    assert (idx_h >= 0).all() and (idx_h < n - np.repeat(bins, bins)[:, None]).all()
+    for r0 in (0, 4970, 30000, n - 32):                  # 4970: straddles the chromosome 1 / 2 boundary
+        oidx, odist = c_oracle.get_reference_rows(Xh, bins, r0, r0 + 32, 100)
+        _assert_same(idx_h[r0:r0 + 32], dist_h[r0:r0 + 32], oidx, odist)
