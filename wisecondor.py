@@ -238,17 +238,19 @@ def _testSamples(samples, sampleBinSizes, ref, args):
 
 
 def _saveResult(outfile, args, binsize, res):
-    np.savez_compressed(outfile,
-                        arguments=vars(args),
-                        runtime=getRuntime(),
-                        binsize=binsize,
-                        results_r=_ragged(res['results_r']),
-                        results_z=_ragged(res['results_z']),
-                        results_cwz=res['results_cwz'],
-                        results_calls=res['results_calls'],
-                        threshold_z=res['threshold_z'],
-                        asdef=res['asdef'],
-                        aasdef=res['aasdef'])
+    # np.load reads compressed and stored npz alike; -uncompressed (testbatch) skips zlib, the slowest host step
+    save = np.savez if getattr(args, 'uncompressed', False) else np.savez_compressed
+    save(outfile,
+         arguments=vars(args),
+         runtime=getRuntime(),
+         binsize=binsize,
+         results_r=_ragged(res['results_r']),
+         results_z=_ragged(res['results_z']),
+         results_cwz=res['results_cwz'],
+         results_calls=res['results_calls'],
+         threshold_z=res['threshold_z'],
+         asdef=res['asdef'],
+         aasdef=res['aasdef'])
 
 
 def toolTest(args):
@@ -376,6 +378,7 @@ def buildParser():
     testFlags(p)
     p.add_argument('-batch', type=int, default=256, help='Samples per device batch')
     p.add_argument('-iothreads', type=int, default=8, help='Threads loading / writing npz files')
+    p.add_argument('-uncompressed', action='store_true', help='Write result npz files without zlib compression')
     p.set_defaults(func=toolTestBatch)
 
     p = sub.add_parser('plot', description='Plot results produced by sample testing')
