@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int SEG_THREADS = 256;
+constexpr int SEG_THREADS = 128;
 constexpr int SEG_WARPS = SEG_THREADS / 32;
 constexpr int SEG_R = 5;                      // run lengths per lane in the sweep (odd: conflict-free prefix reads)
 constexpr int SEG_TILE = 32 * SEG_R;          // run lengths per warp tile
