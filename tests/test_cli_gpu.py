@@ -95,6 +95,7 @@ def test_newref_cluster_steps_match_reference(workdir, tiny):
     assert np.array_equal(p['maskedChromBinSums'], tiny['prep_maskedChromBinSums'])
     assert np.array_equal(p['maskedData'], tiny['prep_maskedData'])
     _close(p['correctedData'], tiny['prep_correctedData'])
+    assert p['correctedData'].flags.f_contiguous          # the layout the reference's prep file has
     assert set(p.files) == {'arguments', 'runtime', 'binsize', 'chromosomeBins', 'maskedData', 'mask', 'maskedChromBins',
                             'maskedChromBinSums', 'correctedData', 'pca_components', 'pca_mean'}
     r = np.load(str(workdir / "ref.npz"), allow_pickle=True)

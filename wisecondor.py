@@ -151,7 +151,9 @@ def toolNewrefPrep(args):
                         mask=mask,
                         maskedChromBins=maskedChromBins,
                         maskedChromBinSums=maskedChromBinSums,
-                        correctedData=correctedData.cpu().numpy(),
+                        # Fortran order, like the transposed view the reference saves (wisetools.py:101): a reference CPU
+                        # worker that reads this file then sums over samples in the same (sequential) order
+                        correctedData=np.asfortranarray(correctedData.cpu().numpy()),
                         pca_components=pca.components_,
                         pca_mean=pca.mean_)
 
