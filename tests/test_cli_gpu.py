@@ -242,3 +242,33 @@ def test_newref_on_two_gpus_equals_reference(workdir, tiny):
     assert np.array_equal(r['indexes'], tiny['ref_indexes'])
     _close(r['distances'], tiny['ref_distances'])
     assert not os.path.exists(str(workdir / "two_part_3.npz"))
+
+
+def test_parts_interchangeable_with_the_reference_workers(workdir, tiny):
+    """Cluster mode with mixed workers: the reference's own `newrefpart` (CPU, oracle/_ref) run on THIS build's prep file
+    gives bit for bit the part this build computes on the GPU, and a reference of mixed parts assembles with either
+    `newrefpost`.  (TEST INFRASTRUCTURE use of oracle/_ref; skipped where it did not travel.)"""
+    import subprocess
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "wisecondor.py")
+    if not os.path.isfile(ref_cli):
+        pytest.skip("oracle/_ref not generated")
+    prep = str(workdir / "ref_prep.npz")                     # written by this build in test_newref_cluster_steps...
+    assert os.path.isfile(prep)
+    r = subprocess.run([sys.executable, ref_cli, "newrefpart", prep, str(workdir / "mix_part"), "2", "3", "-refsize", "40"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    theirs = np.load(str(workdir / "mix_part_2.npz"), allow_pickle=True)
+    mine = np.load(str(workdir / "ref_part_2.npz"), allow_pickle=True)
+    assert np.array_equal(theirs['indexes'], mine['indexes'])
+    assert np.array_equal(theirs['distances'], mine['distances'])          # same prep file -> bit-identical distances
+    # assemble: parts 1 and 3 from this build, part 2 from the reference, post-processed by the reference
+    import shutil
+    shutil.copy(str(workdir / "ref_part_1.npz"), str(workdir / "mix_part_1.npz"))
+    shutil.copy(str(workdir / "ref_part_3.npz"), str(workdir / "mix_part_3.npz"))
+    r = subprocess.run([sys.executable, ref_cli, "newrefpost", prep, str(workdir / "mix_part"), "3", str(workdir / "mix.npz")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    mixed = np.load(str(workdir / "mix.npz"), allow_pickle=True)
+    whole = np.load(str(workdir / "ref.npz"), allow_pickle=True)
+    for key in ("indexes", "distances", "mask", "masked_sizes", "chromosome_sizes", "pca_mean", "pca_components"):
+        assert np.array_equal(mixed[key], whole[key]), key
