@@ -42,7 +42,9 @@ def write_sample_npz(path, row, bins, binsize):
         pos += n
     s['X'] = np.zeros(5, dtype=np.int32)
     s['Y'] = np.zeros(3, dtype=np.int32)
-    np.savez_compressed(path, arguments={'binsize': float(binsize)}, runtime={}, sample=s, quality={})
+    quality = {key: 0 for key in ('mapped', 'unmapped', 'no_coordinate', 'filter_rmdup', 'filter_mapq', 'pre_retro',
+                                  'post_retro', 'pair_fail')}          # the keys convert writes (wisetools.py:209-216)
+    np.savez_compressed(path, arguments={'binsize': float(binsize)}, runtime={}, sample=s, quality=quality)
 
 
 def run_ref_cli(argv, cwd):

@@ -272,3 +272,23 @@ def test_parts_interchangeable_with_the_reference_workers(workdir, tiny):
     whole = np.load(str(workdir / "ref.npz"), allow_pickle=True)
     for key in ("indexes", "distances", "mask", "masked_sizes", "chromosome_sizes", "pca_mean", "pca_components"):
         assert np.array_equal(mixed[key], whole[key]), key
+
+
+def test_reference_consumers_read_our_results(workdir, tiny):
+    """The reference's own `report` tool (a pure consumer of sample + result npz, wisecondor.py:304-342) and its `test`
+    tool accept the files this build writes."""
+    import subprocess
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "wisecondor.py")
+    if not os.path.isfile(ref_cli):
+        pytest.skip("oracle/_ref not generated")
+    out = str(workdir / "o1.npz")                            # this build's result for test sample 1
+    assert os.path.isfile(out)
+    r = subprocess.run([sys.executable, ref_cli, "report", str(workdir / "t1.npz"), out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "z-score" in r.stdout.lower() or "chr" in r.stdout.lower() or len(r.stdout) > 50
+    # the reference's test tool on the reference file THIS build wrote
+    r = subprocess.run([sys.executable, ref_cli, "test", str(workdir / "t1.npz"), str(workdir / "theirs_on_ours.npz"),
+                        str(workdir / "ref.npz"), "-minrefbins", "10"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    res = np.load(str(workdir / "theirs_on_ours.npz"), allow_pickle=True)
+    _check_result(res, tiny, 1)
