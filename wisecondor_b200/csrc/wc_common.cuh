@@ -47,7 +47,7 @@ enum {
     SLOT_PROF = 20,
     SLOT_T_COPY = 24, SLOT_T_ZT, SLOT_T_RT, SLOT_T_NT, SLOT_T_SD, SLOT_T_FLAGS, SLOT_T_TOTALS, SLOT_T_PROJ,   // test
     SLOT_T_REVCNT = 44, SLOT_T_REVCUR, SLOT_T_DIRTY, SLOT_T_PAIRS,
-    SLOT_S_ISQ = 32, SLOT_S_META, SLOT_S_STATUS, SLOT_S_RC, SLOT_S_AUX,                                                       // segmentation
+    SLOT_S_ZC = 32, SLOT_S_META, SLOT_S_STATUS, SLOT_S_RC, SLOT_S_AUX,                                                       // segmentation
     SLOT_P_FIRST = 40                                                                                  // newref prep
 };
 

@@ -478,7 +478,7 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const double* r_
     }
     double* zc; double* rcomp = nullptr; int* meta_d; int* status_d;
     int rc;
-    if ((rc = wc_reserve(ctx, SLOT_S_ISQ, (size_t)B * N * sizeof(double), (void**)&zc))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_S_ZC, (size_t)B * N * sizeof(double), (void**)&zc))) return rc;
     if (mineff && (rc = wc_reserve(ctx, SLOT_S_RC, (size_t)B * N * sizeof(double), (void**)&rcomp))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_S_META, (size_t)3 * nsel * sizeof(int), (void**)&meta_d))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_S_STATUS, 4 * sizeof(int), (void**)&status_d))) return rc;
