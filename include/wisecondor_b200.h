@@ -63,6 +63,15 @@ double wc_last_phase_ms(wc_ctx* ctx, int which);
  * 16 + p = (bin, sample) pairs that z-score pass p of the last wc_zscore_batch computed (synchronises). */
 long long wc_last_counter(const wc_ctx* ctx, int which);
 
+/* Raw device buffers for hosts without an allocator of their own (the command line runs without PyTorch this way;
+ * library users normally pass pointers of their own tensors).  Copies are synchronous on the legacy default stream. */
+int wc_device_count(void);
+void* wc_dev_alloc(wc_ctx* ctx, size_t bytes);                 /* NULL on failure */
+int wc_dev_free(wc_ctx* ctx, void* p);
+int wc_copy_h2d(wc_ctx* ctx, void* dst_d, const void* src_h, size_t bytes);
+int wc_copy_d2h(wc_ctx* ctx, void* dst_h, const void* src_d, size_t bytes);
+int wc_dev_sync(wc_ctx* ctx);                                  /* cudaDeviceSynchronize on the context's device */
+
 /* Debug aid: enable (1) / disable (0) per-CTA cycle counters in the distance kernel and copy the counters of the
  * most recent search to out_h (grid x 8 int64: total, wait-on-TMA, epilogue, prune, tiles, prunes, emitted by
  * thread 0, reserved).  Returns the number of CTAs copied, or a negative wc_status. */

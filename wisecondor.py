@@ -31,7 +31,7 @@ import time
 
 import numpy as np
 
-from wisecondor_b200 import wisetools
+from wisecondor_b200 import _mem, wisetools
 
 curTime = datetime.datetime.now()
 
@@ -147,13 +147,13 @@ def toolNewrefPrep(args):
                         runtime=getRuntime(),
                         binsize=binsize,
                         chromosomeBins=chromosomeBins,
-                        maskedData=maskedData.cpu().numpy(),
+                        maskedData=_mem.to_host(maskedData),
                         mask=mask,
                         maskedChromBins=maskedChromBins,
                         maskedChromBinSums=maskedChromBinSums,
                         # Fortran order, like the transposed view the reference saves (wisetools.py:101): a reference CPU
                         # worker that reads this file then sums over samples in the same (sequential) order
-                        correctedData=np.asfortranarray(correctedData.cpu().numpy()),
+                        correctedData=np.asfortranarray(_mem.to_host(correctedData)),
                         pca_components=pca.components_,
                         pca_mean=pca.mean_)
 
@@ -408,7 +408,16 @@ def main(argv=None):
         buildParser().print_help()
         sys.exit(2)
     printArgs(args)
-    args.func(args)
+    before = _mem.BACKEND
+    if 'WISECONDOR_BACKEND' not in os.environ:
+        # Device buffers: `testbatch` pipelines chunks over torch streams and pinned memory; everything else handles one
+        # reference or one sample and takes the library's own cudaMalloc buffers - importing PyTorch alone would cost
+        # more than their whole run.
+        _mem.BACKEND = 'torch' if args.func is toolTestBatch else 'native'
+    try:
+        args.func(args)
+    finally:
+        _mem.BACKEND = before            # main() may be called in-process (tests, notebooks): leave no global behind
 
 
 if __name__ == '__main__':

@@ -12,7 +12,7 @@ _LIB = None
 
 SYMBOLS = [
     "wc_create", "wc_destroy", "wc_last_error", "wc_version", "wc_sm_count", "wc_last_phase_ms",
-    "wc_last_counter", "wc_newref_topk", "wc_newref_topk_host", "wc_debug_profile", "wc_set_option",
+    "wc_last_counter", "wc_device_count", "wc_dev_alloc", "wc_dev_free", "wc_copy_h2d", "wc_copy_d2h", "wc_dev_sync", "wc_newref_topk", "wc_newref_topk_host", "wc_debug_profile", "wc_set_option",
     "wc_newref_mask", "wc_newref_normalize", "wc_pca_gram", "wc_pca_apply",
     "wc_table_stride", "wc_test_table", "wc_test_prep", "wc_apply_pca", "wc_zscore_batch", "wc_segment_batch",
 ]
@@ -49,6 +49,18 @@ def lib():
     L.wc_last_phase_ms.argtypes = [vp, ci]
     L.wc_last_counter.restype = ctypes.c_longlong
     L.wc_last_counter.argtypes = [vp, ci]
+    L.wc_device_count.restype = ci
+    L.wc_device_count.argtypes = []
+    L.wc_dev_alloc.restype = vp
+    L.wc_dev_alloc.argtypes = [vp, ctypes.c_size_t]
+    L.wc_dev_free.restype = ci
+    L.wc_dev_free.argtypes = [vp, vp]
+    L.wc_copy_h2d.restype = ci
+    L.wc_copy_h2d.argtypes = [vp, vp, vp, ctypes.c_size_t]
+    L.wc_copy_d2h.restype = ci
+    L.wc_copy_d2h.argtypes = [vp, vp, vp, ctypes.c_size_t]
+    L.wc_dev_sync.restype = ci
+    L.wc_dev_sync.argtypes = [vp]
     L.wc_newref_topk.restype = ci
     L.wc_newref_topk.argtypes = [vp, vp, ci, ci, vp, ci, ci, ci, ci, vp, vp, vp]
     L.wc_newref_topk_host.restype = ci

@@ -130,3 +130,51 @@ int wc_reserve(wc_ctx* ctx, int slot, size_t bytes, void** out) {
     *out = b.p;
     return WC_OK;
 }
+
+// ---- raw device buffers for hosts that do not bring an allocator of their own (the command line without PyTorch) ----
+extern "C" int wc_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+extern "C" void* wc_dev_alloc(wc_ctx* ctx, size_t bytes) {
+    if (!ctx) { wc_set_error("wc_dev_alloc: no context"); return nullptr; }
+    void* p = nullptr;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        wc_set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" int wc_dev_free(wc_ctx* ctx, void* p) {
+    WC_CHECK_ARG(ctx != nullptr);
+    if (!p) return WC_OK;
+    WC_CUDA(cudaSetDevice(ctx->device));
+    WC_CUDA(cudaFree(p));
+    return WC_OK;
+}
+
+extern "C" int wc_copy_h2d(wc_ctx* ctx, void* dst_d, const void* src_h, size_t bytes) {
+    WC_CHECK_ARG(ctx != nullptr && (bytes == 0 || (dst_d != nullptr && src_h != nullptr)));
+    WC_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) WC_CUDA(cudaMemcpy(dst_d, src_h, bytes, cudaMemcpyHostToDevice));
+    return WC_OK;
+}
+
+extern "C" int wc_copy_d2h(wc_ctx* ctx, void* dst_h, const void* src_d, size_t bytes) {
+    WC_CHECK_ARG(ctx != nullptr && (bytes == 0 || (dst_h != nullptr && src_d != nullptr)));
+    WC_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) WC_CUDA(cudaMemcpy(dst_h, src_d, bytes, cudaMemcpyDeviceToHost));     // waits for prior work on the null stream
+    return WC_OK;
+}
+
+extern "C" int wc_dev_sync(wc_ctx* ctx) {
+    WC_CHECK_ARG(ctx != nullptr);
+    WC_CUDA(cudaSetDevice(ctx->device));
+    WC_CUDA(cudaDeviceSynchronize());
+    return WC_OK;
+}

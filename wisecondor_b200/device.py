@@ -1,28 +1,17 @@
-"""Device-resident entry points: torch tensors own the HBM buffers, the C ABI does the work.
+"""Device-resident entry points: device arrays own the HBM buffers, the C ABI does the work.
 
-PyTorch is plumbing here (allocation, streams, torch.distributed); every kernel lives in libwisecondor_b200.so.
+The arrays are torch CUDA tensors (library use: streams, pinned memory, torch.distributed) or _mem.DevArray blocks
+(the command line without PyTorch); every function returns the kind it was given.  Either way this is plumbing: every
+kernel lives in libwisecondor_b200.so.
 """
 import ctypes
 
 import numpy as np
-import torch
 
-from . import _cabi
+from . import _cabi, _mem
+from ._mem import ptr as _ptr, stream_ptr as _stream_ptr, require as _require_cuda
 
-
-def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr())
-
-
-def _stream_ptr(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-
-
-def _require_cuda(t, dtype, name):
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
-        raise _cabi.WisecondorError("%s must be a CUDA tensor (there is no CPU path)" % name)
-    if t.dtype != dtype or not t.is_contiguous():
-        raise _cabi.WisecondorError("%s must be contiguous %s" % (name, dtype))
+F64, I32, U8 = np.float64, np.int32, np.uint8
 
 
 def newref_topk(corrected, chrom_bins, row_begin, row_end, refsize, out_idx=None, out_dist=None):
@@ -31,19 +20,18 @@ def newref_topk(corrected, chrom_bins, row_begin, row_end, refsize, out_idx=None
     corrected: CUDA float64 [N][S] (bin-major).  Returns (indexes int32 [rows][refsize], distances float64
     [rows][refsize]) on the same device; indexes are positions in the other-chromosome concatenation.
     """
-    _require_cuda(corrected, torch.float64, "corrected")
+    _require_cuda(corrected, F64, "corrected")
     n, s = corrected.shape
-    dev = corrected.device
     cb = np.ascontiguousarray(chrom_bins, dtype=np.int32)
     rows = int(row_end) - int(row_begin)
     if out_idx is None:
-        out_idx = torch.empty((max(rows, 0), refsize), dtype=torch.int32, device=dev)
+        out_idx = _mem.empty((max(rows, 0), refsize), I32, like=corrected)
     if out_dist is None:
-        out_dist = torch.empty((max(rows, 0), refsize), dtype=torch.float64, device=dev)
-    ctx = _cabi.context(dev.index if dev.index is not None else torch.cuda.current_device())
+        out_dist = _mem.empty((max(rows, 0), refsize), F64, like=corrected)
+    ctx = _cabi.context(_mem.device_index(corrected))
     rc = _cabi.lib().wc_newref_topk(ctx.handle, _ptr(corrected), n, s, cb.ctypes.data_as(ctypes.c_void_p), len(cb),
                                     int(row_begin), int(row_end), int(refsize), _ptr(out_idx), _ptr(out_dist),
-                                    _stream_ptr(dev))
+                                    _stream_ptr(corrected))
     _cabi.check(rc)
     return out_idx, out_dist
 
@@ -85,10 +73,6 @@ def last_search_stats(device=0):
 CALL_DTYPE = np.dtype([("sample", np.int32), ("chrom", np.int32), ("x", np.int32), ("y", np.int32), ("z", np.float64)])
 
 
-def _dev_index(dev):
-    return dev.index if dev.index is not None else torch.cuda.current_device()
-
-
 def _ints(values):
     arr = np.ascontiguousarray(values, dtype=np.int32)
     return arr, arr.ctypes.data_as(ctypes.c_void_p)
@@ -103,25 +87,24 @@ class ReferenceTable(object):
     bins (`index[distances < cutoff]` mapped out of other-chromosome coordinates, wisetools.py:420-424)."""
 
     def __init__(self, indexes, distances, masked_sizes, cutoff, device=0):
-        dev = torch.device("cuda", device)
-        self.device = dev
         self.masked_sizes = [int(v) for v in masked_sizes]
         self.n, self.k = int(indexes.shape[0]), int(indexes.shape[1])
         self.cutoff = float(cutoff)
-        idx = torch.as_tensor(np.ascontiguousarray(indexes, dtype=np.int32), device=dev)
-        dst = torch.as_tensor(np.ascontiguousarray(distances, dtype=np.float64), device=dev)
-        self.table = torch.empty((self.n, _cabi.lib().wc_table_stride(self.k)), dtype=torch.int32, device=dev)
-        self.count = torch.empty((self.n,), dtype=torch.int32, device=dev)
+        idx = _mem.to_device(np.ascontiguousarray(indexes, dtype=np.int32), device)
+        dst = _mem.to_device(np.ascontiguousarray(distances, dtype=np.float64), device)
+        self.device = idx.device
+        self.table = _mem.empty((self.n, _cabi.lib().wc_table_stride(self.k)), I32, like=idx)
+        self.count = _mem.empty((self.n,), I32, like=idx)
         # reverse table (CSR): which bins use bin j as a reference bin
-        self.rev_off = torch.empty((self.n + 1,), dtype=torch.int32, device=dev)
-        self.rev_idx = torch.empty((self.n, self.table.shape[1]), dtype=torch.int32, device=dev)
+        self.rev_off = _mem.empty((self.n + 1,), I32, like=idx)
+        self.rev_idx = _mem.empty((self.n, self.table.shape[1]), I32, like=idx)
         cb, cbp = _ints(self.masked_sizes)
-        ctx = _cabi.context(_dev_index(dev))
+        ctx = _cabi.context(_mem.device_index(idx))
         rc = _cabi.lib().wc_test_table(ctx.handle, _ptr(idx), _ptr(dst), self.n, self.k, cbp, len(cb), self.cutoff,
                                        _ptr(self.table), _ptr(self.count), _ptr(self.rev_off), _ptr(self.rev_idx),
-                                       _stream_ptr(dev))
+                                       _stream_ptr(idx))
         _cabi.check(rc)
-        torch.cuda.current_stream(dev).synchronize()
+        _mem.synchronize(idx)
 
 
 def test_prep(counts, masked_raw, pca_mean, pca_components, nsamples=None):
@@ -129,21 +112,21 @@ def test_prep(counts, masked_raw, pca_mean, pca_components, nsamples=None):
 
     counts: CUDA int32 [B][Nraw] (chromosomes already padded/truncated to the reference sizes); masked_raw: CUDA
     int32 [N]; pca_mean CUDA f64 [N]; pca_components CUDA f64 [ncomp][N].  Returns T: CUDA f64 [N][pad32(B)]."""
-    _require_cuda(counts, torch.int32, "counts")
-    _require_cuda(masked_raw, torch.int32, "masked_raw")
+    _require_cuda(counts, I32, "counts")
+    _require_cuda(masked_raw, I32, "masked_raw")
     b, nraw = counts.shape
     n = masked_raw.shape[0]
-    dev = counts.device
+    dev = counts          # outputs follow its kind, device and stream
     if pca_components is None:        # normalise + mask only (toNumpyRefFormat)
         ncomp = 0
-        pca_mean = pca_components = torch.empty((0,), dtype=torch.float64, device=dev)
+        pca_mean = pca_components = _mem.empty((0,), F64, like=dev)
     else:
-        _require_cuda(pca_mean, torch.float64, "pca_mean")
-        _require_cuda(pca_components, torch.float64, "pca_components")
+        _require_cuda(pca_mean, F64, "pca_mean")
+        _require_cuda(pca_components, F64, "pca_components")
         ncomp = pca_components.shape[0]
     ldb = pad32(b)
-    out = torch.empty((n, ldb), dtype=torch.float64, device=dev)
-    ctx = _cabi.context(_dev_index(dev))
+    out = _mem.empty((n, ldb), F64, like=dev)
+    ctx = _cabi.context(_mem.device_index(dev))
     rc = _cabi.lib().wc_test_prep(ctx.handle, _ptr(counts), b, nraw, _ptr(masked_raw), n, _ptr(pca_mean),
                                   _ptr(pca_components), ncomp, _ptr(out), ldb, _stream_ptr(dev))
     _cabi.check(rc)
@@ -153,14 +136,14 @@ def test_prep(counts, masked_raw, pca_mean, pca_components, nsamples=None):
 def apply_pca(x, pca_mean, pca_components):
     """applyPCA (wisetools.py:104-113) for a batch of normalised masked vectors x: CUDA f64 [B][N].
     Returns T: CUDA f64 [N][pad32(B)] (sample-minor)."""
-    _require_cuda(x, torch.float64, "x")
-    _require_cuda(pca_mean, torch.float64, "pca_mean")
-    _require_cuda(pca_components, torch.float64, "pca_components")
+    _require_cuda(x, F64, "x")
+    _require_cuda(pca_mean, F64, "pca_mean")
+    _require_cuda(pca_components, F64, "pca_components")
     b, n = x.shape
-    dev = x.device
+    dev = x          # outputs follow its kind, device and stream
     ldb = pad32(b)
-    out = torch.empty((n, ldb), dtype=torch.float64, device=dev)
-    ctx = _cabi.context(_dev_index(dev))
+    out = _mem.empty((n, ldb), F64, like=dev)
+    ctx = _cabi.context(_mem.device_index(dev))
     rc = _cabi.lib().wc_apply_pca(ctx.handle, _ptr(x), b, n, _ptr(pca_mean), _ptr(pca_components),
                                   pca_components.shape[0], _ptr(out), ldb, _stream_ptr(dev))
     _cabi.check(rc)
@@ -171,19 +154,19 @@ def zscore_batch(test, nsamples, table, z_threshold, repeats, copy_init=None):
     """repeatTest (wisetools.py:438-448) for a batch.  test: CUDA f64 [N][ldb] sample-minor; table: ReferenceTable;
     copy_init: optional CUDA f64 [N][ldb], trySample's pre-marked `testCopy`.
     Returns (z [B][N], r [B][N], refsizes int32 [B][N], asdef [B]) on the device."""
-    _require_cuda(test, torch.float64, "test")
+    _require_cuda(test, F64, "test")
     if copy_init is not None:
-        _require_cuda(copy_init, torch.float64, "copy_init")
+        _require_cuda(copy_init, F64, "copy_init")
         if copy_init.shape != test.shape:
             raise _cabi.WisecondorError("copy_init must have the shape of test")
     n, ldb = test.shape
     b = int(nsamples)
-    dev = test.device
-    z = torch.empty((b, n), dtype=torch.float64, device=dev)
-    r = torch.empty((b, n), dtype=torch.float64, device=dev)
-    sizes = torch.empty((b, n), dtype=torch.int32, device=dev)
-    asdef = torch.empty((b,), dtype=torch.float64, device=dev)
-    ctx = _cabi.context(_dev_index(dev))
+    dev = test          # outputs follow its kind, device and stream
+    z = _mem.empty((b, n), F64, like=dev)
+    r = _mem.empty((b, n), F64, like=dev)
+    sizes = _mem.empty((b, n), I32, like=dev)
+    asdef = _mem.empty((b,), F64, like=dev)
+    ctx = _cabi.context(_mem.device_index(dev))
     rc = _cabi.lib().wc_zscore_batch(ctx.handle, _ptr(test), _ptr(copy_init) if copy_init is not None else None, n, b, ldb,
                                      _ptr(table.table), _ptr(table.count), _ptr(table.rev_off), _ptr(table.rev_idx), table.k,
                                      float(z_threshold), int(repeats), _ptr(z), _ptr(r), _ptr(sizes), _ptr(asdef),
@@ -198,22 +181,22 @@ def segment_batch(z, refsizes, masked_sizes, chromosomes, minrefbins, z_threshol
     int32 [B][N]; chromosomes: 0-based indices; r (CUDA f64 [B][N], resultsR) and mineffectsize select fillTriMin's
     effect-size filter (wisetools.py:475-487).  Returns (cwz [B][nsel] CUDA, cleaned_bins int32 [B][nsel] CUDA,
     calls: numpy structured array (sample, chrom, x, y, z) sorted by (sample, chrom, x))."""
-    _require_cuda(z, torch.float64, "z")
-    _require_cuda(refsizes, torch.int32, "refsizes")
+    _require_cuda(z, F64, "z")
+    _require_cuda(refsizes, I32, "refsizes")
     if mineffectsize != 0:
-        _require_cuda(r, torch.float64, "r")
+        _require_cuda(r, F64, "r")
         if r.shape != z.shape:
             raise _cabi.WisecondorError("r must have the shape of z")
     b, n = z.shape
-    dev = z.device
+    dev = z          # outputs follow its kind, device and stream
     cb, cbp = _ints(masked_sizes)
     sel, selp = _ints(chromosomes)
-    cwz = torch.empty((b, len(sel)), dtype=torch.float64, device=dev)
-    cleaned = torch.empty((b, len(sel)), dtype=torch.int32, device=dev)
-    ctx = _cabi.context(_dev_index(dev))
+    cwz = _mem.empty((b, len(sel)), F64, like=dev)
+    cleaned = _mem.empty((b, len(sel)), I32, like=dev)
+    ctx = _cabi.context(_mem.device_index(dev))
     while True:
-        calls = torch.empty((b, max_calls * CALL_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-        ncalls = torch.empty((b,), dtype=torch.int32, device=dev)
+        calls = _mem.empty((b, max_calls * CALL_DTYPE.itemsize), U8, like=dev)
+        ncalls = _mem.empty((b,), I32, like=dev)
         rc = _cabi.lib().wc_segment_batch(ctx.handle, _ptr(z), _ptr(r) if r is not None else None, _ptr(refsizes), n, b,
                                           cbp, len(cb), selp, len(sel), int(minrefbins), float(z_threshold),
                                           float(mineffectsize), int(min_search), _ptr(cwz), _ptr(cleaned),
@@ -223,8 +206,8 @@ def segment_batch(z, refsizes, masked_sizes, chromosomes, minrefbins, z_threshol
             continue
         _cabi.check(rc)
         break
-    nc = ncalls.cpu().numpy()
-    raw = calls.cpu().numpy().view(CALL_DTYPE).reshape(b, max_calls)
+    nc = _mem.to_host(ncalls)
+    raw = _mem.to_host(calls).view(CALL_DTYPE).reshape(b, max_calls)
     rows = [raw[i, :nc[i]] for i in range(b)]
     flat = np.concatenate(rows) if rows else np.zeros(0, dtype=CALL_DTYPE)
     flat = flat[np.lexsort((flat["x"], flat["chrom"], flat["sample"]))]
@@ -250,16 +233,16 @@ def last_test_stats(device=0):
 def newref_normalize(counts):
     """toNumpyArray's arithmetic (wisetools.py:255-261).  counts: CUDA int32 [S][Nraw].
     Returns (maskedData CUDA f64 [N][S] bin-major, mask numpy bool [Nraw])."""
-    _require_cuda(counts, torch.int32, "counts")
+    _require_cuda(counts, I32, "counts")
     s, nraw = counts.shape
-    dev = counts.device
-    ctx = _cabi.context(_dev_index(dev))
-    mask_d = torch.empty((nraw,), dtype=torch.uint8, device=dev)
+    dev = counts          # outputs follow its kind, device and stream
+    ctx = _cabi.context(_mem.device_index(dev))
+    mask_d = _mem.empty((nraw,), U8, like=dev)
     _cabi.check(_cabi.lib().wc_newref_mask(ctx.handle, _ptr(counts), s, nraw, _ptr(mask_d), _stream_ptr(dev)))
-    mask = mask_d.cpu().numpy().astype(bool)
-    masked_raw = torch.as_tensor(np.flatnonzero(mask).astype(np.int32), device=dev)
+    mask = _mem.to_host(mask_d).astype(bool)
+    masked_raw = _mem.to_device(np.flatnonzero(mask).astype(np.int32), like=dev)
     n = int(masked_raw.shape[0])
-    masked = torch.empty((n, s), dtype=torch.float64, device=dev)
+    masked = _mem.empty((n, s), F64, like=dev)
     if n > 0:
         _cabi.check(_cabi.lib().wc_newref_normalize(ctx.handle, _ptr(counts), s, nraw, _ptr(masked_raw), n, _ptr(masked),
                                                     _stream_ptr(dev)))
@@ -285,25 +268,25 @@ def pca_fit_apply(masked, ncomp=3):
     """trainPCA (wisetools.py:89-101) with the exact top-`ncomp` principal subspace.  masked: CUDA f64 [N][S].
     Returns (corrected CUDA f64 [N][S], components numpy [ncomp][N] with scikit-learn's sign convention,
     mean numpy [N])."""
-    _require_cuda(masked, torch.float64, "masked")
+    _require_cuda(masked, F64, "masked")
     n, s = masked.shape
-    dev = masked.device
-    ctx = _cabi.context(_dev_index(dev))
-    mean = torch.empty((n,), dtype=torch.float64, device=dev)
-    gram = torch.empty((s, s), dtype=torch.float64, device=dev)
+    dev = masked          # outputs follow its kind, device and stream
+    ctx = _cabi.context(_mem.device_index(dev))
+    mean = _mem.empty((n,), F64, like=dev)
+    gram = _mem.empty((s, s), F64, like=dev)
     _cabi.check(_cabi.lib().wc_pca_gram(ctx.handle, _ptr(masked), n, s, _ptr(mean), _ptr(gram), _stream_ptr(dev)))
-    vec, sigma = top_eigenpairs(gram.cpu().numpy(), ncomp)
+    vec, sigma = top_eigenpairs(_mem.to_host(gram), ncomp)
     if not (sigma > 0).all():
         raise _cabi.WisecondorError("PCA: fewer than %d non-zero singular values (degenerate sample matrix)" % ncomp)
-    vec_d = torch.as_tensor(vec, device=dev)
-    comps = torch.empty((ncomp, n), dtype=torch.float64, device=dev)
-    corrected = torch.empty((n, s), dtype=torch.float64, device=dev)
+    vec_d = _mem.to_device(vec, like=dev)
+    comps = _mem.empty((ncomp, n), F64, like=dev)
+    corrected = _mem.empty((n, s), F64, like=dev)
     sig = np.ascontiguousarray(sigma, dtype=np.float64)
     _cabi.check(_cabi.lib().wc_pca_apply(ctx.handle, _ptr(masked), n, s, _ptr(mean), _ptr(vec_d),
                                          sig.ctypes.data_as(ctypes.c_void_p), ncomp, _ptr(comps), _ptr(corrected),
                                          _stream_ptr(dev)))
-    comps_h = comps.cpu().numpy()
+    comps_h = _mem.to_host(comps)
     # scikit-learn svd_flip(u_based_decision=False): the largest-magnitude entry of every component is positive
     signs = np.sign(comps_h[np.arange(ncomp), np.argmax(np.abs(comps_h), axis=1)])
     signs[signs == 0] = 1.0
-    return corrected, comps_h * signs[:, None], mean.cpu().numpy()
+    return corrected, comps_h * signs[:, None], _mem.to_host(mean)

@@ -8,6 +8,7 @@ import time
 
 import numpy as np
 
+from . import _mem
 from . import device as _dev
 
 DEVICE = 0   # CUDA device the host-facing functions use
@@ -26,7 +27,7 @@ def getReference(correctedData, chromosomeBins, chromosomeBinSums, selectRefAmou
     bin the positions, within the concatenation of all other chromosomes, of the selectRefAmount nearest bins
     ordered by (squared distance, index), and those distances.  The chromosome split of the reference's
     splitByChrom/getRefForBins loop happens inside the kernel (per-row exclusion ranges).  correctedData may be a
-    numpy array [N][S] or a CUDA tensor; `device` overrides the module-level DEVICE (one host thread per GPU).
+    numpy array [N][S] or a device array; `device` overrides the module-level DEVICE (one host thread per GPU).
     """
     timeStart = time.time()
     bincount = int(chromosomeBinSums[-1])
@@ -34,11 +35,11 @@ def getReference(correctedData, chromosomeBins, chromosomeBinSums, selectRefAmou
     print('Working on part', part, 'of', splitParts, 'meaning bins', startNum, 'up to', endNum)
     dev = DEVICE if device is None else device
     bins = [int(b) for b in chromosomeBins]
-    if not isinstance(correctedData, np.ndarray) and hasattr(correctedData, "is_cuda"):
+    if _mem.is_device(correctedData):
         if correctedData.shape[0] != bincount:
             raise ValueError("correctedData has %d bins, chromosomeBinSums says %d" % (correctedData.shape[0], bincount))
         idx, dist = _dev.newref_topk(correctedData, bins, startNum, endNum, int(selectRefAmount))
-        idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+        idx, dist = _mem.to_host(idx), _mem.to_host(dist)
     else:
         X = np.ascontiguousarray(correctedData, dtype=np.float64)
         if X.shape[0] != bincount:
@@ -74,21 +75,18 @@ def _stackCounts(samples):
 
 def toNumpyArray(samples, as_device=False):
     """reference wisetools.py:240-264.  Returns (maskedData [N][S], chromBins, mask)."""
-    torch = _torch()
     counts, chromBins = _stackCounts(samples)
-    masked, mask = _dev.newref_normalize(torch.as_tensor(counts, device=torch.device("cuda", DEVICE)))
+    masked, mask = _dev.newref_normalize(_mem.to_device(counts, DEVICE))
     print('Applying nonzero mask on the data:', (counts.shape[1], counts.shape[0]), 'becomes', tuple(masked.shape))
-    return (masked if as_device else masked.cpu().numpy()), chromBins, mask
+    return (masked if as_device else _mem.to_host(masked)), chromBins, mask
 
 
 def trainPCA(refData, pcacomp=3, as_device=False):
-    """reference wisetools.py:89-101.  refData: [N][S] numpy or CUDA tensor.  Returns (corrected [N][S], pca) where
+    """reference wisetools.py:89-101.  refData: [N][S] numpy or device array.  Returns (corrected [N][S], pca) where
     pca carries components_ and mean_."""
-    torch = _torch()
-    dev = torch.device("cuda", DEVICE)
-    X = refData if isinstance(refData, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(refData, dtype=np.float64), device=dev)
+    X = refData if _mem.is_device(refData) else _mem.to_device(np.ascontiguousarray(refData, dtype=np.float64), DEVICE)
     corrected, comps, mean = _dev.pca_fit_apply(X, pcacomp)
-    return (corrected if as_device else corrected.cpu().numpy()), _FittedPCA(comps, mean)
+    return (corrected if as_device else _mem.to_host(corrected)), _FittedPCA(comps, mean)
 
 
 def getOptimalCutoff(reference, repeats):
@@ -139,9 +137,8 @@ def inflateArrayMulti(array, mask_list):
 # ------------------------------------------------------------------------------------------------------------
 # test path
 # ------------------------------------------------------------------------------------------------------------
-def _torch():
-    import torch
-    return torch
+def _f64(array):
+    return _mem.to_device(np.ascontiguousarray(array, dtype=np.float64), DEVICE)
 
 
 def _refFormatCounts(sample, chromBins):
@@ -165,12 +162,8 @@ def toNumpyRefFormat(sample, chromBins, mask):
 
 def applyPCA(sampleData, mean, components):
     """reference wisetools.py:104-113: sampleData / ((sampleData - mean) C^T C + mean)."""
-    torch = _torch()
-    dev = torch.device("cuda", DEVICE)
-    x = torch.as_tensor(np.ascontiguousarray(sampleData, dtype=np.float64)[None, :], device=dev)
-    out = _dev.apply_pca(x, torch.as_tensor(np.ascontiguousarray(mean, dtype=np.float64), device=dev),
-                         torch.as_tensor(np.ascontiguousarray(components, dtype=np.float64), device=dev))
-    return out[:, 0].cpu().numpy()
+    out = _dev.apply_pca(_f64(np.asarray(sampleData, dtype=np.float64)[None, :]), _f64(mean), _f64(components))
+    return _mem.to_host(out)[:, 0].copy()
 
 
 def prepSample(sample, chromosome_sizes, mask, pca_mean, pca_components):
@@ -181,18 +174,15 @@ def prepSample(sample, chromosome_sizes, mask, pca_mean, pca_components):
 def prepSamples(samples, chromosome_sizes, mask, pca_mean, pca_components, as_device=False):
     """prepSample for a batch: returns T [N][B'] (bin-major, sample-minor; B' = B rounded up to 32 when
     as_device, else exactly B as numpy)."""
-    torch = _torch()
-    dev = torch.device("cuda", DEVICE)
     counts = np.stack([_refFormatCounts(s, chromosome_sizes) for s in samples])
     masked_raw = np.flatnonzero(np.asarray(mask, dtype=bool)).astype(np.int32)
     pm = pc = None
     if pca_components is not None:
-        pm = torch.as_tensor(np.ascontiguousarray(pca_mean, dtype=np.float64), device=dev)
-        pc = torch.as_tensor(np.ascontiguousarray(pca_components, dtype=np.float64), device=dev)
-    T = _dev.test_prep(torch.as_tensor(counts, device=dev), torch.as_tensor(masked_raw, device=dev), pm, pc)
+        pm, pc = _f64(pca_mean), _f64(pca_components)
+    T = _dev.test_prep(_mem.to_device(counts, DEVICE), _mem.to_device(masked_raw, DEVICE), pm, pc)
     if as_device:
         return T
-    return T[:, :len(samples)].cpu().numpy()
+    return _mem.to_host(T)[:, :len(samples)]
 
 
 _TABLE_CACHE = {}
@@ -209,33 +199,27 @@ def _table(indexes, distances, chromosomeBins, cutoff):
 
 
 def repeatTestBatch(testData, indexes, distances, chromosomeBins, chromosomeBinSums, cutoff, threshold, repeats):
-    """repeatTest for many samples at once.  testData: numpy [B][N] (one corrected sample per row) or a CUDA
-    tensor [N][ldb] from prepSamples(as_device=True) together with B = testData.nsamples... plain numpy here.
+    """repeatTest for many samples at once.  testData: numpy [B][N] (one corrected sample per row).
     Returns (resultsZ [B][N], resultsR [B][N], refSizes [B][N] float, stdDevAvg [B])."""
-    torch = _torch()
-    dev = torch.device("cuda", DEVICE)
-    X = np.ascontiguousarray(testData, dtype=np.float64)
+    X = np.asarray(testData, dtype=np.float64)
     b, n = X.shape
-    ldb = _dev.pad32(b)
-    T = torch.ones((n, ldb), dtype=torch.float64, device=dev)
-    T[:, :b] = torch.as_tensor(X, device=dev).T
+    T = np.ones((n, _dev.pad32(b)))                      # bin-major, sample-minor, padded to whole warps of samples
+    T[:, :b] = X.T
     table = _table(indexes, distances, chromosomeBins, cutoff)
-    z, r, sizes, asdef = _dev.zscore_batch(T, b, table, threshold, repeats)
-    return z.cpu().numpy(), r.cpu().numpy(), sizes.cpu().numpy().astype(float), asdef.cpu().numpy()
+    z, r, sizes, asdef = _dev.zscore_batch(_f64(T), b, table, threshold, repeats)
+    return _mem.to_host(z), _mem.to_host(r), _mem.to_host(sizes).astype(float), _mem.to_host(asdef)
 
 
 def trySample(testData, testCopy, indexes, distances, chromosomeBins, chromosomeBinSums, cutoff):
     """reference wisetools.py:407-435: one z-score pass.  `testCopy` carries the -1 marks of earlier passes."""
-    torch = _torch()
-    dev = torch.device("cuda", DEVICE)
     n = len(testData)
-    T = torch.ones((n, 32), dtype=torch.float64, device=dev)
-    C = torch.ones((n, 32), dtype=torch.float64, device=dev)
-    T[:, 0] = torch.as_tensor(np.ascontiguousarray(testData, dtype=np.float64), device=dev)
-    C[:, 0] = torch.as_tensor(np.ascontiguousarray(testCopy, dtype=np.float64), device=dev)
+    T = np.ones((n, 32))
+    C = np.ones((n, 32))
+    T[:, 0] = np.asarray(testData, dtype=np.float64)
+    C[:, 0] = np.asarray(testCopy, dtype=np.float64)
     table = _table(indexes, distances, chromosomeBins, cutoff)
-    z, r, sizes, asdef = _dev.zscore_batch(T, 1, table, float("inf"), 1, copy_init=C)
-    return z[0].cpu().numpy(), r[0].cpu().numpy(), sizes[0].cpu().numpy().astype(float), float(asdef[0].item())
+    z, r, sizes, asdef = _dev.zscore_batch(_f64(T), 1, table, float("inf"), 1, copy_init=_f64(C))
+    return _mem.to_host(z)[0], _mem.to_host(r)[0], _mem.to_host(sizes)[0].astype(float), float(_mem.to_host(asdef)[0])
 
 
 def repeatTest(testData, indexes, distances, chromosomeBins, chromosomeBinSums, cutoff, threshold, repeats):
@@ -251,16 +235,14 @@ def segmentChromosomes(cleanedZ_or_z, refSizes, masked_sizes, chromosomes, minre
     wisecondor.py:233-238, wisetools.py:466-487, triarray.py:59-84).  z, refSizes (and resultsR when
     mineffectsize != 0): numpy [B][N].
     Returns (chromWide [B][nsel], cleanedBins [B][nsel], calls structured array sorted by (sample, chrom, x))."""
-    torch = _torch()
-    dev = torch.device("cuda", DEVICE)
-    z = torch.as_tensor(np.ascontiguousarray(cleanedZ_or_z, dtype=np.float64), device=dev)
-    sizes = torch.as_tensor(np.ascontiguousarray(refSizes).astype(np.int32), device=dev)
+    z = _f64(cleanedZ_or_z)
+    sizes = _mem.to_device(np.ascontiguousarray(refSizes).astype(np.int32), DEVICE)
     r = None
     if mineffectsize != 0:
-        r = torch.as_tensor(np.ascontiguousarray(resultsR, dtype=np.float64), device=dev)
+        r = _f64(resultsR)
     cwz, cleaned, calls = _dev.segment_batch(z, sizes, masked_sizes, [c - 1 for c in chromosomes], minrefbins,
                                              z_threshold, min_search, r=r, mineffectsize=mineffectsize)
-    return cwz.cpu().numpy(), cleaned.cpu().numpy(), calls
+    return _mem.to_host(cwz), _mem.to_host(cleaned), calls
 
 
 def testSamples(samples, ref, z_threshold, chromosomes=tuple(range(1, 23)), mineffectsize=0, minrefbins=25, repeats=5,
@@ -271,7 +253,6 @@ def testSamples(samples, ref, z_threshold, chromosomes=tuple(range(1, 23)), mine
 
     Device: prepSample (K7), repeatTest (K8), fillTriMin + segmentTri (K9).  Host: getOptimalCutoff (once per
     reference), the cleaned->raw coordinate walk and the per-call median of R (wisecondor.py:241-257), inflate."""
-    torch = _torch()
     chromosome_sizes = [int(v) for v in ref['chromosome_sizes']]
     masked_sizes = [int(v) for v in ref['masked_sizes']]
     mask = np.asarray(ref['mask'], dtype=bool)
@@ -283,14 +264,18 @@ def testSamples(samples, ref, z_threshold, chromosomes=tuple(range(1, 23)), mine
     sel = [c - 1 for c in chromosomes]
     out = []
     timeStartTest = time.time()
-    dev = torch.device("cuda", DEVICE)
-    copy_stream = torch.cuda.Stream(device=dev)
+    native = _mem.BACKEND == "native"
+    if not native:
+        torch = _mem.torch()
+        dev = torch.device("cuda", DEVICE)
+        copy_stream = torch.cuda.Stream(device=dev)
 
     def assemble(pending):
         """Host glue of one finished chunk (wisecondor.py:214-222, 241-268): keep mask, cleaned->raw walk, medians, inflate."""
         nb, host, calls, done = pending
-        done.synchronize()
-        z_h, r_h, sizes_h, asdef_h, cwz_h = [t.numpy() for t in host]
+        if done is not None:
+            done.synchronize()
+        z_h, r_h, sizes_h, asdef_h, cwz_h = [t if isinstance(t, np.ndarray) else t.numpy() for t in host]
         call_lo = np.searchsorted(calls['sample'], np.arange(nb), side='left')
         call_hi = np.searchsorted(calls['sample'], np.arange(nb), side='right')
         for b in range(nb):
@@ -331,6 +316,9 @@ def testSamples(samples, ref, z_threshold, chromosomes=tuple(range(1, 23)), mine
             assemble(pending)
         cwz_d, cleaned_d, calls = _dev.segment_batch(z_d, sizes_d, masked_sizes, sel, minrefbins, z_threshold, min_search,
                                                      r=r_d if mineffectsize != 0 else None, mineffectsize=mineffectsize)
+        if native:                                        # synchronous copies on the default stream
+            pending = (nb, [_mem.to_host(t) for t in (z_d, r_d, sizes_d, asdef_d, cwz_d)], calls, None)
+            continue
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(dev))
         host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (z_d, r_d, sizes_d, asdef_d, cwz_d)]
