@@ -1,0 +1,93 @@
+"""GPU parity of the SYMMETRIC reference-bin search (option k5_sym: every unordered pair of bin blocks is contracted
+once and serves both bins, wc_search.cu) against the oracle and against the plain search, through the C ABI."""
+import numpy as np
+import pytest
+
+import c_oracle
+from wisecondor_b200 import _cabi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def sym():
+    """Switches the symmetric search on for the test's calls; hands back a function that sets the first-pass fraction."""
+    ctx = _cabi.context(0)
+
+    def set_frac(frac):
+        _cabi.check(_cabi.lib().wc_set_option(ctx.handle, b"k5_sym", float(frac)))
+    set_frac(8)
+    yield set_frac
+    set_frac(0)
+
+
+def _gpu_search(X, bins, k):
+    from wisecondor_b200 import device
+    idx, dist = device.newref_topk_host(X, bins, 0, X.shape[0], k)
+    return idx, dist, device.last_search_stats(0)
+
+
+def _assert_same(idx, dist, oidx, odist):
+    assert idx.shape == oidx.shape and dist.shape == odist.shape
+    bad = np.flatnonzero((idx != oidx).any(axis=1))
+    assert bad.size == 0, "index rows differ: %d rows, first %s (%s vs %s)" % (bad.size, bad[:8], idx[bad[0]][:10], oidx[bad[0]][:10])
+    assert np.array_equal(dist, odist)
+
+
+@pytest.mark.parametrize("S,k,frac", [(64, 100, 8), (37, 100, 4), (50, 200, 16), (24, 7, 2), (130, 128, 8)])
+def test_symmetric_vs_c_oracle(sym, S, k, frac):
+    sym(frac)
+    bins = [int(b) for b in np.array(synth.chrom_bins(250000)) // 2]          # N ~ 5760: 46 row blocks
+    X = synth.corrected_like(bins, S, seed=5 + S)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, X.shape[0], k)
+    idx, dist, st = _gpu_search(X, bins, k)
+    _assert_same(idx, dist, oidx, odist)
+    assert st["launches"] >= 6                                                 # two K5 passes ran
+
+
+def test_symmetric_equals_plain_search_and_halves_the_tiles(sym):
+    bins = synth.chrom_bins(250000)                                            # BASELINE config 2 shape
+    X = synth.corrected_like(bins, 600, seed=4)
+    idx, dist, st = _gpu_search(X, bins, 100)
+    sym(0)
+    pidx, pdist, pst = _gpu_search(X, bins, 100)
+    _assert_same(idx, dist, pidx, pdist)
+    assert pst["launches"] == 5 and st["launches"] >= 6
+    assert 0.5 < st["tiles"] / pst["tiles"] < 0.62                             # 1/8 + 7/16 = 0.5625 of the plain tiles
+    assert st["exhaustive_rows"] == pst["exhaustive_rows"] == 0
+
+
+def test_symmetric_ties_nan_and_short_candidate_lists(sym):
+    rng = np.random.default_rng(9)
+    bins = [1500, 700, 1400, 60]
+    X = synth.corrected_like(bins, 24, seed=4)
+    X[1500:2200] = X[1500]                  # chromosome 2 = 700 copies of one bin: tie plateaus -> exact fallback rows
+    X[5] = X[1500]
+    X[2300] = X[3] + rng.normal(0, 1e-9, 24)
+    X[10, 3] = np.nan
+    X[2500, 0] = np.inf
+    X[3000] = 1e6                           # distances >= 1e10 are never inserted (wisetools.py:312-314)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, X.shape[0], 100)
+    idx, dist, st = _gpu_search(X, bins, 100)
+    _assert_same(idx, dist, oidx, odist)
+    assert (idx[10] == -1).all() and (idx[2500] == -1).all()
+    bins = [3100, 30, 20]                   # rows of chromosome 1 have 50 candidates only: fillers (wisetools.py:305-306)
+    X = synth.corrected_like(bins, 16, seed=2)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, X.shape[0], 60)
+    idx, dist, st = _gpu_search(X, bins, 60)
+    _assert_same(idx, dist, oidx, odist)
+    assert (idx[:3100, 50:] == -1).all()
+
+
+def test_partial_ranges_and_small_genomes_take_the_plain_path(sym):
+    bins = [int(b) for b in np.array(synth.chrom_bins(250000)) // 2]
+    X = synth.corrected_like(bins, 20, seed=8)
+    from wisecondor_b200 import device
+    idx, dist = device.newref_topk_host(X, bins, 100, 900, 10)
+    assert device.last_search_stats(0)["launches"] == 5
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 100, 900, 10)
+    _assert_same(idx, dist, oidx, odist)
+    small = [300, 200, 250]
+    Xs = synth.corrected_like(small, 20, seed=8)
+    idx, dist = device.newref_topk_host(Xs, small, 0, 750, 10)
+    assert device.last_search_stats(0)["launches"] == 5

@@ -43,7 +43,8 @@ enum { WC_NBUF = 48, WC_NPHASE = 8, WC_NCOUNTER = 8 };
 // Workspace slots (one grow-only device buffer each).
 enum {
     SLOT_XC = 0, SLOT_NORMS, SLOT_ROWCS, SLOT_ROWCE, SLOT_RBMETA, SLOT_CAND_D, SLOT_CAND_J, SLOT_SEGCNT,
-    SLOT_SEGFLAG, SLOT_SLOW, SLOT_SCRATCH, SLOT_IO_X, SLOT_IO_IDX, SLOT_IO_DIST, SLOT_ROWTHR,          // search
+    SLOT_SEGFLAG, SLOT_SLOW, SLOT_SCRATCH, SLOT_IO_X, SLOT_IO_IDX, SLOT_IO_DIST, SLOT_ROWTHR,
+    SLOT_IN_KEY, SLOT_IN_J, SLOT_IN_CNT,                                                               // search
     SLOT_PROF = 20,
     SLOT_T_COPY = 24, SLOT_T_ZT, SLOT_T_RT, SLOT_T_NT, SLOT_T_SD, SLOT_T_FLAGS, SLOT_T_TOTALS, SLOT_T_PROJ,   // test
     SLOT_T_REVCNT = 44, SLOT_T_REVCUR, SLOT_T_DIRTY, SLOT_T_PAIRS,
@@ -65,6 +66,7 @@ struct wc_ctx {
     unsigned timed_mask = 0;        // phases whose event pair is recorded but not yet read (asynchronous calls)
     int k5_stages = 0;              // 0 = automatic TMA ring depth
     int k5_group = 0;               // CTAs sharing a row block per scheduling round of K5 (0 = automatic)
+    int k5_sym = 0;                 // symmetric search: 0 = off, f >= 2 = on with 1/f of the block pairs in the first pass
     int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones
     int debug_profile = 0;          // K5 writes per-CTA cycle counters when set (wc_debug_profile)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)

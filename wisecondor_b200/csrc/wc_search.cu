@@ -48,7 +48,7 @@ constexpr int EXH_THREADS = 256;
 constexpr u64 KEY_NEVER = 0ull;     // threshold key of an inactive row: no finite negative score passes
 
 // Shared memory of K5: [nstages x STAGE_BYTES operand ring, 1024-byte aligned][TopkState][8 warps x scratch]
-struct TopkState {
+struct __align__(16) TopkState {
     uint64_t full[MAX_STAGES];
     uint64_t empty[MAX_STAGES];
     uint64_t gate;       // opened by the leading warps after `lag` chunks; the lagging warps start behind it
@@ -85,6 +85,14 @@ struct TopkArgs {
     u64* row_thr;                // [rows] tightest threshold key any CTA has found for the row (shared between segments)
     int lag;                     // chunks by which warps 4-7 trail warps 0-3 (0 = all in phase)
     int nstages;                 // depth of the TMA ring (3..MAX_STAGES)
+    // --- symmetric search (each unordered pair of bin blocks contracted once), see the host side ---
+    const int* tile_list;        // list mode: the column tile of every list entry (nullptr: arithmetic progression mode)
+    const int* rb_list_off;      // [nrb] first list entry of the row block; a piece's q indexes the list from there
+    int final_prune;             // 1: prune and publish every row's threshold when a piece ends
+    u64* in_key;                 // [Nrows][in_cap] candidates found for a bin while it was on the COLUMN side of a tile
+    int* in_j;
+    int* in_cnt;                 // [Nrows] entries offered (may exceed in_cap: the row then takes the exact fallback)
+    int in_cap;
 };
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -203,6 +211,9 @@ __device__ __noinline__ void prune_row(u64* ck, int* cj, int n, int k, double nr
 // ---------------------------------------------------------------------------------------------------------
 // K5: score tiles on the FP64 tensor cores + streaming top-k filter
 // ---------------------------------------------------------------------------------------------------------
+// SYM = true: besides the row-side filter, every score is also tested against the threshold of its COLUMN's bin and
+// offered to that bin's incoming buffer - the tile (I, J) then serves the row blocks I and J, and (J, I) is never computed.
+template <bool SYM>
 __global__ void __launch_bounds__(TOPK_THREADS, 1)
 wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -240,9 +251,10 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                 const int* pc = a.pieces + (size_t)pi * 5;
                 const int rbp = pc[0], q1 = pc[2], qs = pc[3];
                 const int skip_lo = a.rb_skip_lo[rbp], skip_n = a.rb_skip_n[rbp];
+                const int* tl = a.tile_list ? a.tile_list + a.rb_list_off[rbp] : nullptr;
                 const int row0 = a.row_begin + rbp * BM;
                 for (int q = pc[1]; q < q1; q += qs) {
-                    const int t = q < skip_lo ? q : q + skip_n;
+                    const int t = tl ? tl[q] : (q < skip_lo ? q : q + skip_n);
                     const int col0 = t * BN;
                     for (int kc = 0; kc < a.nkc; ++kc) {
                         mbar_wait(&sm.empty[stage], phase ^ 1u);
@@ -281,6 +293,8 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     const size_t scratch_per_warp = (size_t)a.cap * 12 > 8192 ? (size_t)a.cap * 12 : 8192;
     u64* w_sk = reinterpret_cast<u64*>(scratch + (size_t)warp * scratch_per_warp);
     int* w_sj = reinterpret_cast<int*>(w_sk + a.cap);
+    // SYM: this warp's copy of the 128 column-side thresholds of the current tile (after the 8 scratch areas)
+    u64* w_ct = reinterpret_cast<u64*>(scratch + (size_t)CONSUMER_WARPS * scratch_per_warp) + warp * BN;
     const int r0w = warp * WROWS;               // first tile row of this warp
     u64* w_thr = sm.thr + r0w;
     double* w_nrm = sm.nrm + r0w;
@@ -303,12 +317,52 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     const int* pc = a.pieces + (size_t)pi * 5;
     int rb = pc[0], q = pc[1], q1 = pc[2], qs = pc[3], seg = pc[4];
     int skip_lo = a.rb_skip_lo[rb], skip_n = a.rb_skip_n[rb];
+    const int* tl = a.tile_list ? a.tile_list + a.rb_list_off[rb] : nullptr;
     bool new_piece = true;
+
+    // Prune the rows named in `need` (a warp-uniform mask over the warp's 16 rows): tighten and publish their thresholds.
+    auto prune_rows = [&](unsigned need, u64* ck, int* cj) {
+        while (need) {
+            const int rw = __ffs(need) - 1;
+            need &= need - 1;
+            int n = w_cnt[rw];
+            if (n > a.cap) n = a.cap;
+            u64 thr;
+            int kept;
+            ++pf_nprune;
+            u64* rk = ck + (size_t)(r0w + rw) * a.cap;
+            int* rj = cj + (size_t)(r0w + rw) * a.cap;
+            __threadfence_block();
+            if (a.cap <= 512)
+                prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sk, w_sj, &thr, &kept);
+            else
+                prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sk, w_sj, &thr, &kept);
+            if (lane == 0) {
+                if (kept > a.cap - BN) {       // a tie plateau wider than the buffer: exact fallback
+                    w_flag[rw] = 1;
+                    w_thr[rw] = KEY_NEVER;
+                    w_cnt[rw] = 0;
+                } else {
+                    const int row = a.row_begin + rb * BM + r0w + rw;
+                    const u64 other = atomicMin(a.row_thr + (row - a.row_begin), thr);   // publish; adopt a tighter one
+                    w_thr[rw] = other < thr ? other : thr;
+                    w_cnt[rw] = kept;
+                }
+            }
+            __syncwarp();
+        }
+    };
     int tcount = 0;                             // tiles done by this CTA (debug timeline index)
     while (true) {
         if (q >= q1) {
             // piece finished: flush this warp's rows of its segment, move to the next piece
             __syncwarp();
+            if (a.final_prune) {
+                // every row leaves its best threshold behind: the bins on the column side of later tiles are filtered by it
+                const unsigned need = __ballot_sync(0xffffffffu, lane < WROWS && w_cnt[lane] > a.k + 24 &&
+                                                                     w_cnt[lane] <= a.cap && !w_flag[lane]);
+                prune_rows(need, a.cand_key + (size_t)seg * seg_stride, a.cand_j + (size_t)seg * seg_stride);
+            }
             if (lane < WROWS) {
                 a.seg_cnt[(size_t)seg * BM + r0w + lane] = w_cnt[lane] > a.cap ? a.cap : w_cnt[lane];
                 a.seg_flag[(size_t)seg * BM + r0w + lane] = w_flag[lane];
@@ -317,6 +371,7 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             pc = a.pieces + (size_t)pi * 5;
             rb = pc[0]; q = pc[1]; q1 = pc[2]; qs = pc[3]; seg = pc[4];
             skip_lo = a.rb_skip_lo[rb]; skip_n = a.rb_skip_n[rb];
+            tl = a.tile_list ? a.tile_list + a.rb_list_off[rb] : nullptr;
             new_piece = true;
             continue;
         }
@@ -341,9 +396,16 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             }
             __syncwarp();
         }
-        const int t = q < skip_lo ? q : q + skip_n;
+        const int t = tl ? tl[q] : (q < skip_lo ? q : q + skip_n);
         const int col0 = t * BN;
         q += qs;
+        if (SYM) {
+            // the column bins' published thresholds (L2 -> this warp's shared copy), landed long before the epilogue
+            __syncwarp();                           // the previous tile's epilogue has finished reading the copy
+            cp_async_16(w_ct + 2 * lane, a.row_thr + col0 + 2 * lane);
+            cp_async_16(w_ct + 64 + 2 * lane, a.row_thr + col0 + 64 + 2 * lane);
+            cp_async_commit();
+        }
         u64 shared_thr = ~0ull;                 // issued now, consumed after the tile's MMAs: latency fully hidden
         if (lane < WROWS) {
             const int row = a.row_begin + rb * BM + r0w + lane;
@@ -433,6 +495,7 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
         const long long pf_e0 = clock64();
         if (tr_on) tr[1] = pf_e0;
         if (lane < WROWS && shared_thr < w_thr[lane]) w_thr[lane] = shared_thr;
+        if (SYM) cp_async_wait<0>();
         __syncwarp();
         u64* ck = a.cand_key + (size_t)seg * seg_stride;
         int* cj = a.cand_j + (size_t)seg * seg_stride;
@@ -440,14 +503,17 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
         for (int mt = 0; mt < 2; ++mt) {
             const int rw = mt * 8 + pg;                   // row within the warp's 16
             const u64 thr = w_thr[rw];
-            unsigned mask = 0;
+            unsigned mask = 0, cmask = 0;
 #pragma unroll
             for (int nt = 0; nt < 16; ++nt) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    if ((u64)__double_as_longlong(acc[mt][nt][e]) <= thr) mask |= 1u << (nt * 2 + e);
+                for (int e = 0; e < 2; ++e) {
+                    const u64 bits = (u64)__double_as_longlong(acc[mt][nt][e]);
+                    if (bits <= thr) mask |= 1u << (nt * 2 + e);
+                    if (SYM && bits <= w_ct[nt * 8 + 4 * e + q4]) cmask |= 1u << (nt * 2 + e);
+                }
             }
-            if (mask) {
+            if (mask | cmask) {
                 // Rare path, kept deliberately compact (a fully unrolled version pushed the kernel far past the
                 // instruction cache; a local-memory copy thrashed the tiny L1): park this row's 32 accumulators in
                 // the warp's shared scratch, lane-interleaved, and walk the set bits.
@@ -485,6 +551,26 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                         ++w;
                     }
                 }
+                if (SYM && cmask) {
+                    // column side: offer (bin j <- candidate i) to j's incoming buffer.  Rare (the thresholds are tight
+                    // by the time the symmetric pass runs), so one global atomic per entry is affordable.
+                    const int i = a.row_begin + rb * BM + r0w + rw;
+                    while (cmask) {
+                        const int bit = __ffs(cmask) - 1;
+                        cmask &= cmask - 1;
+                        const int j = col0 + (bit >> 1) * 8 + 4 * (bit & 1) + q4;
+                        const u64 key = tmp[bit * 32];
+                        if (((unsigned)(key >> 32) & 0x7ff00000u) == 0x7ff00000u || j >= a.N || i >= a.row_end) continue;
+                        const int jcs = __ldg(a.row_cs + j);
+                        if ((unsigned)(i - jcs) < (unsigned)(__ldg(a.row_ce + j) - jcs)) continue;   // j's own chromosome
+                        const int w = atomicAdd(a.in_cnt + j, 1);
+                        if (w < a.in_cap) {
+                            a.in_key[(size_t)j * a.in_cap + w] = key;
+                            a.in_j[(size_t)j * a.in_cap + w] = i;
+                        }
+                        ++pf_emit;
+                    }
+                }
             }
         }
         __syncwarp();
@@ -493,38 +579,7 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
         if (tr_on) tr[2] = pf_p0;
         // ---- prune rows whose buffer could overflow during the next tile ----
         // (one ballot finds them: the common case - nothing to prune - costs a single shared-memory read per lane)
-        unsigned need = __ballot_sync(0xffffffffu, lane < WROWS && w_cnt[lane] > a.cap - BN && !w_flag[lane]);
-        while (need) {
-            const int rw = __ffs(need) - 1;
-            need &= need - 1;
-            int n = w_cnt[rw];
-            if (n > a.cap) n = a.cap;
-            {
-                u64 thr;
-                int kept;
-                ++pf_nprune;
-                u64* rk = ck + (size_t)(r0w + rw) * a.cap;
-                int* rj = cj + (size_t)(r0w + rw) * a.cap;
-                __threadfence_block();
-                if (a.cap <= 512)
-                    prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sk, w_sj, &thr, &kept);
-                else
-                    prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sk, w_sj, &thr, &kept);
-                if (lane == 0) {
-                    if (kept > a.cap - BN) {       // a tie plateau wider than the buffer: exact fallback
-                        w_flag[rw] = 1;
-                        w_thr[rw] = KEY_NEVER;
-                        w_cnt[rw] = 0;
-                    } else {
-                        const int row = a.row_begin + rb * BM + r0w + rw;
-                        const u64 other = atomicMin(a.row_thr + (row - a.row_begin), thr);   // publish; adopt a tighter one
-                        w_thr[rw] = other < thr ? other : thr;
-                        w_cnt[rw] = kept;
-                    }
-                }
-                __syncwarp();
-            }
-        }
+        prune_rows(__ballot_sync(0xffffffffu, lane < WROWS && w_cnt[lane] > a.cap - BN && !w_flag[lane]), ck, cj);
         pf_prune += clock64() - pf_p0;
         if (tr_on) tr[3] = clock64();
     }
@@ -601,6 +656,10 @@ struct FinArgs {
     int* slow_list;
     int* slow_count;
     int bulk;               // 1: rows are 16-byte aligned (S even): stage candidate rows with 16-byte cp.async
+    const u64* in_key;      // symmetric search: the row's incoming (column-side) candidates, or nullptr
+    const int* in_j;
+    const int* in_cnt;
+    int in_cap;
 };
 
 // One CTA per target row.
@@ -629,11 +688,31 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     int* out_i = a.idx_out + (size_t)rloc * a.k;
     double* out_d = a.dist_out + (size_t)rloc * a.k;
 
+    // candidate sources of the row: its segments (one per K5 piece of the row block) and, after a symmetric search,
+    // the incoming buffer
+    const int nsrc = nseg + (a.in_key != nullptr ? 1 : 0);
+    auto source = [&](int s, const u64*& keys, const int*& js) -> int {
+        if (s < nseg) {
+            const size_t off = ((size_t)(seg0 + s) * BM + rl) * a.cap;
+            keys = a.cand_key + off;
+            js = a.cand_j + off;
+            return a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
+        }
+        keys = a.in_key + (size_t)rloc * a.in_cap;
+        js = a.in_j + (size_t)rloc * a.in_cap;
+        const int n = a.in_cnt[rloc];
+        return n < a.in_cap ? n : a.in_cap;
+    };
     if (tid == 0) {
         int tot = 0, fl = 0;
         for (int s = 0; s < nseg; ++s) {
             tot += a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
             fl |= a.seg_flag[(size_t)(seg0 + s) * BM + rl];
+        }
+        if (a.in_key != nullptr) {
+            const int n = a.in_cnt[rloc];
+            if (n > a.in_cap) fl = 1;                   // more offers than the buffer holds: exact fallback
+            tot += n;
         }
         s_total = tot;
         s_flag = fl;
@@ -654,9 +733,10 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
 
     // ---- 1. select ----
     double mn = INFINITY, mx = -INFINITY;
-    for (int s = 0; s < nseg; ++s) {
-        const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
-        const u64* cd = a.cand_key + ((size_t)(seg0 + s) * BM + rl) * a.cap;
+    for (int s = 0; s < nsrc; ++s) {
+        const u64* cd;
+        const int* cjs;
+        const int n = source(s, cd, cjs);
         for (int e = tid; e < n; e += FIN_THREADS) {
             double d = dist_of_key(cd[e]);
             mn = fmin(mn, d);
@@ -670,9 +750,10 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
 #pragma unroll
     for (int w = 0; w < FIN_THREADS / 32; ++w) { mn = fmin(mn, s_red[0][w]); mx = fmax(mx, s_red[1][w]); }
     const float scale = (mx > mn) ? (float)(HIST_BINS - 1) / (float)(mx - mn) : 0.0f;
-    for (int s = 0; s < nseg; ++s) {
-        const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
-        const u64* cd = a.cand_key + ((size_t)(seg0 + s) * BM + rl) * a.cap;
+    for (int s = 0; s < nsrc; ++s) {
+        const u64* cd;
+        const int* cjs;
+        const int n = source(s, cd, cjs);
         for (int e = tid; e < n; e += FIN_THREADS) atomicAdd(&hist[bucket_of(dist_of_key(cd[e]), mn, scale)], 1);
     }
     __syncthreads();
@@ -700,9 +781,10 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     __syncthreads();
     const int bstar = s_bstar;
     double vstar = -INFINITY;
-    for (int s = 0; s < nseg; ++s) {
-        const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
-        const u64* cd = a.cand_key + ((size_t)(seg0 + s) * BM + rl) * a.cap;
+    for (int s = 0; s < nsrc; ++s) {
+        const u64* cd;
+        const int* cjs;
+        const int n = source(s, cd, cjs);
         for (int e = tid; e < n; e += FIN_THREADS) {
             double d = dist_of_key(cd[e]);
             if (bucket_of(d, mn, scale) <= bstar) vstar = fmax(vstar, d);
@@ -715,13 +797,14 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
 #pragma unroll
     for (int w = 0; w < FIN_THREADS / 32; ++w) vstar = fmax(vstar, s_red[0][w]);
     const double window = vstar + a.mcoef * (a.norms[row] + fabs(vstar));
-    for (int s = 0; s < nseg; ++s) {
-        const int n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
-        const size_t off = ((size_t)(seg0 + s) * BM + rl) * a.cap;
+    for (int s = 0; s < nsrc; ++s) {
+        const u64* cd;
+        const int* cjs;
+        const int n = source(s, cd, cjs);
         for (int e = tid; e < n; e += FIN_THREADS) {
-            if (dist_of_key(a.cand_key[off + e]) <= window) {
+            if (dist_of_key(cd[e]) <= window) {
                 int slot = atomicAdd(&s_p, 1);
-                if (slot < a.shortcap) ex_j[slot] = a.cand_j[off + e];
+                if (slot < a.shortcap) ex_j[slot] = cjs[e];
             }
         }
     }
@@ -959,6 +1042,64 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 }  // namespace
 
+namespace {
+// Which CTA computes which tiles, in which order.  prefix[rb+1]-prefix[rb] = number of tiles of row block rb; a piece
+// is (row block, arithmetic progression q0, q0+step, ... < q1 over that block's tile indices).
+// The centred matrix (Npad x ld doubles; 288 MB at 600 x 50 kb) does not fit the 126 MB L2, and every tile needs a
+// 128-row A panel and a 128-row B panel of it.  With CTAs spread over unrelated columns every panel comes from DRAM for
+// every tile (measured: 188 GB per launch at 600 x 50 kb).  So work is handed out in *rounds*: in a round a group of G
+// CTAs shares one row block and walks its tiles interleaved (CTA j takes tiles j, j+G, ...), all groups starting
+// together.  The CTAs then sit on (nearly) the same B panel at the same time - it is read from DRAM once per round -
+// and the live A panels (grid/G of them) stay L2-resident.  Row blocks left after the last full round are cut into
+// contiguous ranges that level the CTAs' tile counts (water-filling), so the balance of the plain equal split is kept.
+struct Piece { int cta, rb, q0, q1, step, seg, pass; };
+void schedule_pieces(const std::vector<int>& prefix, int nrb, int grid, int G, bool rounds_on, int pass,
+                     std::vector<Piece>& pieces) {
+    std::vector<long long> load(grid, 0);
+    if (G > grid) G = grid;
+    if (G < 1) G = 1;
+    const int groups = grid / G;
+    const int rounds = rounds_on ? nrb / groups : 0;
+    for (int r = 0; r < rounds; ++r)
+        for (int g = 0; g < groups; ++g) {
+            const int rb = r * groups + g;
+            const int nv = prefix[rb + 1] - prefix[rb];
+            for (int j = 0; j < G && j < nv; ++j) {
+                pieces.push_back({g * G + j, rb, j, nv, G, 0, pass});
+                load[g * G + j] += (nv - j + G - 1) / G;
+            }
+        }
+    const int rb_left = rounds * groups;
+    long long left = prefix[nrb] - prefix[rb_left];
+    if (left > 0) {
+        long long lo = 0, hi = 0;
+        for (int c = 0; c < grid; ++c) hi = std::max(hi, load[c]);
+        hi += left;                                       // level with sum(max(0, level - load)) >= left
+        while (lo < hi) {
+            const long long mid = (lo + hi) / 2;
+            long long cap_sum = 0;
+            for (int c = 0; c < grid; ++c) cap_sum += std::max(0ll, mid - load[c]);
+            if (cap_sum >= left) hi = mid; else lo = mid + 1;
+        }
+        int rb = rb_left, q = 0;
+        for (int c = 0; c < grid && left > 0; ++c) {
+            long long want = std::min(left, std::max(0ll, lo - load[c]));
+            while (want > 0) {
+                const int nv = prefix[rb + 1] - prefix[rb];
+                if (q >= nv) { ++rb; q = 0; continue; }
+                const int take = (int)std::min<long long>(want, nv - q);
+                pieces.push_back({c, rb, q, q + take, 1, 0, pass});
+                load[c] += take;
+                q += take;
+                want -= take;
+                left -= take;
+            }
+        }
+    }
+}
+
+}  // namespace
+
 extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int S, const int* chrom_bins_h,
                               int nchrom, int row_begin, int row_end, int refsize, int32_t* idx_d, double* dist_d,
                               void* stream_v) {
@@ -1037,60 +1178,65 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     // same time - it is read from DRAM once per round - and the live A panels (grid/G of them) stay L2-resident.
     // Row blocks left after the last full round are cut into contiguous column ranges that level the CTAs' tile
     // counts (water-filling), so the balance of the plain equal split is kept.
-    struct Piece { int cta, rb, q0, q1, step, seg; };
+    const double tile_bytes = (double)BM * ld * sizeof(double);
+    const double matrix_bytes = (double)Npad * ld * sizeof(double);
+    int G = ctx->k5_group;
+    if (G <= 0) {
+        G = 1;
+        if (matrix_bytes > 64e6)
+            while (G < 8 && (double)(grid / G) * tile_bytes > 48e6) G *= 2;
+    }
+    const bool rounds_on = matrix_bytes > 64e6 || ctx->k5_group > 0;
+
+    // Symmetric search (whole-matrix calls): d(i, j) = d(j, i), so each unordered pair of bin blocks {I, J} needs one
+    // tile, not two - the tile's scores are filtered against the ROW bins' thresholds and against the COLUMN bins'
+    // thresholds, and the column side's survivors go to per-bin incoming buffers through global atomics.  That only
+    // pays once thresholds are tight (an unfiltered column side would flood the buffers), hence two passes:
+    //   pass A  a symmetric subset of the block pairs ((I + J) % sym_frac == 0, and the diagonal) is computed
+    //           from both sides the ordinary way, rows only; every bin leaves a threshold ~ its k-th smallest distance
+    //           among 1/sym_frac of all candidates;
+    //   pass B  the other pairs, once each: block I takes J = I + 1 ... I + nb/2 (cyclically), so the load is level and all
+    //           CTAs slide over the same window of B panels (L2-resident) at the same time.
+    // Work: (1/sym_frac + (1 - 1/sym_frac) / 2) of the plain search.
+    const int sym_frac = ctx->k5_sym;
+    const bool sym = sym_frac >= 2 && row_begin == 0 && row_end == N && nrb >= 24;
     std::vector<Piece> pieces;
-    std::vector<long long> load(grid, 0);
-    {
-        const double tile_bytes = (double)BM * ld * sizeof(double);
-        const double matrix_bytes = (double)Npad * ld * sizeof(double);
-        int G = ctx->k5_group;
-        if (G <= 0) {
-            G = 1;
-            if (matrix_bytes > 64e6)
-                while (G < 8 && (double)(grid / G) * tile_bytes > 48e6) G *= 2;
+    std::vector<int> listA, listB, offA, offB;
+    int gridA = 0, gridB = 0;
+    long long tilesA = 0, tilesB = 0;
+    if (!sym) {
+        schedule_pieces(prefix, nrb, grid, G, rounds_on, 0, pieces);
+    } else {
+        const int nb = nrb;
+        // symmetric in (I, J), and every block meets exactly 1/sym_frac of the others, spread evenly over the genome
+        auto in_sample = [&](int I, int J) { return I == J || (I + J) % sym_frac == 0; };
+        auto valid = [&](int I, int t) { return !(t >= skip_lo[I] && t < skip_lo[I] + skip_n[I]); };
+        offA.assign(nb + 1, 0);
+        offB.assign(nb + 1, 0);
+        for (int I = 0; I < nb; ++I) {
+            for (int t = 0; t < nb; ++t)
+                if (valid(I, t) && in_sample(I, t)) listA.push_back(t);
+            offA[I + 1] = (int)listA.size();
+            for (int dlt = 1; dlt <= nb / 2; ++dlt) {
+                if (2 * dlt == nb && I >= nb / 2) continue;      // the antipodal pair belongs to its lower block
+                const int t = (I + dlt) % nb;
+                if (valid(I, t) && !in_sample(I, t)) listB.push_back(t);
+            }
+            offB[I + 1] = (int)listB.size();
         }
-        if (G > grid) G = grid;
-        const int groups = grid / G;
-        const int rounds = (matrix_bytes > 64e6 || ctx->k5_group > 0) ? nrb / groups : 0;
-        for (int r = 0; r < rounds; ++r)
-            for (int g = 0; g < groups; ++g) {
-                const int rb = r * groups + g;
-                const int nv = prefix[rb + 1] - prefix[rb];
-                for (int j = 0; j < G && j < nv; ++j) {
-                    pieces.push_back({g * G + j, rb, j, nv, G, 0});
-                    load[g * G + j] += (nv - j + G - 1) / G;
-                }
-            }
-        const int rb_left = rounds * groups;
-        long long left = prefix[nrb] - prefix[rb_left];
-        if (left > 0) {
-            long long lo = 0, hi = 0;
-            for (int c = 0; c < grid; ++c) hi = std::max(hi, load[c]);
-            hi += left;                                       // level with sum(max(0, level - load)) >= left
-            while (lo < hi) {
-                const long long mid = (lo + hi) / 2;
-                long long cap_sum = 0;
-                for (int c = 0; c < grid; ++c) cap_sum += std::max(0ll, mid - load[c]);
-                if (cap_sum >= left) hi = mid; else lo = mid + 1;
-            }
-            int rb = rb_left, q = 0;
-            for (int c = 0; c < grid && left > 0; ++c) {
-                long long want = std::min(left, std::max(0ll, lo - load[c]));
-                while (want > 0) {
-                    const int nv = prefix[rb + 1] - prefix[rb];
-                    if (q >= nv) { ++rb; q = 0; continue; }
-                    const int take = (int)std::min<long long>(want, nv - q);
-                    pieces.push_back({c, rb, q, q + take, 1, 0});
-                    load[c] += take;
-                    q += take;
-                    want -= take;
-                    left -= take;
-                }
-            }
-        }
+        tilesA = (long long)listA.size();
+        tilesB = (long long)listB.size();
+        gridA = (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesA + 7) / 8));
+        gridB = (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesB + 7) / 8));
+        schedule_pieces(offA, nb, gridA, 1, false, 0, pieces);       // pass A: whole row blocks per CTA, one threshold each
+        int GB = G;
+        if (GB > gridB) GB = gridB;
+        schedule_pieces(offB, nb, gridB, GB, rounds_on, 1, pieces);
     }
     // segments (one candidate buffer set per piece) are numbered row-block-major so that K6 finds a row's pieces side by side
-    std::vector<int> rb_seg_first(nrb, 0), rb_seg_count(nrb, 0), cta_piece_begin(grid + 1, 0), piece_tab;
+    // One piece table for both passes (pass A's pieces first); cta_piece_begin holds, per pass, grid+1 absolute indices.
+    const int grid0 = sym ? gridA : grid;            // CTAs of the first (or only) launch
+    std::vector<int> rb_seg_first(nrb, 0), rb_seg_count(nrb, 0), cta_piece_begin, piece_tab;
     const int nseg = (int)pieces.size();
     {
         for (const Piece& pc : pieces) rb_seg_count[pc.rb]++;
@@ -1098,18 +1244,36 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         for (int rb = 0; rb < nrb; ++rb) { rb_seg_first[rb] = run; run += rb_seg_count[rb]; }
         std::vector<int> next(rb_seg_first);
         for (Piece& pc : pieces) pc.seg = next[pc.rb]++;
-        std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.cta < y.cta; });
+        std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) {
+            return x.pass != y.pass ? x.pass < y.pass : x.cta < y.cta;
+        });
         piece_tab.resize((size_t)std::max(nseg, 1) * 5);
+        std::vector<int> per_cta0(grid0 + 1, 0), per_cta1(gridB + 1, 0);
+        int n0 = 0;
         for (int i = 0; i < nseg; ++i) {
             const Piece& pc = pieces[i];
-            cta_piece_begin[pc.cta + 1]++;
+            if (pc.pass == 0) { per_cta0[pc.cta + 1]++; ++n0; } else { per_cta1[pc.cta + 1]++; }
             piece_tab[(size_t)i * 5 + 0] = pc.rb;
             piece_tab[(size_t)i * 5 + 1] = pc.q0;
             piece_tab[(size_t)i * 5 + 2] = pc.q1;
             piece_tab[(size_t)i * 5 + 3] = pc.step;
             piece_tab[(size_t)i * 5 + 4] = pc.seg;
         }
-        for (int c = 0; c < grid; ++c) cta_piece_begin[c + 1] += cta_piece_begin[c];
+        for (int c = 0; c < grid0; ++c) per_cta0[c + 1] += per_cta0[c];
+        cta_piece_begin = per_cta0;
+        if (sym) {
+            per_cta1[0] = n0;
+            for (int c = 0; c < gridB; ++c) per_cta1[c + 1] += per_cta1[c];
+            cta_piece_begin.insert(cta_piece_begin.end(), per_cta1.begin(), per_cta1.end());
+        }
+    }
+    // the symmetric search's tile lists travel behind the piece table: [offA nrb+1][offB nrb+1][listA][listB]
+    std::vector<int> sym_tab;
+    if (sym) {
+        sym_tab.insert(sym_tab.end(), offA.begin(), offA.end());
+        sym_tab.insert(sym_tab.end(), offB.begin(), offB.end());
+        sym_tab.insert(sym_tab.end(), listA.begin(), listA.end());
+        sym_tab.insert(sym_tab.end(), listB.begin(), listB.end());
     }
 
     // ---- workspace ----------------------------------------------------------------------------------------
@@ -1120,7 +1284,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     if ((rc = wc_reserve(ctx, SLOT_NORMS, Npad * sizeof(double), (void**)&norms))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_ROWCS, (size_t)N * sizeof(int), (void**)&d_row_cs))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_ROWCE, (size_t)N * sizeof(int), (void**)&d_row_ce))) return rc;
-    const size_t meta_ints = 4 * (size_t)nrb + (size_t)grid + 1 + piece_tab.size();
+    const size_t meta_ints = 4 * (size_t)nrb + cta_piece_begin.size() + piece_tab.size() + sym_tab.size();
     if ((rc = wc_reserve(ctx, SLOT_RBMETA, meta_ints * sizeof(int), (void**)&d_meta))) return rc;
     const size_t cand_n = (size_t)std::max(nseg, 1) * BM * cap;
     if ((rc = wc_reserve(ctx, SLOT_CAND_D, cand_n * sizeof(u64), (void**)&cand_key))) return rc;
@@ -1129,13 +1293,25 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     if ((rc = wc_reserve(ctx, SLOT_SEGFLAG, (size_t)std::max(nseg, 1) * BM * sizeof(int), (void**)&seg_flag))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_SLOW, ((size_t)rows + 1) * sizeof(int), (void**)&slow))) return rc;
     u64* row_thr;
-    if ((rc = wc_reserve(ctx, SLOT_ROWTHR, (size_t)rows * sizeof(u64), (void**)&row_thr))) return rc;
+    const size_t thr_n = (size_t)nrb * BM + BN;            // padded: the symmetric pass reads whole column tiles of it
+    if ((rc = wc_reserve(ctx, SLOT_ROWTHR, thr_n * sizeof(u64), (void**)&row_thr))) return rc;
+    u64* in_key = nullptr; int* in_j = nullptr; int* in_cnt = nullptr;
+    // a bin's threshold after pass A lets through ~ k * sym_frac / 2 of the column-side scores; 4x head room
+    int in_cap = 0;
+    if (sym) {
+        in_cap = 256;
+        while (in_cap < 2 * k * sym_frac) in_cap *= 2;
+        if ((rc = wc_reserve(ctx, SLOT_IN_KEY, (size_t)rows * in_cap * sizeof(u64), (void**)&in_key))) return rc;
+        if ((rc = wc_reserve(ctx, SLOT_IN_J, (size_t)rows * in_cap * sizeof(int), (void**)&in_j))) return rc;
+        if ((rc = wc_reserve(ctx, SLOT_IN_CNT, (size_t)rows * sizeof(int), (void**)&in_cnt))) return rc;
+    }
     int* d_skip_lo = d_meta;
     int* d_skip_n = d_skip_lo + nrb;
     int* d_seg_first = d_skip_n + nrb;
     int* d_seg_count = d_seg_first + nrb;
     int* d_cta_piece = d_seg_count + nrb;
-    int* d_pieces = d_cta_piece + grid + 1;
+    int* d_pieces = d_cta_piece + cta_piece_begin.size();
+    int* d_sym = d_pieces + piece_tab.size();
 
     {
         // the metadata is a pure function of (N, chromosome sizes, row range, grid): repeated calls on the same problem
@@ -1148,9 +1324,10 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         const unsigned long long ptrs[2] = {(unsigned long long)(uintptr_t)d_row_cs, (unsigned long long)(uintptr_t)d_meta};
         mix(ptrs, sizeof(ptrs));
         mix(chrom_bins_h, (size_t)nchrom * sizeof(int));
-        const int dims[6] = {N, row_begin, row_end, grid, nrb, nseg};
+        const int dims[8] = {N, row_begin, row_end, grid0, nrb, nseg, sym ? sym_frac : 0, gridB};
         mix(dims, sizeof(dims));
         mix(piece_tab.data(), piece_tab.size() * sizeof(int));
+        mix(cta_piece_begin.data(), cta_piece_begin.size() * sizeof(int));
         if (h != ctx->sched_hash) {
             WC_CUDA(cudaMemcpyAsync(d_row_cs, row_cs.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, stream));
             WC_CUDA(cudaMemcpyAsync(d_row_ce, row_ce.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1158,14 +1335,17 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
             WC_CUDA(cudaMemcpyAsync(d_skip_n, skip_n.data(), (size_t)nrb * sizeof(int), cudaMemcpyHostToDevice, stream));
             WC_CUDA(cudaMemcpyAsync(d_seg_first, rb_seg_first.data(), (size_t)nrb * sizeof(int), cudaMemcpyHostToDevice, stream));
             WC_CUDA(cudaMemcpyAsync(d_seg_count, rb_seg_count.data(), (size_t)nrb * sizeof(int), cudaMemcpyHostToDevice, stream));
-            WC_CUDA(cudaMemcpyAsync(d_cta_piece, cta_piece_begin.data(), (size_t)(grid + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+            WC_CUDA(cudaMemcpyAsync(d_cta_piece, cta_piece_begin.data(), cta_piece_begin.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
             WC_CUDA(cudaMemcpyAsync(d_pieces, piece_tab.data(), piece_tab.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            if (sym)
+                WC_CUDA(cudaMemcpyAsync(d_sym, sym_tab.data(), sym_tab.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
             ctx->sched_hash = h;
         }
     }
     WC_CUDA(cudaMemsetAsync(slow, 0, sizeof(int), stream));
     WC_CUDA(cudaMemsetAsync(seg_cnt, 0, (size_t)std::max(nseg, 1) * BM * sizeof(int), stream));
     WC_CUDA(cudaMemsetAsync(seg_flag, 0, (size_t)std::max(nseg, 1) * BM * sizeof(int), stream));
+    if (sym) WC_CUDA(cudaMemsetAsync(in_cnt, 0, (size_t)rows * sizeof(int), stream));
 
     // ---- K4 -------------------------------------------------------------------------------------------------
     WC_CUDA(cudaEventRecord(ctx->ev[0], stream));
@@ -1204,22 +1384,40 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     ta.cap = cap; ta.k = k; ta.mcoef = mcoef; ta.tau_init = 1e10 * (1.0 + 1e-6);
     ta.row_thr = row_thr;
     ta.lag = ctx->k5_lag;
-    ta.nstages = cap <= 512 ? 5 : 3;
+    ta.nstages = cap <= 512 ? (sym ? 4 : 5) : 3;          // the symmetric pass keeps 8 KiB of column thresholds in shared memory
     if (ctx->k5_stages >= 3 && ctx->k5_stages <= MAX_STAGES) ta.nstages = ctx->k5_stages;
+    ta.tile_list = nullptr; ta.rb_list_off = nullptr; ta.final_prune = sym ? 1 : 0;
+    ta.in_key = in_key; ta.in_j = in_j; ta.in_cnt = in_cnt; ta.in_cap = in_cap;
     ta.prof = nullptr;
     ta.trace = nullptr;
+    const int grid_prof = sym ? std::max(gridA, gridB) : grid;
     if (ctx->debug_profile) {
-        if ((rc = wc_reserve(ctx, SLOT_PROF, ((size_t)grid * 8 + 512) * sizeof(long long), (void**)&ta.prof))) return rc;
-        WC_CUDA(cudaMemsetAsync(ta.prof, 0, ((size_t)grid * 8 + 512) * sizeof(long long), stream));
-        ta.trace = ta.prof + (size_t)grid * 8;
+        if ((rc = wc_reserve(ctx, SLOT_PROF, ((size_t)grid_prof * 8 + 512) * sizeof(long long), (void**)&ta.prof))) return rc;
+        WC_CUDA(cudaMemsetAsync(ta.prof, 0, ((size_t)grid_prof * 8 + 512) * sizeof(long long), stream));
+        ta.trace = ta.prof + (size_t)grid_prof * 8;
     }
     const size_t topk_smem = (size_t)ta.nstages * STAGE_BYTES + sizeof(TopkState) +
-                             (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192);
+                             (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192) +
+                             (sym ? (size_t)CONSUMER_WARPS * BN * sizeof(u64) : 0);
     if (topk_smem > 227 * 1024) { wc_set_error("K5 shared memory %zu exceeds 227 KiB", topk_smem); return WC_ERR_INTERNAL; }
-    WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+    WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
     wc_fill_u64_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(row_thr, (size_t)rows, host_key_of_tau(ta.tau_init));
+    wc_fill_u64_kernel<<<(unsigned)((thr_n - rows + 255) / 256), 256, 0, stream>>>(row_thr + rows, thr_n - (size_t)rows, KEY_NEVER);
     WC_CUDA(cudaEventRecord(ctx->ev[2], stream));
-    wc_dist_topk_kernel<<<grid, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+    if (!sym) {
+        wc_dist_topk_kernel<false><<<grid, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+    } else {
+        WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+        const int nb1 = nrb + 1;
+        ta.tile_list = d_sym + 2 * nb1;                                  // pass A
+        ta.rb_list_off = d_sym;
+        wc_dist_topk_kernel<false><<<gridA, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+        WC_CUDA(cudaGetLastError());
+        ta.tile_list = d_sym + 2 * nb1 + (int)listA.size();              // pass B
+        ta.rb_list_off = d_sym + nb1;
+        ta.cta_piece_begin = d_cta_piece + (gridA + 1);
+        wc_dist_topk_kernel<true><<<gridB, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+    }
     WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[3], stream));
 
@@ -1231,6 +1429,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     fa.shortcap = k <= 128 ? 256 : 512;
     fa.mcoef = mcoef; fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
     fa.bulk = (S % 2 == 0 && (reinterpret_cast<uintptr_t>(corrected_d) & 15) == 0) ? 1 : 0;
+    fa.in_key = in_key; fa.in_j = in_j; fa.in_cnt = in_cnt; fa.in_cap = in_cap;
     const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 +
                             HIST_BINS * 4;
     WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
@@ -1242,7 +1441,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     int nslow = 0;
     WC_CUDA(cudaMemcpyAsync(&nslow, slow, sizeof(int), cudaMemcpyDeviceToHost, stream));
     WC_CUDA(cudaStreamSynchronize(stream));
-    long long launches = 5;
+    long long launches = sym ? 6 : 5;          // two fills, K4, K5 (one or two passes), K6
     if (nslow > 0) {
         const int batch = 64;
         double* scratch;
@@ -1267,8 +1466,9 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     if (nslow > 0) { WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7])); ctx->phase_ms[3] = ms; }
     ctx->counter[0] = launches;
     ctx->counter[1] = nslow;
-    ctx->counter[3] = total_tiles;
-    ctx->counter[4] = grid;
+    ctx->counter[2] = sym ? tilesA : 0;                  // tiles of the symmetric search's first pass (0: plain search)
+    ctx->counter[3] = sym ? tilesA + tilesB : total_tiles;
+    ctx->counter[4] = sym ? std::max(gridA, gridB) : grid;
     return WC_OK;
 }
 
@@ -1324,6 +1524,11 @@ extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
     if (strcmp(key, "k5_group") == 0) {      // CTAs sharing a row block per round (0 = automatic; 1, 2, 4, 8)
         WC_CHECK_ARG(value >= 0 && value <= 64);
         ctx->k5_group = (int)value;
+        return WC_OK;
+    }
+    if (strcmp(key, "k5_sym") == 0) {        // symmetric search for whole-matrix calls: 0 = off, f in 2..64 = on (first pass 1/f)
+        if (value != 0 && (value < 2 || value > 64)) { wc_set_error("k5_sym must be 0 or 2..64"); return WC_ERR_ARG; }
+        ctx->k5_sym = (int)value;
         return WC_OK;
     }
     if (strcmp(key, "k5_stages") == 0) {
