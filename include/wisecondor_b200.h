@@ -55,10 +55,10 @@ int wc_sm_count(const wc_ctx* ctx);
 /* Device-time (ms, CUDA events on `stream`) of the named phases of the most recent call:
  * which: 0 = centre+norms (K4), 1 = distance+streaming top-k (K5), 2 = exact re-score/finalise (K6),
  *        3 = exhaustive fallback rows, 4 = z-score passes (K8), 5 = segmentation (K9), 6 = test sample prep (K7),
- *        7 = PCA bin means + Gram matrix (K2).  Phases of asynchronous calls are read lazily (this call waits). */
+ *        7 = PCA bin means + Gram matrix (K2), 8 = the first (threshold) pass of a symmetric K5, part of 1.  Phases of asynchronous calls are read lazily (this call waits). */
 double wc_last_phase_ms(wc_ctx* ctx, int which);
 /* Counters of the most recent calls: which: 0 = kernel launches of wc_newref_topk, 1 = its rows sent to the exhaustive
- * fallback, 2 = candidate entries emitted by K5, 3 = tiles computed, 4 = CTAs launched for K5, 5 = kernel launches of
+ * fallback, 2 = tiles of the plain search, 3 = tiles computed (fewer: symmetric search), 4 = CTAs launched for K5, 5 = kernel launches of
  * the last wc_zscore_batch, 6 = of the last wc_segment_batch, 7 = of the last wc_newref_prep;
  * 16 + p = (bin, sample) pairs that z-score pass p of the last wc_zscore_batch computed (synchronises). */
 long long wc_last_counter(const wc_ctx* ctx, int which);

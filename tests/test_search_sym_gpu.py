@@ -1,5 +1,6 @@
-"""GPU parity of the SYMMETRIC reference-bin search (option k5_sym: every unordered pair of bin blocks is contracted
-once and serves both bins, wc_search.cu) against the oracle and against the plain search, through the C ABI."""
+"""GPU parity of the SYMMETRIC reference-bin search (the default for whole-matrix calls; option k5_sym: every unordered
+pair of bin blocks is contracted once and serves both bins, wc_search.cu) against the oracle and against the plain
+search, through the C ABI."""
 import numpy as np
 import pytest
 
@@ -11,14 +12,14 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def sym():
-    """Switches the symmetric search on for the test's calls; hands back a function that sets the first-pass fraction."""
+    """Hands back a function that sets the first-pass fraction (0 = plain search); restores the default afterwards."""
     ctx = _cabi.context(0)
 
     def set_frac(frac):
         _cabi.check(_cabi.lib().wc_set_option(ctx.handle, b"k5_sym", float(frac)))
     set_frac(8)
     yield set_frac
-    set_frac(0)
+    set_frac(8)
 
 
 def _gpu_search(X, bins, k):
@@ -54,6 +55,7 @@ def test_symmetric_equals_plain_search_and_halves_the_tiles(sym):
     _assert_same(idx, dist, pidx, pdist)
     assert pst["launches"] == 5 and st["launches"] >= 6
     assert 0.5 < st["tiles"] / pst["tiles"] < 0.62                             # 1/8 + 7/16 = 0.5625 of the plain tiles
+    assert st["tiles_plain"] == pst["tiles"] == pst["tiles_plain"]
     assert st["exhaustive_rows"] == pst["exhaustive_rows"] == 0
 
 

@@ -28,7 +28,8 @@ buf = np.zeros((320, 8), dtype=np.int64)   # 148 CTAs x 8 counters, then 512 tim
 g = _cabi.lib().wc_debug_profile(ctx.handle, 1, buf.ctypes.data_as(ctypes.c_void_p), 320)
 p = buf[:g].astype(float)
 st = device.last_search_stats(0)
-out = {"workload": name, "lag": (sys.argv[2] if len(sys.argv) > 2 else "default"), "ctas": g, "k5_ms": st["dist_topk_ms"], "finalize_ms": st["finalize_ms"],
+out = {"workload": name, "lag": (sys.argv[2] if len(sys.argv) > 2 else "default"), "ctas": g, "k5_ms": st["dist_topk_ms"], "k5_first_pass_ms": st["dist_topk_first_pass_ms"],
+       "tiles": st["tiles"], "exhaustive_rows": st["exhaustive_rows"], "finalize_ms": st["finalize_ms"],
        "cycles_total_max": p[:, 0].max(), "cycles_total_mean": p[:, 0].mean(), "cycles_total_min": p[:, 0].min(),
        "wait_tma_frac": (p[:, 1] / p[:, 0]).mean(), "epilogue_frac": (p[:, 2] / p[:, 0]).mean(),
        "prune_frac": (p[:, 3] / p[:, 0]).mean(), "tiles_per_cta": p[:, 4].mean(),

@@ -38,7 +38,7 @@ struct wc_buf {
     size_t bytes = 0;
 };
 
-enum { WC_NBUF = 48, WC_NPHASE = 8, WC_NCOUNTER = 8 };
+enum { WC_NBUF = 48, WC_NPHASE = 9, WC_NCOUNTER = 8 };
 
 // Workspace slots (one grow-only device buffer each).
 enum {
@@ -66,7 +66,7 @@ struct wc_ctx {
     unsigned timed_mask = 0;        // phases whose event pair is recorded but not yet read (asynchronous calls)
     int k5_stages = 0;              // 0 = automatic TMA ring depth
     int k5_group = 0;               // CTAs sharing a row block per scheduling round of K5 (0 = automatic)
-    int k5_sym = 0;                 // symmetric search: 0 = off, f >= 2 = on with 1/f of the block pairs in the first pass
+    int k5_sym = 8;                 // symmetric search: 0 = off, f >= 2 = on with 1/f of the block pairs in the first pass
     int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones
     int debug_profile = 0;          // K5 writes per-CTA cycle counters when set (wc_debug_profile)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)

@@ -45,6 +45,7 @@ constexpr int FIN_CHUNK = 32;       // samples staged per pipeline step of the r
 constexpr int FIN_LD = FIN_CHUNK + 1;   // padded tile row (bank-conflict free per-thread row walks)
 constexpr int FIN_LDB = FIN_CHUNK + 2;  // tile row of the 16-byte copy path: 16-byte aligned rows (2-way conflicts, cheap)
 constexpr int EXH_THREADS = 256;
+constexpr int STG = 128;            // per-warp staging entries for column-side candidates (symmetric pass)
 constexpr u64 KEY_NEVER = 0ull;     // threshold key of an inactive row: no finite negative score passes
 
 // Shared memory of K5: [nstages x STAGE_BYTES operand ring, 1024-byte aligned][TopkState][8 warps x scratch]
@@ -56,6 +57,7 @@ struct __align__(16) TopkState {
     double nrm[BM];      // n_i
     int cnt[BM];         // entries in the row's candidate buffer
     unsigned char flag[BM];   // 1 = buffer could not be bounded -> exhaustive fallback
+    int stg_cnt[CONSUMER_WARPS];   // symmetric pass: column-side candidates staged by each warp
 };
 
 struct TopkArgs {
@@ -232,6 +234,7 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             mbar_init(&sm.empty[s], CONSUMER_WARPS);
         }
         mbar_init(&sm.gate, CONSUMER_WARPS / 2);
+        for (int w = 0; w < CONSUMER_WARPS; ++w) sm.stg_cnt[w] = 0;
         mbar_fence_init();
         tma_prefetch_desc(&tmap);
     }
@@ -295,6 +298,11 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     int* w_sj = reinterpret_cast<int*>(w_sk + a.cap);
     // SYM: this warp's copy of the 128 column-side thresholds of the current tile (after the 8 scratch areas)
     u64* w_ct = reinterpret_cast<u64*>(scratch + (size_t)CONSUMER_WARPS * scratch_per_warp) + warp * BN;
+    // SYM: column-side candidates (key, bin j, candidate i) wait here until a warp-wide flush appends them to the bins'
+    // incoming buffers - 32 global atomics in flight at once instead of one round trip per entry
+    uint4* w_stg = reinterpret_cast<uint4*>(scratch + (size_t)CONSUMER_WARPS * scratch_per_warp +
+                                            (size_t)CONSUMER_WARPS * BN * sizeof(u64)) + warp * STG;
+    int* w_stgc = &sm.stg_cnt[warp];
     const int r0w = warp * WROWS;               // first tile row of this warp
     u64* w_thr = sm.thr + r0w;
     double* w_nrm = sm.nrm + r0w;
@@ -352,11 +360,29 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             __syncwarp();
         }
     };
+    auto flush_incoming = [&]() {
+        __syncwarp();
+        int n = *w_stgc;
+        if (n > STG) n = STG;
+        for (int e = lane; e < n; e += 32) {
+            const uint4 v = w_stg[e];
+            const int j = (int)v.z;
+            const int w = atomicAdd(a.in_cnt + j, 1);
+            if (w < a.in_cap) {
+                a.in_key[(size_t)j * a.in_cap + w] = ((u64)v.y << 32) | (u64)v.x;
+                a.in_j[(size_t)j * a.in_cap + w] = (int)v.w;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) *w_stgc = 0;
+        __syncwarp();
+    };
     int tcount = 0;                             // tiles done by this CTA (debug timeline index)
     while (true) {
         if (q >= q1) {
             // piece finished: flush this warp's rows of its segment, move to the next piece
             __syncwarp();
+            if (SYM) flush_incoming();
             if (a.final_prune) {
                 // every row leaves its best threshold behind: the bins on the column side of later tiles are filtered by it
                 const unsigned need = __ballot_sync(0xffffffffu, lane < WROWS && w_cnt[lane] > a.k + 24 &&
@@ -561,12 +587,16 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
                         const int j = col0 + (bit >> 1) * 8 + 4 * (bit & 1) + q4;
                         const u64 key = tmp[bit * 32];
                         if (((unsigned)(key >> 32) & 0x7ff00000u) == 0x7ff00000u || j >= a.N || i >= a.row_end) continue;
-                        const int jcs = __ldg(a.row_cs + j);
-                        if ((unsigned)(i - jcs) < (unsigned)(__ldg(a.row_ce + j) - jcs)) continue;   // j's own chromosome
-                        const int w = atomicAdd(a.in_cnt + j, 1);
-                        if (w < a.in_cap) {
-                            a.in_key[(size_t)j * a.in_cap + w] = key;
-                            a.in_j[(size_t)j * a.in_cap + w] = i;
+                        if ((unsigned)(j - cs) < clen) continue;     // same chromosome (i in j's range <=> j in i's range)
+                        const int pos = atomicAdd(w_stgc, 1);
+                        if (pos < STG) {
+                            w_stg[pos] = make_uint4((unsigned)key, (unsigned)(key >> 32), (unsigned)j, (unsigned)i);
+                        } else {                                     // staging full (loose thresholds): append directly
+                            const int w = atomicAdd(a.in_cnt + j, 1);
+                            if (w < a.in_cap) {
+                                a.in_key[(size_t)j * a.in_cap + w] = key;
+                                a.in_j[(size_t)j * a.in_cap + w] = i;
+                            }
                         }
                         ++pf_emit;
                     }
@@ -574,6 +604,7 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             }
         }
         __syncwarp();
+        if (SYM && *w_stgc >= 32) flush_incoming();
         const long long pf_p0 = clock64();
         pf_epi += pf_p0 - pf_e0;
         if (tr_on) tr[2] = pf_p0;
@@ -1228,7 +1259,11 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         tilesB = (long long)listB.size();
         gridA = (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesA + 7) / 8));
         gridB = (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesB + 7) / 8));
-        schedule_pieces(offA, nb, gridA, 1, false, 0, pieces);       // pass A: whole row blocks per CTA, one threshold each
+        // pass A: contiguous split, so a row block is cut at most once or twice and every bin's threshold comes from (nearly)
+        // its whole sample.  (Rounds would chop the left-over row blocks into ~20 pieces of 2-3 tiles: thresholds loose
+        // enough to flood those bins' incoming buffers - measured: ~900 rows in the exhaustive fallback, +240 ms.)  All CTAs
+        // still walk their ascending lists in step, so the B panels are shared through L2 all the same.
+        schedule_pieces(offA, nb, gridA, 1, false, 0, pieces);
         int GB = G;
         if (GB > gridB) GB = gridB;
         schedule_pieces(offB, nb, gridB, GB, rounds_on, 1, pieces);
@@ -1398,7 +1433,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     }
     const size_t topk_smem = (size_t)ta.nstages * STAGE_BYTES + sizeof(TopkState) +
                              (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192) +
-                             (sym ? (size_t)CONSUMER_WARPS * BN * sizeof(u64) : 0);
+                             (sym ? (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4)) : 0);
     if (topk_smem > 227 * 1024) { wc_set_error("K5 shared memory %zu exceeds 227 KiB", topk_smem); return WC_ERR_INTERNAL; }
     WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
     wc_fill_u64_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(row_thr, (size_t)rows, host_key_of_tau(ta.tau_init));
@@ -1413,6 +1448,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         ta.rb_list_off = d_sym;
         wc_dist_topk_kernel<false><<<gridA, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
         WC_CUDA(cudaGetLastError());
+        WC_CUDA(cudaEventRecord(ctx->ev[16], stream));
         ta.tile_list = d_sym + 2 * nb1 + (int)listA.size();              // pass B
         ta.rb_list_off = d_sym + nb1;
         ta.cta_piece_begin = d_cta_piece + (gridA + 1);
@@ -1462,11 +1498,13 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     float ms;
     WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->phase_ms[0] = ms;
     WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->phase_ms[1] = ms;
+    ctx->phase_ms[8] = 0.0;
+    if (sym) { WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[16])); ctx->phase_ms[8] = ms; }
     WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->phase_ms[2] = ms;
     if (nslow > 0) { WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7])); ctx->phase_ms[3] = ms; }
     ctx->counter[0] = launches;
     ctx->counter[1] = nslow;
-    ctx->counter[2] = sym ? tilesA : 0;                  // tiles of the symmetric search's first pass (0: plain search)
+    ctx->counter[2] = total_tiles;                       // tiles the plain search computes (= counter 3 unless symmetric)
     ctx->counter[3] = sym ? tilesA + tilesB : total_tiles;
     ctx->counter[4] = sym ? std::max(gridA, gridB) : grid;
     return WC_OK;

@@ -62,8 +62,9 @@ def last_search_stats(device=0):
     ctx = _cabi.context(device)
     return {
         "center_norms_ms": ctx.phase_ms(0), "dist_topk_ms": ctx.phase_ms(1), "finalize_ms": ctx.phase_ms(2),
+        "dist_topk_first_pass_ms": ctx.phase_ms(8),
         "exhaustive_ms": ctx.phase_ms(3), "launches": ctx.counter(0), "exhaustive_rows": ctx.counter(1),
-        "tiles": ctx.counter(3), "ctas": ctx.counter(4),
+        "tiles": ctx.counter(3), "tiles_plain": ctx.counter(2), "ctas": ctx.counter(4),
     }
 
 
