@@ -77,8 +77,11 @@ int wc_dev_sync(wc_ctx* ctx);                                  /* cudaDeviceSync
  * thread 0, reserved).  Returns the number of CTAs copied, or a negative wc_status. */
 int wc_debug_profile(wc_ctx* ctx, int enable, long long* out_h, int max_ctas);
 
-/* Tuning knob for experiments: key "k5_lag" = chunks (0..4) by which half of the distance kernel's MMA warps
- * trail the other half.  Results never depend on it. */
+/* Tuning knobs.  Results never depend on them.
+ *   "k5_sym"    whole-matrix searches contract every unordered pair of bin blocks once (symmetric search): 0 = off (plain
+ *               search), f in 2..64 = on, with 1/f of the block pairs computed in the first (threshold) pass.  Default 8.
+ *   "k5_group"  CTAs sharing a row block per scheduling round (0 = automatic), "k5_stages" TMA ring depth (0 = automatic),
+ *   "k5_lag"    chunks (0..4) by which half of the distance kernel's MMA warps trail the other half. */
 int wc_set_option(wc_ctx* ctx, const char* key, double value);
 
 /* ---- newref: reference-bin search --------------------------------------------------------------------- */
