@@ -55,7 +55,8 @@ int wc_sm_count(const wc_ctx* ctx);
 /* Device-time (ms, CUDA events on `stream`) of the named phases of the most recent call:
  * which: 0 = centre+norms (K4), 1 = distance+streaming top-k (K5), 2 = exact re-score/finalise (K6),
  *        3 = exhaustive fallback rows, 4 = z-score passes (K8), 5 = segmentation (K9), 6 = test sample prep (K7),
- *        7 = PCA bin means + Gram matrix (K2), 8 = the first (threshold) pass of a symmetric K5, part of 1.  Phases of asynchronous calls are read lazily (this call waits). */
+ *        7 = PCA bin means + Gram matrix (K2), 8 = the first (threshold) pass of a symmetric K5, part of 1,
+ *        9 = the symmetric pass of a sharded search, part of 1.  Phases of asynchronous calls are read lazily (this call waits). */
 double wc_last_phase_ms(wc_ctx* ctx, int which);
 /* Counters of the most recent calls: which: 0 = kernel launches of wc_newref_topk, 1 = its rows sent to the exhaustive
  * fallback, 2 = tiles of the plain search, 3 = tiles computed (fewer: symmetric search), 4 = CTAs launched for K5, 5 = kernel launches of
@@ -103,6 +104,29 @@ int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int S, const i
  * (wisecondor.py:111-132) would bind. */
 int wc_newref_topk_host(wc_ctx* ctx, const double* corrected_h, int N, int S, const int* chrom_bins_h,
                         int nchrom, int row_begin, int row_end, int refsize, int32_t* idx_h, double* dist_h);
+
+/* ---- newref on several GPUs: sharded symmetric search ------------------------------------------------------------
+ * Replaces the `newrefpart` fan-out + `newrefpost` concatenation (wisecondor.py:111-158) when all parts run on the GPUs of
+ * one node: since d(i, j) = d(j, i), every unordered pair of 128-bin blocks is contracted ONCE in the whole job and serves
+ * both bins.  Rank r of `world` (one process per GPU, each holding the whole corrected matrix) owns nb/world consecutive
+ * blocks of bins: it computes the tiles whose row block it owns and finalises its own bins.  Call order on every rank:
+ *   wc_newref_shard_dims    sizes of the exchange buffers (out6: rows_per, in_cap, thr_len, row0, row1, nb)
+ *   wc_newref_shard_begin   K4 + threshold pass; writes thr_d[thr_len] (u64 keys; the owned bins' thresholds)
+ *   -> all-reduce MIN of thr_d over the ranks, read as int64 (all real keys are negative int64, padding is 0)
+ *   wc_newref_shard_sweep   symmetric pass; fills in_key_d / in_j_d [world*rows_per][in_cap], in_cnt_d [world*rows_per]:
+ *                           what this rank's tiles found for EVERY bin on their column side
+ *   -> all-to-all of the three arrays in `world` equal splits of rows_per bins (split o goes to rank o)
+ *   wc_newref_shard_finish  exact re-score / ranking of the bins [row0, row1): idx_d, dist_d (row1-row0) x refsize, as
+ *                           wc_newref_topk writes them; recv_* = the all-to-all's outputs.  Synchronous.
+ * The caller gathers the ranks' rows (they are consecutive and ordered by rank).  Results are identical to
+ * wc_newref_topk over the same rows.  All pointers DEVICE except chrom_bins_h. */
+int wc_newref_shard_dims(const wc_ctx* ctx, int N, int refsize, int world, int rank, long long* out6);
+int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int N, int S, const int* chrom_bins_h, int nchrom,
+                          int refsize, int rank, int world, unsigned long long* thr_d, void* stream);
+int wc_newref_shard_sweep(wc_ctx* ctx, unsigned long long* thr_d, unsigned long long* in_key_d, int* in_j_d,
+                          int* in_cnt_d, void* stream);
+int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* recv_key_d, const int* recv_j_d, const int* recv_cnt_d,
+                           int32_t* idx_d, double* dist_d, void* stream);
 
 /* ---- newref: normalisation, mask, PCA residual ------------------------------------------------------------ */
 /* Together these replace toNumpyArray (wisetools.py:240-264) and trainPCA (wisetools.py:89-101) as called from

@@ -142,3 +142,110 @@ def test_row_sharded_gather_over_gloo(world, n):
         assert p.exitcode == 0
     got = sorted(q.get(timeout=10) for _ in range(world))
     assert got == [(r, True) for r in range(world)]
+
+
+class _CpuStandInEngine(object):
+    """Test stand-in for the three device steps of a sharded symmetric search (shard._DeviceEngine): same contract on CPU
+    tensors with brute-force numpy, so that the collectives and buffer layouts of SymmetricShardedSearch run under gloo.
+    begin: the owned bins' thresholds; sweep: for EVERY bin its in_cap nearest candidates among this rank's bins;
+    finish: merge the received candidates per owned bin and rank them (distance, index)."""
+    BLOCK = 128
+
+    def __init__(self, in_cap):
+        self.in_cap = in_cap
+
+    def dims(self, n, refsize, world, rank, device):
+        nb = (n + self.BLOCK - 1) // self.BLOCK
+        bp = (nb + world - 1) // world
+        rows_per = bp * self.BLOCK
+        return {"rows_per": rows_per, "in_cap": self.in_cap, "thr_len": world * rows_per + self.BLOCK,
+                "row0": min(n, rank * rows_per), "row1": min(n, (rank + 1) * rows_per), "blocks": nb}
+
+    def begin(self, x, chrom_bins, refsize, rank, world, thr):
+        self.x, self.bins, self.k, self.rank, self.world = x.numpy(), list(chrom_bins), refsize, rank, world
+        self.n = self.x.shape[0]
+        self.d = self.dims(self.n, refsize, world, rank, None)
+        thr.fill_(-1)
+        thr[self.d["row0"]:self.d["row1"]] = -(rank + 2)            # "tighter" (smaller) than everybody else's -1
+        thr[self.n:] = 0
+
+    def sweep(self, thr, in_key, in_j, in_cnt):
+        t = thr.numpy()
+        for r in range(self.world):                                  # the all-reduce(MIN) delivered every owner's value
+            dr = self.dims(self.n, self.k, self.world, r, None)
+            assert (t[dr["row0"]:dr["row1"]] == -(r + 2)).all()
+        assert (t[self.n:] == 0).all()
+        chrom = np.repeat(np.arange(len(self.bins)), self.bins)
+        own = np.arange(self.d["row0"], self.d["row1"])
+        in_cnt.zero_()
+        for j in range(self.n):
+            cand = own[chrom[own] != chrom[j]]
+            dist2 = ((self.x[cand] - self.x[j]) ** 2).sum(axis=1)
+            order = np.lexsort((cand, dist2))[:self.in_cap]
+            in_cnt[j] = len(order)
+            in_key[j, :len(order)] = __import__("torch").from_numpy(dist2[order].view(np.int64).copy())
+            in_j[j, :len(order)] = __import__("torch").from_numpy(cand[order].astype(np.int32))
+
+    def finish(self, recv_key, recv_j, recv_cnt, idx, dist_out):
+        chrom = np.repeat(np.arange(len(self.bins)), self.bins)
+        starts = np.concatenate(([0], np.cumsum(self.bins)))
+        rk, rj, rc = recv_key.numpy(), recv_j.numpy(), recv_cnt.numpy()
+        rows_per = self.d["rows_per"]
+        for r in range(self.d["row1"] - self.d["row0"]):
+            j = self.d["row0"] + r
+            ds, js = [], []
+            for s in range(self.world):
+                c = rc[s * rows_per + r]
+                ds.append(rk[s * rows_per + r, :c].view(np.float64))
+                js.append(rj[s * rows_per + r, :c])
+            ds, js = np.concatenate(ds), np.concatenate(js)
+            order = np.lexsort((js, ds))[:self.k]
+            out_i = np.full(self.k, -1, dtype=np.int32)
+            out_d = np.full(self.k, 1e10)
+            sel = js[order]
+            # other-chromosome coordinates (wisetools.py:386-393): bins after j's chromosome shift down by its length
+            out_i[:len(order)] = np.where(sel >= starts[chrom[j] + 1], sel - self.bins[chrom[j]], sel)
+            out_d[:len(order)] = ds[order]
+            idx[r] = __import__("torch").from_numpy(out_i)
+            dist_out[r] = __import__("torch").from_numpy(out_d)
+
+
+def _sym_shard_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from wisecondor_b200 import shard, synth
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        bins = [150, 90, 201, 60]                                    # 501 bins: 4 blocks of 128, the last one partial
+        X = synth.corrected_like(bins, 12, seed=7)
+        k = 20
+        search = shard.SymmetricShardedSearch(X.shape[0], k, rank, world, torch.device("cpu"), engine=_CpuStandInEngine(32))
+        search.run(torch.from_numpy(X), bins)
+        idx, dst = search.gather()
+        oidx, odst = wc_oracle.get_reference(X, bins, list(np.cumsum(bins)), k, 1, 1)
+        ok = np.array_equal(idx.numpy(), oidx) and np.allclose(dst.numpy(), odst, rtol=1e-12, atol=0)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_symmetric_sharded_search_collectives_over_gloo(world):
+    """The N>1 symmetric search on CPU: threshold all-reduce(MIN), candidate all-to-all in equal row splits, ordered
+    gather - with a numpy stand-in for the three device steps (the kernels are covered by the GPU tests)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sym_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=10) for _ in range(world))
+    assert got == [(r, True) for r in range(world)]

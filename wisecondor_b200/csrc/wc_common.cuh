@@ -38,7 +38,7 @@ struct wc_buf {
     size_t bytes = 0;
 };
 
-enum { WC_NBUF = 48, WC_NPHASE = 9, WC_NCOUNTER = 8 };
+enum { WC_NBUF = 48, WC_NPHASE = 10, WC_NCOUNTER = 8 };
 
 // Workspace slots (one grow-only device buffer each).
 enum {
@@ -50,6 +50,20 @@ enum {
     SLOT_T_REVCNT = 44, SLOT_T_REVCUR, SLOT_T_DIRTY, SLOT_T_PAIRS,
     SLOT_S_ZC = 32, SLOT_S_META, SLOT_S_STATUS, SLOT_S_RC, SLOT_S_AUX,                                                       // segmentation
     SLOT_P_FIRST = 40                                                                                  // newref prep
+};
+
+// State of a sharded symmetric search between its three calls (wc_newref_shard_begin / _sweep / _finish).
+struct wc_shard_plan {
+    int valid = 0;
+    int N = 0, S = 0, k = 0, cap = 0, in_cap = 0, world = 1, rank = 0;
+    int nb = 0, bp = 0, b0 = 0, b1 = 0;          // blocks of 128 bins: all, per rank, this rank's [b0, b1)
+    int row0 = 0, row1 = 0, rows_per = 0;        // this rank's bins [row0, row1) (row1 <= N), bins per rank (padded)
+    int nkc = 0, nd_last = 0, extra_h = 0, ld = 0, nstages = 0, nrb = 0, nseg = 0, gridA = 0, gridB = 0;
+    size_t Npad = 0, smem = 0, nlistA = 0;
+    long long tilesA = 0, tilesB = 0, tiles_plain = 0;
+    double mcoef = 0.0;
+    const double* corrected = nullptr;
+    int stage = 0;                               // 1 after begin, 2 after sweep
 };
 
 struct wc_ctx {
@@ -70,6 +84,7 @@ struct wc_ctx {
     int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones
     int debug_profile = 0;          // K5 writes per-CTA cycle counters when set (wc_debug_profile)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)
+    wc_shard_plan shard;            // the sharded symmetric search in flight on this context, if any
 };
 
 int wc_reserve(wc_ctx* ctx, int slot, size_t bytes, void** out);

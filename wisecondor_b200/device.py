@@ -57,6 +57,53 @@ def newref_topk_host(corrected, chrom_bins, row_begin, row_end, refsize, device=
     return idx, dist
 
 
+# ---- sharded symmetric search: the three steps of one rank (wisecondor_b200.shard.SymmetricShardedSearch drives them) ----
+I64 = np.int64
+
+
+def shard_dims(n, refsize, world, rank, device=0, ctx=None):
+    """Sizes of the exchange buffers of a sharded symmetric search (wc_newref_shard_dims)."""
+    ctx = ctx or _cabi.context(device)
+    out = (ctypes.c_longlong * 6)()
+    _cabi.check(_cabi.lib().wc_newref_shard_dims(ctx.handle, int(n), int(refsize), int(world), int(rank), out))
+    return {"rows_per": int(out[0]), "in_cap": int(out[1]), "thr_len": int(out[2]), "row0": int(out[3]),
+            "row1": int(out[4]), "blocks": int(out[5])}
+
+
+def shard_begin(corrected, chrom_bins, refsize, rank, world, thr, ctx=None):
+    """K4 + threshold pass over this rank's row blocks; thr: device int64 [thr_len] (u64 keys), written."""
+    _require_cuda(corrected, F64, "corrected")
+    _require_cuda(thr, I64, "thr")
+    n, s = corrected.shape
+    cb = np.ascontiguousarray(chrom_bins, dtype=np.int32)
+    ctx = ctx or _cabi.context(_mem.device_index(corrected))
+    _cabi.check(_cabi.lib().wc_newref_shard_begin(ctx.handle, _ptr(corrected), n, s, cb.ctypes.data_as(ctypes.c_void_p), len(cb),
+                                                  int(refsize), int(rank), int(world), _ptr(thr), _stream_ptr(corrected)))
+
+
+def shard_sweep(thr, in_key, in_j, in_cnt, ctx=None):
+    """Symmetric pass; thr after the all-reduce(MIN); in_key int64 / in_j int32 [world*rows_per][in_cap], in_cnt int32."""
+    _require_cuda(thr, I64, "thr")
+    _require_cuda(in_key, I64, "in_key")
+    _require_cuda(in_j, I32, "in_j")
+    _require_cuda(in_cnt, I32, "in_cnt")
+    ctx = ctx or _cabi.context(_mem.device_index(thr))
+    _cabi.check(_cabi.lib().wc_newref_shard_sweep(ctx.handle, _ptr(thr), _ptr(in_key), _ptr(in_j), _ptr(in_cnt), _stream_ptr(thr)))
+
+
+def shard_finish(recv_key, recv_j, recv_cnt, out_idx, out_dist, ctx=None):
+    """Exact re-score and ranking of this rank's bins from its own segments and the received column-side candidates."""
+    _require_cuda(recv_key, I64, "recv_key")
+    _require_cuda(recv_j, I32, "recv_j")
+    _require_cuda(recv_cnt, I32, "recv_cnt")
+    _require_cuda(out_idx, I32, "out_idx")
+    _require_cuda(out_dist, F64, "out_dist")
+    ctx = ctx or _cabi.context(_mem.device_index(recv_key))
+    _cabi.check(_cabi.lib().wc_newref_shard_finish(ctx.handle, _ptr(recv_key), _ptr(recv_j), _ptr(recv_cnt), _ptr(out_idx),
+                                                   _ptr(out_dist), _stream_ptr(recv_key)))
+    return out_idx, out_dist
+
+
 def last_search_stats(device=0):
     """Device timings (ms) and counters of the most recent search on `device`."""
     ctx = _cabi.context(device)

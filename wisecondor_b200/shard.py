@@ -5,6 +5,10 @@ exactly what `newrefpart r+1 W` would - every rank holds the full corrected matr
 (rows x refsize) int32 + float64 blocks replaces toolNewrefPost's file concatenation (wisecondor.py:146-158).
 test: samples are sharded; no communication.  Works with the nccl backend (CUDA tensors) and gloo (CPU tensors; used
 by the CPU tests).
+
+SymmetricShardedSearch divides the BLOCK PAIRS of the symmetric search over the ranks instead (every unordered pair of
+128-bin blocks is contracted once in the whole job); it has the path's one real exchange step: an all-reduce(MIN) of
+the bins' thresholds after the first pass and an all-to-all of the column-side candidates before the final ranking.
 """
 import torch
 import torch.distributed as dist
@@ -96,3 +100,77 @@ class ShardedSearch(object):
         self.h_dist.copy_(self.dist, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self.h_idx.numpy(), self.h_dist.numpy()
+
+
+class _DeviceEngine(object):
+    """The three C-ABI steps of one rank (device.shard_*).  Tests substitute a CPU stand-in to exercise the collectives."""
+
+    def __init__(self, ctx=None):
+        from . import device as _dev
+        self._dev, self._ctx = _dev, ctx
+
+    def dims(self, n, refsize, world, rank, device):
+        index = device.index if getattr(device, "index", None) is not None else 0
+        return self._dev.shard_dims(n, refsize, world, rank, device=index, ctx=self._ctx)
+
+    def begin(self, x, chrom_bins, refsize, rank, world, thr):
+        self._dev.shard_begin(x, chrom_bins, refsize, rank, world, thr, ctx=self._ctx)
+
+    def sweep(self, thr, in_key, in_j, in_cnt):
+        self._dev.shard_sweep(thr, in_key, in_j, in_cnt, ctx=self._ctx)
+
+    def finish(self, recv_key, recv_j, recv_cnt, idx, dist_out):
+        self._dev.shard_finish(recv_key, recv_j, recv_cnt, idx, dist_out, ctx=self._ctx)
+
+
+class SymmetricShardedSearch(object):
+    """newref search of one device-resident matrix on all ranks of the group with the symmetric search
+    (wc_newref_shard_*, include/wisecondor_b200.h): rank r owns blocks_per = ceil(blocks / world) consecutive 128-bin
+    blocks, computes the tiles whose row block it owns and finalises its own bins.  run() returns this rank's rows;
+    gather() the whole (N x refsize) result on every rank."""
+
+    def __init__(self, n, refsize, rank, world, device, group=None, engine=None):
+        self.n, self.k, self.rank, self.world, self.group, self.device = int(n), int(refsize), rank, world, group, device
+        self.engine = engine or _DeviceEngine()
+        d = self.engine.dims(self.n, self.k, world, rank, device)
+        self.rows_per, self.in_cap, self.row0, self.row1 = d["rows_per"], d["in_cap"], d["row0"], d["row1"]
+        total = world * self.rows_per
+        self.thr = torch.empty((d["thr_len"],), dtype=torch.int64, device=device)
+        self.in_key = torch.empty((total, self.in_cap), dtype=torch.int64, device=device)
+        self.in_j = torch.empty((total, self.in_cap), dtype=torch.int32, device=device)
+        self.in_cnt = torch.empty((total,), dtype=torch.int32, device=device)
+        if world > 1:
+            self.recv_key, self.recv_j, self.recv_cnt = (torch.empty_like(t) for t in (self.in_key, self.in_j, self.in_cnt))
+        else:
+            self.recv_key, self.recv_j, self.recv_cnt = self.in_key, self.in_j, self.in_cnt
+        rows = max(0, self.row1 - self.row0)
+        self.idx = torch.empty((rows, self.k), dtype=torch.int32, device=device)
+        self.dist = torch.empty((rows, self.k), dtype=torch.float64, device=device)
+
+    def run(self, x, chrom_bins):
+        """x: the whole corrected matrix [N][S] on this rank's device.  Returns (indexes, distances) of the bins
+        [row0, row1) this rank owns."""
+        self.engine.begin(x, chrom_bins, self.k, self.rank, self.world, self.thr)
+        if self.world > 1:
+            dist.all_reduce(self.thr, op=dist.ReduceOp.MIN, group=self.group)       # every bin's threshold, everywhere
+        self.engine.sweep(self.thr, self.in_key, self.in_j, self.in_cnt)
+        if self.world > 1:                                                            # candidates travel to the bins' owners
+            dist.all_to_all_single(self.recv_cnt, self.in_cnt, group=self.group)
+            dist.all_to_all_single(self.recv_key, self.in_key, group=self.group)
+            dist.all_to_all_single(self.recv_j, self.in_j, group=self.group)
+        self.engine.finish(self.recv_key, self.recv_j, self.recv_cnt, self.idx, self.dist)
+        return self.idx, self.dist
+
+    def gather(self):
+        """All ranks' rows in order -> (N x refsize) indexes and distances on every rank."""
+        if self.world == 1:
+            return self.idx, self.dist
+        pad_i = torch.zeros((self.rows_per, self.k), dtype=torch.int32, device=self.device)
+        pad_d = torch.zeros((self.rows_per, self.k), dtype=torch.float64, device=self.device)
+        pad_i[:self.idx.shape[0]].copy_(self.idx)
+        pad_d[:self.dist.shape[0]].copy_(self.dist)
+        all_i = torch.empty((self.world * self.rows_per, self.k), dtype=torch.int32, device=self.device)
+        all_d = torch.empty((self.world * self.rows_per, self.k), dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(all_i, pad_i, group=self.group)
+        dist.all_gather_into_tensor(all_d, pad_d, group=self.group)
+        return all_i[:self.n], all_d[:self.n]           # owned ranges are consecutive: rank r holds rows [r*rows_per, ...)
