@@ -406,6 +406,34 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
 # --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
+def symmetric_shards_agree(dev, rank, world):
+    """One sharded symmetric search of a small matrix on all ranks, compared with the single-GPU search of the same
+    matrix (itself parity-tested against the oracle): every rank votes, the verdict is unanimous or 'no'."""
+    import torch
+    import torch.distributed as dist
+    from wisecondor_b200 import device, shard, synth
+    ok, note = 1, "agreed on every rank"
+    try:
+        tb = [int(b) for b in np.array(synth.chrom_bins(250000)) // 2]
+        tx = torch.as_tensor(synth.corrected_like(tb, 32, seed=9), device=dev)
+        tn = int(tx.shape[0])
+        trial = shard.SymmetricShardedSearch(tn, 50, rank, world, dev)
+        trial.run(tx, tb)
+        gi, gd = trial.gather()
+        pi, pd = device.newref_topk(tx, tb, 0, tn, 50)
+        if not (torch.equal(gi, pi) and torch.equal(gd, pd)):
+            ok, note = 0, "rank %d: sharded result differs from the single-GPU search" % rank
+    except Exception as exc:          # noqa: BLE001 - any failure means: do not use it
+        ok, note = 0, "rank %d: %s: %s" % (rank, type(exc).__name__, exc)
+        sys.stderr.write("symmetric sharded search disabled: %s\n" % note)
+    vote = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(vote, op=dist.ReduceOp.MIN)
+    agreed = bool(int(vote.item()))
+    if not agreed and ok:
+        note = "another rank disagreed"
+    return agreed, note
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -461,7 +489,21 @@ def main():
         full_dist = torch.empty((n, k), dtype=torch.float64, device=dev)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # 512 MiB > 126 MB L2
 
+    # N > 1: the block pairs of the symmetric search divided over the ranks (shard.SymmetricShardedSearch), if a trial run
+    # on a small matrix agrees with the single-GPU search on every rank; otherwise the reference's getPart row shards.
+    sym_search, sym_note = None, None
+    if world > 1 and os.environ.get("WC_SHARD_SYM", "1") != "0":
+        agreed, sym_note = symmetric_shards_agree(dev, rank, world)
+        if agreed:
+            sym_search = shard.SymmetricShardedSearch(n, k, rank, world, dev)
+            r0, r1 = sym_search.row0, max(sym_search.row0, sym_search.row1)
+            rows = r1 - r0
+
     def step():
+        if sym_search is not None:
+            sym_search.run(X, bins)      # threshold all-reduce + candidate all-to-all inside
+            sym_search.gather()          # NCCL all-gather: every rank ends with the whole table
+            return
         device.newref_topk(X, bins, r0, r1, k, out_idx[:rows], out_dist[:rows])
         if world > 1:       # NCCL all-gather of the row shards over NVLink: every rank ends with the whole table
             shard.allgather_rows(out_idx[:rows], out_dist[:rows], n, out_idx=full_idx, out_dist=full_dist, scratch=scratch)
@@ -514,14 +556,15 @@ def main():
         e2e_steps = max(2, min(args.steps, 5))
         if world > 1:
             # every rank uploads 1/N of the matrix, NCCL all-gathers it over NVLink, searches its rows, copies them back
-            sharded = shard.ShardedSearch(n, S, k, rank, world, dev)
+            sharded = shard.ShardedSearch(n, S, k, rank, world, dev, symmetric=sym_search is not None)
             sharded.run(X_pinned, bins)
             barrier()
             t0 = time.time()
             for _ in range(e2e_steps):
                 hi, hd = sharded.run(X_pinned, bins)
             h2d_bytes = sharded.rows_per * S * 8
-            e2e_api = "wisecondor_b200.shard.ShardedSearch.run (pinned host matrix; 1/N upload + NCCL all-gather of the matrix)"
+            e2e_api = "wisecondor_b200.shard.ShardedSearch.run (pinned host matrix; 1/N upload + NCCL all-gather of the matrix%s)" % (
+                "; symmetric search over block pairs" if sym_search is not None else "")
         else:
             h_idx = torch.empty((rows, k), dtype=torch.int32).pin_memory().numpy()      # pinned result buffers
             h_dist = torch.empty((rows, k), dtype=torch.float64).pin_memory().numpy()
@@ -574,8 +617,12 @@ def main():
             "warmup": max(3, args.warmup) if not big else max(1, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "baseline_config": cfg, "bins": n, "samples": S, "refsize": k,
-                       "bin_pairs": pairs_total, "parallelism": "rows sharded by getPart over %d GPU(s)%s" %
-                       (world, " + NCCL all-gather" if world > 1 else ""),
+                       "bin_pairs": pairs_total, "parallelism": (
+                           "block pairs of the symmetric search divided over %d GPUs; NCCL all-reduce(MIN) of the bins' "
+                           "thresholds, all-to-all of the column-side candidates, all-gather of the rows" % world
+                           if sym_search is not None else
+                           "rows sharded by getPart over %d GPU(s)%s" % (world, " + NCCL all-gather" if world > 1 else "")),
+                       "sharded_symmetric_trial": sym_note,
                        "l2": "512 MiB buffer written between timed iterations (L2 flush)"},
             "phases_ms": {"center_norms": float(np.mean(k4_ms)), "dist_topk": k5, "finalize": float(np.mean(k6_ms))},
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -592,8 +639,13 @@ def main():
     # ---- the test half of the path (BASELINE metric "test samples/s"): batched z-scores + segmentation ----------
     test_line = None
     if not args.no_test:
-        test_line = bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins, k, out_idx[:rows] if world == 1 else full_idx,
-                                    out_dist[:rows] if world == 1 else full_dist)
+        if sym_search is not None:
+            table_idx, table_dist = (t.contiguous() for t in sym_search.gather())
+        elif world == 1:
+            table_idx, table_dist = out_idx[:rows], out_dist[:rows]
+        else:
+            table_idx, table_dist = full_idx, full_dist
+        test_line = bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins, k, table_idx, table_dist)
     if rank == 0:
         line["test"] = test_line
         print(json.dumps(line))

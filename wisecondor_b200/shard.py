@@ -68,7 +68,7 @@ class ShardedSearch(object):
     for eight simultaneous full uploads); each rank then searches its getPart rows and copies them back to (pinned)
     host memory - the counterpart of the reference's per-part npz files (wisecondor.py:128-132)."""
 
-    def __init__(self, n, s, refsize, rank, world, device, group=None):
+    def __init__(self, n, s, refsize, rank, world, device, group=None, symmetric=False):
         from . import device as _dev
         self._dev = _dev
         self.n, self.s, self.k, self.rank, self.world, self.group = int(n), int(s), int(refsize), rank, world, group
@@ -77,6 +77,10 @@ class ShardedSearch(object):
         self.local = torch.empty((self.rows_per, self.s), dtype=torch.float64, device=device)
         self.full = torch.empty((world * self.rows_per, self.s), dtype=torch.float64, device=device)
         self.r0, self.r1 = row_shard(rank, world, self.n)            # search rows: the reference's getPart
+        self.sym = None
+        if symmetric:        # block pairs instead of rows: this rank's bins are the blocks it owns (SymmetricShardedSearch)
+            self.sym = SymmetricShardedSearch(self.n, self.k, rank, world, device, group=group)
+            self.r0, self.r1 = self.sym.row0, max(self.sym.row0, self.sym.row1)
         rows = self.r1 - self.r0
         self.idx = torch.empty((rows, self.k), dtype=torch.int32, device=device)
         self.dist = torch.empty((rows, self.k), dtype=torch.float64, device=device)
@@ -95,7 +99,10 @@ class ShardedSearch(object):
             x = self.full[:self.n]
         else:
             x = self.local[:self.n]
-        self._dev.newref_topk(x, chrom_bins, self.r0, self.r1, self.k, self.idx, self.dist)
+        if self.sym is not None:
+            self.idx, self.dist = self.sym.run(x, chrom_bins)
+        else:
+            self._dev.newref_topk(x, chrom_bins, self.r0, self.r1, self.k, self.idx, self.dist)
         self.h_idx.copy_(self.idx, non_blocking=True)
         self.h_dist.copy_(self.dist, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
@@ -146,6 +153,7 @@ class SymmetricShardedSearch(object):
         rows = max(0, self.row1 - self.row0)
         self.idx = torch.empty((rows, self.k), dtype=torch.int32, device=device)
         self.dist = torch.empty((rows, self.k), dtype=torch.float64, device=device)
+        self._gather = None
 
     def run(self, x, chrom_bins):
         """x: the whole corrected matrix [N][S] on this rank's device.  Returns (indexes, distances) of the bins
@@ -165,12 +173,14 @@ class SymmetricShardedSearch(object):
         """All ranks' rows in order -> (N x refsize) indexes and distances on every rank."""
         if self.world == 1:
             return self.idx, self.dist
-        pad_i = torch.zeros((self.rows_per, self.k), dtype=torch.int32, device=self.device)
-        pad_d = torch.zeros((self.rows_per, self.k), dtype=torch.float64, device=self.device)
+        if self._gather is None:
+            self._gather = (torch.zeros((self.rows_per, self.k), dtype=torch.int32, device=self.device),
+                            torch.zeros((self.rows_per, self.k), dtype=torch.float64, device=self.device),
+                            torch.empty((self.world * self.rows_per, self.k), dtype=torch.int32, device=self.device),
+                            torch.empty((self.world * self.rows_per, self.k), dtype=torch.float64, device=self.device))
+        pad_i, pad_d, all_i, all_d = self._gather
         pad_i[:self.idx.shape[0]].copy_(self.idx)
         pad_d[:self.dist.shape[0]].copy_(self.dist)
-        all_i = torch.empty((self.world * self.rows_per, self.k), dtype=torch.int32, device=self.device)
-        all_d = torch.empty((self.world * self.rows_per, self.k), dtype=torch.float64, device=self.device)
         dist.all_gather_into_tensor(all_i, pad_i, group=self.group)
         dist.all_gather_into_tensor(all_d, pad_d, group=self.group)
         return all_i[:self.n], all_d[:self.n]           # owned ranges are consecutive: rank r holds rows [r*rows_per, ...)
