@@ -612,6 +612,9 @@ def main():
                                    "MEASURED_PEAKS.json has no FP64 entry" %
                                    (peak_src, "sustained" if use_peak == sustained else "burst"),
                     "share_of_step": k5 / ms_per_step}
+        if os.environ.get("WC_K5_F16") == "1":
+            roofline["note"] += ("; EXPERIMENTAL fp16 filter (WC_K5_F16=1): K5 then runs on the fp16 tensor cores and the "
+                                 "FP64 peak / frac above do not apply")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup) if not big else max(1, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -44,7 +44,7 @@ enum { WC_NBUF = 48, WC_NPHASE = 10, WC_NCOUNTER = 8 };
 enum {
     SLOT_XC = 0, SLOT_NORMS, SLOT_ROWCS, SLOT_ROWCE, SLOT_RBMETA, SLOT_CAND_D, SLOT_CAND_J, SLOT_SEGCNT,
     SLOT_SEGFLAG, SLOT_SLOW, SLOT_SCRATCH, SLOT_IO_X, SLOT_IO_IDX, SLOT_IO_DIST, SLOT_ROWTHR,
-    SLOT_IN_KEY, SLOT_IN_J, SLOT_IN_CNT,                                                               // search
+    SLOT_IN_KEY, SLOT_IN_J, SLOT_IN_CNT, SLOT_N32, SLOT_F16STAT,                                                             // search
     SLOT_PROF = 20,
     SLOT_T_COPY = 24, SLOT_T_ZT, SLOT_T_RT, SLOT_T_NT, SLOT_T_SD, SLOT_T_FLAGS, SLOT_T_TOTALS, SLOT_T_PROJ,   // test
     SLOT_T_REVCNT = 44, SLOT_T_REVCUR, SLOT_T_DIRTY, SLOT_T_PAIRS,
@@ -81,6 +81,7 @@ struct wc_ctx {
     int k5_stages = 0;              // 0 = automatic TMA ring depth
     int k5_group = 0;               // CTAs sharing a row block per scheduling round of K5 (0 = automatic)
     int k5_sym = 8;                 // symmetric search: 0 = off, f >= 2 = on with 1/f of the block pairs in the first pass
+    int k5_f16 = 0;                 // 1: fp16 tensor-core filter (HMMA) instead of the fp64 one (DMMA) in K5
     int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones
     int debug_profile = 0;          // K5 writes per-CTA cycle counters when set (wc_debug_profile)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)

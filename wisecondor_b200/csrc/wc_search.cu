@@ -23,6 +23,7 @@
 // "d~ <= tau" is one unsigned 64-bit compare per entry, and the candidate buffers, the prune and the emission
 // path need no FP64 arithmetic at all.
 #include "wc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -96,6 +97,8 @@ struct TopkArgs {
     int* in_cnt;                 // [Nrows] entries offered (may exceed in_cap: the row then takes the exact fallback)
     int in_cap;
     const u64* col_thr;          // thresholds indexed by GLOBAL bin (== row_thr when the launch starts at row 0)
+    double madd;                 // margin(v) = mcoef * (n_i + |v|) + madd  (0 for the fp64 filter)
+    const float* n32;            // fp16 filter: the bins' squared norms in fp32, +inf for padding rows
 };
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -148,8 +151,8 @@ __device__ __forceinline__ double dist_of_key(u64 key) { return -2.0 * __longlon
 // final k-th smallest distance from above, and everything within the error margin of it is written back compacted.
 // Integer-only apart from the five FP64 operations that turn v* into the new threshold.
 template <int PER_LANE>   // cap / 32: every load of the buffer is issued before the first one is consumed
-__device__ __noinline__ void prune_row(u64* ck, int* cj, int n, int k, double nrm, double mcoef, int lane, u64* sk,
-                                       int* sj, u64* thr_out, int* n_out) {
+__device__ __noinline__ void prune_row(u64* ck, int* cj, int n, int k, double nrm, double mcoef, double madd, int lane,
+                                       u64* sk, int* sj, u64* thr_out, int* n_out) {
     // The row's buffer lives in registers for the whole prune (16 or 32 keys + column ids per lane; the accumulators
     // are dead between tiles): the bisection counts, the v* search and the compaction never touch memory again.
     (void)sk; (void)sj;
@@ -190,7 +193,7 @@ __device__ __noinline__ void prune_row(u64* ck, int* cj, int n, int k, double nr
         if (d[t] <= cut && d[t] > vstar) vstar = d[t];
     vstar = warp_max_u64(vstar);
     const double dv = dist_of_key(vstar);
-    double tau = dv + mcoef * (nrm + fabs(dv));
+    double tau = dv + mcoef * (nrm + fabs(dv)) + madd;
     const double tiny = fmax(mcoef * nrm, 1e-300);
     if (!(tau > tiny)) tau = tiny;
     const u64 thr = key_of_tau(tau);
@@ -343,9 +346,9 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             int* rj = cj + (size_t)(r0w + rw) * a.cap;
             __threadfence_block();
             if (a.cap <= 512)
-                prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sk, w_sj, &thr, &kept);
+                prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
             else
-                prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, lane, w_sk, w_sj, &thr, &kept);
+                prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
             if (lane == 0) {
                 if (kept > a.cap - BN) {       // a tie plateau wider than the buffer: exact fallback
                     w_flag[rw] = 1;
@@ -624,6 +627,421 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K4h / K5h: the same search with an FP16 tensor-core filter (option "k5_f16"; off until measured)
+// ---------------------------------------------------------------------------------------------------------
+// The filter only has to produce a SUPERSET of every bin's true top-k - K6 re-scores the shortlist exactly in fp64 - so
+// the contraction does not need fp64 at all.  With x' = x - 1 rounded once to fp16 (relative error 2^-11 per operand)
+// and fp32 accumulation, |d~ - d| <= eps * (n_i + n_j) with eps ~ 1.1e-3 (a priori; tools/bf16x3_study.py measures the
+// candidate inflation of such a margin: 109 instead of 100 candidates per bin at 600 x 250 kb).  The norms are NOT part
+// of the contraction here (n/2 ~ 1 would lose all precision in fp16): d~ = (n_i + n_j) - 2 s in fp32 in the epilogue.
+// Same persistent grid, TMA ring, warp-private rows, candidate buffers, prunes and symmetric column side as K5; the
+// operand tile has the same bytes (128 rows x 64 halves = 128 rows x 128 B, SWIZZLE_128B), fragments come from
+// ldmatrix.x4, the MMA is mma.sync.m16n8k16.f16 with fp32 accumulators (SASS HMMA.16816.F32).
+constexpr int BKH = 64;             // halves per pipeline stage and operand row (128 bytes)
+constexpr int F16_SCRATCH = 4096;   // per-warp parking area of the rare path (32 lanes x 32 fp32)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void hmma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                           uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// threshold key -> the fp32 bound used by the per-entry compare, rounded up (conservative)
+__device__ __forceinline__ float tau32_of_key(u64 key) { return __double2float_ru(dist_of_key(key)); }
+
+// K4h: X' = X - 1 in fp16 (padded with zeros to whole 64-sample chunks), n_i in fp64 (margins) and fp32 (epilogue;
+// +inf for padding rows so that they never pass), the largest finite norm and a flag for values fp16 cannot hold.
+__global__ void wc_prepare_f16_kernel(const double* __restrict__ X, int N, int Npad, int S, int ldh,
+                                      __half* __restrict__ Xh, double* __restrict__ norms, float* __restrict__ n32,
+                                      unsigned long long* __restrict__ stats) {
+    const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= Npad) return;
+    __half* dst = Xh + (size_t)row * ldh;
+    double acc = 0.0;
+    bool big = false;
+    if (row < N) {
+        const double* src = X + (size_t)row * S;
+        for (int s = lane; s < ldh; s += 32) {
+            const double v = s < S ? src[s] - 1.0 : 0.0;
+            dst[s] = __double2half(v);
+            acc = fma(v, v, acc);
+            if (fabs(v) > 60000.0 && fabs(v) < INFINITY) big = true;
+        }
+    } else {
+        for (int s = lane; s < ldh; s += 32) dst[s] = __float2half(0.0f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    big = __any_sync(0xffffffffu, big);
+    if (lane == 0) {
+        norms[row] = row < N ? acc : 0.0;
+        n32[row] = row < N ? (float)acc : INFINITY;
+        if (row < N && acc < INFINITY) atomicMax(stats, (unsigned long long)__double_as_longlong(acc));   // acc >= 0
+        if (big) atomicOr(stats + 1, 1ull);
+    }
+}
+
+template <bool SYM>
+__global__ void __launch_bounds__(TOPK_THREADS, 1)
+wc_dist_topk_f16_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    if (smem_u32(smem_raw) & 1023u) __trap();
+    const int STAGES = a.nstages;
+    unsigned char* tiles = smem_raw;
+    TopkState& sm = *reinterpret_cast<TopkState*>(smem_raw + (size_t)STAGES * STAGE_BYTES);
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(&sm + 1);
+    const int tid = threadIdx.x;
+    const int warp_all = tid >> 5, lane = tid & 31;
+    const int warp = warp_all - PRODUCER_WARPS;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], CONSUMER_WARPS);
+        }
+        for (int w = 0; w < CONSUMER_WARPS; ++w) sm.stg_cnt[w] = 0;
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap);
+    }
+    __syncthreads();
+
+    const int pb = a.cta_piece_begin[blockIdx.x], pe = a.cta_piece_begin[blockIdx.x + 1];
+    if (pb >= pe) return;
+
+    if (warp_all < PRODUCER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp_all == 0 && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pi = pb; pi < pe; ++pi) {
+                const int* pc = a.pieces + (size_t)pi * 5;
+                const int rbp = pc[0], q1 = pc[2], qs = pc[3];
+                const int skip_lo = a.rb_skip_lo[rbp], skip_n = a.rb_skip_n[rbp];
+                const int* tl = a.tile_list ? a.tile_list + a.rb_list_off[rbp] : nullptr;
+                const int row0 = a.row_begin + rbp * BM;
+                for (int q = pc[1]; q < q1; q += qs) {
+                    const int t = tl ? tl[q] : (q < skip_lo ? q : q + skip_n);
+                    const int col0 = t * BN;
+                    for (int kc = 0; kc < a.nkc; ++kc) {
+                        mbar_wait(&sm.empty[stage], phase ^ 1u);
+                        mbar_arrive_expect_tx(&sm.full[stage], STAGE_BYTES);
+                        tma_load_2d(tiles + (size_t)stage * STAGE_BYTES, &tmap, kc * BKH, row0, &sm.full[stage]);
+                        tma_load_2d(tiles + (size_t)stage * STAGE_BYTES + TILE_BYTES, &tmap, kc * BKH, col0, &sm.full[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: warp w owns rows [16w, 16w+16) x 128 columns = 16 m16n8 accumulator tiles (64 fp32 per lane) =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // m16n8k16 fragments: lane (g = lane/4, q = lane%4) holds C rows g and g+8, columns 2q, 2q+1 of every n-tile.
+    // ldmatrix.x4 addresses (A: matrices = rows 0-7 / 8-15 x k 0-7 / 8-15; B: n 0-7 / 8-15 x k 0-7 / 8-15 of an n-tile pair);
+    // the TMA 128-byte swizzle XORs the 16-byte chunk index with (row & 7).
+    const int g = lane >> 2, q4 = lane & 3;
+    const uint32_t a_row = (uint32_t)(warp * WROWS + (lane & 7) + ((lane >> 3) & 1) * 8);
+    const uint32_t a_off = a_row * 128u;
+    const uint32_t a_kc = (uint32_t)(lane >> 4);            // which 8-sample half of the k16 step this lane addresses
+    const uint32_t b_row = (uint32_t)(((lane >> 4) & 1) * 8 + (lane & 7));
+    const uint32_t b_off = (uint32_t)TILE_BYTES + b_row * 128u;
+    const uint32_t b_kc = (uint32_t)((lane >> 3) & 1);
+    const uint32_t xr = (uint32_t)(lane & 7);               // row & 7 of both addresses
+
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    const size_t scratch_per_warp = F16_SCRATCH;       // the prune works on registers: only the parking area is needed
+    u64* w_sk = reinterpret_cast<u64*>(scratch + (size_t)warp * scratch_per_warp);
+    int* w_sj = nullptr;
+    u64* w_ct = reinterpret_cast<u64*>(scratch + (size_t)CONSUMER_WARPS * scratch_per_warp) + warp * BN;
+    uint4* w_stg = reinterpret_cast<uint4*>(scratch + (size_t)CONSUMER_WARPS * scratch_per_warp +
+                                            (size_t)CONSUMER_WARPS * BN * sizeof(u64)) + warp * STG;
+    // fp32 side tables of the warp: norms of the tile's 128 columns, their thresholds (SYM), thresholds of the 16 rows
+    float* w_cn = reinterpret_cast<float*>(scratch + (size_t)CONSUMER_WARPS * scratch_per_warp +
+                                           (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4))) + warp * (2 * BN + 32);
+    float* w_ctf = w_cn + BN;
+    float* w_rt = w_ctf + BN;
+    int* w_stgc = &sm.stg_cnt[warp];
+    const int r0w = warp * WROWS;
+    u64* w_thr = sm.thr + r0w;
+    double* w_nrm = sm.nrm + r0w;
+    int* w_cnt = sm.cnt + r0w;
+    unsigned char* w_flag = sm.flag + r0w;
+    int my_cs[2] = {0, 0}, my_ce[2] = {0, 0};
+    float my_n[2] = {INFINITY, INFINITY};       // fp32 norms of this lane's two rows (g and g+8)
+    int stage = 0;
+    uint32_t phase = 0;
+    const size_t seg_stride = (size_t)BM * a.cap;
+    bool ready = false;
+
+    long long pf_wait = 0, pf_epi = 0, pf_prune = 0, pf_nprune = 0, pf_emit = 0;
+    const long long pf_t0 = clock64();
+    int pi = pb;
+    const int* pc = a.pieces + (size_t)pi * 5;
+    int rb = pc[0], q = pc[1], q1 = pc[2], qs = pc[3], seg = pc[4];
+    int skip_lo = a.rb_skip_lo[rb], skip_n = a.rb_skip_n[rb];
+    const int* tl = a.tile_list ? a.tile_list + a.rb_list_off[rb] : nullptr;
+    bool new_piece = true;
+
+    auto prune_rows = [&](unsigned need, u64* ck, int* cj) {
+        while (need) {
+            const int rw = __ffs(need) - 1;
+            need &= need - 1;
+            int n = w_cnt[rw];
+            if (n > a.cap) n = a.cap;
+            u64 thr;
+            int kept;
+            ++pf_nprune;
+            u64* rk = ck + (size_t)(r0w + rw) * a.cap;
+            int* rj = cj + (size_t)(r0w + rw) * a.cap;
+            __threadfence_block();
+            if (a.cap <= 512)
+                prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
+            else
+                prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
+            if (lane == 0) {
+                if (kept > a.cap - BN) {
+                    w_flag[rw] = 1;
+                    w_thr[rw] = KEY_NEVER;
+                    w_cnt[rw] = 0;
+                } else {
+                    const int row = a.row_begin + rb * BM + r0w + rw;
+                    const u64 other = atomicMin(a.row_thr + (row - a.row_begin), thr);
+                    w_thr[rw] = other < thr ? other : thr;
+                    w_cnt[rw] = kept;
+                }
+            }
+            __syncwarp();
+        }
+    };
+    auto flush_incoming = [&]() {
+        __syncwarp();
+        int n = *w_stgc;
+        if (n > STG) n = STG;
+        for (int e = lane; e < n; e += 32) {
+            const uint4 v = w_stg[e];
+            const int j = (int)v.z;
+            const int w = atomicAdd(a.in_cnt + j, 1);
+            if (w < a.in_cap) {
+                a.in_key[(size_t)j * a.in_cap + w] = ((u64)v.y << 32) | (u64)v.x;
+                a.in_j[(size_t)j * a.in_cap + w] = (int)v.w;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) *w_stgc = 0;
+        __syncwarp();
+    };
+    int tcount = 0;
+    while (true) {
+        if (q >= q1) {
+            __syncwarp();
+            if (SYM) flush_incoming();
+            if (a.final_prune) {
+                const unsigned need = __ballot_sync(0xffffffffu, lane < WROWS && w_cnt[lane] > a.k + 24 &&
+                                                                     w_cnt[lane] <= a.cap && !w_flag[lane]);
+                prune_rows(need, a.cand_key + (size_t)seg * seg_stride, a.cand_j + (size_t)seg * seg_stride);
+            }
+            if (lane < WROWS) {
+                a.seg_cnt[(size_t)seg * BM + r0w + lane] = w_cnt[lane] > a.cap ? a.cap : w_cnt[lane];
+                a.seg_flag[(size_t)seg * BM + r0w + lane] = w_flag[lane];
+            }
+            if (++pi >= pe) break;
+            pc = a.pieces + (size_t)pi * 5;
+            rb = pc[0]; q = pc[1]; q1 = pc[2]; qs = pc[3]; seg = pc[4];
+            skip_lo = a.rb_skip_lo[rb]; skip_n = a.rb_skip_n[rb];
+            tl = a.tile_list ? a.tile_list + a.rb_list_off[rb] : nullptr;
+            new_piece = true;
+            continue;
+        }
+        if (new_piece) {
+            new_piece = false;
+            __syncwarp();
+            if (lane < WROWS) {
+                const int row = a.row_begin + rb * BM + r0w + lane;
+                const bool valid = row < a.row_end;
+                w_nrm[lane] = valid ? a.norms[row] : 0.0;
+                w_thr[lane] = valid ? __ldcg(a.row_thr + (row - a.row_begin)) : KEY_NEVER;
+                w_cnt[lane] = 0;
+                w_flag[lane] = 0;
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int row = a.row_begin + rb * BM + r0w + hh * 8 + g;
+                const bool valid = row < a.row_end;
+                my_cs[hh] = valid ? a.row_cs[row] : 0;
+                my_ce[hh] = valid ? a.row_ce[row] : 0;
+                my_n[hh] = valid ? a.n32[row] : INFINITY;
+            }
+            __syncwarp();
+        }
+        const int t = tl ? tl[q] : (q < skip_lo ? q : q + skip_n);
+        const int col0 = t * BN;
+        q += qs;
+        // the tile's column norms (and, SYM, the column bins' thresholds): L2 -> this warp's shared copies
+        __syncwarp();
+        cp_async_16(w_cn + 4 * lane, a.n32 + col0 + 4 * lane);
+        if (SYM) {
+            cp_async_16(w_ct + 2 * lane, a.col_thr + col0 + 2 * lane);
+            cp_async_16(w_ct + 64 + 2 * lane, a.col_thr + col0 + 64 + 2 * lane);
+        }
+        cp_async_commit();
+        u64 shared_thr = ~0ull;
+        if (lane < WROWS) {
+            const int row = a.row_begin + rb * BM + r0w + lane;
+            if (row < a.row_end) shared_thr = __ldcg(a.row_thr + (row - a.row_begin));
+        }
+        ++tcount;
+
+        float acc[16][4];
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
+
+        for (int kc = 0; kc < a.nkc; ++kc) {
+            if (!ready) {
+                const long long pf_w0 = clock64();
+                mbar_wait(&sm.full[stage], phase);
+                pf_wait += clock64() - pf_w0;
+            }
+            const uint32_t base = tiles_u32 + (uint32_t)stage * STAGE_BYTES;
+            int nstage = stage + 1;
+            uint32_t nphase = phase;
+            if (nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+            const bool ready_next = mbar_test_wait(&sm.full[nstage], nphase);
+#pragma unroll
+            for (int ks = 0; ks < BKH / 16; ++ks) {
+                uint32_t fa0, fa1, fa2, fa3;
+                ldsm_x4(base + a_off + ((((uint32_t)(2 * ks) + a_kc) ^ xr) << 4), fa0, fa1, fa2, fa3);
+                const uint32_t bsw = (((uint32_t)(2 * ks) + b_kc) ^ xr) << 4;
+#pragma unroll
+                for (int np = 0; np < 8; ++np) {
+                    uint32_t fb0, fb1, fb2, fb3;
+                    ldsm_x4(base + b_off + (uint32_t)np * 2048u + bsw, fb0, fb1, fb2, fb3);
+                    hmma_16816(acc[2 * np], fa0, fa1, fa2, fa3, fb0, fb1);
+                    hmma_16816(acc[2 * np + 1], fa0, fa1, fa2, fa3, fb2, fb3);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);
+            stage = nstage;
+            phase = nphase;
+            ready = ready_next;
+        }
+
+        // ---- epilogue: d~ = (n_i + n_j) - 2 s in fp32, one compare per entry against the row's (and, SYM, the column's) bound
+        const long long pf_e0 = clock64();
+        if (lane < WROWS) {
+            if (shared_thr < w_thr[lane]) w_thr[lane] = shared_thr;
+            w_rt[lane] = tau32_of_key(w_thr[lane]);
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        if (SYM) {
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) w_ctf[lane + 32 * i] = tau32_of_key(w_ct[lane + 32 * i]);
+            __syncwarp();
+        }
+        u64* ck = a.cand_key + (size_t)seg * seg_stride;
+        int* cj = a.cand_j + (size_t)seg * seg_stride;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int rw = hh * 8 + g;
+            const float taui = w_rt[rw];
+            const float ni = my_n[hh];
+            unsigned mask = 0, cmask = 0;
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+                const float2 nj = *reinterpret_cast<const float2*>(w_cn + nt * 8 + 2 * q4);
+                const float d0 = fmaf(-2.0f, acc[nt][2 * hh], ni + nj.x);
+                const float d1 = fmaf(-2.0f, acc[nt][2 * hh + 1], ni + nj.y);
+                if (d0 <= taui) mask |= 1u << (nt * 2);
+                if (d1 <= taui) mask |= 1u << (nt * 2 + 1);
+                if (SYM) {
+                    const float2 tj = *reinterpret_cast<const float2*>(w_ctf + nt * 8 + 2 * q4);
+                    if (d0 <= tj.x) cmask |= 1u << (nt * 2);
+                    if (d1 <= tj.y) cmask |= 1u << (nt * 2 + 1);
+                }
+            }
+            if (mask | cmask) {
+                // rare path: park this row's 32 distances in the warp's scratch (lane-interleaved) and walk the set bits
+                float* tmp = reinterpret_cast<float*>(w_sk) + lane;        // entry b lives at tmp[b * 32]
+#pragma unroll
+                for (int nt = 0; nt < 16; ++nt) {
+                    const float2 nj = *reinterpret_cast<const float2*>(w_cn + nt * 8 + 2 * q4);
+                    tmp[(nt * 2) * 32] = fmaf(-2.0f, acc[nt][2 * hh], ni + nj.x);
+                    tmp[(nt * 2 + 1) * 32] = fmaf(-2.0f, acc[nt][2 * hh + 1], ni + nj.y);
+                }
+                const int cs = my_cs[hh];
+                const unsigned clen = (unsigned)(my_ce[hh] - cs);
+                unsigned m2 = mask;
+                while (m2) {                               // drop non-finite distances and the row's own chromosome
+                    const int bit = __ffs(m2) - 1;
+                    m2 &= m2 - 1;
+                    const int cl = (bit >> 1) * 8 + 2 * q4 + (bit & 1);
+                    if (!(fabsf(tmp[bit * 32]) < INFINITY) || (unsigned)(col0 + cl - cs) < clen) mask &= ~(1u << bit);
+                }
+                if (mask) {
+                    pf_emit += __popc(mask);
+                    int w = atomicAdd(&w_cnt[rw], __popc(mask));
+                    u64* rk = ck + (size_t)(r0w + rw) * a.cap;
+                    int* rj = cj + (size_t)(r0w + rw) * a.cap;
+                    while (mask) {
+                        const int bit = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int cl = (bit >> 1) * 8 + 2 * q4 + (bit & 1);
+                        if (w < a.cap) {
+                            rk[w] = (u64)__double_as_longlong(-0.5 * (double)tmp[bit * 32]);
+                            rj[w] = col0 + cl;
+                        } else {
+                            w_flag[rw] = 1;
+                        }
+                        ++w;
+                    }
+                }
+                if (SYM && cmask) {
+                    const int i = a.row_begin + rb * BM + r0w + rw;
+                    while (cmask) {
+                        const int bit = __ffs(cmask) - 1;
+                        cmask &= cmask - 1;
+                        const int j = col0 + (bit >> 1) * 8 + 2 * q4 + (bit & 1);
+                        const float dv = tmp[bit * 32];
+                        if (!(fabsf(dv) < INFINITY) || j >= a.N || i >= a.row_end) continue;
+                        if ((unsigned)(j - cs) < clen) continue;
+                        const u64 key = (u64)__double_as_longlong(-0.5 * (double)dv);
+                        const int pos = atomicAdd(w_stgc, 1);
+                        if (pos < STG) {
+                            w_stg[pos] = make_uint4((unsigned)key, (unsigned)(key >> 32), (unsigned)j, (unsigned)i);
+                        } else {
+                            const int w = atomicAdd(a.in_cnt + j, 1);
+                            if (w < a.in_cap) {
+                                a.in_key[(size_t)j * a.in_cap + w] = key;
+                                a.in_j[(size_t)j * a.in_cap + w] = i;
+                            }
+                        }
+                        ++pf_emit;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (SYM && *w_stgc >= 32) flush_incoming();
+        const long long pf_p0 = clock64();
+        pf_epi += pf_p0 - pf_e0;
+        prune_rows(__ballot_sync(0xffffffffu, lane < WROWS && w_cnt[lane] > a.cap - BN && !w_flag[lane]), ck, cj);
+        pf_prune += clock64() - pf_p0;
+    }
+    __syncwarp();
+    if (a.prof != nullptr && warp == 0 && lane == 0) {
+        long long* o = a.prof + (size_t)blockIdx.x * 8;
+        o[0] = clock64() - pf_t0; o[1] = pf_wait; o[2] = pf_epi; o[3] = pf_prune;
+        o[4] = tcount; o[5] = pf_nprune; o[6] = pf_emit; o[7] = 0;
+    }
+}
+
 __global__ void wc_fill_u64_kernel(u64* p, size_t n, u64 v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -692,6 +1110,7 @@ struct FinArgs {
     const int* in_j;
     const int* in_cnt;
     int in_cap;
+    double madd;            // window(v) = v + mcoef * (n_i + |v|) + madd
     int in_nsrc;            // incoming sources (1; one per rank after the exchange of a sharded symmetric search)
     int in_src_rows;        // rows between two sources: source s holds row r at (s * in_src_rows + r)
 };
@@ -833,7 +1252,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < FIN_THREADS / 32; ++w) vstar = fmax(vstar, s_red[0][w]);
-    const double window = vstar + a.mcoef * (a.norms[row] + fabs(vstar));
+    const double window = vstar + a.mcoef * (a.norms[row] + fabs(vstar)) + a.madd;
     for (int s = 0; s < nsrc; ++s) {
         const u64* cd;
         const int* cjs;
@@ -1389,13 +1808,38 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     if (sym) WC_CUDA(cudaMemsetAsync(in_cnt, 0, (size_t)rows * sizeof(int), stream));
 
     // ---- K4 -------------------------------------------------------------------------------------------------
+    // Option k5_f16: the filter runs on the fp16 tensor cores (K4h + K5h); falls back to the fp64 filter when the matrix
+    // holds finite values fp16 cannot represent.
+    bool f16 = ctx->k5_f16 != 0;
+    const int ldh = (S + BKH - 1) / BKH * BKH;
+    float* n32 = nullptr;
+    double nmax = 0.0;
     WC_CUDA(cudaEventRecord(ctx->ev[0], stream));
-    {
+    if (f16) {
+        unsigned long long* stats;
+        if ((rc = wc_reserve(ctx, SLOT_N32, Npad * sizeof(float), (void**)&n32))) return rc;
+        if ((rc = wc_reserve(ctx, SLOT_F16STAT, 2 * sizeof(unsigned long long), (void**)&stats))) return rc;
+        WC_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), stream));
+        wc_prepare_f16_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ldh,
+                                                                                  reinterpret_cast<__half*>(Xc), norms, n32, stats);
+        WC_CUDA(cudaGetLastError());
+        unsigned long long st_h[2] = {0, 0};
+        WC_CUDA(cudaMemcpyAsync(st_h, stats, sizeof(st_h), cudaMemcpyDeviceToHost, stream));
+        WC_CUDA(cudaStreamSynchronize(stream));
+        memcpy(&nmax, &st_h[0], sizeof(double));
+        if (st_h[1] != 0) f16 = false;            // |x - 1| > 60000 somewhere: outside fp16's range
+    }
+    if (!f16) {
         const int blocks = (int)((Npad * 32 + 255) / 256);
         wc_prepare_kernel<<<blocks, 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ld, Sx, Xc, norms);
     }
     WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[1], stream));
+    // error of the fp16 filter: |d~ - d| <= eps * (n_i + n_j) + sub; eps = operand rounding (2 x 2^-11), fp32 accumulation
+    // of ldh products (taken one bit worse than IEEE), the fp32 epilogue; sub = fp16 subnormal spacing on tiny values
+    const double eps16 = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (double)ldh * ldexp(1.0, -23) + ldexp(1.0, -21);
+    const double filt_mcoef = f16 ? 2.0 * eps16 : mcoef;
+    const double filt_madd = f16 ? 2.0 * eps16 * nmax + ldexp(1.0, -20) * sqrt((double)S * nmax) : 0.0;
 
     // ---- K5 -------------------------------------------------------------------------------------------------
     CUtensorMap tmap;
@@ -1404,13 +1848,14 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
             wc_set_error("cuTensorMapEncodeTiled is not available from this driver");
             return WC_ERR_CUDA;
         }
-        cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)Npad};
-        cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
-        cuuint32_t box[2] = {BK, BM};
+        cuuint64_t dims[2] = {(cuuint64_t)(f16 ? ldh : ld), (cuuint64_t)Npad};
+        cuuint64_t strides[1] = {f16 ? (cuuint64_t)ldh * sizeof(__half) : (cuuint64_t)ld * sizeof(double)};
+        cuuint32_t box[2] = {(cuuint32_t)(f16 ? BKH : BK), BM};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = reinterpret_cast<PFN_encodeTiled>(ctx->encode_tiled)(
-            &tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, Xc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            &tmap, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, Xc, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             wc_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
             return WC_ERR_CUDA;
@@ -1422,13 +1867,15 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     ta.rb_skip_lo = d_skip_lo; ta.rb_skip_n = d_skip_n; ta.nrb = nrb;
     ta.cta_piece_begin = d_cta_piece; ta.pieces = d_pieces;
     ta.cand_key = cand_key; ta.cand_j = cand_j; ta.seg_cnt = seg_cnt; ta.seg_flag = seg_flag;
-    ta.cap = cap; ta.k = k; ta.mcoef = mcoef; ta.tau_init = 1e10 * (1.0 + 1e-6);
+    ta.cap = cap; ta.k = k; ta.mcoef = filt_mcoef; ta.tau_init = f16 ? 3e38 : 1e10 * (1.0 + 1e-6);
     ta.row_thr = row_thr;
     ta.lag = ctx->k5_lag;
     ta.nstages = cap <= 512 ? (sym ? 4 : 5) : 3;          // the symmetric pass keeps 8 KiB of column thresholds in shared memory
+    if (f16) { ta.nstages = 4; ta.nkc = ldh / BKH; }
     if (ctx->k5_stages >= 3 && ctx->k5_stages <= MAX_STAGES) ta.nstages = ctx->k5_stages;
     ta.tile_list = nullptr; ta.rb_list_off = nullptr; ta.final_prune = sym ? 1 : 0;
     ta.in_key = in_key; ta.in_j = in_j; ta.in_cnt = in_cnt; ta.in_cap = in_cap; ta.col_thr = row_thr;
+    ta.madd = filt_madd; ta.n32 = n32;
     ta.prof = nullptr;
     ta.trace = nullptr;
     const int grid_prof = sym ? std::max(gridA, gridB) : grid;
@@ -1437,28 +1884,33 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         WC_CUDA(cudaMemsetAsync(ta.prof, 0, ((size_t)grid_prof * 8 + 512) * sizeof(long long), stream));
         ta.trace = ta.prof + (size_t)grid_prof * 8;
     }
-    const size_t topk_smem = (size_t)ta.nstages * STAGE_BYTES + sizeof(TopkState) +
-                             (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192) +
-                             (sym ? (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4)) : 0);
+    const size_t topk_smem = f16
+        ? (size_t)ta.nstages * STAGE_BYTES + sizeof(TopkState) + (size_t)CONSUMER_WARPS * F16_SCRATCH +
+              (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4) + (2 * BN + 32) * sizeof(float))
+        : (size_t)ta.nstages * STAGE_BYTES + sizeof(TopkState) +
+              (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192) +
+              (sym ? (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4)) : 0);
     if (topk_smem > 227 * 1024) { wc_set_error("K5 shared memory %zu exceeds 227 KiB", topk_smem); return WC_ERR_INTERNAL; }
-    WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+    auto k5_plain = f16 ? wc_dist_topk_f16_kernel<false> : wc_dist_topk_kernel<false>;
+    auto k5_sym = f16 ? wc_dist_topk_f16_kernel<true> : wc_dist_topk_kernel<true>;
+    WC_CUDA(cudaFuncSetAttribute(k5_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
     wc_fill_u64_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(row_thr, (size_t)rows, host_key_of_tau(ta.tau_init));
     wc_fill_u64_kernel<<<(unsigned)((thr_n - rows + 255) / 256), 256, 0, stream>>>(row_thr + rows, thr_n - (size_t)rows, KEY_NEVER);
     WC_CUDA(cudaEventRecord(ctx->ev[2], stream));
     if (!sym) {
-        wc_dist_topk_kernel<false><<<grid, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+        k5_plain<<<grid, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
     } else {
-        WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+        WC_CUDA(cudaFuncSetAttribute(k5_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
         const int nb1 = nrb + 1;
         ta.tile_list = d_sym + 2 * nb1;                                  // pass A
         ta.rb_list_off = d_sym;
-        wc_dist_topk_kernel<false><<<gridA, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+        k5_plain<<<gridA, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
         WC_CUDA(cudaGetLastError());
         WC_CUDA(cudaEventRecord(ctx->ev[16], stream));
         ta.tile_list = d_sym + 2 * nb1 + (int)listA.size();              // pass B
         ta.rb_list_off = d_sym + nb1;
         ta.cta_piece_begin = d_cta_piece + (gridA + 1);
-        wc_dist_topk_kernel<true><<<gridB, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+        k5_sym<<<gridB, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
     }
     WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[3], stream));
@@ -1468,10 +1920,11 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     fa.X = corrected_d; fa.N = N; fa.S = S; fa.norms = norms; fa.row_cs = d_row_cs; fa.row_ce = d_row_ce;
     fa.row_begin = row_begin; fa.row_end = row_end; fa.rb_seg_first = d_seg_first; fa.rb_seg_count = d_seg_count;
     fa.cand_key = cand_key; fa.cand_j = cand_j; fa.seg_cnt = seg_cnt; fa.seg_flag = seg_flag; fa.cap = cap; fa.k = k;
-    fa.shortcap = k <= 128 ? 256 : 512;
-    fa.mcoef = mcoef; fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
+    fa.shortcap = k <= (f16 ? 96 : 128) ? 256 : 512;          // the fp16 filter's wider window lets ~10-25 % more through
+    fa.mcoef = filt_mcoef; fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
     fa.bulk = (S % 2 == 0 && (reinterpret_cast<uintptr_t>(corrected_d) & 15) == 0) ? 1 : 0;
     fa.in_key = in_key; fa.in_j = in_j; fa.in_cnt = in_cnt; fa.in_cap = in_cap; fa.in_nsrc = 1; fa.in_src_rows = 0;
+    fa.madd = filt_madd;
     const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 +
                             HIST_BINS * 4;
     WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
@@ -1627,6 +2080,7 @@ int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned
     ta.rb_list_off = pass == 0 ? d_offA : d_offB;
     ta.final_prune = 1;
     ta.in_key = in_key_d; ta.in_j = in_j_d; ta.in_cnt = in_cnt_d; ta.in_cap = pl.in_cap;
+    ta.madd = 0.0; ta.n32 = nullptr;
     if (pass == 0) {
         WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         wc_dist_topk_kernel<false><<<pl.gridA, TOPK_THREADS, pl.smem, stream>>>(tmap, ta);
@@ -1875,7 +2329,7 @@ extern "C" int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* rec
         fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
         fa.bulk = (pl.S % 2 == 0 && (reinterpret_cast<uintptr_t>(pl.corrected) & 15) == 0) ? 1 : 0;
         fa.in_key = recv_key_d; fa.in_j = recv_j_d; fa.in_cnt = recv_cnt_d; fa.in_cap = pl.in_cap;
-        fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per;
+        fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per; fa.madd = 0.0;
         const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
         WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
         WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
@@ -1950,6 +2404,10 @@ extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
     if (strcmp(key, "k5_sym") == 0) {        // symmetric search for whole-matrix calls: 0 = off, f in 2..64 = on (first pass 1/f)
         if (value != 0 && (value < 2 || value > 64)) { wc_set_error("k5_sym must be 0 or 2..64"); return WC_ERR_ARG; }
         ctx->k5_sym = (int)value;
+        return WC_OK;
+    }
+    if (strcmp(key, "k5_f16") == 0) {        // 1: fp16 tensor-core filter (K4h + K5h), 0: fp64 filter
+        ctx->k5_f16 = value != 0 ? 1 : 0;
         return WC_OK;
     }
     if (strcmp(key, "k5_stages") == 0) {
