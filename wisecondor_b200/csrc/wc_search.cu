@@ -627,420 +627,7 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// K4h / K5h: the same search with an FP16 tensor-core filter (option "k5_f16"; off until measured)
-// ---------------------------------------------------------------------------------------------------------
-// The filter only has to produce a SUPERSET of every bin's true top-k - K6 re-scores the shortlist exactly in fp64 - so
-// the contraction does not need fp64 at all.  With x' = x - 1 rounded once to fp16 (relative error 2^-11 per operand)
-// and fp32 accumulation, |d~ - d| <= eps * (n_i + n_j) with eps ~ 1.1e-3 (a priori; tools/bf16x3_study.py measures the
-// candidate inflation of such a margin: 109 instead of 100 candidates per bin at 600 x 250 kb).  The norms are NOT part
-// of the contraction here (n/2 ~ 1 would lose all precision in fp16): d~ = (n_i + n_j) - 2 s in fp32 in the epilogue.
-// Same persistent grid, TMA ring, warp-private rows, candidate buffers, prunes and symmetric column side as K5; the
-// operand tile has the same bytes (128 rows x 64 halves = 128 rows x 128 B, SWIZZLE_128B), fragments come from
-// ldmatrix.x4, the MMA is mma.sync.m16n8k16.f16 with fp32 accumulators (SASS HMMA.16816.F32).
-constexpr int BKH = 64;             // halves per pipeline stage and operand row (128 bytes)
-constexpr int F16_SCRATCH = 4096;   // per-warp parking area of the rare path (32 lanes x 32 fp32)
-
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void hmma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                           uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-// threshold key -> the fp32 bound used by the per-entry compare, rounded up (conservative)
-__device__ __forceinline__ float tau32_of_key(u64 key) { return __double2float_ru(dist_of_key(key)); }
-
-// K4h: X' = X - 1 in fp16 (padded with zeros to whole 64-sample chunks), n_i in fp64 (margins) and fp32 (epilogue;
-// +inf for padding rows so that they never pass), the largest finite norm and a flag for values fp16 cannot hold.
-__global__ void wc_prepare_f16_kernel(const double* __restrict__ X, int N, int Npad, int S, int ldh,
-                                      __half* __restrict__ Xh, double* __restrict__ norms, float* __restrict__ n32,
-                                      unsigned long long* __restrict__ stats) {
-    const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= Npad) return;
-    __half* dst = Xh + (size_t)row * ldh;
-    double acc = 0.0;
-    bool big = false;
-    if (row < N) {
-        const double* src = X + (size_t)row * S;
-        for (int s = lane; s < ldh; s += 32) {
-            const double v = s < S ? src[s] - 1.0 : 0.0;
-            dst[s] = __double2half(v);
-            acc = fma(v, v, acc);
-            if (fabs(v) > 60000.0 && fabs(v) < INFINITY) big = true;
-        }
-    } else {
-        for (int s = lane; s < ldh; s += 32) dst[s] = __float2half(0.0f);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    big = __any_sync(0xffffffffu, big);
-    if (lane == 0) {
-        norms[row] = row < N ? acc : 0.0;
-        n32[row] = row < N ? (float)acc : INFINITY;
-        if (row < N && acc < INFINITY) atomicMax(stats, (unsigned long long)__double_as_longlong(acc));   // acc >= 0
-        if (big) atomicOr(stats + 1, 1ull);
-    }
-}
-
-template <bool SYM>
-__global__ void __launch_bounds__(TOPK_THREADS, 1)
-wc_dist_topk_f16_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    if (smem_u32(smem_raw) & 1023u) __trap();
-    const int STAGES = a.nstages;
-    unsigned char* tiles = smem_raw;
-    TopkState& sm = *reinterpret_cast<TopkState*>(smem_raw + (size_t)STAGES * STAGE_BYTES);
-    unsigned char* scratch = reinterpret_cast<unsigned char*>(&sm + 1);
-    const int tid = threadIdx.x;
-    const int warp_all = tid >> 5, lane = tid & 31;
-    const int warp = warp_all - PRODUCER_WARPS;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], CONSUMER_WARPS);
-        }
-        for (int w = 0; w < CONSUMER_WARPS; ++w) sm.stg_cnt[w] = 0;
-        mbar_fence_init();
-        tma_prefetch_desc(&tmap);
-    }
-    __syncthreads();
-
-    const int pb = a.cta_piece_begin[blockIdx.x], pe = a.cta_piece_begin[blockIdx.x + 1];
-    if (pb >= pe) return;
-
-    if (warp_all < PRODUCER_WARPS) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp_all == 0 && lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int pi = pb; pi < pe; ++pi) {
-                const int* pc = a.pieces + (size_t)pi * 5;
-                const int rbp = pc[0], q1 = pc[2], qs = pc[3];
-                const int skip_lo = a.rb_skip_lo[rbp], skip_n = a.rb_skip_n[rbp];
-                const int* tl = a.tile_list ? a.tile_list + a.rb_list_off[rbp] : nullptr;
-                const int row0 = a.row_begin + rbp * BM;
-                for (int q = pc[1]; q < q1; q += qs) {
-                    const int t = tl ? tl[q] : (q < skip_lo ? q : q + skip_n);
-                    const int col0 = t * BN;
-                    for (int kc = 0; kc < a.nkc; ++kc) {
-                        mbar_wait(&sm.empty[stage], phase ^ 1u);
-                        mbar_arrive_expect_tx(&sm.full[stage], STAGE_BYTES);
-                        tma_load_2d(tiles + (size_t)stage * STAGE_BYTES, &tmap, kc * BKH, row0, &sm.full[stage]);
-                        tma_load_2d(tiles + (size_t)stage * STAGE_BYTES + TILE_BYTES, &tmap, kc * BKH, col0, &sm.full[stage]);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                    }
-                }
-            }
-        }
-        return;
-    }
-
-    // ===== consumers: warp w owns rows [16w, 16w+16) x 128 columns = 16 m16n8 accumulator tiles (64 fp32 per lane) =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // m16n8k16 fragments: lane (g = lane/4, q = lane%4) holds C rows g and g+8, columns 2q, 2q+1 of every n-tile.
-    // ldmatrix.x4 addresses (A: matrices = rows 0-7 / 8-15 x k 0-7 / 8-15; B: n 0-7 / 8-15 x k 0-7 / 8-15 of an n-tile pair);
-    // the TMA 128-byte swizzle XORs the 16-byte chunk index with (row & 7).
-    const int g = lane >> 2, q4 = lane & 3;
-    const uint32_t a_row = (uint32_t)(warp * WROWS + (lane & 7) + ((lane >> 3) & 1) * 8);
-    const uint32_t a_off = a_row * 128u;
-    const uint32_t a_kc = (uint32_t)(lane >> 4);            // which 8-sample half of the k16 step this lane addresses
-    const uint32_t b_row = (uint32_t)(((lane >> 4) & 1) * 8 + (lane & 7));
-    const uint32_t b_off = (uint32_t)TILE_BYTES + b_row * 128u;
-    const uint32_t b_kc = (uint32_t)((lane >> 3) & 1);
-    const uint32_t xr = (uint32_t)(lane & 7);               // row & 7 of both addresses
-
-    const uint32_t tiles_u32 = smem_u32(tiles);
-    const size_t scratch_per_warp = F16_SCRATCH;       // the prune works on registers: only the parking area is needed
-    u64* w_sk = reinterpret_cast<u64*>(scratch + (size_t)warp * scratch_per_warp);
-    int* w_sj = nullptr;
-    u64* w_ct = reinterpret_cast<u64*>(scratch + (size_t)CONSUMER_WARPS * scratch_per_warp) + warp * BN;
-    uint4* w_stg = reinterpret_cast<uint4*>(scratch + (size_t)CONSUMER_WARPS * scratch_per_warp +
-                                            (size_t)CONSUMER_WARPS * BN * sizeof(u64)) + warp * STG;
-    // fp32 side tables of the warp: norms of the tile's 128 columns, their thresholds (SYM), thresholds of the 16 rows
-    float* w_cn = reinterpret_cast<float*>(scratch + (size_t)CONSUMER_WARPS * scratch_per_warp +
-                                           (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4))) + warp * (2 * BN + 32);
-    float* w_ctf = w_cn + BN;
-    float* w_rt = w_ctf + BN;
-    int* w_stgc = &sm.stg_cnt[warp];
-    const int r0w = warp * WROWS;
-    u64* w_thr = sm.thr + r0w;
-    double* w_nrm = sm.nrm + r0w;
-    int* w_cnt = sm.cnt + r0w;
-    unsigned char* w_flag = sm.flag + r0w;
-    int my_cs[2] = {0, 0}, my_ce[2] = {0, 0};
-    float my_n[2] = {INFINITY, INFINITY};       // fp32 norms of this lane's two rows (g and g+8)
-    int stage = 0;
-    uint32_t phase = 0;
-    const size_t seg_stride = (size_t)BM * a.cap;
-    bool ready = false;
-
-    long long pf_wait = 0, pf_epi = 0, pf_prune = 0, pf_nprune = 0, pf_emit = 0;
-    const long long pf_t0 = clock64();
-    int pi = pb;
-    const int* pc = a.pieces + (size_t)pi * 5;
-    int rb = pc[0], q = pc[1], q1 = pc[2], qs = pc[3], seg = pc[4];
-    int skip_lo = a.rb_skip_lo[rb], skip_n = a.rb_skip_n[rb];
-    const int* tl = a.tile_list ? a.tile_list + a.rb_list_off[rb] : nullptr;
-    bool new_piece = true;
-
-    auto prune_rows = [&](unsigned need, u64* ck, int* cj) {
-        while (need) {
-            const int rw = __ffs(need) - 1;
-            need &= need - 1;
-            int n = w_cnt[rw];
-            if (n > a.cap) n = a.cap;
-            u64 thr;
-            int kept;
-            ++pf_nprune;
-            u64* rk = ck + (size_t)(r0w + rw) * a.cap;
-            int* rj = cj + (size_t)(r0w + rw) * a.cap;
-            __threadfence_block();
-            if (a.cap <= 512)
-                prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
-            else
-                prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
-            if (lane == 0) {
-                if (kept > a.cap - BN) {
-                    w_flag[rw] = 1;
-                    w_thr[rw] = KEY_NEVER;
-                    w_cnt[rw] = 0;
-                } else {
-                    const int row = a.row_begin + rb * BM + r0w + rw;
-                    const u64 other = atomicMin(a.row_thr + (row - a.row_begin), thr);
-                    w_thr[rw] = other < thr ? other : thr;
-                    w_cnt[rw] = kept;
-                }
-            }
-            __syncwarp();
-        }
-    };
-    auto flush_incoming = [&]() {
-        __syncwarp();
-        int n = *w_stgc;
-        if (n > STG) n = STG;
-        for (int e = lane; e < n; e += 32) {
-            const uint4 v = w_stg[e];
-            const int j = (int)v.z;
-            const int w = atomicAdd(a.in_cnt + j, 1);
-            if (w < a.in_cap) {
-                a.in_key[(size_t)j * a.in_cap + w] = ((u64)v.y << 32) | (u64)v.x;
-                a.in_j[(size_t)j * a.in_cap + w] = (int)v.w;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) *w_stgc = 0;
-        __syncwarp();
-    };
-    int tcount = 0;
-    while (true) {
-        if (q >= q1) {
-            __syncwarp();
-            if (SYM) flush_incoming();
-            if (a.final_prune) {
-                const unsigned need = __ballot_sync(0xffffffffu, lane < WROWS && w_cnt[lane] > a.k + 24 &&
-                                                                     w_cnt[lane] <= a.cap && !w_flag[lane]);
-                prune_rows(need, a.cand_key + (size_t)seg * seg_stride, a.cand_j + (size_t)seg * seg_stride);
-            }
-            if (lane < WROWS) {
-                a.seg_cnt[(size_t)seg * BM + r0w + lane] = w_cnt[lane] > a.cap ? a.cap : w_cnt[lane];
-                a.seg_flag[(size_t)seg * BM + r0w + lane] = w_flag[lane];
-            }
-            if (++pi >= pe) break;
-            pc = a.pieces + (size_t)pi * 5;
-            rb = pc[0]; q = pc[1]; q1 = pc[2]; qs = pc[3]; seg = pc[4];
-            skip_lo = a.rb_skip_lo[rb]; skip_n = a.rb_skip_n[rb];
-            tl = a.tile_list ? a.tile_list + a.rb_list_off[rb] : nullptr;
-            new_piece = true;
-            continue;
-        }
-        if (new_piece) {
-            new_piece = false;
-            __syncwarp();
-            if (lane < WROWS) {
-                const int row = a.row_begin + rb * BM + r0w + lane;
-                const bool valid = row < a.row_end;
-                w_nrm[lane] = valid ? a.norms[row] : 0.0;
-                w_thr[lane] = valid ? __ldcg(a.row_thr + (row - a.row_begin)) : KEY_NEVER;
-                w_cnt[lane] = 0;
-                w_flag[lane] = 0;
-            }
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int row = a.row_begin + rb * BM + r0w + hh * 8 + g;
-                const bool valid = row < a.row_end;
-                my_cs[hh] = valid ? a.row_cs[row] : 0;
-                my_ce[hh] = valid ? a.row_ce[row] : 0;
-                my_n[hh] = valid ? a.n32[row] : INFINITY;
-            }
-            __syncwarp();
-        }
-        const int t = tl ? tl[q] : (q < skip_lo ? q : q + skip_n);
-        const int col0 = t * BN;
-        q += qs;
-        // the tile's column norms (and, SYM, the column bins' thresholds): L2 -> this warp's shared copies
-        __syncwarp();
-        cp_async_16(w_cn + 4 * lane, a.n32 + col0 + 4 * lane);
-        if (SYM) {
-            cp_async_16(w_ct + 2 * lane, a.col_thr + col0 + 2 * lane);
-            cp_async_16(w_ct + 64 + 2 * lane, a.col_thr + col0 + 64 + 2 * lane);
-        }
-        cp_async_commit();
-        u64 shared_thr = ~0ull;
-        if (lane < WROWS) {
-            const int row = a.row_begin + rb * BM + r0w + lane;
-            if (row < a.row_end) shared_thr = __ldcg(a.row_thr + (row - a.row_begin));
-        }
-        ++tcount;
-
-        float acc[16][4];
-#pragma unroll
-        for (int nt = 0; nt < 16; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
-
-        for (int kc = 0; kc < a.nkc; ++kc) {
-            if (!ready) {
-                const long long pf_w0 = clock64();
-                mbar_wait(&sm.full[stage], phase);
-                pf_wait += clock64() - pf_w0;
-            }
-            const uint32_t base = tiles_u32 + (uint32_t)stage * STAGE_BYTES;
-            int nstage = stage + 1;
-            uint32_t nphase = phase;
-            if (nstage == STAGES) { nstage = 0; nphase ^= 1u; }
-            const bool ready_next = mbar_test_wait(&sm.full[nstage], nphase);
-#pragma unroll
-            for (int ks = 0; ks < BKH / 16; ++ks) {
-                uint32_t fa0, fa1, fa2, fa3;
-                ldsm_x4(base + a_off + ((((uint32_t)(2 * ks) + a_kc) ^ xr) << 4), fa0, fa1, fa2, fa3);
-                const uint32_t bsw = (((uint32_t)(2 * ks) + b_kc) ^ xr) << 4;
-#pragma unroll
-                for (int np = 0; np < 8; ++np) {
-                    uint32_t fb0, fb1, fb2, fb3;
-                    ldsm_x4(base + b_off + (uint32_t)np * 2048u + bsw, fb0, fb1, fb2, fb3);
-                    hmma_16816(acc[2 * np], fa0, fa1, fa2, fa3, fb0, fb1);
-                    hmma_16816(acc[2 * np + 1], fa0, fa1, fa2, fa3, fb2, fb3);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[stage]);
-            stage = nstage;
-            phase = nphase;
-            ready = ready_next;
-        }
-
-        // ---- epilogue: d~ = (n_i + n_j) - 2 s in fp32, one compare per entry against the row's (and, SYM, the column's) bound
-        const long long pf_e0 = clock64();
-        if (lane < WROWS) {
-            if (shared_thr < w_thr[lane]) w_thr[lane] = shared_thr;
-            w_rt[lane] = tau32_of_key(w_thr[lane]);
-        }
-        cp_async_wait<0>();
-        __syncwarp();
-        if (SYM) {
-#pragma unroll
-            for (int i = 0; i < BN / 32; ++i) w_ctf[lane + 32 * i] = tau32_of_key(w_ct[lane + 32 * i]);
-            __syncwarp();
-        }
-        u64* ck = a.cand_key + (size_t)seg * seg_stride;
-        int* cj = a.cand_j + (size_t)seg * seg_stride;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int rw = hh * 8 + g;
-            const float taui = w_rt[rw];
-            const float ni = my_n[hh];
-            unsigned mask = 0, cmask = 0;
-#pragma unroll
-            for (int nt = 0; nt < 16; ++nt) {
-                const float2 nj = *reinterpret_cast<const float2*>(w_cn + nt * 8 + 2 * q4);
-                const float d0 = fmaf(-2.0f, acc[nt][2 * hh], ni + nj.x);
-                const float d1 = fmaf(-2.0f, acc[nt][2 * hh + 1], ni + nj.y);
-                if (d0 <= taui) mask |= 1u << (nt * 2);
-                if (d1 <= taui) mask |= 1u << (nt * 2 + 1);
-                if (SYM) {
-                    const float2 tj = *reinterpret_cast<const float2*>(w_ctf + nt * 8 + 2 * q4);
-                    if (d0 <= tj.x) cmask |= 1u << (nt * 2);
-                    if (d1 <= tj.y) cmask |= 1u << (nt * 2 + 1);
-                }
-            }
-            if (mask | cmask) {
-                // rare path: park this row's 32 distances in the warp's scratch (lane-interleaved) and walk the set bits
-                float* tmp = reinterpret_cast<float*>(w_sk) + lane;        // entry b lives at tmp[b * 32]
-#pragma unroll
-                for (int nt = 0; nt < 16; ++nt) {
-                    const float2 nj = *reinterpret_cast<const float2*>(w_cn + nt * 8 + 2 * q4);
-                    tmp[(nt * 2) * 32] = fmaf(-2.0f, acc[nt][2 * hh], ni + nj.x);
-                    tmp[(nt * 2 + 1) * 32] = fmaf(-2.0f, acc[nt][2 * hh + 1], ni + nj.y);
-                }
-                const int cs = my_cs[hh];
-                const unsigned clen = (unsigned)(my_ce[hh] - cs);
-                unsigned m2 = mask;
-                while (m2) {                               // drop non-finite distances and the row's own chromosome
-                    const int bit = __ffs(m2) - 1;
-                    m2 &= m2 - 1;
-                    const int cl = (bit >> 1) * 8 + 2 * q4 + (bit & 1);
-                    if (!(fabsf(tmp[bit * 32]) < INFINITY) || (unsigned)(col0 + cl - cs) < clen) mask &= ~(1u << bit);
-                }
-                if (mask) {
-                    pf_emit += __popc(mask);
-                    int w = atomicAdd(&w_cnt[rw], __popc(mask));
-                    u64* rk = ck + (size_t)(r0w + rw) * a.cap;
-                    int* rj = cj + (size_t)(r0w + rw) * a.cap;
-                    while (mask) {
-                        const int bit = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int cl = (bit >> 1) * 8 + 2 * q4 + (bit & 1);
-                        if (w < a.cap) {
-                            rk[w] = (u64)__double_as_longlong(-0.5 * (double)tmp[bit * 32]);
-                            rj[w] = col0 + cl;
-                        } else {
-                            w_flag[rw] = 1;
-                        }
-                        ++w;
-                    }
-                }
-                if (SYM && cmask) {
-                    const int i = a.row_begin + rb * BM + r0w + rw;
-                    while (cmask) {
-                        const int bit = __ffs(cmask) - 1;
-                        cmask &= cmask - 1;
-                        const int j = col0 + (bit >> 1) * 8 + 2 * q4 + (bit & 1);
-                        const float dv = tmp[bit * 32];
-                        if (!(fabsf(dv) < INFINITY) || j >= a.N || i >= a.row_end) continue;
-                        if ((unsigned)(j - cs) < clen) continue;
-                        const u64 key = (u64)__double_as_longlong(-0.5 * (double)dv);
-                        const int pos = atomicAdd(w_stgc, 1);
-                        if (pos < STG) {
-                            w_stg[pos] = make_uint4((unsigned)key, (unsigned)(key >> 32), (unsigned)j, (unsigned)i);
-                        } else {
-                            const int w = atomicAdd(a.in_cnt + j, 1);
-                            if (w < a.in_cap) {
-                                a.in_key[(size_t)j * a.in_cap + w] = key;
-                                a.in_j[(size_t)j * a.in_cap + w] = i;
-                            }
-                        }
-                        ++pf_emit;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (SYM && *w_stgc >= 32) flush_incoming();
-        const long long pf_p0 = clock64();
-        pf_epi += pf_p0 - pf_e0;
-        prune_rows(__ballot_sync(0xffffffffu, lane < WROWS && w_cnt[lane] > a.cap - BN && !w_flag[lane]), ck, cj);
-        pf_prune += clock64() - pf_p0;
-    }
-    __syncwarp();
-    if (a.prof != nullptr && warp == 0 && lane == 0) {
-        long long* o = a.prof + (size_t)blockIdx.x * 8;
-        o[0] = clock64() - pf_t0; o[1] = pf_wait; o[2] = pf_epi; o[3] = pf_prune;
-        o[4] = tcount; o[5] = pf_nprune; o[6] = pf_emit; o[7] = 0;
-    }
-}
+#include "wc_search_f16.cuh"      // K4h / K5h: the same search with an fp16 tensor-core filter (option k5_f16)
 
 __global__ void wc_fill_u64_kernel(u64* p, size_t n, u64 v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1994,383 +1581,7 @@ extern "C" int wc_newref_topk_host(wc_ctx* ctx, const double* corrected_h, int N
     return WC_OK;
 }
 
-// =====================================================================================================================
-// Sharded symmetric search: the block pairs of the symmetric search divided over `world` ranks (one GPU each, every
-// GPU holding the whole matrix).  Rank r owns the bin blocks [b0, b1) (nb / world consecutive blocks of 128 bins): it
-// computes the tiles whose ROW block it owns - pass A, then pass B with the column side - and finalises its own bins.
-// Three calls per rank with two collectives in between, issued by the host layer (wisecondor_b200/shard.py):
-//   wc_newref_shard_begin   K4, pass A over the owned row blocks; thr[bin] = the owned bins' thresholds, the rest untouched
-//     -> all-reduce(MIN) of thr over the ranks: every rank knows every bin's threshold
-//   wc_newref_shard_sweep   pass B: row side into the rank's segments, column side into in_*[bin] for ALL bins
-//     -> all-to-all of in_* by owner (equal splits of rows_per bins): a rank receives what every rank found for its bins
-//   wc_newref_shard_finish  K6 over the owned bins: own segments + `world` incoming sources
-// The column-side thresholds of bins owned elsewhere stay at their pass-A value during pass B (a rank cannot see the
-// other ranks' prunes), so a bin receives ~ k * frac / 2 offers in total; in_cap leaves 4x head room per source.
-// =====================================================================================================================
-namespace {
-
-struct ShardDims { int nb, bp, b0, b1, row0, row1, rows_per, in_cap, frac; size_t thr_len; };
-
-ShardDims shard_dims(const wc_ctx* ctx, int N, int k, int world, int rank) {
-    ShardDims d;
-    d.frac = ctx->k5_sym >= 2 ? ctx->k5_sym : 8;
-    d.nb = (N + BM - 1) / BM;
-    d.bp = (d.nb + world - 1) / world;
-    d.b0 = std::min(d.nb, rank * d.bp);
-    d.b1 = std::min(d.nb, d.b0 + d.bp);
-    d.row0 = std::min(N, d.b0 * BM);
-    d.row1 = std::min(N, d.b1 * BM);
-    d.rows_per = d.bp * BM;
-    d.thr_len = (size_t)world * d.rows_per + BN;
-    const int want = world == 1 ? 2 * k * d.frac : (4 * k * d.frac + world - 1) / world;
-    d.in_cap = 256;
-    while (d.in_cap < want) d.in_cap *= 2;
-    return d;
-}
-
-// One K5 launch of a sharded symmetric search: pass 0 = threshold pass (rows only), pass 1 = symmetric pass.
-int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned long long* in_key_d, int* in_j_d,
-                      int* in_cnt_d, cudaStream_t stream) {
-    const wc_shard_plan& pl = ctx->shard;
-    if (!ctx->encode_tiled) {
-        wc_set_error("cuTensorMapEncodeTiled is not available from this driver");
-        return WC_ERR_CUDA;
-    }
-    CUtensorMap tmap;
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)pl.ld, (cuuint64_t)pl.Npad};
-        cuuint64_t strides[1] = {(cuuint64_t)pl.ld * sizeof(double)};
-        cuuint32_t box[2] = {BK, BM};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = reinterpret_cast<PFN_encodeTiled>(ctx->encode_tiled)(
-            &tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->buf[SLOT_XC].p, dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            wc_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-            return WC_ERR_CUDA;
-        }
-    }
-    const int nrb1 = std::max(pl.nrb, 1);
-    int* d_meta = static_cast<int*>(ctx->buf[SLOT_RBMETA].p);
-    int* d_ctaA = d_meta + 4 * nrb1;
-    int* d_ctaB = d_ctaA + pl.gridA + 1;
-    int* d_pieces = d_ctaB + pl.gridB + 1;
-    int* d_offA = d_pieces + (size_t)std::max(pl.nseg, 1) * 5;
-    int* d_offB = d_offA + pl.nrb + 1;
-    int* d_listA = d_offB + pl.nrb + 1;
-    int* d_listB = d_listA + pl.nlistA;
-    TopkArgs ta;
-    ta.norms = static_cast<double*>(ctx->buf[SLOT_NORMS].p);
-    ta.row_cs = static_cast<int*>(ctx->buf[SLOT_ROWCS].p);
-    ta.row_ce = static_cast<int*>(ctx->buf[SLOT_ROWCE].p);
-    ta.N = pl.N; ta.row_begin = pl.row0; ta.row_end = pl.row1;
-    ta.nkc = pl.nkc; ta.nd_last = pl.nd_last; ta.extra_h = pl.extra_h;
-    ta.rb_skip_lo = d_meta; ta.rb_skip_n = d_meta + nrb1; ta.nrb = pl.nrb;
-    ta.cta_piece_begin = pass == 0 ? d_ctaA : d_ctaB;
-    ta.pieces = d_pieces;
-    ta.cand_key = static_cast<u64*>(ctx->buf[SLOT_CAND_D].p); ta.cand_j = static_cast<int*>(ctx->buf[SLOT_CAND_J].p);
-    ta.seg_cnt = static_cast<int*>(ctx->buf[SLOT_SEGCNT].p); ta.seg_flag = static_cast<int*>(ctx->buf[SLOT_SEGFLAG].p);
-    ta.cap = pl.cap; ta.k = pl.k; ta.mcoef = pl.mcoef; ta.tau_init = 1e10 * (1.0 + 1e-6);
-    ta.prof = nullptr; ta.trace = nullptr;
-    ta.row_thr = thr_d + pl.row0;             // indexed by (bin - row_begin) on the row side ...
-    ta.col_thr = thr_d;                       // ... and by global bin on the column side
-    ta.lag = ctx->k5_lag; ta.nstages = pl.nstages;
-    ta.tile_list = pass == 0 ? d_listA : d_listB;
-    ta.rb_list_off = pass == 0 ? d_offA : d_offB;
-    ta.final_prune = 1;
-    ta.in_key = in_key_d; ta.in_j = in_j_d; ta.in_cnt = in_cnt_d; ta.in_cap = pl.in_cap;
-    ta.madd = 0.0; ta.n32 = nullptr;
-    if (pass == 0) {
-        WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        wc_dist_topk_kernel<false><<<pl.gridA, TOPK_THREADS, pl.smem, stream>>>(tmap, ta);
-    } else {
-        WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        wc_dist_topk_kernel<true><<<pl.gridB, TOPK_THREADS, pl.smem, stream>>>(tmap, ta);
-    }
-    WC_CUDA(cudaGetLastError());
-    return WC_OK;
-}
-
-}  // namespace
-
-extern "C" int wc_newref_shard_dims(const wc_ctx* ctx, int N, int refsize, int world, int rank, long long* out6) {
-    WC_CHECK_ARG(ctx != nullptr && out6 != nullptr);
-    WC_CHECK_ARG(N > 0 && refsize >= 1 && refsize <= 384 && world >= 1 && rank >= 0 && rank < world);
-    const ShardDims d = shard_dims(ctx, N, refsize, world, rank);
-    out6[0] = d.rows_per; out6[1] = d.in_cap; out6[2] = (long long)d.thr_len; out6[3] = d.row0; out6[4] = d.row1; out6[5] = d.nb;
-    return WC_OK;
-}
-
-extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int N, int S, const int* chrom_bins_h,
-                                     int nchrom, int refsize, int rank, int world, unsigned long long* thr_d,
-                                     void* stream_v) {
-    WC_CHECK_ARG(ctx != nullptr && corrected_d != nullptr && chrom_bins_h != nullptr && thr_d != nullptr);
-    WC_CHECK_ARG(N > 0 && S > 0 && nchrom > 0 && refsize >= 1 && refsize <= 384);
-    WC_CHECK_ARG(world >= 1 && rank >= 0 && rank < world);
-    long long tot = 0;
-    for (int c = 0; c < nchrom; ++c) {
-        WC_CHECK_ARG(chrom_bins_h[c] >= 0);
-        tot += chrom_bins_h[c];
-    }
-    WC_CHECK_ARG(tot == N);
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    WC_CUDA(cudaSetDevice(ctx->device));
-    wc_shard_plan& pl = ctx->shard;
-    pl = wc_shard_plan();
-    ctx->sched_hash = 0;                       // the schedule slots are about to be overwritten
-    for (int i = 0; i < 4; ++i) ctx->phase_ms[i] = 0.0;
-    ctx->phase_ms[8] = ctx->phase_ms[9] = 0.0;
-    for (int i = 0; i < 5; ++i) ctx->counter[i] = 0;
-    ctx->timed_mask &= ~0xfu;
-
-    const ShardDims d = shard_dims(ctx, N, refsize, world, rank);
-    const int k = refsize;
-    const int cap = k <= 128 ? 512 : 1024;
-    const int nblocks = (S + 7) / 8;
-    const int Sx = nblocks * 8;
-    const int nkc = nblocks / 2 + 1;
-    const int nd_last = nblocks - 2 * (nkc - 1);
-    const int ld = nkc * BK;
-    const size_t Npad = (size_t)(N + BN - 1) / BN * BN + BN;
-    const int nb = d.nb, nrb = d.b1 - d.b0;
-
-    // exclusion ranges of every bin; skipped (own-chromosome interior) column tiles of every block
-    std::vector<int> row_cs(N), row_ce(N), skip_lo(nb), skip_n(nb);
-    {
-        int pos = 0;
-        for (int c = 0; c < nchrom; ++c) {
-            for (int i = 0; i < chrom_bins_h[c]; ++i) { row_cs[pos + i] = pos; row_ce[pos + i] = pos + chrom_bins_h[c]; }
-            pos += chrom_bins_h[c];
-        }
-    }
-    long long tiles_plain = 0;
-    for (int I = 0; I < nb; ++I) {
-        const int r0 = I * BM, r1 = std::min(N, r0 + BM) - 1;
-        int lo = nb, n = 0;
-        if (row_cs[r0] == row_cs[r1]) {
-            const int first = (row_cs[r0] + BN - 1) / BN, last = row_ce[r0] / BN;
-            if (last > first) { lo = first; n = last - first; }
-        }
-        skip_lo[I] = lo;
-        skip_n[I] = n;
-        if (I >= d.b0 && I < d.b1) tiles_plain += nb - n;
-    }
-    const int frac = d.frac;
-    auto in_sample = [&](int I, int J) { return I == J || (I + J) % frac == 0; };
-    auto valid = [&](int I, int t) { return !(t >= skip_lo[I] && t < skip_lo[I] + skip_n[I]); };
-    std::vector<int> listA, listB, offA(nrb + 1, 0), offB(nrb + 1, 0);
-    for (int I = d.b0; I < d.b1; ++I) {
-        for (int t = 0; t < nb; ++t)
-            if (valid(I, t) && in_sample(I, t)) listA.push_back(t);
-        offA[I - d.b0 + 1] = (int)listA.size();
-        for (int dlt = 1; dlt <= nb / 2; ++dlt) {
-            if (2 * dlt == nb && I >= nb / 2) continue;
-            const int t = (I + dlt) % nb;
-            if (valid(I, t) && !in_sample(I, t)) listB.push_back(t);
-        }
-        offB[I - d.b0 + 1] = (int)listB.size();
-    }
-    const long long tilesA = (long long)listA.size(), tilesB = (long long)listB.size();
-    const int gridA = tilesA ? (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesA + 7) / 8)) : 0;
-    const int gridB = tilesB ? (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesB + 7) / 8)) : 0;
-    std::vector<Piece> pieces;
-    if (gridA) schedule_pieces(offA, nrb, gridA, 1, false, 0, pieces);
-    if (gridB) {
-        const double tile_bytes = (double)BM * ld * sizeof(double);
-        const double matrix_bytes = (double)Npad * ld * sizeof(double);
-        int G = ctx->k5_group;
-        if (G <= 0) {
-            G = 1;
-            if (matrix_bytes > 64e6)
-                while (G < 8 && (double)(gridB / G) * tile_bytes > 48e6) G *= 2;
-        }
-        schedule_pieces(offB, nrb, gridB, G, matrix_bytes > 64e6 || ctx->k5_group > 0, 1, pieces);
-    }
-    // segments numbered row-block-major; one piece table, pass A's pieces first
-    const int nseg = (int)pieces.size();
-    std::vector<int> seg_first(std::max(nrb, 1), 0), seg_count(std::max(nrb, 1), 0), ctaA(gridA + 1, 0), ctaB(gridB + 1, 0);
-    std::vector<int> piece_tab((size_t)std::max(nseg, 1) * 5, 0);
-    {
-        for (const Piece& pc : pieces) seg_count[pc.rb]++;
-        int run = 0;
-        for (int rb = 0; rb < nrb; ++rb) { seg_first[rb] = run; run += seg_count[rb]; }
-        std::vector<int> next(seg_first);
-        for (Piece& pc : pieces) pc.seg = next[pc.rb]++;
-        std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) {
-            return x.pass != y.pass ? x.pass < y.pass : x.cta < y.cta;
-        });
-        int n0 = 0;
-        for (int i = 0; i < nseg; ++i) {
-            const Piece& pc = pieces[i];
-            if (pc.pass == 0) { ctaA[pc.cta + 1]++; ++n0; } else { ctaB[pc.cta + 1]++; }
-            piece_tab[(size_t)i * 5 + 0] = pc.rb;
-            piece_tab[(size_t)i * 5 + 1] = pc.q0;
-            piece_tab[(size_t)i * 5 + 2] = pc.q1;
-            piece_tab[(size_t)i * 5 + 3] = pc.step;
-            piece_tab[(size_t)i * 5 + 4] = pc.seg;
-        }
-        for (int c = 0; c < gridA; ++c) ctaA[c + 1] += ctaA[c];
-        ctaB[0] = n0;
-        for (int c = 0; c < gridB; ++c) ctaB[c + 1] += ctaB[c];
-    }
-    // device metadata: [zeros nrb][zeros nrb][seg_first nrb][seg_count nrb][ctaA][ctaB][pieces][offA][offB][listA][listB]
-    const int nrb1 = std::max(nrb, 1);
-    std::vector<int> meta;
-    meta.insert(meta.end(), (size_t)2 * nrb1, 0);             // the arithmetic-mode skip tables (unused in list mode)
-    meta.insert(meta.end(), seg_first.begin(), seg_first.end());
-    meta.insert(meta.end(), seg_count.begin(), seg_count.end());
-    meta.insert(meta.end(), ctaA.begin(), ctaA.end());
-    meta.insert(meta.end(), ctaB.begin(), ctaB.end());
-    meta.insert(meta.end(), piece_tab.begin(), piece_tab.end());
-    meta.insert(meta.end(), offA.begin(), offA.end());
-    meta.insert(meta.end(), offB.begin(), offB.end());
-    meta.insert(meta.end(), listA.begin(), listA.end());
-    meta.insert(meta.end(), listB.begin(), listB.end());
-
-    double* Xc; double* norms; int* d_row_cs; int* d_row_ce; int* d_meta;
-    u64* cand_key; int* cand_j; int* seg_cnt; int* seg_flag; int* slow;
-    int rc;
-    if ((rc = wc_reserve(ctx, SLOT_XC, Npad * ld * sizeof(double), (void**)&Xc))) return rc;
-    if ((rc = wc_reserve(ctx, SLOT_NORMS, Npad * sizeof(double), (void**)&norms))) return rc;
-    if ((rc = wc_reserve(ctx, SLOT_ROWCS, (size_t)N * sizeof(int), (void**)&d_row_cs))) return rc;
-    if ((rc = wc_reserve(ctx, SLOT_ROWCE, (size_t)N * sizeof(int), (void**)&d_row_ce))) return rc;
-    if ((rc = wc_reserve(ctx, SLOT_RBMETA, meta.size() * sizeof(int), (void**)&d_meta))) return rc;
-    const size_t cand_n = (size_t)std::max(nseg, 1) * BM * cap;
-    if ((rc = wc_reserve(ctx, SLOT_CAND_D, cand_n * sizeof(u64), (void**)&cand_key))) return rc;
-    if ((rc = wc_reserve(ctx, SLOT_CAND_J, cand_n * sizeof(int), (void**)&cand_j))) return rc;
-    if ((rc = wc_reserve(ctx, SLOT_SEGCNT, (size_t)std::max(nseg, 1) * BM * sizeof(int), (void**)&seg_cnt))) return rc;
-    if ((rc = wc_reserve(ctx, SLOT_SEGFLAG, (size_t)std::max(nseg, 1) * BM * sizeof(int), (void**)&seg_flag))) return rc;
-    const int rows = d.row1 - d.row0;
-    if ((rc = wc_reserve(ctx, SLOT_SLOW, ((size_t)std::max(rows, 0) + 1) * sizeof(int), (void**)&slow))) return rc;
-    WC_CUDA(cudaMemcpyAsync(d_row_cs, row_cs.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, stream));
-    WC_CUDA(cudaMemcpyAsync(d_row_ce, row_ce.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, stream));
-    WC_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-    WC_CUDA(cudaMemsetAsync(slow, 0, sizeof(int), stream));
-    WC_CUDA(cudaMemsetAsync(seg_cnt, 0, (size_t)std::max(nseg, 1) * BM * sizeof(int), stream));
-    WC_CUDA(cudaMemsetAsync(seg_flag, 0, (size_t)std::max(nseg, 1) * BM * sizeof(int), stream));
-
-    WC_CUDA(cudaEventRecord(ctx->ev[0], stream));
-    wc_prepare_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ld, Sx, Xc, norms);
-    WC_CUDA(cudaGetLastError());
-    WC_CUDA(cudaEventRecord(ctx->ev[1], stream));
-    const double tau_init = 1e10 * (1.0 + 1e-6);
-    wc_fill_u64_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(thr_d, (size_t)N, host_key_of_tau(tau_init));
-    wc_fill_u64_kernel<<<(unsigned)((d.thr_len - N + 255) / 256), 256, 0, stream>>>(thr_d + N, d.thr_len - (size_t)N, KEY_NEVER);
-    WC_CUDA(cudaGetLastError());
-
-    pl.N = N; pl.S = S; pl.k = k; pl.cap = cap; pl.in_cap = d.in_cap; pl.world = world; pl.rank = rank;
-    pl.nb = nb; pl.bp = d.bp; pl.b0 = d.b0; pl.b1 = d.b1; pl.row0 = d.row0; pl.row1 = d.row1; pl.rows_per = d.rows_per;
-    pl.nkc = nkc; pl.nd_last = nd_last; pl.extra_h = nd_last; pl.ld = ld; pl.nrb = nrb; pl.nseg = nseg;
-    pl.gridA = gridA; pl.gridB = gridB; pl.Npad = Npad; pl.nlistA = listA.size();
-    pl.tilesA = tilesA; pl.tilesB = tilesB; pl.tiles_plain = tiles_plain;
-    pl.mcoef = 16.0 * (double)(S + 16) * 1.1102230246251565e-16;
-    pl.corrected = corrected_d;
-    pl.nstages = cap <= 512 ? 4 : 3;
-    pl.smem = (size_t)pl.nstages * STAGE_BYTES + sizeof(TopkState) +
-              (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192) +
-              (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4));
-    if (pl.smem > 227 * 1024) { wc_set_error("K5 shared memory %zu exceeds 227 KiB", pl.smem); return WC_ERR_INTERNAL; }
-
-    WC_CUDA(cudaEventRecord(ctx->ev[2], stream));
-    if (gridA > 0) {
-        if ((rc = shard_launch_pass(ctx, 0, thr_d, nullptr, nullptr, nullptr, stream))) return rc;
-    }
-    WC_CUDA(cudaEventRecord(ctx->ev[16], stream));
-    pl.valid = 1;
-    pl.stage = 1;
-    return WC_OK;
-}
-
-extern "C" int wc_newref_shard_sweep(wc_ctx* ctx, unsigned long long* thr_d, unsigned long long* in_key_d, int* in_j_d,
-                                     int* in_cnt_d, void* stream_v) {
-    WC_CHECK_ARG(ctx != nullptr && thr_d != nullptr && in_key_d != nullptr && in_j_d != nullptr && in_cnt_d != nullptr);
-    wc_shard_plan& pl = ctx->shard;
-    if (!pl.valid || pl.stage != 1) { wc_set_error("wc_newref_shard_sweep: call wc_newref_shard_begin first"); return WC_ERR_ARG; }
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    WC_CUDA(cudaSetDevice(ctx->device));
-    WC_CUDA(cudaMemsetAsync(in_cnt_d, 0, (size_t)pl.world * pl.rows_per * sizeof(int), stream));
-    WC_CUDA(cudaEventRecord(ctx->ev[18], stream));
-    if (pl.gridB > 0) {
-        int rc;
-        if ((rc = shard_launch_pass(ctx, 1, thr_d, in_key_d, in_j_d, in_cnt_d, stream))) return rc;
-    }
-    WC_CUDA(cudaEventRecord(ctx->ev[19], stream));
-    pl.stage = 2;
-    return WC_OK;
-}
-
-extern "C" int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* recv_key_d, const int* recv_j_d,
-                                      const int* recv_cnt_d, int32_t* idx_d, double* dist_d, void* stream_v) {
-    WC_CHECK_ARG(ctx != nullptr && recv_key_d != nullptr && recv_j_d != nullptr && recv_cnt_d != nullptr);
-    wc_shard_plan& pl = ctx->shard;
-    if (!pl.valid || pl.stage != 2) { wc_set_error("wc_newref_shard_finish: call wc_newref_shard_sweep first"); return WC_ERR_ARG; }
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    WC_CUDA(cudaSetDevice(ctx->device));
-    pl.stage = 0;
-    pl.valid = 0;
-    const int rows = pl.row1 - pl.row0;
-    int nslow = 0;
-    int* d_meta = static_cast<int*>(ctx->buf[SLOT_RBMETA].p);
-    int* d_row_cs = static_cast<int*>(ctx->buf[SLOT_ROWCS].p);
-    int* d_row_ce = static_cast<int*>(ctx->buf[SLOT_ROWCE].p);
-    int* slow = static_cast<int*>(ctx->buf[SLOT_SLOW].p);
-    long long launches = 4 + (pl.gridA > 0) + (pl.gridB > 0);      // K4, two fills, pass A, pass B, K6
-    if (rows > 0) {
-        WC_CHECK_ARG(idx_d != nullptr && dist_d != nullptr);
-        const int nrb1 = std::max(pl.nrb, 1);
-        FinArgs fa;
-        fa.X = pl.corrected; fa.N = pl.N; fa.S = pl.S; fa.norms = static_cast<double*>(ctx->buf[SLOT_NORMS].p);
-        fa.row_cs = d_row_cs; fa.row_ce = d_row_ce; fa.row_begin = pl.row0; fa.row_end = pl.row1;
-        fa.rb_seg_first = d_meta + 2 * nrb1; fa.rb_seg_count = d_meta + 3 * nrb1;
-        fa.cand_key = static_cast<u64*>(ctx->buf[SLOT_CAND_D].p); fa.cand_j = static_cast<int*>(ctx->buf[SLOT_CAND_J].p);
-        fa.seg_cnt = static_cast<int*>(ctx->buf[SLOT_SEGCNT].p); fa.seg_flag = static_cast<int*>(ctx->buf[SLOT_SEGFLAG].p);
-        fa.cap = pl.cap; fa.k = pl.k; fa.shortcap = pl.k <= 128 ? 256 : 512; fa.mcoef = pl.mcoef;
-        fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
-        fa.bulk = (pl.S % 2 == 0 && (reinterpret_cast<uintptr_t>(pl.corrected) & 15) == 0) ? 1 : 0;
-        fa.in_key = recv_key_d; fa.in_j = recv_j_d; fa.in_cnt = recv_cnt_d; fa.in_cap = pl.in_cap;
-        fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per; fa.madd = 0.0;
-        const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
-        WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-        WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
-        wc_finalize_kernel<<<rows, FIN_THREADS, fin_smem, stream>>>(fa);
-        WC_CUDA(cudaGetLastError());
-        WC_CUDA(cudaEventRecord(ctx->ev[5], stream));
-        WC_CUDA(cudaMemcpyAsync(&nslow, slow, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        WC_CUDA(cudaStreamSynchronize(stream));
-        if (nslow > 0) {
-            const int batch = 64;
-            double* scratch;
-            int rc;
-            if ((rc = wc_reserve(ctx, SLOT_SCRATCH, (size_t)std::min(nslow, batch) * pl.N * sizeof(double), (void**)&scratch)))
-                return rc;
-            WC_CUDA(cudaEventRecord(ctx->ev[6], stream));
-            for (int off = 0; off < nslow; off += batch) {
-                ExhArgs ea;
-                ea.X = pl.corrected; ea.N = pl.N; ea.S = pl.S; ea.row_cs = d_row_cs; ea.row_ce = d_row_ce; ea.row_begin = pl.row0;
-                ea.slow_list = slow + 1; ea.list_off = off; ea.scratch = scratch; ea.k = pl.k; ea.idx_out = idx_d; ea.dist_out = dist_d;
-                wc_exhaustive_kernel<<<std::min(batch, nslow - off), EXH_THREADS, 0, stream>>>(ea);
-                ++launches;
-            }
-            WC_CUDA(cudaGetLastError());
-            WC_CUDA(cudaEventRecord(ctx->ev[7], stream));
-        }
-    }
-    WC_CUDA(cudaStreamSynchronize(stream));
-    float ms, ms2;
-    WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->phase_ms[0] = ms;
-    WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[16])); ctx->phase_ms[8] = ms;
-    WC_CUDA(cudaEventElapsedTime(&ms2, ctx->ev[18], ctx->ev[19])); ctx->phase_ms[9] = ms2;
-    ctx->phase_ms[1] = (double)ms + (double)ms2;
-    if (rows > 0) { WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->phase_ms[2] = ms; }
-    if (nslow > 0) { WC_CUDA(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7])); ctx->phase_ms[3] = ms; }
-    ctx->counter[0] = launches;
-    ctx->counter[1] = nslow;
-    ctx->counter[2] = pl.tiles_plain;
-    ctx->counter[3] = pl.tilesA + pl.tilesB;
-    ctx->counter[4] = std::max(pl.gridA, pl.gridB);
-    return WC_OK;
-}
+#include "wc_search_shard.cuh"    // sharded symmetric search (wc_newref_shard_*)
 
 // Debug: enable per-CTA cycle counters in K5 and read them back (grid x 8 int64: total, wait-on-TMA, epilogue,
 // prune, tiles, prunes, emitted entries of consumer thread 0, reserved).  Returns the number of CTAs copied.
