@@ -73,6 +73,14 @@ int wc_copy_h2d(wc_ctx* ctx, void* dst_d, const void* src_h, size_t bytes);
 int wc_copy_d2h(wc_ctx* ctx, void* dst_h, const void* src_d, size_t bytes);
 int wc_dev_sync(wc_ctx* ctx);                                  /* cudaDeviceSynchronize on the context's device */
 
+/* Debug aid, host only (no device, no context): the symmetric search's tile lists and CTA schedule for the 128-bin
+ * blocks of rank `rank` of `world` (1/frac of the block pairs in the first pass; `grid` CTAs, `group` CTAs per row block
+ * in rounds when rounds_on).  out: [nb, b0, b1, nA, nB, piecesA, piecesB, 0][off_a][off_b][list_a][list_b][pieces: cta,
+ * row block, q0, q1, step]...[skip_lo nb][skip_n nb]; *used = ints needed.  The CPU tests check that every block pair
+ * that holds a bin pair of different chromosomes reaches both of its blocks exactly once. */
+int wc_debug_sym_plan(int N, const int* chrom_bins_h, int nchrom, int frac, int world, int rank, int grid, int group,
+                      int rounds_on, int* out, long long out_ints, long long* used);
+
 /* Debug aid: enable (1) / disable (0) per-CTA cycle counters in the distance kernel and copy the counters of the
  * most recent search to out_h (grid x 8 int64: total, wait-on-TMA, epilogue, prune, tiles, prunes, emitted by
  * thread 0, reserved).  Returns the number of CTAs copied, or a negative wc_status. */

@@ -249,3 +249,73 @@ def test_symmetric_sharded_search_collectives_over_gloo(world):
         assert p.exitcode == 0
     got = sorted(q.get(timeout=10) for _ in range(world))
     assert got == [(r, True) for r in range(world)]
+
+
+def _sym_plan(bins, frac, world, rank, grid=148, group=2, rounds_on=1):
+    """wc_debug_sym_plan (host only): tile lists and CTA schedule of the symmetric search for one rank."""
+    from wisecondor_b200 import _cabi
+    L = _cabi.lib()
+    cb = np.ascontiguousarray(bins, dtype=np.int32)
+    n = int(cb.sum())
+    used = ctypes.c_longlong(0)
+    buf = np.zeros(1 << 16, dtype=np.int32)
+    rc = L.wc_debug_sym_plan(n, cb.ctypes.data_as(ctypes.c_void_p), len(cb), frac, world, rank, grid, group, rounds_on,
+                             buf.ctypes.data_as(ctypes.c_void_p), len(buf), ctypes.byref(used))
+    if rc != 0:
+        buf = np.zeros(used.value, dtype=np.int32)
+        _cabi.check(L.wc_debug_sym_plan(n, cb.ctypes.data_as(ctypes.c_void_p), len(cb), frac, world, rank, grid, group, rounds_on,
+                                        buf.ctypes.data_as(ctypes.c_void_p), len(buf), ctypes.byref(used)))
+    nb, b0, b1, na, nbb, npa, npb = (int(v) for v in buf[:7])
+    nrb = b1 - b0
+    pos = 8
+    off_a = buf[pos:pos + nrb + 1]; pos += nrb + 1
+    off_b = buf[pos:pos + nrb + 1]; pos += nrb + 1
+    list_a = buf[pos:pos + na]; pos += na
+    list_b = buf[pos:pos + nbb]; pos += nbb
+    pieces_a = buf[pos:pos + 5 * npa].reshape(-1, 5); pos += 5 * npa
+    pieces_b = buf[pos:pos + 5 * npb].reshape(-1, 5); pos += 5 * npb
+    return dict(nb=nb, b0=b0, b1=b1, off_a=off_a, off_b=off_b, list_a=list_a, list_b=list_b, pieces_a=pieces_a,
+                pieces_b=pieces_b)
+
+
+@pytest.mark.parametrize("bins", [
+    [4985, 4864, 3961, 3824, 3619, 3423, 3183, 2928, 2825, 2711, 2701, 2678, 2304, 2147, 2051, 1808, 1624, 1562, 1183, 1261, 963, 1027],
+    [997, 973, 793, 765, 724, 685, 637, 586, 565, 543, 541, 536, 461, 430, 411, 362, 325, 313, 237, 253, 193, 206],
+    [128 * 7, 128 * 3, 128 * 6],                 # chromosome ends on block boundaries
+    [3100, 30, 20],                              # one chromosome holds nearly everything
+    [0, 9, 0, 0, 14, 3, 0],                      # fewer bins than one block
+    [300, 1, 299, 1, 640, 127, 129],
+])
+@pytest.mark.parametrize("world,frac", [(1, 8), (2, 8), (3, 4), (8, 16), (5, 2)])
+def test_symmetric_plan_reaches_every_block_pair_exactly_once(bins, world, frac):
+    """Host logic of the (sharded) symmetric search: over all ranks, every pair of 128-bin blocks that holds at least one
+    bin pair of different chromosomes is seen by BOTH of its blocks exactly once (pass A: from each side; pass B: one
+    tile serves both) - never twice, which would duplicate candidates - and every tile belongs to exactly one CTA piece."""
+    n = int(sum(bins))
+    nb = (n + 127) // 128
+    chrom = np.repeat(np.arange(len(bins)), bins)
+    sets = [frozenset(chrom[i * 128:(i + 1) * 128].tolist()) for i in range(nb)]
+    seen = np.zeros((nb, nb), dtype=np.int32)          # seen[I][J]: how often block I learns about the bins of block J
+    owned = np.zeros(nb, dtype=np.int32)
+    for rank in range(world):
+        p = _sym_plan(bins, frac, world, rank, grid=37, group=2)
+        assert p["nb"] == nb
+        for local in range(p["b1"] - p["b0"]):
+            I = p["b0"] + local
+            owned[I] += 1
+            for t in p["list_a"][p["off_a"][local]:p["off_a"][local + 1]]:
+                seen[I, t] += 1
+            for t in p["list_b"][p["off_b"][local]:p["off_b"][local + 1]]:
+                assert t != I
+                seen[I, t] += 1
+                seen[t, I] += 1
+        for off, pieces in ((p["off_a"], p["pieces_a"]), (p["off_b"], p["pieces_b"])):
+            count = [np.zeros(off[i + 1] - off[i], dtype=np.int32) for i in range(p["b1"] - p["b0"])]
+            for cta, rb, q0, q1, step in pieces:
+                assert 0 <= cta < 37 and q0 < q1 and step >= 1
+                count[rb][q0:q1:step] += 1
+            assert all((c == 1).all() for c in count), "a tile is missing from or repeated in the CTA schedule"
+    assert (owned == 1).all()
+    needed = np.array([[not (len(sets[i]) == 1 and sets[i] == sets[j]) for j in range(nb)] for i in range(nb)])
+    assert (seen <= 1).all(), "a block pair is computed twice"
+    assert (seen[needed] == 1).all(), "a block pair with candidates is never computed"

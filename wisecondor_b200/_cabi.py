@@ -13,7 +13,7 @@ _LIB = None
 SYMBOLS = [
     "wc_create", "wc_destroy", "wc_last_error", "wc_version", "wc_sm_count", "wc_last_phase_ms",
     "wc_last_counter", "wc_device_count", "wc_dev_alloc", "wc_dev_free", "wc_copy_h2d", "wc_copy_d2h", "wc_dev_sync", "wc_newref_topk", "wc_newref_topk_host",
-    "wc_newref_shard_dims", "wc_newref_shard_begin", "wc_newref_shard_sweep", "wc_newref_shard_finish", "wc_debug_profile", "wc_set_option",
+    "wc_newref_shard_dims", "wc_newref_shard_begin", "wc_newref_shard_sweep", "wc_newref_shard_finish", "wc_debug_sym_plan", "wc_debug_profile", "wc_set_option",
     "wc_newref_mask", "wc_newref_normalize", "wc_pca_gram", "wc_pca_apply",
     "wc_table_stride", "wc_test_table", "wc_test_prep", "wc_apply_pca", "wc_zscore_batch", "wc_segment_batch",
 ]
@@ -74,6 +74,8 @@ def lib():
     L.wc_newref_shard_sweep.argtypes = [vp, vp, vp, vp, vp, vp]
     L.wc_newref_shard_finish.restype = ci
     L.wc_newref_shard_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.wc_debug_sym_plan.restype = ci
+    L.wc_debug_sym_plan.argtypes = [ci, vp, ci, ci, ci, ci, ci, ci, ci, vp, ctypes.c_longlong, vp]
     L.wc_set_option.restype = ci
     L.wc_set_option.argtypes = [vp, ctypes.c_char_p, cd]
     L.wc_debug_profile.restype = ci

@@ -1141,7 +1141,90 @@ void schedule_pieces(const std::vector<int>& prefix, int nrb, int grid, int G, b
     }
 }
 
+// Symmetric search: which column tiles each block of 128 bins computes.  skip_lo / skip_n: per block the column tiles
+// wholly inside its own chromosome.  Pass A (list_a): the symmetric subset (I + J) % frac == 0 and the diagonal, from
+// both sides.  Pass B (list_b): every other pair once - block I takes J = I + 1 ... I + nb/2 cyclically, the antipodal
+// pair of an even nb belongs to its lower block.  Lists are built for the blocks [b0, b1) (a rank's share), off_* are
+// relative to b0.  tools: wc_debug_sym_plan exposes this to the CPU tests (coverage: every needed pair exactly once).
+void pair_lists(int nb, const std::vector<int>& skip_lo, const std::vector<int>& skip_n, int frac, int b0, int b1,
+                std::vector<int>& list_a, std::vector<int>& off_a, std::vector<int>& list_b, std::vector<int>& off_b) {
+    auto in_sample = [&](int I, int J) { return I == J || (I + J) % frac == 0; };
+    auto valid = [&](int I, int t) { return !(t >= skip_lo[I] && t < skip_lo[I] + skip_n[I]); };
+    list_a.clear();
+    list_b.clear();
+    off_a.assign(b1 - b0 + 1, 0);
+    off_b.assign(b1 - b0 + 1, 0);
+    for (int I = b0; I < b1; ++I) {
+        for (int t = 0; t < nb; ++t)
+            if (valid(I, t) && in_sample(I, t)) list_a.push_back(t);
+        off_a[I - b0 + 1] = (int)list_a.size();
+        for (int dlt = 1; dlt <= nb / 2; ++dlt) {
+            if (2 * dlt == nb && I >= nb / 2) continue;
+            const int t = (I + dlt) % nb;
+            if (valid(I, t) && !in_sample(I, t)) list_b.push_back(t);
+        }
+        off_b[I - b0 + 1] = (int)list_b.size();
+    }
+}
+
+// Exclusion range [cs, ce) of every bin (its own chromosome) and the skipped column tiles of every whole-matrix block.
+void block_skips(int N, const int* chrom_bins_h, int nchrom, std::vector<int>& row_cs, std::vector<int>& row_ce,
+                 std::vector<int>& skip_lo, std::vector<int>& skip_n) {
+    row_cs.assign(N, 0);
+    row_ce.assign(N, 0);
+    int pos = 0;
+    for (int c = 0; c < nchrom; ++c) {
+        for (int i = 0; i < chrom_bins_h[c]; ++i) { row_cs[pos + i] = pos; row_ce[pos + i] = pos + chrom_bins_h[c]; }
+        pos += chrom_bins_h[c];
+    }
+    const int nb = (N + BM - 1) / BM;
+    skip_lo.assign(nb, nb);
+    skip_n.assign(nb, 0);
+    for (int I = 0; I < nb; ++I) {
+        const int r0 = I * BM, r1 = std::min(N, r0 + BM) - 1;
+        if (row_cs[r0] == row_cs[r1]) {   // block inside one chromosome: its interior column tiles are skipped
+            const int first = (row_cs[r0] + BN - 1) / BN, last = row_ce[r0] / BN;
+            if (last > first) { skip_lo[I] = first; skip_n[I] = last - first; }
+        }
+    }
+}
+
 }  // namespace
+
+// CPU-only debug aid (no device, no context): the symmetric search's tile lists and CTA schedule for the blocks of rank
+// `rank` of `world`.  out: [nb, b0, b1, nA, nB, piecesA, piecesB, 0][off_a nrb+1][off_b nrb+1][list_a][list_b]
+// [pieces of pass A: cta, row block, q0, q1, step]...[pieces of pass B]...[skip_lo nb][skip_n nb].
+extern "C" int wc_debug_sym_plan(int N, const int* chrom_bins_h, int nchrom, int frac, int world, int rank, int grid,
+                                 int group, int rounds_on, int* out, long long out_ints, long long* used) {
+    WC_CHECK_ARG(N > 0 && chrom_bins_h != nullptr && nchrom > 0 && frac >= 2 && world >= 1 && rank >= 0 && rank < world);
+    WC_CHECK_ARG(grid >= 1 && group >= 1 && out != nullptr && used != nullptr);
+    long long tot = 0;
+    for (int c = 0; c < nchrom; ++c) { WC_CHECK_ARG(chrom_bins_h[c] >= 0); tot += chrom_bins_h[c]; }
+    WC_CHECK_ARG(tot == N);
+    std::vector<int> row_cs, row_ce, skip_lo, skip_n, la, oa, lb, ob;
+    block_skips(N, chrom_bins_h, nchrom, row_cs, row_ce, skip_lo, skip_n);
+    const int nb = (N + BM - 1) / BM;
+    const int bp = (nb + world - 1) / world;
+    const int b0 = std::min(nb, rank * bp), b1 = std::min(nb, b0 + bp), nrb = b1 - b0;
+    pair_lists(nb, skip_lo, skip_n, frac, b0, b1, la, oa, lb, ob);
+    std::vector<Piece> pa, pb;
+    if (!la.empty()) schedule_pieces(oa, nrb, std::max(1, std::min<int>(grid, ((int)la.size() + 7) / 8)), 1, false, 0, pa);
+    if (!lb.empty()) schedule_pieces(ob, nrb, std::max(1, std::min<int>(grid, ((int)lb.size() + 7) / 8)), group, rounds_on != 0, 1, pb);
+    const long long need = 8 + 2ll * (nrb + 1) + (long long)la.size() + (long long)lb.size() + 5ll * (pa.size() + pb.size()) + 2ll * nb;
+    *used = need;
+    if (need > out_ints) { wc_set_error("wc_debug_sym_plan: %lld ints needed", need); return WC_ERR_ARG; }
+    int* o = out;
+    *o++ = nb; *o++ = b0; *o++ = b1; *o++ = (int)la.size(); *o++ = (int)lb.size(); *o++ = (int)pa.size(); *o++ = (int)pb.size(); *o++ = 0;
+    for (int v : oa) *o++ = v;
+    for (int v : ob) *o++ = v;
+    for (int v : la) *o++ = v;
+    for (int v : lb) *o++ = v;
+    for (const std::vector<Piece>* pv : {&pa, &pb})
+        for (const Piece& pc : *pv) { *o++ = pc.cta; *o++ = pc.rb; *o++ = pc.q0; *o++ = pc.q1; *o++ = pc.step; }
+    for (int v : skip_lo) *o++ = v;
+    for (int v : skip_n) *o++ = v;
+    return WC_OK;
+}
 
 extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int S, const int* chrom_bins_h,
                               int nchrom, int row_begin, int row_end, int refsize, int32_t* idx_d, double* dist_d,
@@ -1251,30 +1334,15 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         schedule_pieces(prefix, nrb, grid, G, rounds_on, 0, pieces);
     } else {
         const int nb = nrb;
-        // symmetric in (I, J), and every block meets exactly 1/sym_frac of the others, spread evenly over the genome
-        auto in_sample = [&](int I, int J) { return I == J || (I + J) % sym_frac == 0; };
-        auto valid = [&](int I, int t) { return !(t >= skip_lo[I] && t < skip_lo[I] + skip_n[I]); };
-        offA.assign(nb + 1, 0);
-        offB.assign(nb + 1, 0);
-        for (int I = 0; I < nb; ++I) {
-            for (int t = 0; t < nb; ++t)
-                if (valid(I, t) && in_sample(I, t)) listA.push_back(t);
-            offA[I + 1] = (int)listA.size();
-            for (int dlt = 1; dlt <= nb / 2; ++dlt) {
-                if (2 * dlt == nb && I >= nb / 2) continue;      // the antipodal pair belongs to its lower block
-                const int t = (I + dlt) % nb;
-                if (valid(I, t) && !in_sample(I, t)) listB.push_back(t);
-            }
-            offB[I + 1] = (int)listB.size();
-        }
+        pair_lists(nb, skip_lo, skip_n, sym_frac, 0, nb, listA, offA, listB, offB);
         tilesA = (long long)listA.size();
         tilesB = (long long)listB.size();
         gridA = (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesA + 7) / 8));
         gridB = (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesB + 7) / 8));
         // pass A: contiguous split, so a row block is cut at most once or twice and every bin's threshold comes from (nearly)
         // its whole sample.  (Rounds would chop the left-over row blocks into ~20 pieces of 2-3 tiles: thresholds loose
-        // enough to flood those bins' incoming buffers - measured: ~900 rows in the exhaustive fallback, +240 ms.)  All CTAs
-        // still walk their ascending lists in step, so the B panels are shared through L2 all the same.
+        // enough to flood those bins' incoming buffers - measured: ~900 rows in the exhaustive fallback, +240 ms.)  The price:
+        // the CTAs are out of step and pass A's B panels come from DRAM (24 GB at 600 x 50 kb) - see DESIGN.md section 7.
         schedule_pieces(offA, nb, gridA, 1, false, 0, pieces);
         int GB = G;
         if (GB > gridB) GB = gridB;

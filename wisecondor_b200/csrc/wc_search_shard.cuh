@@ -164,21 +164,8 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
         skip_n[I] = n;
         if (I >= d.b0 && I < d.b1) tiles_plain += nb - n;
     }
-    const int frac = d.frac;
-    auto in_sample = [&](int I, int J) { return I == J || (I + J) % frac == 0; };
-    auto valid = [&](int I, int t) { return !(t >= skip_lo[I] && t < skip_lo[I] + skip_n[I]); };
-    std::vector<int> listA, listB, offA(nrb + 1, 0), offB(nrb + 1, 0);
-    for (int I = d.b0; I < d.b1; ++I) {
-        for (int t = 0; t < nb; ++t)
-            if (valid(I, t) && in_sample(I, t)) listA.push_back(t);
-        offA[I - d.b0 + 1] = (int)listA.size();
-        for (int dlt = 1; dlt <= nb / 2; ++dlt) {
-            if (2 * dlt == nb && I >= nb / 2) continue;
-            const int t = (I + dlt) % nb;
-            if (valid(I, t) && !in_sample(I, t)) listB.push_back(t);
-        }
-        offB[I - d.b0 + 1] = (int)listB.size();
-    }
+    std::vector<int> listA, listB, offA, offB;
+    pair_lists(nb, skip_lo, skip_n, d.frac, d.b0, d.b1, listA, offA, listB, offB);
     const long long tilesA = (long long)listA.size(), tilesB = (long long)listB.size();
     const int gridA = tilesA ? (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesA + 7) / 8)) : 0;
     const int gridB = tilesB ? (int)std::max(1ll, std::min<long long>(ctx->sm_count, (tilesB + 7) / 8)) : 0;
