@@ -613,8 +613,17 @@ def main():
                                    (peak_src, "sustained" if use_peak == sustained else "burst"),
                     "share_of_step": k5 / ms_per_step}
         if os.environ.get("WC_K5_F16") == "1":
-            roofline["note"] += ("; EXPERIMENTAL fp16 filter (WC_K5_F16=1): K5 then runs on the fp16 tensor cores and the "
-                                 "FP64 peak / frac above do not apply")
+            # experimental fp16 filter: K5 runs on the fp16 tensor cores; the denominator is the measured dense bf16/fp16 rate
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                    mp = json.load(fh)
+                tc_peak = float(mp["bf16_tflops"] if ms_per_step <= 50.0 else mp.get("bf16_tflops_sustained", mp["bf16_tflops"]))
+                tc_src = "MEASURED_PEAKS.json bf16 dense (cuBLAS)"
+            except Exception:
+                tc_peak, tc_src = 2250.0, "nominal dense fp16 (MEASURED_PEAKS.json missing)"
+            roofline.update({"kernel": "wc_dist_topk_f16_kernel (K5h, fp16 HMMA.16816.F32 + TMA; fp64 exact re-score in K6)",
+                             "peak": tc_peak, "frac": achieved / tc_peak, "peak_source": tc_src})
+            roofline["note"] += "; EXPERIMENTAL fp16 filter (WC_K5_F16=1)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup) if not big else max(1, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
