@@ -319,3 +319,24 @@ def test_symmetric_plan_reaches_every_block_pair_exactly_once(bins, world, frac)
     needed = np.array([[not (len(sets[i]) == 1 and sets[i] == sets[j]) for j in range(nb)] for i in range(nb)])
     assert (seen <= 1).all(), "a block pair is computed twice"
     assert (seen[needed] == 1).all(), "a block pair with candidates is never computed"
+
+
+@pytest.mark.parametrize("n,world", [(501, 3), (57633, 8), (11537, 2), (128, 4), (1, 1)])
+def test_shard_dims_partition_the_bins(n, world):
+    """wc_newref_shard_dims (host arithmetic; NULL context): the ranks' bin ranges are consecutive, block-aligned, cover
+    [0, N) exactly, and the exchange buffers have equal splits."""
+    from wisecondor_b200 import _cabi
+    L = _cabi.lib()
+    prev_end, rows_per = 0, None
+    for rank in range(world):
+        out = (ctypes.c_longlong * 6)()
+        _cabi.check(L.wc_newref_shard_dims(None, n, 100, world, rank, out))
+        rp, in_cap, thr_len, row0, row1, nb = (int(v) for v in out)
+        rows_per = rows_per or rp
+        assert rp == rows_per and rp % 128 == 0 and nb == (n + 127) // 128
+        assert row0 == min(n, rank * rp) == prev_end or (row0 == n and prev_end == n)
+        assert row0 <= row1 <= n and (row1 == n or row1 % 128 == 0)
+        assert thr_len >= world * rp + 128 and thr_len >= nb * 128
+        assert in_cap >= 256 and in_cap & (in_cap - 1) == 0
+        prev_end = row1
+    assert prev_end == n

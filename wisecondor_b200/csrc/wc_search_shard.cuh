@@ -21,7 +21,7 @@ struct ShardDims { int nb, bp, b0, b1, row0, row1, rows_per, in_cap, frac; size_
 
 ShardDims shard_dims(const wc_ctx* ctx, int N, int k, int world, int rank) {
     ShardDims d;
-    d.frac = ctx->k5_sym >= 2 ? ctx->k5_sym : 8;
+    d.frac = (ctx != nullptr && ctx->k5_sym >= 2) ? ctx->k5_sym : 8;
     d.nb = (N + BM - 1) / BM;
     d.bp = (d.nb + world - 1) / world;
     d.b0 = std::min(d.nb, rank * d.bp);
@@ -103,7 +103,7 @@ int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned
 }  // namespace
 
 extern "C" int wc_newref_shard_dims(const wc_ctx* ctx, int N, int refsize, int world, int rank, long long* out6) {
-    WC_CHECK_ARG(ctx != nullptr && out6 != nullptr);
+    WC_CHECK_ARG(out6 != nullptr);                 // ctx may be NULL: sizes for the default first-pass fraction
     WC_CHECK_ARG(N > 0 && refsize >= 1 && refsize <= 384 && world >= 1 && rank >= 0 && rank < world);
     const ShardDims d = shard_dims(ctx, N, refsize, world, rank);
     out6[0] = d.rows_per; out6[1] = d.in_cap; out6[2] = (long long)d.thr_len; out6[3] = d.row0; out6[4] = d.row1; out6[5] = d.nb;
