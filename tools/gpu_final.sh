@@ -9,7 +9,8 @@ timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_r
 timeout 300 python bench.py --steps 20 --warmup 3 --workload newref_600x250kb --no-cpu-baseline > $OUT/bench_newref_600x250kb_$TAG.json 2> /dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 120 --csv --log-file $OUT/launches_default_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"wc_dist_topk|wc_finalize" -s 2 -c 2 -o $OUT/k5k6_50kb_$TAG -f \
+# symmetric search: a step launches K5 twice (threshold pass, symmetric pass) and K6 once: skip one step, capture the next
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"wc_dist_topk|wc_finalize" -s 3 -c 3 -o $OUT/k5k6_50kb_$TAG -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-test > $OUT/ncu_k5k6_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"wc_zscore_kernel|wc_segment_kernel" -s 6 -c 6 -o $OUT/k8k9_$TAG -f \
     python tools/bench_test.py 50000 256 > $OUT/ncu_k8k9_$TAG.log 2>&1
