@@ -91,3 +91,15 @@ def test_f16_filter_config2_shape_equals_fp64_filter(f16):
     pidx, pdist, pst = _search(X, bins, 0, X.shape[0], 100)
     _assert_same(idx, dist, pidx, pdist)
     assert st["exhaustive_rows"] == 0
+
+
+def test_f16_filter_sharded_symmetric_search(monkeypatch):
+    """The sharded symmetric search with the fp16 filter, ranks emulated on one GPU (contexts read WC_K5_F16 at creation)."""
+    from test_search_shard_gpu import _emulated_ranks
+    monkeypatch.setenv("WC_K5_F16", "1")
+    bins = [int(b) for b in np.array(synth.chrom_bins(250000)) // 2]
+    X = synth.corrected_like(bins, 64, seed=31)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, X.shape[0], 100)
+    for world in (2, 3):
+        idx, dist, stats = _emulated_ranks(X, bins, 100, world)
+        _assert_same(idx, dist, oidx, odist)

@@ -61,7 +61,8 @@ struct wc_shard_plan {
     int nkc = 0, nd_last = 0, extra_h = 0, ld = 0, nstages = 0, nrb = 0, nseg = 0, gridA = 0, gridB = 0;
     size_t Npad = 0, smem = 0, nlistA = 0;
     long long tilesA = 0, tilesB = 0, tiles_plain = 0;
-    double mcoef = 0.0;
+    double mcoef = 0.0, madd = 0.0;              // margins of the filter (fp64: madd = 0; fp16: see wc_newref_topk)
+    int f16 = 0, ldh = 0;                        // fp16 tensor-core filter in use, its padded sample count
     const double* corrected = nullptr;
     int stage = 0;                               // 1 after begin, 2 after sweep
 };

@@ -46,12 +46,13 @@ int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned
     }
     CUtensorMap tmap;
     {
-        cuuint64_t dims[2] = {(cuuint64_t)pl.ld, (cuuint64_t)pl.Npad};
-        cuuint64_t strides[1] = {(cuuint64_t)pl.ld * sizeof(double)};
-        cuuint32_t box[2] = {BK, BM};
+        cuuint64_t dims[2] = {(cuuint64_t)(pl.f16 ? pl.ldh : pl.ld), (cuuint64_t)pl.Npad};
+        cuuint64_t strides[1] = {pl.f16 ? (cuuint64_t)pl.ldh * sizeof(__half) : (cuuint64_t)pl.ld * sizeof(double)};
+        cuuint32_t box[2] = {(cuuint32_t)(pl.f16 ? BKH : BK), BM};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = reinterpret_cast<PFN_encodeTiled>(ctx->encode_tiled)(
-            &tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->buf[SLOT_XC].p, dims, strides, box, estr,
+            &tmap, pl.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->buf[SLOT_XC].p, dims,
+            strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -79,7 +80,7 @@ int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned
     ta.pieces = d_pieces;
     ta.cand_key = static_cast<u64*>(ctx->buf[SLOT_CAND_D].p); ta.cand_j = static_cast<int*>(ctx->buf[SLOT_CAND_J].p);
     ta.seg_cnt = static_cast<int*>(ctx->buf[SLOT_SEGCNT].p); ta.seg_flag = static_cast<int*>(ctx->buf[SLOT_SEGFLAG].p);
-    ta.cap = pl.cap; ta.k = pl.k; ta.mcoef = pl.mcoef; ta.tau_init = 1e10 * (1.0 + 1e-6);
+    ta.cap = pl.cap; ta.k = pl.k; ta.mcoef = pl.mcoef; ta.tau_init = pl.f16 ? 3e38 : 1e10 * (1.0 + 1e-6);
     ta.prof = nullptr; ta.trace = nullptr;
     ta.row_thr = thr_d + pl.row0;             // indexed by (bin - row_begin) on the row side ...
     ta.col_thr = thr_d;                       // ... and by global bin on the column side
@@ -88,14 +89,11 @@ int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned
     ta.rb_list_off = pass == 0 ? d_offA : d_offB;
     ta.final_prune = 1;
     ta.in_key = in_key_d; ta.in_j = in_j_d; ta.in_cnt = in_cnt_d; ta.in_cap = pl.in_cap;
-    ta.madd = 0.0; ta.n32 = nullptr;
-    if (pass == 0) {
-        WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        wc_dist_topk_kernel<false><<<pl.gridA, TOPK_THREADS, pl.smem, stream>>>(tmap, ta);
-    } else {
-        WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        wc_dist_topk_kernel<true><<<pl.gridB, TOPK_THREADS, pl.smem, stream>>>(tmap, ta);
-    }
+    ta.madd = pl.madd; ta.n32 = pl.f16 ? static_cast<float*>(ctx->buf[SLOT_N32].p) : nullptr;
+    auto kernel = pass == 0 ? (pl.f16 ? wc_dist_topk_f16_kernel<false> : wc_dist_topk_kernel<false>)
+                            : (pl.f16 ? wc_dist_topk_f16_kernel<true> : wc_dist_topk_kernel<true>);
+    WC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    kernel<<<pass == 0 ? pl.gridA : pl.gridB, TOPK_THREADS, pl.smem, stream>>>(tmap, ta);
     WC_CUDA(cudaGetLastError());
     return WC_OK;
 }
@@ -245,11 +243,32 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
     WC_CUDA(cudaMemsetAsync(seg_cnt, 0, (size_t)std::max(nseg, 1) * BM * sizeof(int), stream));
     WC_CUDA(cudaMemsetAsync(seg_flag, 0, (size_t)std::max(nseg, 1) * BM * sizeof(int), stream));
 
+    // option k5_f16: fp16 tensor-core filter (every rank holds the whole matrix, so all ranks take the same decision)
+    bool f16 = ctx->k5_f16 != 0;
+    const int ldh = (S + BKH - 1) / BKH * BKH;
+    double nmax = 0.0;
     WC_CUDA(cudaEventRecord(ctx->ev[0], stream));
-    wc_prepare_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ld, Sx, Xc, norms);
+    if (f16) {
+        float* n32;
+        unsigned long long* stats;
+        if ((rc = wc_reserve(ctx, SLOT_N32, Npad * sizeof(float), (void**)&n32))) return rc;
+        if ((rc = wc_reserve(ctx, SLOT_F16STAT, 2 * sizeof(unsigned long long), (void**)&stats))) return rc;
+        WC_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), stream));
+        wc_prepare_f16_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ldh,
+                                                                                  reinterpret_cast<__half*>(Xc), norms, n32, stats);
+        WC_CUDA(cudaGetLastError());
+        unsigned long long st_h[2] = {0, 0};
+        WC_CUDA(cudaMemcpyAsync(st_h, stats, sizeof(st_h), cudaMemcpyDeviceToHost, stream));
+        WC_CUDA(cudaStreamSynchronize(stream));
+        memcpy(&nmax, &st_h[0], sizeof(double));
+        if (st_h[1] != 0) f16 = false;
+    }
+    if (!f16)
+        wc_prepare_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ld, Sx, Xc, norms);
     WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[1], stream));
-    const double tau_init = 1e10 * (1.0 + 1e-6);
+    const double eps16 = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (double)ldh * ldexp(1.0, -23) + ldexp(1.0, -21);
+    const double tau_init = f16 ? 3e38 : 1e10 * (1.0 + 1e-6);
     wc_fill_u64_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(thr_d, (size_t)N, host_key_of_tau(tau_init));
     wc_fill_u64_kernel<<<(unsigned)((d.thr_len - N + 255) / 256), 256, 0, stream>>>(thr_d + N, d.thr_len - (size_t)N, KEY_NEVER);
     WC_CUDA(cudaGetLastError());
@@ -259,10 +278,17 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
     pl.nkc = nkc; pl.nd_last = nd_last; pl.extra_h = nd_last; pl.ld = ld; pl.nrb = nrb; pl.nseg = nseg;
     pl.gridA = gridA; pl.gridB = gridB; pl.Npad = Npad; pl.nlistA = listA.size();
     pl.tilesA = tilesA; pl.tilesB = tilesB; pl.tiles_plain = tiles_plain;
-    pl.mcoef = 16.0 * (double)(S + 16) * 1.1102230246251565e-16;
+    pl.f16 = f16 ? 1 : 0;
+    pl.ldh = ldh;
+    pl.mcoef = f16 ? 2.0 * eps16 : 16.0 * (double)(S + 16) * 1.1102230246251565e-16;
+    pl.madd = f16 ? 2.0 * eps16 * nmax + ldexp(1.0, -20) * sqrt((double)S * nmax) : 0.0;
+    if (f16) pl.nkc = ldh / BKH;
     pl.corrected = corrected_d;
-    pl.nstages = cap <= 512 ? 4 : 3;
-    pl.smem = (size_t)pl.nstages * STAGE_BYTES + sizeof(TopkState) +
+    pl.nstages = f16 ? 4 : (cap <= 512 ? 4 : 3);
+    pl.smem = f16
+        ? (size_t)pl.nstages * STAGE_BYTES + sizeof(TopkState) + (size_t)CONSUMER_WARPS * F16_SCRATCH +
+              (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4) + (2 * BN + 32) * sizeof(float))
+        : (size_t)pl.nstages * STAGE_BYTES + sizeof(TopkState) +
               (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192) +
               (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4));
     if (pl.smem > 227 * 1024) { wc_set_error("K5 shared memory %zu exceeds 227 KiB", pl.smem); return WC_ERR_INTERNAL; }
@@ -320,11 +346,11 @@ extern "C" int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* rec
         fa.rb_seg_first = d_meta + 2 * nrb1; fa.rb_seg_count = d_meta + 3 * nrb1;
         fa.cand_key = static_cast<u64*>(ctx->buf[SLOT_CAND_D].p); fa.cand_j = static_cast<int*>(ctx->buf[SLOT_CAND_J].p);
         fa.seg_cnt = static_cast<int*>(ctx->buf[SLOT_SEGCNT].p); fa.seg_flag = static_cast<int*>(ctx->buf[SLOT_SEGFLAG].p);
-        fa.cap = pl.cap; fa.k = pl.k; fa.shortcap = pl.k <= 128 ? 256 : 512; fa.mcoef = pl.mcoef;
+        fa.cap = pl.cap; fa.k = pl.k; fa.shortcap = pl.k <= (pl.f16 ? 96 : 128) ? 256 : 512; fa.mcoef = pl.mcoef;
         fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
         fa.bulk = (pl.S % 2 == 0 && (reinterpret_cast<uintptr_t>(pl.corrected) & 15) == 0) ? 1 : 0;
         fa.in_key = recv_key_d; fa.in_j = recv_j_d; fa.in_cnt = recv_cnt_d; fa.in_cap = pl.in_cap;
-        fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per; fa.madd = 0.0;
+        fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per; fa.madd = pl.madd;
         const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
         WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
         WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
