@@ -1,4 +1,5 @@
-"""CPU study for a bf16x3 tensor-core filter in front of the exact fp64 re-score (K5 successor).
+"""CPU study of reduced-precision tensor-core filters in front of the exact fp64 re-score (K5 successors): a bf16 x 3
+split and the single-pass fp16 scheme K5h implements (wc_search_f16.cuh).
 
 x' = x - 1 is split into two bf16 numbers h + l (|x' - h - l| <= 2^-17 |x'|); the filter score is
     s~ = sum_s (h_i h_j + h_i l_j + l_i h_j)      accumulated in fp32 in chunks of `chunk` samples, chunks added in fp64,

@@ -8,7 +8,7 @@
 // ---------------------------------------------------------------------------------------------------------
 // The filter only has to produce a SUPERSET of every bin's true top-k - K6 re-scores the shortlist exactly in fp64 - so
 // the contraction does not need fp64 at all.  With x' = x - 1 rounded once to fp16 (relative error 2^-11 per operand)
-// and fp32 accumulation, |d~ - d| <= eps * (n_i + n_j) with eps ~ 1.1e-3 (a priori; tools/bf16x3_study.py measures the
+// and fp32 accumulation, |d~ - d| <= eps * (n_i + n_j) with eps ~ 1.1e-3 (a priori; tools/filter_precision_study.py measures the
 // candidate inflation of such a margin: 109 instead of 100 candidates per bin at 600 x 250 kb).  The norms are NOT part
 // of the contraction here (n/2 ~ 1 would lose all precision in fp16): d~ = (n_i + n_j) - 2 s in fp32 in the epilogue.
 // Same persistent grid, TMA ring, warp-private rows, candidate buffers, prunes and symmetric column side as K5; the
