@@ -403,6 +403,42 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
     }
 
 
+
+def parity_check(device, torch, X, X_host_np, bins, k, table_idx, table_dist, rank, world, local, rows_per=None, rows_per_range=32):
+    """After the timed region: the table the timed code path produced against (a) the C restatement of the oracle on
+    sampled row ranges (random ones, and ranges straddling the shard boundaries) and (b) at N > 1 the whole table of a
+    single-GPU search on rank 0.  TEST INFRASTRUCTURE use of oracle/ - the checker, never the thing measured."""
+    if rank != 0:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    n = int(sum(bins))
+    rng = np.random.default_rng(11)
+    starts = [int(v) for v in rng.integers(0, n - rows_per_range, size=4)]
+    if world > 1 and rows_per:
+        for r in range(1, world):           # straddle the boundary between the bins of rank r-1 and rank r
+            b = min(n - rows_per_range, max(0, r * rows_per - rows_per_range // 2))
+            if len(starts) < 8:
+                starts.append(int(b))
+    ti, td = table_idx.cpu().numpy(), table_dist.cpu().numpy()
+    Xh = X_host_np if X_host_np is not None else X.cpu().numpy()
+    ranges, ok_all = [], True
+    t0 = time.time()
+    for r0 in sorted(set(starts)):
+        oi, od = c_oracle.get_reference_rows(Xh, bins, r0, r0 + rows_per_range, k)
+        ok = bool(np.array_equal(ti[r0:r0 + rows_per_range], oi) and np.array_equal(td[r0:r0 + rows_per_range], od))
+        ranges.append({"row0": r0, "rows": rows_per_range, "identical": ok})
+        ok_all = ok_all and ok
+    out = {"oracle": "oracle/wc_oracle.c (C restatement, bit-exact compare of indexes and distances)",
+           "rows_checked": rows_per_range * len(ranges), "ranges": ranges, "identical": ok_all,
+           "oracle_s": time.time() - t0}
+    if world > 1:
+        si, sd = device.newref_topk(X, bins, 0, n, k)
+        out["whole_table_equals_single_gpu_search"] = bool(torch.equal(si, table_idx) and torch.equal(sd, table_dist))
+    import hashlib
+    out["table_sha256"] = hashlib.sha256(ti.tobytes() + td.tobytes()).hexdigest()[:16]
+    return out
+
 # --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
@@ -444,6 +480,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work in the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-test", action="store_true", help="skip the batched test (z-score + segmentation) section")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the sampled-row comparison with the C oracle")
     ap.add_argument("--test-batch", type=int, default=512, help="test samples per GPU in the test section")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -648,15 +685,24 @@ def main():
             line["cpu_baseline"] = desc
         else:
             line["cpu_baseline"] = None
+    # ---- parity of what the timed code path produced (after the timed region; rank 0 checks, all ranks gather) ----
+    if sym_search is not None:
+        table_idx, table_dist = (t.contiguous() for t in sym_search.gather())
+    elif world == 1:
+        table_idx, table_dist = out_idx[:rows], out_dist[:rows]
+    else:
+        table_idx, table_dist = full_idx, full_dist
+    pc = None
+    if not args.no_parity_check:
+        pc = parity_check(device, torch, X, X_host_np, bins, k, table_idx, table_dist, rank, world, local,
+                          rows_per=sym_search.rows_per if sym_search is not None else rows_max)
+    if rank == 0:
+        line["config"]["parity_check"] = pc
+    if world > 1:
+        dist.barrier()
     # ---- the test half of the path (BASELINE metric "test samples/s"): batched z-scores + segmentation ----------
     test_line = None
     if not args.no_test:
-        if sym_search is not None:
-            table_idx, table_dist = (t.contiguous() for t in sym_search.gather())
-        elif world == 1:
-            table_idx, table_dist = out_idx[:rows], out_dist[:rows]
-        else:
-            table_idx, table_dist = full_idx, full_dist
         test_line = bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins, k, table_idx, table_dist)
     if rank == 0:
         line["test"] = test_line

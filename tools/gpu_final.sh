@@ -13,5 +13,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 12
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"wc_dist_topk|wc_finalize" -s 3 -c 3 -o $OUT/k5k6_50kb_$TAG -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-test > $OUT/ncu_k5k6_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"wc_zscore_kernel|wc_segment_kernel" -s 6 -c 6 -o $OUT/k8k9_$TAG -f \
-    python tools/bench_test.py 50000 256 > $OUT/ncu_k8k9_$TAG.log 2>&1
+    python tools/bench_testpath.py 50000 256 > $OUT/ncu_k8k9_$TAG.log 2>&1
 ls -la $OUT | tail -12
