@@ -90,8 +90,19 @@ int wc_debug_profile(wc_ctx* ctx, int enable, long long* out_h, int max_ctas);
  *   "k5_sym"    whole-matrix searches contract every unordered pair of bin blocks once (symmetric search): 0 = off (plain
  *               search), f in 2..64 = on, with 1/f of the block pairs computed in the first (threshold) pass.  Default 8.
  *   "k5_group"  CTAs sharing a row block per scheduling round (0 = automatic), "k5_stages" TMA ring depth (0 = automatic),
- *   "k5_lag"    chunks (0..4) by which half of the distance kernel's MMA warps trail the other half. */
+ *   "k5_lag"    chunks (0..4) by which half of the distance kernel's MMA warps trail the other half,
+ *   "k5_f16"    the FILTER of the distance kernel (the exact fp64 re-score that decides the result is the same for all):
+ *               0 = fp64 contraction on DMMA, 1 = fp16 on mma.sync, 2 = fp16 on tcgen05 with TMEM accumulators. */
 int wc_set_option(wc_ctx* ctx, const char* key, double value);
+
+/* Debug: searches that run the tcgen05 filter (k5_f16 = 2) also store every filter distance they compute into
+ * out_d[(i - row_begin) * ld + j] (DEVICE float, caller-owned).  NULL switches it off.  Used by the tests that measure the
+ * filter's error against the margin its exactness argument assumes. */
+int wc_debug_filter_scores(wc_ctx* ctx, float* out_d, int ld);
+
+/* ABI version of this header; wc_abi_version() returns the one the library was built from (the binding refuses a mismatch). */
+#define WC_ABI_VERSION 2
+int wc_abi_version(void);
 
 /* ---- newref: reference-bin search --------------------------------------------------------------------- */
 /* Replaces getReference + getRefForBins (wisetools.py:364-398, 298-325) for target rows

@@ -12,7 +12,8 @@ void wc_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* wc_last_error(void) { return g_err; }
-extern "C" const char* wc_version(void) { return "wisecondor_b200 0.1 (sm_100a)"; }
+extern "C" const char* wc_version(void) { return "wisecondor_b200 0.2 (sm_100a)"; }
+extern "C" int wc_abi_version(void) { return WC_ABI_VERSION; }
 
 extern "C" wc_ctx* wc_create(int device) {
     int ndev = 0;

@@ -45,7 +45,7 @@ enum {
     SLOT_XC = 0, SLOT_NORMS, SLOT_ROWCS, SLOT_ROWCE, SLOT_RBMETA, SLOT_CAND_D, SLOT_CAND_J, SLOT_SEGCNT,
     SLOT_SEGFLAG, SLOT_SLOW, SLOT_SCRATCH, SLOT_IO_X, SLOT_IO_IDX, SLOT_IO_DIST, SLOT_ROWTHR,
     SLOT_IN_KEY, SLOT_IN_J, SLOT_IN_CNT, SLOT_N32, SLOT_F16STAT,                                                             // search
-    SLOT_PROF = 20,
+    SLOT_PROF = 20, SLOT_PIV_IDS = 21, SLOT_PIV_X = 22, SLOT_PIV_N = 23, SLOT_PIV_META = 37,
     SLOT_T_COPY = 24, SLOT_T_ZT, SLOT_T_RT, SLOT_T_NT, SLOT_T_SD, SLOT_T_FLAGS, SLOT_T_TOTALS, SLOT_T_PROJ,   // test
     SLOT_T_REVCNT = 44, SLOT_T_REVCUR, SLOT_T_DIRTY, SLOT_T_PAIRS,
     SLOT_S_ZC = 32, SLOT_S_META, SLOT_S_STATUS, SLOT_S_RC, SLOT_S_AUX,                                                       // segmentation
@@ -62,7 +62,8 @@ struct wc_shard_plan {
     size_t Npad = 0, smem = 0, nlistA = 0;
     long long tilesA = 0, tilesB = 0, tiles_plain = 0;
     double mcoef = 0.0, madd = 0.0;              // margins of the filter (fp64: madd = 0; fp16: see wc_newref_topk)
-    int f16 = 0, ldh = 0;                        // fp16 tensor-core filter in use, its padded sample count
+    int f16 = 0, ldh = 0;                        // fp16 tensor-core filter in use (1 mma.sync, 2 tcgen05), its padded sample count
+    int pivots = 0;                              // pivots of the K5t pivot pass (0: none)
     const double* corrected = nullptr;
     int stage = 0;                               // 1 after begin, 2 after sweep
 };
@@ -82,7 +83,11 @@ struct wc_ctx {
     int k5_stages = 0;              // 0 = automatic TMA ring depth
     int k5_group = 0;               // CTAs sharing a row block per scheduling round of K5 (0 = automatic)
     int k5_sym = 8;                 // symmetric search: 0 = off, f >= 2 = on with 1/f of the block pairs in the first pass
-    int k5_f16 = 0;                 // 1: fp16 tensor-core filter (HMMA) instead of the fp64 one (DMMA) in K5
+    int k5_f16 = 2;                 // filter of K5: 0 fp64 (DMMA), 1 fp16 on mma.sync (HMMA), 2 fp16 on tcgen05 / TMEM (UTCHMMA)
+    int k5_pivots = 1;              // K5t: pivot pass before a symmetric search (0 = off)
+    unsigned long long piv_hash = 0;   // fingerprint of the pivot pass' piece table on the device
+    float* dbg_scores = nullptr;    // wc_debug_filter_scores: where K5t dumps its filter distances (caller-owned), or NULL
+    int dbg_ld = 0;
     int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones
     int debug_profile = 0;          // K5 writes per-CTA cycle counters when set (wc_debug_profile)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)

@@ -99,6 +99,10 @@ struct TopkArgs {
     const u64* col_thr;          // thresholds indexed by GLOBAL bin (== row_thr when the launch starts at row 0)
     double madd;                 // margin(v) = mcoef * (n_i + |v|) + madd  (0 for the fp64 filter)
     const float* n32;            // fp16 filter: the bins' squared norms in fp32, +inf for padding rows
+    const float* coln32;         // K5t: norms of the COLUMN rows (== n32, or the pivot matrix' norms in the pivot pass)
+    const int* col_ids;          // K5t pivot pass: global bin of every row of the pivot matrix (nullptr: columns are bins)
+    float* dbg;                  // debug (K5t, DBG instantiation): every filter distance d~ lands in dbg[row - row_begin][column]
+    int dbg_ld;
 };
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -627,7 +631,8 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
     }
 }
 
-#include "wc_search_f16.cuh"      // K4h / K5h: the same search with an fp16 tensor-core filter (option k5_f16)
+#include "wc_search_f16.cuh"      // K4h / K5h: the same search with an fp16 tensor-core filter (option k5_f16 = 1, mma.sync)
+#include "wc_search_tc.cuh"       // K5t: the fp16 filter on tcgen05 / TMEM (option k5_f16 = 2)
 
 __global__ void wc_fill_u64_kernel(u64* p, size_t n, u64 v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -710,14 +715,15 @@ struct FinArgs {
 //     operands: sequential over samples, separately rounded subtract / multiply / add); one thread per
 //     candidate, candidate rows staged through shared memory by cp.async in 32-sample chunks, double buffered.
 //  3. rank by (distance, index), write the first k with indices remapped to other-chromosome coordinates.
-__global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs a) {
+template <int FT>      // threads = shortlisted candidates re-scored per round: 128, or 160 behind the wider window of the fp16 filters
+__global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     extern __shared__ __align__(16) unsigned char fin_raw[];
-    double* tile0 = reinterpret_cast<double*>(fin_raw);                    // 2 x FIN_THREADS x FIN_LDB (or FIN_LD)
-    double* xi0 = tile0 + 2 * FIN_THREADS * FIN_LDB;                       // 2 x FIN_CHUNK
+    double* tile0 = reinterpret_cast<double*>(fin_raw);                    // 2 x FT x FIN_LDB (or FIN_LD)
+    double* xi0 = tile0 + 2 * FT * FIN_LDB;                       // 2 x FIN_CHUNK
     double* ex_d = xi0 + 2 * FIN_CHUNK;                                    // shortcap
     int* ex_j = reinterpret_cast<int*>(ex_d + a.shortcap);                 // shortcap
     int* hist = ex_j + a.shortcap;                                         // HIST_BINS
-    __shared__ double s_red[2][FIN_THREADS / 32];
+    __shared__ double s_red[2][FT / 32];
     __shared__ int s_total, s_flag, s_p, s_bstar, s_valid;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -762,7 +768,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
         s_p = 0;
         s_valid = 0;
     }
-    for (int b = tid; b < HIST_BINS; b += FIN_THREADS) hist[b] = 0;
+    for (int b = tid; b < HIST_BINS; b += FT) hist[b] = 0;
     __syncthreads();
     const int total = s_total;
     if (s_flag) {
@@ -770,7 +776,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
         return;
     }
     if (total == 0) {
-        for (int e = tid; e < a.k; e += FIN_THREADS) { out_i[e] = -1; out_d[e] = 1e10; }
+        for (int e = tid; e < a.k; e += FT) { out_i[e] = -1; out_d[e] = 1e10; }
         return;
     }
 
@@ -780,7 +786,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
         const u64* cd;
         const int* cjs;
         const int n = source(s, cd, cjs);
-        for (int e = tid; e < n; e += FIN_THREADS) {
+        for (int e = tid; e < n; e += FT) {
             double d = dist_of_key(cd[e]);
             mn = fmin(mn, d);
             mx = fmax(mx, d);
@@ -791,13 +797,13 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < FIN_THREADS / 32; ++w) { mn = fmin(mn, s_red[0][w]); mx = fmax(mx, s_red[1][w]); }
+    for (int w = 0; w < FT / 32; ++w) { mn = fmin(mn, s_red[0][w]); mx = fmax(mx, s_red[1][w]); }
     const float scale = (mx > mn) ? (float)(HIST_BINS - 1) / (float)(mx - mn) : 0.0f;
     for (int s = 0; s < nsrc; ++s) {
         const u64* cd;
         const int* cjs;
         const int n = source(s, cd, cjs);
-        for (int e = tid; e < n; e += FIN_THREADS) atomicAdd(&hist[bucket_of(dist_of_key(cd[e]), mn, scale)], 1);
+        for (int e = tid; e < n; e += FT) atomicAdd(&hist[bucket_of(dist_of_key(cd[e]), mn, scale)], 1);
     }
     __syncthreads();
     if (warp == 0) {
@@ -828,7 +834,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
         const u64* cd;
         const int* cjs;
         const int n = source(s, cd, cjs);
-        for (int e = tid; e < n; e += FIN_THREADS) {
+        for (int e = tid; e < n; e += FT) {
             double d = dist_of_key(cd[e]);
             if (bucket_of(d, mn, scale) <= bstar) vstar = fmax(vstar, d);
         }
@@ -838,13 +844,13 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     if (lane == 0) s_red[0][warp] = vstar;
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < FIN_THREADS / 32; ++w) vstar = fmax(vstar, s_red[0][w]);
+    for (int w = 0; w < FT / 32; ++w) vstar = fmax(vstar, s_red[0][w]);
     const double window = vstar + a.mcoef * (a.norms[row] + fabs(vstar)) + a.madd;
     for (int s = 0; s < nsrc; ++s) {
         const u64* cd;
         const int* cjs;
         const int n = source(s, cd, cjs);
-        for (int e = tid; e < n; e += FIN_THREADS) {
+        for (int e = tid; e < n; e += FT) {
             if (dist_of_key(cd[e]) <= window) {
                 int slot = atomicAdd(&s_p, 1);
                 if (slot < a.shortcap) ex_j[slot] = cjs[e];
@@ -867,8 +873,8 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
         // (cp.async.bulk - one copy per thread - was tried: UBLKCP takes warp-uniform operands, so the compiler
         // serialises it into a 32-iteration loop per warp and the copies alone were 40 % of the kernel's instructions.)
         unsigned long long* rowp = reinterpret_cast<unsigned long long*>(hist);    // the histogram is dead by now
-        for (int c0 = 0; c0 < p; c0 += FIN_THREADS) {
-            const int nc = (p - c0) < FIN_THREADS ? (p - c0) : FIN_THREADS;
+        for (int c0 = 0; c0 < p; c0 += FT) {
+            const int nc = (p - c0) < FT ? (p - c0) : FT;
             __syncthreads();
             if (tid < nc) rowp[tid] = (unsigned long long)(a.X + (size_t)ex_j[c0 + tid] * a.S);
             __syncthreads();
@@ -876,9 +882,9 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
             auto issue = [&](int chunk, int buf) {
                 const int s0 = chunk * FIN_CHUNK;
                 const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;       // even
-                double* tile = tile0 + (size_t)buf * FIN_THREADS * FIN_LDB;
+                double* tile = tile0 + (size_t)buf * FT * FIN_LDB;
                 if (l2 < ns)
-                    for (int c = warp * 2 + half; c < nc; c += (FIN_THREADS / 32) * 2)
+                    for (int c = warp * 2 + half; c < nc; c += (FT / 32) * 2)
                         cp_async_16(tile + c * FIN_LDB + l2, reinterpret_cast<const double*>(rowp[c]) + s0 + l2);
                 if (tid * 2 < ns) cp_async_16(xi0 + buf * FIN_CHUNK + tid * 2, xrow + s0 + tid * 2);
                 cp_async_commit();
@@ -896,7 +902,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
                 const int s0 = ch * FIN_CHUNK;
                 const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
                 if (tid < nc) {
-                    const double* tr = tile0 + ((size_t)(ch & 1) * FIN_THREADS + tid) * FIN_LDB;
+                    const double* tr = tile0 + ((size_t)(ch & 1) * FT + tid) * FIN_LDB;
                     const double* xi = xi0 + (ch & 1) * FIN_CHUNK;
                     if (ns == FIN_CHUNK) {
 #pragma unroll
@@ -922,13 +928,13 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
             __syncthreads();
         }
     } else
-    for (int c0 = 0; c0 < p; c0 += FIN_THREADS) {
-        const int nc = (p - c0) < FIN_THREADS ? (p - c0) : FIN_THREADS;
+    for (int c0 = 0; c0 < p; c0 += FT) {
+        const int nc = (p - c0) < FT ? (p - c0) : FT;
         auto issue = [&](int chunk, int buf) {
             const int s0 = chunk * FIN_CHUNK;
             const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
-            double* tile = tile0 + buf * FIN_THREADS * FIN_LD;
-            for (int e = tid; e < nc * FIN_CHUNK; e += FIN_THREADS) {
+            double* tile = tile0 + buf * FT * FIN_LD;
+            for (int e = tid; e < nc * FIN_CHUNK; e += FT) {
                 const int c = e >> 5, l = e & 31;
                 if (l < ns) cp_async_8(tile + c * FIN_LD + l, a.X + (size_t)ex_j[c0 + c] * a.S + s0 + l);
             }
@@ -948,7 +954,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
             const int s0 = ch * FIN_CHUNK;
             const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
             if (tid < nc) {
-                const double* tr = tile0 + (ch & 1) * FIN_THREADS * FIN_LD + tid * FIN_LD;
+                const double* tr = tile0 + (ch & 1) * FT * FIN_LD + tid * FIN_LD;
                 const double* xi = xi0 + (ch & 1) * FIN_CHUNK;
                 if (ns == FIN_CHUNK) {
 #pragma unroll
@@ -977,7 +983,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     // ---- 3. rank by (distance, index) and write ----
     const int cs = a.row_cs[row], ce = a.row_ce[row];
     int nvalid_local = 0;
-    for (int e = tid; e < p; e += FIN_THREADS) {
+    for (int e = tid; e < p; e += FT) {
         const double d = ex_d[e];
         const int j = ex_j[e];
         if (j == 0x7fffffff) continue;
@@ -991,7 +997,7 @@ __global__ void __launch_bounds__(FIN_THREADS) wc_finalize_kernel(const FinArgs 
     }
     atomicAdd(&s_valid, nvalid_local);
     __syncthreads();
-    for (int e = s_valid + tid; e < a.k; e += FIN_THREADS) { out_i[e] = -1; out_d[e] = 1e10; }
+    for (int e = s_valid + tid; e < a.k; e += FT) { out_i[e] = -1; out_d[e] = 1e10; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1189,6 +1195,84 @@ void block_skips(int N, const int* chrom_bins_h, int nchrom, std::vector<int>& r
     }
 }
 
+}  // namespace
+
+
+namespace {
+// Tensor map of a row-major fp16 matrix [rows][ldh] with boxes of 64 halves x 128 rows, SWIZZLE_128B (the operand tiles of
+// K5h / K5t).
+int encode_f16_map(wc_ctx* ctx, CUtensorMap* tmap, const void* base, int ldh, size_t rows) {
+    if (!ctx->encode_tiled) {
+        wc_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return WC_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)ldh, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ldh * sizeof(__half)};
+    cuuint32_t box[2] = {(cuuint32_t)BKH, BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<PFN_encodeTiled>(ctx->encode_tiled)(
+        tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        wc_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return WC_ERR_CUDA;
+    }
+    return WC_OK;
+}
+
+// Pivots of a search over N bins with refsize k: TC_PIVOTS (their distances to 128 bins fill the tensor memory), or 0 - no
+// pivot pass - when the matrix is too small for it to pay or refsize leaves too few pivots per bin.
+int pivot_count(int N, int k) {
+    return (k <= 128 && (long long)TC_PIVOTS * 4 <= N) ? TC_PIVOTS : 0;
+}
+
+// The pivot pass of K5t (see wc_search_tc.cuh): thresholds of the target bins of row blocks [0, nrb) (relative to
+// ta.row_begin) from their distances to the R bins of smallest norm.  `ta` arrives prepared for the search proper (norms,
+// exclusion ranges, candidate buffers, margins, row_thr, n32); rb_seg_first[rb] names a segment of row block rb whose
+// candidate buffers serve as scratch - the search proper overwrites them afterwards.
+int tc_pivot_pass(wc_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmap_a, TopkArgs ta, const __half* Xh, int ldh, int N,
+                  int nrb, const std::vector<int>& rb_seg_first, int R) {
+    int* ids; __half* P; float* n32p; int* meta;
+    int rc;
+    if ((rc = wc_reserve(ctx, SLOT_PIV_IDS, (size_t)R * sizeof(int), (void**)&ids))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_PIV_X, (size_t)R * ldh * sizeof(__half), (void**)&P))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_PIV_N, (size_t)R * sizeof(float), (void**)&n32p))) return rc;
+    if (R != TC_PIVOTS) { wc_set_error("pivot pass: %d pivots unsupported", R); return WC_ERR_INTERNAL; }
+    const int gridP = std::max(1, std::min(ctx->sm_count, nrb));
+    std::vector<int> m((size_t)gridP + 1 + (size_t)nrb * 5);
+    {
+        int w = 0;
+        for (int c = 0; c < gridP; ++c) {
+            m[c] = w;
+            for (int rb = c; rb < nrb; rb += gridP, ++w) {
+                int* pc = &m[(size_t)gridP + 1 + (size_t)w * 5];
+                pc[0] = rb; pc[1] = 0; pc[2] = R / BN; pc[3] = 1; pc[4] = rb_seg_first[rb];
+            }
+        }
+        m[gridP] = w;
+    }
+    if ((rc = wc_reserve(ctx, SLOT_PIV_META, m.size() * sizeof(int), (void**)&meta))) return rc;
+    unsigned long long h = 1469598103934665603ull;
+    for (int v : m) { h ^= (unsigned)v; h *= 1099511628211ull; }
+    h ^= (unsigned long long)(uintptr_t)meta;
+    if (h != ctx->piv_hash) {
+        WC_CUDA(cudaMemcpyAsync(meta, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+        ctx->piv_hash = h;
+    }
+    wc_pivot_select_kernel<<<1, 1024, 0, stream>>>(ta.n32, N, R, ids);
+    wc_pivot_gather_kernel<<<R, 128, 0, stream>>>(Xh, ldh, ta.n32, ids, P, n32p);
+    WC_CUDA(cudaGetLastError());
+    CUtensorMap tmap_p;
+    if ((rc = encode_f16_map(ctx, &tmap_p, P, ldh, (size_t)R))) return rc;
+    ta.cta_piece_begin = meta; ta.pieces = meta + gridP + 1;
+    ta.tile_list = nullptr; ta.rb_list_off = nullptr; ta.final_prune = 1;
+    ta.in_key = nullptr; ta.in_j = nullptr; ta.in_cnt = nullptr; ta.in_cap = 0; ta.col_thr = nullptr;
+    ta.coln32 = n32p; ta.col_ids = ids; ta.dbg = nullptr; ta.dbg_ld = 0; ta.prof = nullptr; ta.trace = nullptr;
+    WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    wc_dist_topk_tc_kernel<2, false><<<gridP, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmap_a, tmap_p, ta);
+    WC_CUDA(cudaGetLastError());
+    return WC_OK;
+}
 }  // namespace
 
 // CPU-only debug aid (no device, no context): the symmetric search's tile lists and CTA schedule for the blocks of rank
@@ -1466,6 +1550,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     // Option k5_f16: the filter runs on the fp16 tensor cores (K4h + K5h); falls back to the fp64 filter when the matrix
     // holds finite values fp16 cannot represent.
     bool f16 = ctx->k5_f16 != 0;
+    const bool tc = ctx->k5_f16 == 2;          // tcgen05 / TMEM filter (K5t); 1 = mma.sync filter (K5h)
     const int ldh = (S + BKH - 1) / BKH * BKH;
     float* n32 = nullptr;
     double nmax = 0.0;
@@ -1531,6 +1616,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     ta.tile_list = nullptr; ta.rb_list_off = nullptr; ta.final_prune = sym ? 1 : 0;
     ta.in_key = in_key; ta.in_j = in_j; ta.in_cnt = in_cnt; ta.in_cap = in_cap; ta.col_thr = row_thr;
     ta.madd = filt_madd; ta.n32 = n32;
+    ta.dbg = f16 && tc ? ctx->dbg_scores : nullptr; ta.dbg_ld = ctx->dbg_ld;
     ta.prof = nullptr;
     ta.trace = nullptr;
     const int grid_prof = sym ? std::max(gridA, gridB) : grid;
@@ -1539,33 +1625,71 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         WC_CUDA(cudaMemsetAsync(ta.prof, 0, ((size_t)grid_prof * 8 + 512) * sizeof(long long), stream));
         ta.trace = ta.prof + (size_t)grid_prof * 8;
     }
-    const size_t topk_smem = f16
+    const size_t topk_smem_legacy = f16
         ? (size_t)ta.nstages * STAGE_BYTES + sizeof(TopkState) + (size_t)CONSUMER_WARPS * F16_SCRATCH +
               (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4) + (2 * BN + 32) * sizeof(float))
         : (size_t)ta.nstages * STAGE_BYTES + sizeof(TopkState) +
               (size_t)CONSUMER_WARPS * std::max<size_t>((size_t)cap * 12, 8192) +
               (sym ? (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4)) : 0);
+    const bool use_tc = f16 && tc;
+    const size_t topk_smem = use_tc ? TC_SMEM_BYTES : topk_smem_legacy;
     if (topk_smem > 227 * 1024) { wc_set_error("K5 shared memory %zu exceeds 227 KiB", topk_smem); return WC_ERR_INTERNAL; }
-    auto k5_plain = f16 ? wc_dist_topk_f16_kernel<false> : wc_dist_topk_kernel<false>;
-    auto k5_sym = f16 ? wc_dist_topk_f16_kernel<true> : wc_dist_topk_kernel<true>;
-    WC_CUDA(cudaFuncSetAttribute(k5_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+    const bool dbg = use_tc && ta.dbg != nullptr;
+    {   // opt in to the large dynamic shared memory for every kernel this call may launch
+        const int sm_bytes = (int)topk_smem;
+        if (use_tc) {
+            WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+            WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+            if (dbg) {
+                WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+                WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+            }
+        } else if (f16) {
+            WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+            WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+        } else {
+            WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+            WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+        }
+    }
     wc_fill_u64_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(row_thr, (size_t)rows, host_key_of_tau(ta.tau_init));
     wc_fill_u64_kernel<<<(unsigned)((thr_n - rows + 255) / 256), 256, 0, stream>>>(row_thr + rows, thr_n - (size_t)rows, KEY_NEVER);
     WC_CUDA(cudaEventRecord(ctx->ev[2], stream));
+    ta.coln32 = n32; ta.col_ids = nullptr;
+    // K5t takes a second tensor map for the column operand (the pivot pass reads a different matrix); the legacy kernels one
+    auto launch = [&](bool symmetric, int g) {
+        if (use_tc) {
+            auto kern = symmetric ? (dbg ? wc_dist_topk_tc_kernel<1, true> : wc_dist_topk_tc_kernel<1, false>)
+                                  : (dbg ? wc_dist_topk_tc_kernel<0, true> : wc_dist_topk_tc_kernel<0, false>);
+            kern<<<g, TC_THREADS, topk_smem, stream>>>(tmap, tmap, ta);
+        } else if (f16) {
+            if (symmetric) wc_dist_topk_f16_kernel<true><<<g, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+            else wc_dist_topk_f16_kernel<false><<<g, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+        } else {
+            if (symmetric) wc_dist_topk_kernel<true><<<g, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+            else wc_dist_topk_kernel<false><<<g, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+        }
+    };
+    long long pivot_launches = 0;
     if (!sym) {
-        k5_plain<<<grid, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+        launch(false, grid);
     } else {
-        WC_CUDA(cudaFuncSetAttribute(k5_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
         const int nb1 = nrb + 1;
+        const int R = (use_tc && !dbg && ctx->k5_pivots != 0) ? pivot_count(N, k) : 0;
+        if (R > 0) {                                                     // pivot pass: thresholds only
+            if ((rc = tc_pivot_pass(ctx, stream, tmap, ta, reinterpret_cast<const __half*>(Xc), ldh, N, nrb, rb_seg_first, R))) return rc;
+            pivot_launches = 3;
+        }
+        WC_CUDA(cudaEventRecord(ctx->ev[17], stream));
         ta.tile_list = d_sym + 2 * nb1;                                  // pass A
         ta.rb_list_off = d_sym;
-        k5_plain<<<gridA, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+        launch(false, gridA);
         WC_CUDA(cudaGetLastError());
         WC_CUDA(cudaEventRecord(ctx->ev[16], stream));
         ta.tile_list = d_sym + 2 * nb1 + (int)listA.size();              // pass B
         ta.rb_list_off = d_sym + nb1;
         ta.cta_piece_begin = d_cta_piece + (gridA + 1);
-        k5_sym<<<gridB, TOPK_THREADS, topk_smem, stream>>>(tmap, ta);
+        launch(true, gridB);
     }
     WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[3], stream));
@@ -1580,18 +1704,24 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     fa.bulk = (S % 2 == 0 && (reinterpret_cast<uintptr_t>(corrected_d) & 15) == 0) ? 1 : 0;
     fa.in_key = in_key; fa.in_j = in_j; fa.in_cnt = in_cnt; fa.in_cap = in_cap; fa.in_nsrc = 1; fa.in_src_rows = 0;
     fa.madd = filt_madd;
-    const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 +
-                            HIST_BINS * 4;
-    WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    const int fin_threads = f16 ? 160 : FIN_THREADS;
+    const size_t fin_smem = (size_t)(2 * fin_threads * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 +
+                            std::max<size_t>(HIST_BINS * 4, (size_t)fin_threads * 8);     // histogram, later the candidates' row pointers
     WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
-    wc_finalize_kernel<<<rows, FIN_THREADS, fin_smem, stream>>>(fa);
+    if (f16) {
+        WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        wc_finalize_kernel<160><<<rows, 160, fin_smem, stream>>>(fa);
+    } else {
+        WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<FIN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        wc_finalize_kernel<FIN_THREADS><<<rows, FIN_THREADS, fin_smem, stream>>>(fa);
+    }
     WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[5], stream));
 
     int nslow = 0;
     WC_CUDA(cudaMemcpyAsync(&nslow, slow, sizeof(int), cudaMemcpyDeviceToHost, stream));
     WC_CUDA(cudaStreamSynchronize(stream));
-    long long launches = sym ? 6 : 5;          // two fills, K4, K5 (one or two passes), K6
+    long long launches = (sym ? 6 : 5) + pivot_launches;          // two fills, K4, K5 (one or two passes; pivot select + gather + pass), K6
     if (nslow > 0) {
         const int batch = 64;
         double* scratch;
@@ -1667,6 +1797,15 @@ extern "C" int wc_debug_profile(wc_ctx* ctx, int enable, long long* out_h, int m
     return grid;
 }
 
+// Debug: the next searches with the tcgen05 filter (k5_f16 = 2) also store every filter distance d~(i, j) they compute into
+// out_d[(i - row_begin) * ld + j] (float, device memory owned by the caller; j < ld).  NULL switches it off.
+extern "C" int wc_debug_filter_scores(wc_ctx* ctx, float* out_d, int ld) {
+    WC_CHECK_ARG(ctx != nullptr && (out_d == nullptr || ld > 0));
+    ctx->dbg_scores = out_d;
+    ctx->dbg_ld = out_d ? ld : 0;
+    return WC_OK;
+}
+
 // Tuning knobs (debug / experiments).  key "k5_lag": chunks by which the trailing consumer warps lag (0..4).
 extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
     WC_CHECK_ARG(ctx != nullptr && key != nullptr);
@@ -1685,8 +1824,13 @@ extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
         ctx->k5_sym = (int)value;
         return WC_OK;
     }
-    if (strcmp(key, "k5_f16") == 0) {        // 1: fp16 tensor-core filter (K4h + K5h), 0: fp64 filter
-        ctx->k5_f16 = value != 0 ? 1 : 0;
+    if (strcmp(key, "k5_f16") == 0) {        // 0: fp64 filter (DMMA); 1: fp16 filter on mma.sync (K5h); 2: fp16 filter on tcgen05 / TMEM (K5t)
+        WC_CHECK_ARG(value == 0 || value == 1 || value == 2);
+        ctx->k5_f16 = (int)value;
+        return WC_OK;
+    }
+    if (strcmp(key, "k5_pivots") == 0) {     // K5t: pivot pass before a symmetric search (1 = on, 0 = off)
+        ctx->k5_pivots = value != 0 ? 1 : 0;
         return WC_OK;
     }
     if (strcmp(key, "k5_stages") == 0) {

@@ -37,8 +37,9 @@ ShardDims shard_dims(const wc_ctx* ctx, int N, int k, int world, int rank) {
 }
 
 // One K5 launch of a sharded symmetric search: pass 0 = threshold pass (rows only), pass 1 = symmetric pass.
+// pass 2 = the pivot pass of K5t (thresholds only; seg_first names the scratch segment of every owned row block).
 int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned long long* in_key_d, int* in_j_d,
-                      int* in_cnt_d, cudaStream_t stream) {
+                      int* in_cnt_d, cudaStream_t stream, const std::vector<int>* seg_first = nullptr, int pivots = 0) {
     const wc_shard_plan& pl = ctx->shard;
     if (!ctx->encode_tiled) {
         wc_set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -90,6 +91,17 @@ int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned
     ta.final_prune = 1;
     ta.in_key = in_key_d; ta.in_j = in_j_d; ta.in_cnt = in_cnt_d; ta.in_cap = pl.in_cap;
     ta.madd = pl.madd; ta.n32 = pl.f16 ? static_cast<float*>(ctx->buf[SLOT_N32].p) : nullptr;
+    ta.dbg = nullptr; ta.dbg_ld = 0; ta.coln32 = ta.n32; ta.col_ids = nullptr;
+    const bool tc = pl.f16 == 2;
+    if (pass == 2)
+        return tc_pivot_pass(ctx, stream, tmap, ta, static_cast<const __half*>(ctx->buf[SLOT_XC].p), pl.ldh, pl.N, pl.nrb, *seg_first, pivots);
+    if (tc) {
+        auto kern = pass == 0 ? wc_dist_topk_tc_kernel<0, false> : wc_dist_topk_tc_kernel<1, false>;
+        WC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        kern<<<pass == 0 ? pl.gridA : pl.gridB, TC_THREADS, pl.smem, stream>>>(tmap, tmap, ta);
+        WC_CUDA(cudaGetLastError());
+        return WC_OK;
+    }
     auto kernel = pass == 0 ? (pl.f16 ? wc_dist_topk_f16_kernel<false> : wc_dist_topk_kernel<false>)
                             : (pl.f16 ? wc_dist_topk_f16_kernel<true> : wc_dist_topk_kernel<true>);
     WC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
@@ -278,14 +290,14 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
     pl.nkc = nkc; pl.nd_last = nd_last; pl.extra_h = nd_last; pl.ld = ld; pl.nrb = nrb; pl.nseg = nseg;
     pl.gridA = gridA; pl.gridB = gridB; pl.Npad = Npad; pl.nlistA = listA.size();
     pl.tilesA = tilesA; pl.tilesB = tilesB; pl.tiles_plain = tiles_plain;
-    pl.f16 = f16 ? 1 : 0;
+    pl.f16 = f16 ? ctx->k5_f16 : 0;
     pl.ldh = ldh;
     pl.mcoef = f16 ? 2.0 * eps16 : 16.0 * (double)(S + 16) * 1.1102230246251565e-16;
     pl.madd = f16 ? 2.0 * eps16 * nmax + ldexp(1.0, -20) * sqrt((double)S * nmax) : 0.0;
     if (f16) pl.nkc = ldh / BKH;
     pl.corrected = corrected_d;
     pl.nstages = f16 ? 4 : (cap <= 512 ? 4 : 3);
-    pl.smem = f16
+    pl.smem = f16 && ctx->k5_f16 == 2 ? TC_SMEM_BYTES : f16
         ? (size_t)pl.nstages * STAGE_BYTES + sizeof(TopkState) + (size_t)CONSUMER_WARPS * F16_SCRATCH +
               (size_t)CONSUMER_WARPS * (BN * sizeof(u64) + STG * sizeof(uint4) + (2 * BN + 32) * sizeof(float))
         : (size_t)pl.nstages * STAGE_BYTES + sizeof(TopkState) +
@@ -294,6 +306,10 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
     if (pl.smem > 227 * 1024) { wc_set_error("K5 shared memory %zu exceeds 227 KiB", pl.smem); return WC_ERR_INTERNAL; }
 
     WC_CUDA(cudaEventRecord(ctx->ev[2], stream));
+    pl.pivots = (pl.f16 == 2 && ctx->k5_pivots != 0 && nrb > 0 && nb >= 24) ? pivot_count(N, k) : 0;
+    if (pl.pivots > 0) {
+        if ((rc = shard_launch_pass(ctx, 2, thr_d, nullptr, nullptr, nullptr, stream, &seg_first, pl.pivots))) return rc;
+    }
     if (gridA > 0) {
         if ((rc = shard_launch_pass(ctx, 0, thr_d, nullptr, nullptr, nullptr, stream))) return rc;
     }
@@ -336,7 +352,7 @@ extern "C" int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* rec
     int* d_row_cs = static_cast<int*>(ctx->buf[SLOT_ROWCS].p);
     int* d_row_ce = static_cast<int*>(ctx->buf[SLOT_ROWCE].p);
     int* slow = static_cast<int*>(ctx->buf[SLOT_SLOW].p);
-    long long launches = 4 + (pl.gridA > 0) + (pl.gridB > 0);      // K4, two fills, pass A, pass B, K6
+    long long launches = 4 + (pl.gridA > 0) + (pl.gridB > 0) + (pl.pivots > 0 ? 3 : 0);      // K4, two fills, [pivots], pass A, pass B, K6
     if (rows > 0) {
         WC_CHECK_ARG(idx_d != nullptr && dist_d != nullptr);
         const int nrb1 = std::max(pl.nrb, 1);
@@ -351,10 +367,16 @@ extern "C" int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* rec
         fa.bulk = (pl.S % 2 == 0 && (reinterpret_cast<uintptr_t>(pl.corrected) & 15) == 0) ? 1 : 0;
         fa.in_key = recv_key_d; fa.in_j = recv_j_d; fa.in_cnt = recv_cnt_d; fa.in_cap = pl.in_cap;
         fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per; fa.madd = pl.madd;
-        const size_t fin_smem = (size_t)(2 * FIN_THREADS * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
-        WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        const int fin_threads = pl.f16 ? 160 : FIN_THREADS;
+        const size_t fin_smem = (size_t)(2 * fin_threads * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 + std::max<size_t>(HIST_BINS * 4, (size_t)fin_threads * 8);
         WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
-        wc_finalize_kernel<<<rows, FIN_THREADS, fin_smem, stream>>>(fa);
+        if (pl.f16) {
+            WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+            wc_finalize_kernel<160><<<rows, 160, fin_smem, stream>>>(fa);
+        } else {
+            WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<FIN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+            wc_finalize_kernel<FIN_THREADS><<<rows, FIN_THREADS, fin_smem, stream>>>(fa);
+        }
         WC_CUDA(cudaGetLastError());
         WC_CUDA(cudaEventRecord(ctx->ev[5], stream));
         WC_CUDA(cudaMemcpyAsync(&nslow, slow, sizeof(int), cudaMemcpyDeviceToHost, stream));
