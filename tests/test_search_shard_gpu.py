@@ -35,8 +35,9 @@ def _emulated_ranks(X, bins, k, world):
             in_key = torch.empty((world * rows_per, in_cap), dtype=torch.int64, device=dev)
             in_j = torch.empty((world * rows_per, in_cap), dtype=torch.int32, device=dev)
             in_cnt = torch.empty((world * rows_per,), dtype=torch.int32, device=dev)
-            device.shard_sweep(tmin.clone(), in_key, in_j, in_cnt, ctx=ctxs[r])
-            found.append((in_key, in_j, in_cnt))
+            thr_r = tmin.clone()          # stays alive until shard_finish (K6 reads the bins' final thresholds from it)
+            device.shard_sweep(thr_r, in_key, in_j, in_cnt, ctx=ctxs[r])
+            found.append((in_key, in_j, in_cnt, thr_r))
         torch.cuda.synchronize()
         idx_parts, dist_parts, stats = [], [], []
         for o in range(world):                                       # all-to-all: split o of every rank, in rank order

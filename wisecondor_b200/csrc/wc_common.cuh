@@ -65,6 +65,7 @@ struct wc_shard_plan {
     int f16 = 0, ldh = 0;                        // fp16 tensor-core filter in use (1 mma.sync, 2 tcgen05), its padded sample count
     int pivots = 0;                              // pivots of the K5t pivot pass (0: none)
     const double* corrected = nullptr;
+    const unsigned long long* thr = nullptr;     // the threshold table handed to wc_newref_shard_sweep
     int stage = 0;                               // 1 after begin, 2 after sweep
 };
 

@@ -43,6 +43,7 @@ constexpr int MAX_STAGES = 6;
 constexpr int HIST_BINS = 256;
 constexpr int FIN_THREADS = 128;    // one thread per shortlisted candidate during the exact re-score
 constexpr int FIN_CHUNK = 32;       // samples staged per pipeline step of the re-score
+constexpr int FIN_ECAP = 2048;      // candidate entries of one row K6 collects in shared memory (24 KiB); more: exact fallback
 constexpr int FIN_LD = FIN_CHUNK + 1;   // padded tile row (bank-conflict free per-thread row walks)
 constexpr int FIN_LDB = FIN_CHUNK + 2;  // tile row of the 16-byte copy path: 16-byte aligned rows (2-way conflicts, cheap)
 constexpr int EXH_THREADS = 256;
@@ -134,6 +135,11 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// 256-bit read-only streaming load (SASS LDG.E.NA.256.CONSTANT): four consecutive doubles, no L1 allocation, the rest of
+// the 128-byte line prefetched into L2
+__device__ __forceinline__ void ldg_nc_v4f64(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 __device__ __forceinline__ int bucket_of(double d, double mn, float scale) {
     int b = (int)((float)(d - mn) * scale);
     return b < 0 ? 0 : (b > HIST_BINS - 1 ? HIST_BINS - 1 : b);
@@ -697,12 +703,13 @@ struct FinArgs {
     double* dist_out;
     int* slow_list;
     int* slow_count;
-    int bulk;               // 1: rows are 16-byte aligned (S even): stage candidate rows with 16-byte cp.async
+    int vec;                // 4: rows are 32-byte aligned (S % 4 == 0): 256-bit loads; 1: scalar loads
     const u64* in_key;      // symmetric search: the row's incoming (column-side) candidates, or nullptr
     const int* in_j;
     const int* in_cnt;
     int in_cap;
     double madd;            // window(v) = v + mcoef * (n_i + |v|) + madd
+    const u64* row_thr;     // [rows] the tightest threshold key K5 published for the row (entries beyond it cannot rank), or nullptr
     int in_nsrc;            // incoming sources (1; one per rank after the exchange of a sharded symmetric search)
     int in_src_rows;        // rows between two sources: source s holds row r at (s * in_src_rows + r)
 };
@@ -717,10 +724,9 @@ struct FinArgs {
 //  3. rank by (distance, index), write the first k with indices remapped to other-chromosome coordinates.
 template <int FT>      // threads = shortlisted candidates re-scored per round: 128, or 160 behind the wider window of the fp16 filters
 __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
-    extern __shared__ __align__(16) unsigned char fin_raw[];
-    double* tile0 = reinterpret_cast<double*>(fin_raw);                    // 2 x FT x FIN_LDB (or FIN_LD)
-    double* xi0 = tile0 + 2 * FT * FIN_LDB;                       // 2 x FIN_CHUNK
-    double* ex_d = xi0 + 2 * FIN_CHUNK;                                    // shortcap
+    extern __shared__ __align__(32) unsigned char fin_raw[];
+    constexpr int ecap = FIN_ECAP;                                         // collected entries: [ecap] keys, [ecap] bins
+    double* ex_d = reinterpret_cast<double*>(fin_raw + (size_t)ecap * 12); // shortcap
     int* ex_j = reinterpret_cast<int*>(ex_d + a.shortcap);                 // shortcap
     int* hist = ex_j + a.shortcap;                                         // HIST_BINS
     __shared__ double s_red[2][FT / 32];
@@ -734,41 +740,55 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     int* out_i = a.idx_out + (size_t)rloc * a.k;
     double* out_d = a.dist_out + (size_t)rloc * a.k;
 
-    // candidate sources of the row: its segments (one per K5 piece of the row block) and, after a symmetric search,
-    // the incoming buffer
+    // candidate sources of the row: its segments (one per K5 piece of the row block and column half) and, after a symmetric
+    // search, the incoming buffer(s)
     const int nsrc = nseg + (a.in_key != nullptr ? a.in_nsrc : 0);
-    auto source = [&](int s, const u64*& keys, const int*& js) -> int {
+    auto source = [&](int s, const u64*& keys, const int*& js, int& flagged) -> int {
         if (s < nseg) {
             const size_t off = ((size_t)(seg0 + s) * BM + rl) * a.cap;
             keys = a.cand_key + off;
             js = a.cand_j + off;
+            flagged = a.seg_flag[(size_t)(seg0 + s) * BM + rl];
             return a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
         }
         const size_t r = (size_t)(s - nseg) * a.in_src_rows + rloc;
         keys = a.in_key + r * a.in_cap;
         js = a.in_j + r * a.in_cap;
         const int n = a.in_cnt[r];
+        flagged = n > a.in_cap ? 1 : 0;               // more offers than the buffer holds: exact fallback
         return n < a.in_cap ? n : a.in_cap;
     };
-    if (tid == 0) {
-        int tot = 0, fl = 0;
-        for (int s = 0; s < nseg; ++s) {
-            tot += a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
-            fl |= a.seg_flag[(size_t)(seg0 + s) * BM + rl];
-        }
-        if (a.in_key != nullptr) {
-            for (int s = 0; s < a.in_nsrc; ++s) {
-                const int n = a.in_cnt[(size_t)s * a.in_src_rows + rloc];
-                if (n > a.in_cap) fl = 1;               // more offers than the buffer holds: exact fallback
-                tot += n;
+    // ---- 0. collect: every warp walks its share of the sources, the row's entries land side by side in shared memory (the
+    //         staging tiles are idle until the re-score) - the select passes below never touch global memory again ----
+    u64* en_k = reinterpret_cast<u64*>(fin_raw);                                     // [ecap]
+    int* en_j = reinterpret_cast<int*>(en_k + ecap);                                 // [ecap]
+    if (tid == 0) { s_total = 0; s_flag = 0; s_p = 0; s_valid = 0; }
+    for (int b = tid; b < HIST_BINS; b += FT) hist[b] = 0;
+    const u64 tfinal = a.row_thr != nullptr ? __ldcg(a.row_thr + rloc) : ~0ull;
+    __syncthreads();
+    for (int s = warp; s < nsrc; s += FT / 32) {
+        const u64* cd;
+        const int* cjs;
+        int fl;
+        const int n = source(s, cd, cjs, fl);
+        if (fl) { if (lane == 0) s_flag = 1; continue; }
+        for (int e0 = 0; e0 < n; e0 += 32) {
+            const int e = e0 + lane;
+            // Entries beyond the row's final threshold are dead weight: every published threshold is (k-th smallest filter
+            // distance of a SUBSET of the candidates) + margin, hence >= the window the shortlist is cut at below.
+            const u64 key = e < n ? cd[e] : ~0ull;
+            const bool keep = e < n && key <= tfinal;
+            const unsigned bm = __ballot_sync(0xffffffffu, keep);
+            if (bm == 0u) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_total, __popc(bm));
+            base = __shfl_sync(0xffffffffu, base, 0) + __popc(bm & ((1u << lane) - 1u));
+            if (keep && base < ecap) {
+                en_k[base] = key;
+                en_j[base] = cjs[e];
             }
         }
-        s_total = tot;
-        s_flag = fl;
-        s_p = 0;
-        s_valid = 0;
     }
-    for (int b = tid; b < HIST_BINS; b += FT) hist[b] = 0;
     __syncthreads();
     const int total = s_total;
     if (s_flag) {
@@ -779,19 +799,33 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
         for (int e = tid; e < a.k; e += FT) { out_i[e] = -1; out_d[e] = 1e10; }
         return;
     }
+    // The select passes visit every live entry of the row: from shared memory when the collection fitted (the normal case),
+    // else straight from the sources (rows no segment ever pruned: small matrices).
+    const bool in_smem = total <= ecap;
+    auto for_each_entry = [&](auto&& f) {
+        if (in_smem) {
+            for (int e = tid; e < total; e += FT) f(en_k[e], en_j[e]);
+        } else {
+            for (int s2 = 0; s2 < nsrc; ++s2) {
+                const u64* cd;
+                const int* cjs;
+                int fl;
+                const int n = source(s2, cd, cjs, fl);
+                for (int e = tid; e < n; e += FT) {
+                    const u64 key = cd[e];
+                    if (key <= tfinal) f(key, cjs[e]);
+                }
+            }
+        }
+    };
 
     // ---- 1. select ----
     double mn = INFINITY, mx = -INFINITY;
-    for (int s = 0; s < nsrc; ++s) {
-        const u64* cd;
-        const int* cjs;
-        const int n = source(s, cd, cjs);
-        for (int e = tid; e < n; e += FT) {
-            double d = dist_of_key(cd[e]);
-            mn = fmin(mn, d);
-            mx = fmax(mx, d);
-        }
-    }
+    for_each_entry([&](u64 key, int) {
+        const double d = dist_of_key(key);
+        mn = fmin(mn, d);
+        mx = fmax(mx, d);
+    });
     mn = warp_min(mn);
     mx = warp_max(mx);
     if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
@@ -799,12 +833,7 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
 #pragma unroll
     for (int w = 0; w < FT / 32; ++w) { mn = fmin(mn, s_red[0][w]); mx = fmax(mx, s_red[1][w]); }
     const float scale = (mx > mn) ? (float)(HIST_BINS - 1) / (float)(mx - mn) : 0.0f;
-    for (int s = 0; s < nsrc; ++s) {
-        const u64* cd;
-        const int* cjs;
-        const int n = source(s, cd, cjs);
-        for (int e = tid; e < n; e += FT) atomicAdd(&hist[bucket_of(dist_of_key(cd[e]), mn, scale)], 1);
-    }
+    for_each_entry([&](u64 key, int) { atomicAdd(&hist[bucket_of(dist_of_key(key), mn, scale)], 1); });
     __syncthreads();
     if (warp == 0) {
         int c[HIST_BINS / 32], sum = 0;
@@ -830,15 +859,10 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     __syncthreads();
     const int bstar = s_bstar;
     double vstar = -INFINITY;
-    for (int s = 0; s < nsrc; ++s) {
-        const u64* cd;
-        const int* cjs;
-        const int n = source(s, cd, cjs);
-        for (int e = tid; e < n; e += FT) {
-            double d = dist_of_key(cd[e]);
-            if (bucket_of(d, mn, scale) <= bstar) vstar = fmax(vstar, d);
-        }
-    }
+    for_each_entry([&](u64 key, int) {
+        const double d = dist_of_key(key);
+        if (bucket_of(d, mn, scale) <= bstar) vstar = fmax(vstar, d);
+    });
     vstar = warp_max(vstar);
     __syncthreads();                                    // s_red reuse
     if (lane == 0) s_red[0][warp] = vstar;
@@ -846,17 +870,12 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
 #pragma unroll
     for (int w = 0; w < FT / 32; ++w) vstar = fmax(vstar, s_red[0][w]);
     const double window = vstar + a.mcoef * (a.norms[row] + fabs(vstar)) + a.madd;
-    for (int s = 0; s < nsrc; ++s) {
-        const u64* cd;
-        const int* cjs;
-        const int n = source(s, cd, cjs);
-        for (int e = tid; e < n; e += FT) {
-            if (dist_of_key(cd[e]) <= window) {
-                int slot = atomicAdd(&s_p, 1);
-                if (slot < a.shortcap) ex_j[slot] = cjs[e];
-            }
+    for_each_entry([&](u64 key, int j) {
+        if (dist_of_key(key) <= window) {
+            const int slot = atomicAdd(&s_p, 1);
+            if (slot < a.shortcap) ex_j[slot] = j;
         }
-    }
+    });
     __syncthreads();
     const int p = s_p;
     if (p > a.shortcap) {                               // tie plateau wider than the shortlist: exact fallback
@@ -865,120 +884,65 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     }
 
     // ---- 2. exact re-score ----
+    // One thread per shortlisted candidate.  The candidate's row streams from L2 straight into registers - eight 256-bit
+    // loads (32 samples) in flight per thread, nothing staged, no barrier inside the loop - while the target's own row is a
+    // broadcast operand in shared memory.  The sum runs strictly in sample order with separately rounded subtract, multiply
+    // and add (wisetools.py:302 on Fortran-ordered operands).
     const double* xrow = a.X + (size_t)row * a.S;
-    const int nchunks = (a.S + FIN_CHUNK - 1) / FIN_CHUNK;
-    if (a.bulk) {
-        // Rows are 16-byte aligned (S even): 16-byte cp.async, one warp instruction stages the 32-sample slices of two
-        // candidates (lanes 0-15 / 16-31); the candidates' row pointers are computed once per round into shared memory.
-        // (cp.async.bulk - one copy per thread - was tried: UBLKCP takes warp-uniform operands, so the compiler
-        // serialises it into a 32-iteration loop per warp and the copies alone were 40 % of the kernel's instructions.)
-        unsigned long long* rowp = reinterpret_cast<unsigned long long*>(hist);    // the histogram is dead by now
-        for (int c0 = 0; c0 < p; c0 += FT) {
-            const int nc = (p - c0) < FT ? (p - c0) : FT;
-            __syncthreads();
-            if (tid < nc) rowp[tid] = (unsigned long long)(a.X + (size_t)ex_j[c0 + tid] * a.S);
-            __syncthreads();
-            const int half = lane >> 4, l2 = (lane & 15) * 2;
-            auto issue = [&](int chunk, int buf) {
-                const int s0 = chunk * FIN_CHUNK;
-                const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;       // even
-                double* tile = tile0 + (size_t)buf * FT * FIN_LDB;
-                if (l2 < ns)
-                    for (int c = warp * 2 + half; c < nc; c += (FT / 32) * 2)
-                        cp_async_16(tile + c * FIN_LDB + l2, reinterpret_cast<const double*>(rowp[c]) + s0 + l2);
-                if (tid * 2 < ns) cp_async_16(xi0 + buf * FIN_CHUNK + tid * 2, xrow + s0 + tid * 2);
-                cp_async_commit();
-            };
-            double accd = 0.0;
-            issue(0, 0);
-            for (int ch = 0; ch < nchunks; ++ch) {
-                if (ch + 1 < nchunks) {
-                    issue(ch + 1, (ch + 1) & 1);
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                __syncthreads();
-                const int s0 = ch * FIN_CHUNK;
-                const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
-                if (tid < nc) {
-                    const double* tr = tile0 + ((size_t)(ch & 1) * FT + tid) * FIN_LDB;
-                    const double* xi = xi0 + (ch & 1) * FIN_CHUNK;
-                    if (ns == FIN_CHUNK) {
-#pragma unroll
-                        for (int l = 0; l < FIN_CHUNK; ++l) {
-                            double v = __dsub_rn(tr[l], xi[l]);
-                            accd = __dadd_rn(accd, __dmul_rn(v, v));
-                        }
-                    } else {
-                        for (int l = 0; l < ns; ++l) {
-                            double v = __dsub_rn(tr[l], xi[l]);
-                            accd = __dadd_rn(accd, __dmul_rn(v, v));
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            if (tid < nc) {
-                const bool ok = accd < 1e10;     // wisetools.py:312-314: strict `<` against the 1e10 start value; NaN fails
-                const int j = ex_j[c0 + tid];
-                ex_d[c0 + tid] = ok ? accd : INFINITY;
-                ex_j[c0 + tid] = ok ? j : 0x7fffffff;
-            }
-            __syncthreads();
-        }
-    } else
+    double* xi_s = reinterpret_cast<double*>(fin_raw);          // the collected entries are dead: the area now holds the row
+    const bool xi_in_smem = (size_t)a.S * 8 <= (size_t)ecap * 12;
+    __syncthreads();
+    if (xi_in_smem)
+        for (int t = tid; t < a.S; t += FT) xi_s[t] = xrow[t];
+    __syncthreads();
+    const uint32_t xi_u32 = smem_u32(xi_s);
     for (int c0 = 0; c0 < p; c0 += FT) {
-        const int nc = (p - c0) < FT ? (p - c0) : FT;
-        auto issue = [&](int chunk, int buf) {
-            const int s0 = chunk * FIN_CHUNK;
-            const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
-            double* tile = tile0 + buf * FT * FIN_LD;
-            for (int e = tid; e < nc * FIN_CHUNK; e += FT) {
-                const int c = e >> 5, l = e & 31;
-                if (l < ns) cp_async_8(tile + c * FIN_LD + l, a.X + (size_t)ex_j[c0 + c] * a.S + s0 + l);
-            }
-            if (tid < ns) cp_async_8(xi0 + buf * FIN_CHUNK + tid, xrow + s0 + tid);
-            cp_async_commit();
-        };
-        double accd = 0.0;
-        issue(0, 0);
-        for (int ch = 0; ch < nchunks; ++ch) {
-            if (ch + 1 < nchunks) {
-                issue(ch + 1, (ch + 1) & 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncthreads();
-            const int s0 = ch * FIN_CHUNK;
-            const int ns = (a.S - s0) < FIN_CHUNK ? (a.S - s0) : FIN_CHUNK;
-            if (tid < nc) {
-                const double* tr = tile0 + (ch & 1) * FT * FIN_LD + tid * FIN_LD;
-                const double* xi = xi0 + (ch & 1) * FIN_CHUNK;
-                if (ns == FIN_CHUNK) {
+        if (c0 + tid < p) {
+            const int j = ex_j[c0 + tid];
+            const double* xr = a.X + (size_t)j * a.S;
+            double accd = 0.0;
+            int t0 = 0;
+            if (a.vec == 4 && xi_in_smem) {
+                for (; t0 + 32 <= a.S; t0 += 32) {
+                    double v[32];
 #pragma unroll
-                    for (int l = 0; l < FIN_CHUNK; ++l) {
-                        double v = __dsub_rn(tr[l], xi[l]);
-                        accd = __dadd_rn(accd, __dmul_rn(v, v));
-                    }
-                } else {
-                    for (int l = 0; l < ns; ++l) {
-                        double v = __dsub_rn(tr[l], xi[l]);
-                        accd = __dadd_rn(accd, __dmul_rn(v, v));
+                    for (int u = 0; u < 8; ++u) ldg_nc_v4f64(xr + t0 + 4 * u, v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        double x0, x1;
+                        lds_v2f64(xi_u32 + (uint32_t)(t0 + 2 * u) * 8u, x0, x1);
+                        double d = __dsub_rn(v[2 * u], x0);
+                        accd = __dadd_rn(accd, __dmul_rn(d, d));
+                        d = __dsub_rn(v[2 * u + 1], x1);
+                        accd = __dadd_rn(accd, __dmul_rn(d, d));
                     }
                 }
+                for (; t0 + 4 <= a.S; t0 += 4) {
+                    double v0, v1, v2, v3;
+                    ldg_nc_v4f64(xr + t0, v0, v1, v2, v3);
+                    double d = __dsub_rn(v0, xi_s[t0]);     accd = __dadd_rn(accd, __dmul_rn(d, d));
+                    d = __dsub_rn(v1, xi_s[t0 + 1]);        accd = __dadd_rn(accd, __dmul_rn(d, d));
+                    d = __dsub_rn(v2, xi_s[t0 + 2]);        accd = __dadd_rn(accd, __dmul_rn(d, d));
+                    d = __dsub_rn(v3, xi_s[t0 + 3]);        accd = __dadd_rn(accd, __dmul_rn(d, d));
+                }
             }
-            __syncthreads();
-        }
-        if (tid < nc) {
+            if (xi_in_smem) {
+                for (; t0 < a.S; ++t0) {
+                    const double d = __dsub_rn(__ldg(xr + t0), xi_s[t0]);
+                    accd = __dadd_rn(accd, __dmul_rn(d, d));
+                }
+            } else {                                             // more samples than the area holds: both rows from global memory
+                for (; t0 < a.S; ++t0) {
+                    const double d = __dsub_rn(__ldg(xr + t0), __ldg(xrow + t0));
+                    accd = __dadd_rn(accd, __dmul_rn(d, d));
+                }
+            }
             const bool ok = accd < 1e10;     // wisetools.py:312-314: strict `<` against the 1e10 start value; NaN fails
-            const int j = ex_j[c0 + tid];
             ex_d[c0 + tid] = ok ? accd : INFINITY;
             ex_j[c0 + tid] = ok ? j : 0x7fffffff;
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- 3. rank by (distance, index) and write ----
     const int cs = a.row_cs[row], ce = a.row_ce[row];
@@ -1436,20 +1400,23 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     // One piece table for both passes (pass A's pieces first); cta_piece_begin holds, per pass, grid+1 absolute indices.
     const int grid0 = sym ? gridA : grid;            // CTAs of the first (or only) launch
     std::vector<int> rb_seg_first(nrb, 0), rb_seg_count(nrb, 0), cta_piece_begin, piece_tab;
-    const int nseg = (int)pieces.size();
+    // K5t keeps one segment per column half of a piece (its two epilogue warpgroups share no row state)
+    const int spp = ctx->k5_f16 == 2 ? TC_SEGS_PER_PIECE : 1;
+    const int npieces = (int)pieces.size();
+    const int nseg = npieces * spp;
     {
-        for (const Piece& pc : pieces) rb_seg_count[pc.rb]++;
+        for (const Piece& pc : pieces) rb_seg_count[pc.rb] += spp;
         int run = 0;
         for (int rb = 0; rb < nrb; ++rb) { rb_seg_first[rb] = run; run += rb_seg_count[rb]; }
         std::vector<int> next(rb_seg_first);
-        for (Piece& pc : pieces) pc.seg = next[pc.rb]++;
+        for (Piece& pc : pieces) { pc.seg = next[pc.rb]; next[pc.rb] += spp; }
         std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) {
             return x.pass != y.pass ? x.pass < y.pass : x.cta < y.cta;
         });
-        piece_tab.resize((size_t)std::max(nseg, 1) * 5);
+        piece_tab.resize((size_t)std::max(npieces, 1) * 5);
         std::vector<int> per_cta0(grid0 + 1, 0), per_cta1(gridB + 1, 0);
         int n0 = 0;
-        for (int i = 0; i < nseg; ++i) {
+        for (int i = 0; i < npieces; ++i) {
             const Piece& pc = pieces[i];
             if (pc.pass == 0) { per_cta0[pc.cta + 1]++; ++n0; } else { per_cta1[pc.cta + 1]++; }
             piece_tab[(size_t)i * 5 + 0] = pc.rb;
@@ -1701,12 +1668,10 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     fa.cand_key = cand_key; fa.cand_j = cand_j; fa.seg_cnt = seg_cnt; fa.seg_flag = seg_flag; fa.cap = cap; fa.k = k;
     fa.shortcap = k <= (f16 ? 96 : 128) ? 256 : 512;          // the fp16 filter's wider window lets ~10-25 % more through
     fa.mcoef = filt_mcoef; fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
-    fa.bulk = (S % 2 == 0 && (reinterpret_cast<uintptr_t>(corrected_d) & 15) == 0) ? 1 : 0;
+    fa.vec = (S % 4 == 0 && (reinterpret_cast<uintptr_t>(corrected_d) & 31) == 0) ? 4 : 1;
     fa.in_key = in_key; fa.in_j = in_j; fa.in_cnt = in_cnt; fa.in_cap = in_cap; fa.in_nsrc = 1; fa.in_src_rows = 0;
-    fa.madd = filt_madd;
-    const int fin_threads = f16 ? 160 : FIN_THREADS;
-    const size_t fin_smem = (size_t)(2 * fin_threads * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 +
-                            std::max<size_t>(HIST_BINS * 4, (size_t)fin_threads * 8);     // histogram, later the candidates' row pointers
+    fa.madd = filt_madd; fa.row_thr = row_thr;
+    const size_t fin_smem = (size_t)FIN_ECAP * 12 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
     WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
     if (f16) {
         WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));

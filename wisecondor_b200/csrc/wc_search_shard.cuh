@@ -193,20 +193,22 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
         schedule_pieces(offB, nrb, gridB, G, matrix_bytes > 64e6 || ctx->k5_group > 0, 1, pieces);
     }
     // segments numbered row-block-major; one piece table, pass A's pieces first
-    const int nseg = (int)pieces.size();
+    const int spp = ctx->k5_f16 == 2 ? TC_SEGS_PER_PIECE : 1;        // K5t: one segment per column half of a piece
+    const int npieces = (int)pieces.size();
+    const int nseg = npieces * spp;
     std::vector<int> seg_first(std::max(nrb, 1), 0), seg_count(std::max(nrb, 1), 0), ctaA(gridA + 1, 0), ctaB(gridB + 1, 0);
-    std::vector<int> piece_tab((size_t)std::max(nseg, 1) * 5, 0);
+    std::vector<int> piece_tab((size_t)std::max(npieces, 1) * 5, 0);
     {
-        for (const Piece& pc : pieces) seg_count[pc.rb]++;
+        for (const Piece& pc : pieces) seg_count[pc.rb] += spp;
         int run = 0;
         for (int rb = 0; rb < nrb; ++rb) { seg_first[rb] = run; run += seg_count[rb]; }
         std::vector<int> next(seg_first);
-        for (Piece& pc : pieces) pc.seg = next[pc.rb]++;
+        for (Piece& pc : pieces) { pc.seg = next[pc.rb]; next[pc.rb] += spp; }
         std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) {
             return x.pass != y.pass ? x.pass < y.pass : x.cta < y.cta;
         });
         int n0 = 0;
-        for (int i = 0; i < nseg; ++i) {
+        for (int i = 0; i < npieces; ++i) {
             const Piece& pc = pieces[i];
             if (pc.pass == 0) { ctaA[pc.cta + 1]++; ++n0; } else { ctaB[pc.cta + 1]++; }
             piece_tab[(size_t)i * 5 + 0] = pc.rb;
@@ -287,7 +289,7 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
 
     pl.N = N; pl.S = S; pl.k = k; pl.cap = cap; pl.in_cap = d.in_cap; pl.world = world; pl.rank = rank;
     pl.nb = nb; pl.bp = d.bp; pl.b0 = d.b0; pl.b1 = d.b1; pl.row0 = d.row0; pl.row1 = d.row1; pl.rows_per = d.rows_per;
-    pl.nkc = nkc; pl.nd_last = nd_last; pl.extra_h = nd_last; pl.ld = ld; pl.nrb = nrb; pl.nseg = nseg;
+    pl.nkc = nkc; pl.nd_last = nd_last; pl.extra_h = nd_last; pl.ld = ld; pl.nrb = nrb; pl.nseg = npieces;
     pl.gridA = gridA; pl.gridB = gridB; pl.Npad = Npad; pl.nlistA = listA.size();
     pl.tilesA = tilesA; pl.tilesB = tilesB; pl.tiles_plain = tiles_plain;
     pl.f16 = f16 ? ctx->k5_f16 : 0;
@@ -326,6 +328,7 @@ extern "C" int wc_newref_shard_sweep(wc_ctx* ctx, unsigned long long* thr_d, uns
     if (!pl.valid || pl.stage != 1) { wc_set_error("wc_newref_shard_sweep: call wc_newref_shard_begin first"); return WC_ERR_ARG; }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     WC_CUDA(cudaSetDevice(ctx->device));
+    pl.thr = thr_d;            // K6 drops entries beyond the bins' final thresholds
     WC_CUDA(cudaMemsetAsync(in_cnt_d, 0, (size_t)pl.world * pl.rows_per * sizeof(int), stream));
     WC_CUDA(cudaEventRecord(ctx->ev[18], stream));
     if (pl.gridB > 0) {
@@ -364,11 +367,11 @@ extern "C" int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* rec
         fa.seg_cnt = static_cast<int*>(ctx->buf[SLOT_SEGCNT].p); fa.seg_flag = static_cast<int*>(ctx->buf[SLOT_SEGFLAG].p);
         fa.cap = pl.cap; fa.k = pl.k; fa.shortcap = pl.k <= (pl.f16 ? 96 : 128) ? 256 : 512; fa.mcoef = pl.mcoef;
         fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
-        fa.bulk = (pl.S % 2 == 0 && (reinterpret_cast<uintptr_t>(pl.corrected) & 15) == 0) ? 1 : 0;
+        fa.vec = (pl.S % 4 == 0 && (reinterpret_cast<uintptr_t>(pl.corrected) & 31) == 0) ? 4 : 1;
         fa.in_key = recv_key_d; fa.in_j = recv_j_d; fa.in_cnt = recv_cnt_d; fa.in_cap = pl.in_cap;
         fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per; fa.madd = pl.madd;
-        const int fin_threads = pl.f16 ? 160 : FIN_THREADS;
-        const size_t fin_smem = (size_t)(2 * fin_threads * FIN_LDB + 2 * FIN_CHUNK) * 8 + (size_t)fa.shortcap * 12 + std::max<size_t>(HIST_BINS * 4, (size_t)fin_threads * 8);
+        fa.row_thr = pl.thr != nullptr ? pl.thr + pl.row0 : nullptr;
+        const size_t fin_smem = (size_t)FIN_ECAP * 12 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
         WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
         if (pl.f16) {
             WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));

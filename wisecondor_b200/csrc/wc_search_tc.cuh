@@ -11,28 +11,31 @@
 // products s_ij = x'_i . x'_j with fp32 accumulation, d~ = (n_i + n_j) - 2 s, and two compares per entry - against the
 // row bin's threshold and (SYM) against the column bin's.
 //
-// Blackwell-native structure (one persistent CTA per SM, 8 warps, no thread ever holds an MMA fragment):
+// Blackwell-native structure (one persistent CTA per SM, 12 warps, no thread ever holds an MMA fragment):
 //   warp 0, one lane   TMA producer: per 64-sample chunk three SWIZZLE_128B boxes (A: 128 bins, B: 2 x 128 bins, 16 KiB
-//                      each) into a 4-stage mbarrier ring (SASS UTMALDG)
+//                      each) into a 3-stage mbarrier ring (SASS UTMALDG)
 //   warp 1, one lane   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 256 (or 128 for an odd last block),
 //                      K = 16, operands straight from the swizzled shared-memory tiles through matrix descriptors,
 //                      accumulators in TENSOR MEMORY: two buffers of 256 fp32 columns x 128 lanes (all 512 columns);
 //                      tcgen05.commit releases ring stages and publishes finished accumulators (SASS UTCHMMA / UTCBAR)
 //   warp 2             allocates / frees the tensor memory
-//   warps 4-7          epilogue: warp e owns TMEM lanes [32e, 32e+32) = tile rows, ONE THREAD PER TARGET BIN.  The row's
-//                      threshold, norm, candidate count and exclusion range live in that thread's registers; the
-//                      accumulator row arrives with tcgen05.ld.32x32b.x32 (SASS LDTM), 32 columns at a time, while the
-//                      tensor core already works on the next tile in the other TMEM buffer.
+//   warps 4-11         epilogue, two warpgroups: warp 4+e / 8+e own TMEM lanes [32e, 32e+32) = tile rows, ONE THREAD PER
+//                      TARGET BIN, and the first / second candidate block of the item (two warps per scheduler hide each
+//                      other's latencies; each half has its own candidate segment, so they share no row state).  The row's
+//                      threshold, norm and exclusion range live in the thread's registers; the accumulator row arrives with
+//                      tcgen05.ld.32x32b.x32 (SASS LDTM), 32 columns at a time, while the tensor core already works on the
+//                      next tile in the other TMEM buffer.  Registers move from warpgroup 0 to the epilogue (setmaxnreg).
 // Per 128 x 256 tile the tensor core needs 40 x 128 = 5120 cycles, the epilogue ~2000 issue slots per warp: it hides.
 // What bounds the kernel is the L2 -> shared-memory operand stream (48 KiB per 64-sample chunk of a 128 x 256 tile).
-constexpr int TC_THREADS = 256;
-constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 384;                     // warpgroup 0: TMA / MMA / TMEM roles; warpgroups 1, 2: epilogue
+constexpr int TC_STAGES = 3;                        // 144 KiB in flight: the L2 stream, not the latency, bounds the ring
 constexpr int TC_STAGE_BYTES = 3 * TILE_BYTES;      // A, B0, B1 boxes: 128 rows x 64 halves x 2 B = 16 KiB each
 constexpr int TC_NB = 2 * BN;                       // columns of a full item (two candidate blocks)
 constexpr int TC_STG = 256;                         // per-warp staging entries (8 bytes each) for column-side candidates
 constexpr int TC_LIST = 256;                        // per-warp (row, column) pairs of one 32-column chunk handled by the dense path
 constexpr int TC_PIVOTS = 512;                      // pivots of the pivot pass: their distances to 128 bins fill the tensor memory
-constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_EPI_WARPS = 8;                     // two per TMEM lane quarter: columns [0, 128) and [128, 256) of an item
+constexpr int TC_SEGS_PER_PIECE = 2;                // each column half keeps its own candidate buffers (no shared row state)
 constexpr uint32_t TC_TMEM_COLS = 512;
 
 struct __align__(16) TcState {
@@ -41,6 +44,7 @@ struct __align__(16) TcState {
     uint64_t tfull[2];
     uint64_t tempty[2];
     uint32_t tmem_base;
+    int alloc[8];                // per epilogue warp: (row-side | column-side << 16) list slots handed out in the current chunk
 };
 
 constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES                 // operand ring
@@ -48,7 +52,7 @@ constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES             
                                  + (size_t)TC_EPI_WARPS * TC_STG * sizeof(uint2)     // column-side staging
                                  + (size_t)TC_EPI_WARPS * 32 * 33 * sizeof(float)    // per-warp parking of one 32 x 32 chunk
                                  + (size_t)TC_EPI_WARPS * 2 * TC_LIST * sizeof(unsigned short)   // (row, column) lists
-                                 + BM * sizeof(int) + BM                             // per-row candidate counts and overflow flags
+                                 + (size_t)TC_EPI_WARPS * 32 * (sizeof(int) + 1)     // per-row candidate counts and overflow flags
                                  + sizeof(TcState);
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -119,12 +123,12 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     unsigned char* tiles = smem_raw;            // (no pointer arithmetic through integers: every access below stays an LDS / STS)
     float* s_nj = reinterpret_cast<float*>(smem_raw + (size_t)TC_STAGES * TC_STAGE_BYTES);    // [2][TC_NB]
     float* s_tj = s_nj + 2 * TC_NB;                                                            // [2][TC_NB]  (pivot pass: the pivots' bins, as int)
-    uint2* s_stg = reinterpret_cast<uint2*>(s_tj + 2 * TC_NB);                                 // [4][TC_STG]
-    float* s_park = reinterpret_cast<float*>(s_stg + TC_EPI_WARPS * TC_STG);                   // [4][32][33]
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_park + TC_EPI_WARPS * 32 * 33);   // [4][2][TC_LIST]
-    int* s_cnt = reinterpret_cast<int*>(s_list + TC_EPI_WARPS * 2 * TC_LIST);                  // [BM]
-    unsigned char* s_flag = reinterpret_cast<unsigned char*>(s_cnt + BM);                      // [BM]
-    TcState& sm = *reinterpret_cast<TcState*>(s_flag + BM);
+    uint2* s_stg = reinterpret_cast<uint2*>(s_tj + 2 * TC_NB);                                 // [8][TC_STG]
+    float* s_park = reinterpret_cast<float*>(s_stg + TC_EPI_WARPS * TC_STG);                   // [8][32][33]
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_park + TC_EPI_WARPS * 32 * 33);   // [8][2][TC_LIST]
+    int* s_cnt = reinterpret_cast<int*>(s_list + TC_EPI_WARPS * 2 * TC_LIST);                  // [8][32]
+    unsigned char* s_flag = reinterpret_cast<unsigned char*>(s_cnt + TC_EPI_WARPS * 32);       // [8][32]
+    TcState& sm = *reinterpret_cast<TcState*>(s_flag + TC_EPI_WARPS * 32);
     const int tid = threadIdx.x;
     const int warp_all = tid >> 5, lane = tid & 31;
 
@@ -138,7 +142,7 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&sm.tfull[b], 1);
-            mbar_init(&sm.tempty[b], TC_EPI_WARPS);
+            mbar_init(&sm.tempty[b], PIV ? 4 : TC_EPI_WARPS);
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmap);
@@ -166,6 +170,8 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         return tl ? tl[q] : (PIV || q < skip_lo ? q : q + skip_n);      // pivot pass: tiles of the pivot matrix
     };
 
+    if (warp_all < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // warpgroup 0 hands its registers to the epilogue warpgroups
     if (warp_all == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
@@ -231,7 +237,10 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 }
             }
         }
-    } else if (warp_all >= 4 && PIV) {
+    }
+    } else if (PIV) {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+      if (warp_all < 8) {
         // ===== pivot pass epilogue: one thread per target bin, its 512 pivot distances stay in tensor memory =====
         // The thread bisects on the value for a cut with k <= #{valid pivots with d~ <= cut} <= k + 24, re-reading its TMEM lane
         // (16 x tcgen05.ld.32x32b.x32) per round: no candidate buffer, no prune, no global traffic but the final threshold.
@@ -318,17 +327,24 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             __syncwarp();
             if (lane == 0) { mbar_arrive(&sm.tempty[0]); mbar_arrive(&sm.tempty[1]); }
         }
-    } else if (warp_all >= 4) {
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         // ===== epilogue: one thread per target bin =====
-        const int e = warp_all - 4;                 // TMEM lane quarter of this warp (== warp_all % 4)
+        const int e = warp_all & 3;                 // TMEM lane quarter of this warp (== warp_all % 4)
+        const int g = (warp_all - 4) >> 2;          // column half of the item this warp handles (candidate block 0 / 1)
+        const int we = warp_all - 4;                // epilogue warp index 0..7 (per-warp shared-memory areas)
         const int r = e * 32 + lane;                // row of the tile = TMEM lane
-        uint2* w_stg = s_stg + e * TC_STG;          // (float d~ bits, bin j | source lane << 27) of column-side candidates
+        uint2* w_stg = s_stg + we * TC_STG;         // (float d~ bits, bin j | source lane << 27) of column-side candidates
         int stg_n = 0;                              // staged entries: warp-uniform, lives in a register
-        float* w_park = s_park + e * (32 * 33);     // the chunk's 32 x 32 distances: entry (column b, lane l) at [b * 33 + l]
-        unsigned short* w_rlist = s_list + e * (2 * TC_LIST);        // row-side (column b << 5 | lane) pairs of the chunk
+        float* w_park = s_park + we * (32 * 33);    // the chunk's 32 x 32 distances: entry (column b, lane l) at [b * 33 + l]
+        unsigned short* w_rlist = s_list + we * (2 * TC_LIST);       // row-side (column b << 5 | lane) pairs of the chunk
         unsigned short* w_clist = w_rlist + TC_LIST;                 // column-side pairs
-        int* w_cnt = s_cnt + e * 32;                // candidate counts of the warp's 32 rows
-        unsigned char* w_flag = s_flag + e * 32;
+        int* w_cnt = s_cnt + we * 32;               // candidate counts of the warp's 32 rows in ITS segment
+        unsigned char* w_flag = s_flag + we * 32;
+        int* w_alloc = &sm.alloc[we];
+        if (lane == 0) *w_alloc = 0;
+        __syncwarp();
         const size_t seg_stride = (size_t)BM * a.cap;
         long long pf_epi = 0, pf_prune = 0, pf_nprune = 0, pf_emit = 0, pf_wait = 0;
         const long long pf_t0 = clock64();
@@ -365,7 +381,7 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         int it = 0;
         for (int pi = pb; pi < pe; ++pi) {
             const int* pc = a.pieces + (size_t)pi * 5;
-            const int rb = pc[0], q1 = pc[2], qs = pc[3], seg = pc[4];
+            const int rb = pc[0], q1 = pc[2], qs = pc[3], seg = pc[4] + g;      // each column half has its own segment
             const int skip_lo = a.rb_skip_lo[rb], skip_n = a.rb_skip_n[rb];
             const int* tl = a.tile_list ? a.tile_list + a.rb_list_off[rb] : nullptr;
             // this thread's bin
@@ -402,7 +418,7 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                     else
                         prune_row<32>(wk + (size_t)src * a.cap, wj + (size_t)src * a.cap, n, a.k, nr, a.mcoef, a.madd, lane, nullptr, nullptr, &nthr, &kept);
                     if (lane == src) {
-                        if (kept > a.cap - TC_NB) {          // a tie plateau wider than the buffer: exact fallback
+                        if (kept > a.cap - BN) {             // a tie plateau wider than the buffer: exact fallback
                             w_flag[lane] = 1;
                             thr = KEY_NEVER;
                             w_cnt[lane] = 0;
@@ -423,46 +439,45 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 const int c1 = two ? tile_of(tl, q, skip_lo, skip_n) * BN : 0;
                 if (two) q += qs;
                 const int buf = it & 1;
-                // column tables of this item (norms; SYM: thresholds) and the row's shared threshold: issued before the wait
-                const float nj0 = a.coln32[c0 + r];
-                const float nj1 = two ? a.coln32[c1 + r] : INFINITY;
-                u64 ct0 = KEY_NEVER, ct1 = KEY_NEVER;
-                if (SYM) {
-                    ct0 = __ldcg(a.col_thr + c0 + r);
-                    if (two) ct1 = __ldcg(a.col_thr + c1 + r);
-                }
+                const int cg = g == 0 ? c0 : c1;      // first bin of this warp's candidate block
+                const bool mine = g == 0 || two;      // an odd last item has no second block: the second warpgroup only keeps step
+                // column tables of the block (norms; SYM: thresholds) and the row's shared threshold: issued before the wait
+                const float njr = mine ? a.coln32[cg + r] : INFINITY;
+                u64 ctr = KEY_NEVER;
+                if (SYM && mine) ctr = __ldcg(a.col_thr + cg + r);
                 if (valid) {
                     const u64 shared_thr = __ldcg(a.row_thr + (row - a.row_begin));
                     if (shared_thr < thr) thr = shared_thr;
                 }
-                float* nj_t = s_nj + buf * TC_NB;
-                float* tj_t = s_tj + buf * TC_NB;
-                nj_t[r] = nj0;
-                nj_t[BN + r] = nj1;
-                if (SYM) {
-                    tj_t[r] = tc_tau32_of_key(ct0);
-                    tj_t[BN + r] = tc_tau32_of_key(ct1);
-                }
+                float* nj_t = s_nj + buf * TC_NB + g * BN;           // this warpgroup's half of the tables
+                float* tj_t = s_tj + buf * TC_NB + g * BN;
+                nj_t[r] = njr;
+                if (SYM) tj_t[r] = tc_tau32_of_key(ctr);
                 const float taui = tc_tau32_of_key(thr);
-                named_bar_sync(1, TC_EPI_WARPS * 32);              // tables visible to the four epilogue warps
+                named_bar_sync(1 + g, 128);                         // tables visible to the four warps of the warpgroup
                 const long long pf_w0 = clock64();
                 mbar_wait(&sm.tfull[buf], (uint32_t)((it >> 1) & 1));
                 tc_fence_after();
                 const long long pf_e0 = clock64();
                 pf_wait += pf_e0 - pf_w0;
 
-                const int nchunk = two ? TC_NB / 32 : BN / 32;
+                const int nchunk = mine ? BN / 32 : 0;
+                if (!mine) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.tempty[buf]);
+                }
                 for (int ch = 0; ch < nchunk; ++ch) {
                     uint32_t v[32];
-                    tc_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * TC_NB + ch * 32), v);
+                    tc_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * TC_NB + g * BN + ch * 32), v);
                     tc_wait_ld();
                     if (ch == nchunk - 1) {          // the accumulator row is in registers: hand the buffer back to the tensor core
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&sm.tempty[buf]);
                     }
-                    const int cb = ch * 32;          // column of the item (0..255)
-                    const int colbase = (cb < BN ? c0 : c1 - BN) + cb;      // global bin of the chunk's first column
+                    const int cb = ch * 32;          // column within the warp's block (0..127)
+                    const int colbase = cg + cb;     // global bin of the chunk's first column
                     unsigned mask = 0, cmask = 0;
                     float dv[32];
 #pragma unroll
@@ -473,18 +488,22 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                         dv[4 * u + 2] = fmaf(-2.0f, __uint_as_float(v[4 * u + 2]), ni + nj.z);
                         dv[4 * u + 3] = fmaf(-2.0f, __uint_as_float(v[4 * u + 3]), ni + nj.w);
                     }
-#pragma unroll
-                    for (int b = 0; b < 32; ++b)
-                        if (dv[b] <= taui) mask |= 1u << b;
-                    if (SYM) {
+                    {   // eight independent partial masks per side: no 32-deep dependency chain on one register
+                        unsigned pm[8], qm[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const float4 tj = *reinterpret_cast<const float4*>(tj_t + cb + 4 * u);
-                            if (dv[4 * u + 0] <= tj.x) cmask |= 1u << (4 * u + 0);
-                            if (dv[4 * u + 1] <= tj.y) cmask |= 1u << (4 * u + 1);
-                            if (dv[4 * u + 2] <= tj.z) cmask |= 1u << (4 * u + 2);
-                            if (dv[4 * u + 3] <= tj.w) cmask |= 1u << (4 * u + 3);
+                            pm[u] = (dv[4 * u + 0] <= taui ? 1u : 0u) | (dv[4 * u + 1] <= taui ? 2u : 0u) |
+                                    (dv[4 * u + 2] <= taui ? 4u : 0u) | (dv[4 * u + 3] <= taui ? 8u : 0u);
+                            qm[u] = 0u;
+                            if (SYM) {
+                                const float4 tj = *reinterpret_cast<const float4*>(tj_t + cb + 4 * u);
+                                qm[u] = (dv[4 * u + 0] <= tj.x ? 1u : 0u) | (dv[4 * u + 1] <= tj.y ? 2u : 0u) |
+                                        (dv[4 * u + 2] <= tj.z ? 4u : 0u) | (dv[4 * u + 3] <= tj.w ? 8u : 0u);
+                            }
                         }
+                        mask = (pm[0] | (pm[1] << 4)) | ((pm[2] << 8) | (pm[3] << 12)) | ((pm[4] << 16) | (pm[5] << 20)) | ((pm[6] << 24) | (pm[7] << 28));
+                        if (SYM)
+                            cmask = (qm[0] | (qm[1] << 4)) | ((qm[2] << 8) | (qm[3] << 12)) | ((qm[4] << 16) | (qm[5] << 20)) | ((qm[6] << 24) | (qm[7] << 28));
                     }
                     if (DBG) {
                         if (valid && a.dbg != nullptr) {
@@ -507,20 +526,20 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                     }
                     // ---- survivors: compacted over the warp, then handled 32 at a time (no per-thread serial work) ----
                     const int rn = __popc(mask), cn = SYM ? __popc(cmask) : 0;
-                    int incl = rn | (cn << 16);
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    const int tot = __shfl_sync(0xffffffffu, incl, 31);
-                    const int rt = tot & 0xffff, ct = tot >> 16;
-                    if (tot != 0) {
-                        __syncwarp();
+                    const int packed = rn | (cn << 16);
+                    if (__any_sync(0xffffffffu, packed != 0)) {
+                        // list slots: one shared-memory atomic per lane with survivors (the lists need no order)
+                        int mine = 0;
+                        if (packed != 0) mine = atomicAdd(w_alloc, packed);
 #pragma unroll
                         for (int b = 0; b < 32; ++b) w_park[b * 33 + lane] = dv[b];
+                        __syncwarp();
+                        const int tot = *w_alloc;
+                        const int rt = tot & 0xffff, ct = tot >> 16;
+                        __syncwarp();
+                        if (lane == 0) *w_alloc = 0;
                         if (rt <= TC_LIST && ct <= TC_LIST) {
-                            int pr = (incl & 0xffff) - rn, pq = (incl >> 16) - cn;
+                            int pr = mine & 0xffff, pq = mine >> 16;
                             while (mask) {
                                 const int bit = __ffs(mask) - 1;
                                 mask &= mask - 1;
@@ -585,7 +604,7 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 const long long pf_p0 = clock64();
                 pf_epi += pf_p0 - pf_e0;
                 // ---- prune rows whose buffer could overflow during the next item ----
-                prune_rows(__ballot_sync(0xffffffffu, w_cnt[lane] > a.cap - TC_NB && !w_flag[lane]));
+                prune_rows(__ballot_sync(0xffffffffu, w_cnt[lane] > a.cap - BN && !w_flag[lane]));
                 pf_prune += clock64() - pf_p0;
             }
             // piece finished
@@ -597,7 +616,7 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             a.seg_cnt[(size_t)seg * BM + r] = w_cnt[lane] > a.cap ? a.cap : w_cnt[lane];
             a.seg_flag[(size_t)seg * BM + r] = w_flag[lane];
         }
-        if (a.prof != nullptr && e == 0 && lane == 0) {
+        if (a.prof != nullptr && we == 0 && lane == 0) {
             long long* o = a.prof + (size_t)blockIdx.x * 8;
             o[0] = clock64() - pf_t0; o[1] = pf_wait; o[2] = pf_epi; o[3] = pf_prune;
             o[4] = it; o[5] = pf_nprune; o[6] = pf_emit; o[7] = 0;
