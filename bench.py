@@ -480,6 +480,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work in the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-test", action="store_true", help="skip the batched test (z-score + segmentation) section")
+    ap.add_argument("--shard", default="rows", choices=["rows", "sym"],
+                    help="N > 1: getPart row shards + all-gather (default), or the sharded symmetric search")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the sampled-row comparison with the C oracle")
     ap.add_argument("--test-batch", type=int, default=512, help="test samples per GPU in the test section")
     args = ap.parse_args()
@@ -528,8 +530,11 @@ def main():
 
     # N > 1: the block pairs of the symmetric search divided over the ranks (shard.SymmetricShardedSearch), if a trial run
     # on a small matrix agrees with the single-GPU search on every rank; otherwise the reference's getPart row shards.
+    # Default at N > 1: the reference's own partition - getPart row shards (wisetools.py:358-361), every GPU holding the whole
+    # matrix, one NCCL all-gather of the rows.  --shard sym divides the symmetric search's block pairs instead (half the
+    # tensor work per rank, but three more collectives per step).
     sym_search, sym_note = None, None
-    if world > 1 and os.environ.get("WC_SHARD_SYM", "1") != "0":
+    if world > 1 and args.shard == "sym":
         agreed, sym_note = symmetric_shards_agree(dev, rank, world)
         if agreed:
             sym_search = shard.SymmetricShardedSearch(n, k, rank, world, dev)
@@ -559,7 +564,7 @@ def main():
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     k5_ms, k4_ms, k6_ms, launches = [], [], [], 0
-    k5a_ms, work_ratio = [], 1.0
+    k5a_ms, work_ratio, filt = [], 1.0, 0
     barrier()
     t_wall0 = time.time()
     for i in range(args.steps):
@@ -573,6 +578,7 @@ def main():
         k6_ms.append(st["finalize_ms"] + st["exhaustive_ms"])
         k5a_ms.append(st["dist_topk_first_pass_ms"])
         work_ratio = st["tiles"] / float(max(1, st["tiles_plain"]))
+        filt = int(st["filter"])
         launches += int(st["launches"])
     barrier()
     t_wall = time.time() - t_wall0
@@ -625,42 +631,57 @@ def main():
     if rank == 0:
         peak, sustained, peak_src = fp64_peak()
         k5 = float(np.mean(k5_ms))
-        # 2*S flops per ordered bin pair.  A whole-matrix call runs the symmetric search, which contracts every
-        # unordered pair of bin blocks once (+ a threshold pass): work_ratio of those flops are executed.  The roofline
-        # fraction is the EXECUTED rate (what the DMMA pipe sustains); the algorithmic rate is reported next to it.
-        flops = 2.0 * S * pairs_for_rows(bins, r0, r1)
-        achieved = flops * work_ratio / (k5 * 1e-3) / 1e12
-        # a kernel timed inside a long step under the power cap -> the sustained figure; short steps -> burst
-        use_peak = sustained if ms_per_step > 50.0 else peak
-        traffic = None
-        try:      # dram__bytes_read.sum + dram__bytes_write.sum of one K5 launch, from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "k5_traffic.json")) as fh:
-                traffic = json.load(fh).get((args.workload + ("_sym" if work_ratio < 1.0 else "")) if world == 1 else "", None)
+        k6 = float(np.mean(k6_ms))
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                mp = json.load(fh)
+            mp_src = "MEASURED_PEAKS.json"
+        except Exception:
+            mp, mp_src = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)"
+        traffic = {}
+        try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full captures
+            with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as fh:
+                traffic = json.load(fh).get(args.workload if world == 1 else "", {})
         except Exception:
             pass
-        roofline = {"bound": "tensor", "kernel": "wc_dist_topk_kernel (K5, fp64 DMMA.8x8x4 + TMA)",
-                    "achieved": achieved, "peak": use_peak, "unit": "TFLOP/s", "frac": achieved / use_peak,
-                    "traffic": traffic, "flops_per_launch": flops * work_ratio, "kernel_ms": k5,
-                    "algorithmic_flops_per_launch": flops, "algorithmic_tflops": flops / (k5 * 1e-3) / 1e12,
-                    "work_ratio": work_ratio, "first_pass_ms": float(np.mean(k5a_ms)),
-                    "note": "work_ratio < 1: symmetric search, each unordered pair of bin blocks contracted once (two launches: "
-                            "threshold pass + symmetric pass); achieved/frac count the flops actually issued",
-                    "peak_source": "measured FP64 tensor (DMMA) peak of this pool, %s (%s figure); "
-                                   "MEASURED_PEAKS.json has no FP64 entry" %
-                                   (peak_src, "sustained" if use_peak == sustained else "burst"),
-                    "share_of_step": k5 / ms_per_step}
-        if os.environ.get("WC_K5_F16") == "1":
-            # experimental fp16 filter: K5 runs on the fp16 tensor cores; the denominator is the measured dense bf16/fp16 rate
-            try:
-                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                    mp = json.load(fh)
-                tc_peak = float(mp["bf16_tflops"] if ms_per_step <= 50.0 else mp.get("bf16_tflops_sustained", mp["bf16_tflops"]))
-                tc_src = "MEASURED_PEAKS.json bf16 dense (cuBLAS)"
-            except Exception:
-                tc_peak, tc_src = 2250.0, "nominal dense fp16 (MEASURED_PEAKS.json missing)"
-            roofline.update({"kernel": "wc_dist_topk_f16_kernel (K5h, fp16 HMMA.16816.F32 + TMA; fp64 exact re-score in K6)",
-                             "peak": tc_peak, "frac": achieved / tc_peak, "peak_source": tc_src})
-            roofline["note"] += "; EXPERIMENTAL fp16 filter (WC_K5_F16=1)"
+        # K5: SURVEY 8(d): 2*S flops per ordered bin pair of the launch's target rows.  A whole-matrix call runs the symmetric
+        # search (every unordered pair of bin blocks contracted once, plus a threshold pass): work_ratio of those flops are
+        # EXECUTED; achieved / frac count the executed flops, the algorithmic rate is reported next to it.
+        flops = 2.0 * S * pairs_for_rows(bins, r0, r1)
+        achieved = flops * work_ratio / (k5 * 1e-3) / 1e12
+        burst = ms_per_step <= 50.0            # a kernel inside a long step under the power cap -> the sustained figures
+        if filt == 0:
+            use_peak = peak if burst else sustained
+            k5_desc = ("wc_dist_topk_kernel (K5, fp64 DMMA.8x8x4 + TMA)", use_peak,
+                       "measured FP64 tensor (DMMA) peak of this pool, %s (%s figure); MEASURED_PEAKS.json has no FP64 entry" %
+                       (peak_src, "burst" if burst else "sustained"), "f64")
+        else:
+            use_peak = float(mp["bf16_tflops"] if burst else mp.get("bf16_tflops_sustained", mp["bf16_tflops"]))
+            name = ("wc_dist_topk_tc_kernel (K5t: fp16 tcgen05.mma kind::f16, fp32 accumulators in TMEM, TMA operands; FILTER only - "
+                    "the fp64 exact re-score of K6 decides the result)" if filt == 2 else
+                    "wc_dist_topk_f16_kernel (K5h: fp16 mma.sync HMMA.16816.F32 + TMA; filter only)")
+            k5_desc = (name, use_peak, "%s dense bf16/fp16 (cuBLAS, %s figure)" % (mp_src, "burst" if burst else "sustained"), "f16 -> f32")
+        roof_k5 = {"bound": "tensor", "kernel": k5_desc[0], "filter_dtype": k5_desc[3],
+                   "achieved": achieved, "peak": k5_desc[1], "unit": "TFLOP/s", "frac": achieved / k5_desc[1],
+                   "traffic": traffic.get("k5"), "flops_per_launch": flops * work_ratio, "kernel_ms": k5,
+                   "algorithmic_flops_per_launch": flops, "algorithmic_tflops": flops / (k5 * 1e-3) / 1e12,
+                   "work_ratio": work_ratio, "first_pass_ms": float(np.mean(k5a_ms)),
+                   "note": "kernel_ms covers every K5 launch of a step (pivot pass, threshold pass, symmetric pass); work_ratio < 1: "
+                           "symmetric search, each unordered pair of bin blocks contracted once; achieved / frac count the flops issued",
+                   "peak_source": k5_desc[2], "share_of_step": k5 / ms_per_step}
+        # K6: the exact re-score must read, per target bin, the rows of at least `refsize` candidates and its own (S doubles
+        # each) and write refsize (index, distance) pairs: (refsize + 1) * S * 8 + refsize * 12 bytes per target bin
+        rows_mine = r1 - r0
+        k6_bytes = float(rows_mine) * ((k + 1) * S * 8.0 + k * 12.0)
+        hbm = float(mp["hbm_gbs"])
+        roof_k6 = {"bound": "hbm", "kernel": "wc_finalize_kernel (K6: exact fp64 re-score in the reference's operation order, gathered "
+                                             "candidate rows, ranking)",
+                   "achieved": k6_bytes / (k6 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": k6_bytes / (k6 * 1e-3) / 1e9 / hbm,
+                   "traffic": traffic.get("k6"), "bytes_per_launch": k6_bytes, "kernel_ms": k6,
+                   "note": "algorithmic bytes = target bins x ((refsize + 1) rows of S doubles + refsize (index, distance) pairs); the "
+                           "shortlist behind the fp16 filter is ~25 % longer than refsize, and about 60 % of the gathered rows hit the L2",
+                   "peak_source": "%s hbm_gbs (device copy)" % mp_src, "share_of_step": k6 / ms_per_step}
+        roofline, roof_other = (roof_k5, roof_k6) if k5 >= k6 else (roof_k6, roof_k5)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup) if not big else max(1, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -674,7 +695,7 @@ def main():
                        "sharded_symmetric_trial": sym_note,
                        "l2": "512 MiB buffer written between timed iterations (L2 flush)"},
             "phases_ms": {"center_norms": float(np.mean(k4_ms)), "dist_topk": k5, "finalize": float(np.mean(k6_ms))},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "roofline_second_kernel": roof_other, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:

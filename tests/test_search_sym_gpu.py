@@ -53,7 +53,8 @@ def test_symmetric_equals_plain_search_and_halves_the_tiles(sym):
     sym(0)
     pidx, pdist, pst = _gpu_search(X, bins, 100)
     _assert_same(idx, dist, pidx, pdist)
-    assert pst["launches"] == 5 and st["launches"] >= 6
+    # plain: two fills, K4, K5, K6 (+ pivot select, gather, pass with the tcgen05 filter); symmetric: one K5 launch more
+    assert pst["launches"] in (5, 8) and st["launches"] == pst["launches"] + 1
     assert 0.5 < st["tiles"] / pst["tiles"] < 0.62                             # 1/8 + 7/16 = 0.5625 of the plain tiles
     assert st["tiles_plain"] == pst["tiles"] == pst["tiles_plain"]
     assert st["exhaustive_rows"] == pst["exhaustive_rows"] == 0

@@ -53,9 +53,10 @@ def test_zscores_golden_bit_exact(fn):
     assert _same(got[0], want[0]) and _same(got[1], want[1]) and _same(got[2], want[2]) and got[3] == want[3]
 
 
-@pytest.mark.parametrize("B,k,S", [(1, 100, 30), (37, 100, 30), (70, 20, 16), (5, 150, 24), (3, 300, 24)])
+@pytest.mark.parametrize("B,k,S", [(1, 100, 30), (37, 100, 30), (70, 20, 16), (5, 150, 24), (3, 300, 24), (2, 500, 24), (2, 512, 24)])
 def test_zscores_batch_vs_oracle(B, k, S):
-    """Medium genome, batches that do not fill a warp tile, refsize below and above numpy's 128-element block."""
+    """Medium genome, batches that do not fill a warp tile, refsize below and above numpy's 128-element block; 500 / 512
+    reference bins exercise the third level of numpy's pairwise split (a quarter of 489+ values exceeds 128)."""
     from wisecondor_b200 import wisetools
     bins = [int(b) for b in np.maximum(2, np.array(synth.chrom_bins(250000)) // 6)]
     n = sum(bins)

@@ -84,6 +84,13 @@ def toolNewref(args):
         toolNewrefPrep(args)
 
     todo = [p for p in range(1, args.parts + 1) if not os.path.isfile(args.partfile + "_" + str(p) + ".npz")]
+    if gpus > 1 and len(todo) == args.parts and not getattr(args, 'partfiles', False):
+        # The multi-GPU product path: one process per GPU, every rank searches its getPart rows of the whole matrix, the
+        # rows travel over NCCL (all-gather) instead of part files (reference wisecondor.py:146-158) and rank 0 writes the
+        # reference npz.  Resume granularity: the prep file.
+        _spawnRanks(gpus, ['newrefrank', args.prepfile, args.outfile, '-refsize', str(args.refsize)])
+        os.remove(args.prepfile)
+        return
     if gpus > 1 and todo:
         # one host thread per GPU; the C ABI releases the GIL for the duration of each search
         import copy
@@ -114,6 +121,62 @@ def toolNewref(args):
     os.remove(args.prepfile)
     for part in range(1, args.parts + 1):
         os.remove(args.partfile + '_' + str(part) + '.npz')
+
+
+def _spawnRanks(world, argv):
+    """Run `wisecondor.py <argv>` once per GPU with the torch.distributed environment of a single-node job (what torchrun
+    would set); any failing rank fails the command."""
+    import socket as _socket
+    with _socket.socket() as sock:
+        sock.bind(('127.0.0.1', 0))
+        port = sock.getsockname()[1]
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1',
+                   MASTER_PORT=str(port), WISECONDOR_BACKEND='torch')
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__)] + argv, env=env))
+    codes = [p.wait() for p in procs]
+    if any(codes):
+        print('ERROR: rank exit codes', codes)
+        sys.exit(1)
+
+
+def toolNewrefRank(args):
+    """One rank of `newref -gpus N` (internal sub-command, started by _spawnRanks): the reference's newrefpart for part
+    RANK+1 of WORLD_SIZE (wisecondor.py:111-132) with NCCL instead of files - 1/N of the corrected matrix uploaded per rank
+    and all-gathered over NVLink, the search of the rank's getPart rows, an all-gather of the (rows x refsize) blocks -
+    then, on rank 0, newrefpost's writer (wisecondor.py:160-170)."""
+    import torch
+    import torch.distributed as dist
+    from wisecondor_b200 import shard
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    npzdata = _load(args.prepfile)
+    maskedChromBins = [int(v) for v in npzdata['maskedChromBins']]
+    corrected = torch.from_numpy(np.ascontiguousarray(npzdata['correctedData'], dtype=np.float64)).pin_memory()
+    n, s = corrected.shape
+    timeStart = time.time()
+    job = shard.ShardedSearch(n, s, args.refsize, rank, world, dev)
+    job.run(corrected, maskedChromBins)
+    idx, dst = shard.allgather_rows(job.idx, job.dist, n)
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        print('Time spent on the search over', world, 'GPUs:', round(time.time() - timeStart, 3), 'seconds')
+        np.savez_compressed(args.outfile,
+                            arguments=vars(args),
+                            runtime=getRuntime(),
+                            binsize=npzdata['binsize'].item(),
+                            indexes=idx.cpu().numpy(),
+                            distances=dst.cpu().numpy(),
+                            chromosome_sizes=npzdata['chromosomeBins'],
+                            mask=npzdata['mask'],
+                            masked_sizes=npzdata['maskedChromBins'],
+                            pca_components=npzdata['pca_components'],
+                            pca_mean=npzdata['pca_mean'])
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def toolNewrefPrep(args):
@@ -270,8 +333,31 @@ def toolTestBatch(args):
     the sample file).  npz inflate (loading) and deflate (writing) run in a thread pool and overlap the GPU work of
     the neighbouring batches - at 10 k samples host I/O, not the kernels, sets the pace."""
     import concurrent.futures
-    ref = _loadReference(args.reference)
     os.makedirs(args.outdir, exist_ok=True)
+    gpus = max(1, int(getattr(args, 'gpus', 1) or 1))
+    if gpus > 1:
+        # samples are independent: shard them over the GPUs, no communication (one process per GPU)
+        from wisecondor_b200 import partition
+        flags = ['-batch', str(args.batch), '-iothreads', str(args.iothreads), '-chromosomes', ','.join(str(c) for c in args.chromosomes),
+                 '-mineffectsize', str(args.mineffectsize), '-multitest', str(args.multitest), '-minrefbins', str(args.minrefbins),
+                 '-repeats', str(args.repeats)]
+        if args.minzscore is not None:
+            flags += ['-minzscore', str(args.minzscore)]
+        if args.uncompressed:
+            flags.append('-uncompressed')
+        procs = []
+        for rank in range(gpus):
+            a, b = partition.sample_shard(rank, gpus, len(args.infiles))
+            if b > a:
+                env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(rank))
+                procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), 'testbatch'] + list(args.infiles[a:b]) +
+                                              [args.outdir, args.reference] + flags, env=env))
+        codes = [p.wait() for p in procs]
+        if any(codes):
+            print('ERROR: worker exit codes', codes)
+            sys.exit(1)
+        return
+    ref = _loadReference(args.reference)
 
     def load(infile):
         sampleFile = _load(infile)
@@ -319,6 +405,14 @@ def buildParser():
     parser = argparse.ArgumentParser(description="WISECONDOR (WIthin-SamplE COpy Number aberration DetectOR) - B200 build")
     sub = parser.add_subparsers()
 
+    def refsize(text):
+        """-refsize: the reference accepts any positive count (wisecondor.py:379); the device search keeps a bin's candidates
+        in buffers sized for at most 384 of them, so larger values are refused HERE, before any work is done."""
+        value = int(text)
+        if not 1 <= value <= 384:
+            raise argparse.ArgumentTypeError("refsize must be between 1 and 384 on the B200 search (got %d)" % value)
+        return value
+
     p = sub.add_parser('convert', description='Convert and filter a bam file to an npz')
     p.add_argument('infile', type=str)
     p.add_argument('outfile', type=str)
@@ -330,12 +424,19 @@ def buildParser():
     p = sub.add_parser('newref', description='Create a new reference using healthy reference samples')
     p.add_argument('infiles', type=str, nargs='*', help='Reference sample npz files')
     p.add_argument('outfile', type=str, help='Reference output npz')
-    p.add_argument('-refsize', type=int, default=100, help='Amount of reference locations per target')
+    p.add_argument('-refsize', type=refsize, default=100, help='Amount of reference locations per target (1..384)')
     p.add_argument('-binsize', type=int, default=None, help='Scale samples to this binsize (multiples only)')
     p.add_argument('-cpus', type=int, default=1, help='Kept for compatibility: raises the number of parts')
     p.add_argument('-parts', type=int, default=1, help='Split reference finding in this many row parts')
-    p.add_argument('-gpus', type=int, default=1, help='Search the parts on this many B200s of the node concurrently')
+    p.add_argument('-gpus', type=int, default=1, help='Shard the target bins over this many B200s of the node (one process each, NCCL)')
+    p.add_argument('-partfiles', action='store_true', help='With -gpus N: exchange the parts through part files like the reference (resumable per part) instead of NCCL')
     p.set_defaults(func=toolNewref)
+
+    p = sub.add_parser('newrefrank', description='(internal) one rank of newref -gpus N; started once per GPU with RANK / WORLD_SIZE set')
+    p.add_argument('prepfile', type=str)
+    p.add_argument('outfile', type=str)
+    p.add_argument('-refsize', type=refsize, default=100)
+    p.set_defaults(func=toolNewrefRank)
 
     p = sub.add_parser('newrefprep', description='Prepare creation of new reference split over several processes')
     p.add_argument('infiles', type=str, nargs='*')
@@ -347,7 +448,7 @@ def buildParser():
     p.add_argument('prepfile', type=str)
     p.add_argument('partfile', type=str)
     p.add_argument('part', type=int, default=[0, 1], nargs=2)
-    p.add_argument('-refsize', type=int, default=100)
+    p.add_argument('-refsize', type=refsize, default=100)
     p.set_defaults(func=toolNewrefPart)
 
     p = sub.add_parser('newrefpost', description='Combine creation of new reference split over several processes')
@@ -381,6 +482,7 @@ def buildParser():
     p.add_argument('-batch', type=int, default=256, help='Samples per device batch')
     p.add_argument('-iothreads', type=int, default=8, help='Threads loading / writing npz files')
     p.add_argument('-uncompressed', action='store_true', help='Write result npz files without zlib compression')
+    p.add_argument('-gpus', type=int, default=1, help='Shard the samples over this many B200s of the node (one process each, no communication)')
     p.set_defaults(func=toolTestBatch)
 
     p = sub.add_parser('plot', description='Plot results produced by sample testing')
@@ -413,7 +515,7 @@ def main(argv=None):
         # Device buffers: `testbatch` pipelines chunks over torch streams and pinned memory; everything else handles one
         # reference or one sample and takes the library's own cudaMalloc buffers - importing PyTorch alone would cost
         # more than their whole run.
-        _mem.BACKEND = 'torch' if args.func is toolTestBatch else 'native'
+        _mem.BACKEND = 'torch' if args.func in (toolTestBatch, toolNewrefRank) else 'native'
     try:
         args.func(args)
     finally:

@@ -43,7 +43,7 @@ constexpr int MAX_STAGES = 6;
 constexpr int HIST_BINS = 256;
 constexpr int FIN_THREADS = 128;    // one thread per shortlisted candidate during the exact re-score
 constexpr int FIN_CHUNK = 32;       // samples staged per pipeline step of the re-score
-constexpr int FIN_ECAP = 2048;      // candidate entries of one row K6 collects in shared memory (24 KiB); more: exact fallback
+constexpr int FIN_ECAP = 1360;      // candidate entries of one row K6 collects in shared memory (16 KiB; later the target's own row: S <= 2040); more: read from the sources
 constexpr int FIN_LD = FIN_CHUNK + 1;   // padded tile row (bank-conflict free per-thread row walks)
 constexpr int FIN_LDB = FIN_CHUNK + 2;  // tile row of the 16-byte copy path: 16-byte aligned rows (2-way conflicts, cheap)
 constexpr int EXH_THREADS = 256;
@@ -139,6 +139,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // the 128-byte line prefetched into L2
 __device__ __forceinline__ void ldg_nc_v4f64(const double* p, double& a, double& b, double& c, double& d) {
     asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void sts_v2f64(uint32_t addr, double v0, double v1) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory");
 }
 __device__ __forceinline__ int bucket_of(double d, double mn, float scale) {
     int b = (int)((float)(d - mn) * scale);
@@ -884,6 +887,9 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     }
 
     // ---- 2. exact re-score ----
+    // (Tried and dropped, r02u/v: four lanes fetching one whole 128-byte line per load with a swizzled warp-private shared-memory
+    // patch transposing it back - the L2 request count fell 4x (lts 53 % -> 23 %) but the extra shared-memory wavefronts and the
+    // lost occupancy cost more: 6.5 / 9.0 ms against 6.2 ms.)
     // One thread per shortlisted candidate.  The candidate's row streams from L2 straight into registers - eight 256-bit
     // loads (32 samples) in flight per thread, nothing staged, no barrier inside the loop - while the target's own row is a
     // broadcast operand in shared memory.  The sum runs strictly in sample order with separately rounded subtract, multiply
@@ -1638,16 +1644,17 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         }
     };
     long long pivot_launches = 0;
+    // pivot pass (K5t): every target bin of the call starts the search proper with a threshold close to its final one
+    const int R = (use_tc && !dbg && ctx->k5_pivots != 0 && rows >= 2 * BM) ? pivot_count(N, k) : 0;
+    if (R > 0) {
+        if ((rc = tc_pivot_pass(ctx, stream, tmap, ta, reinterpret_cast<const __half*>(Xc), ldh, N, nrb, rb_seg_first, R))) return rc;
+        pivot_launches = 3;
+    }
+    WC_CUDA(cudaEventRecord(ctx->ev[17], stream));
     if (!sym) {
         launch(false, grid);
     } else {
         const int nb1 = nrb + 1;
-        const int R = (use_tc && !dbg && ctx->k5_pivots != 0) ? pivot_count(N, k) : 0;
-        if (R > 0) {                                                     // pivot pass: thresholds only
-            if ((rc = tc_pivot_pass(ctx, stream, tmap, ta, reinterpret_cast<const __half*>(Xc), ldh, N, nrb, rb_seg_first, R))) return rc;
-            pivot_launches = 3;
-        }
-        WC_CUDA(cudaEventRecord(ctx->ev[17], stream));
         ta.tile_list = d_sym + 2 * nb1;                                  // pass A
         ta.rb_list_off = d_sym;
         launch(false, gridA);
@@ -1716,6 +1723,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     ctx->counter[2] = total_tiles;                       // tiles the plain search computes (= counter 3 unless symmetric)
     ctx->counter[3] = sym ? tilesA + tilesB : total_tiles;
     ctx->counter[4] = sym ? std::max(gridA, gridB) : grid;
+    ctx->counter[7] = (f16 ? ctx->k5_f16 : 0) | (R << 4);
     return WC_OK;
 }
 

@@ -415,6 +415,7 @@ extern "C" int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* rec
     ctx->counter[2] = pl.tiles_plain;
     ctx->counter[3] = pl.tilesA + pl.tilesB;
     ctx->counter[4] = std::max(pl.gridA, pl.gridB);
+    ctx->counter[7] = pl.f16 | (pl.pivots << 4);
     return WC_OK;
 }
 

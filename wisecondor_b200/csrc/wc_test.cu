@@ -225,22 +225,22 @@ __device__ __forceinline__ double zs_stream_leaf(const double* cp, const int* ta
     for (; i < n; ++i) res = __dadd_rn(res, term(cp[(size_t)tab[i] * ldb]));
     return res;
 }
-// any n: numpy's halving above 128 elements (two levels cover n <= 512)
+// any n <= 512 (the table stride's limit): numpy's halving above 128 elements.  A half is len/2 rounded DOWN to a multiple of
+// 8 and the other half takes the rest, so a "quarter" of n = 489..512 can still exceed 128 (489 -> 240 + 249 -> 120 + 129):
+// three levels are needed before every piece is a leaf.
+template <bool DEV, int LEVELS>
+__device__ __forceinline__ double zs_stream_split(const double* cp, const int* tab, int n, size_t ldb, double mean,
+                                                  unsigned& worst) {
+    if (LEVELS == 0 || n <= 128) return zs_stream_leaf<DEV>(cp, tab, n, ldb, mean, worst);
+    int h = n / 2;
+    h -= h & 7;
+    const double a0 = zs_stream_split<DEV, (LEVELS > 0 ? LEVELS - 1 : 0)>(cp, tab, h, ldb, mean, worst);
+    return __dadd_rn(a0, zs_stream_split<DEV, (LEVELS > 0 ? LEVELS - 1 : 0)>(cp, tab + h, n - h, ldb, mean, worst));
+}
 template <bool DEV>
 __device__ __forceinline__ double zs_stream_sum(const double* cp, const int* tab, int n, size_t ldb, double mean,
                                                 unsigned& worst) {
-    if (n <= 128) return zs_stream_leaf<DEV>(cp, tab, n, ldb, mean, worst);
-    auto half = [&](const int* t, int len) {
-        if (len <= 128) return zs_stream_leaf<DEV>(cp, t, len, ldb, mean, worst);
-        int h = len / 2;
-        h -= h & 7;
-        const double a0 = zs_stream_leaf<DEV>(cp, t, h, ldb, mean, worst);
-        return __dadd_rn(a0, zs_stream_leaf<DEV>(cp, t + h, len - h, ldb, mean, worst));
-    };
-    int h = n / 2;
-    h -= h & 7;
-    const double a0 = half(tab, h);
-    return __dadd_rn(a0, half(tab + h, n - h));
+    return zs_stream_split<DEV, 3>(cp, tab, n, ldb, mean, worst);      // 3 levels: every piece of n <= 1024 is <= 128 + 7
 }
 
 // Slow path, warp-cooperative, for one lane whose reference values contain marked (-1) / negative / non-finite entries:

@@ -112,6 +112,8 @@ def last_search_stats(device=0):
         "dist_topk_first_pass_ms": ctx.phase_ms(8),
         "exhaustive_ms": ctx.phase_ms(3), "launches": ctx.counter(0), "exhaustive_rows": ctx.counter(1),
         "tiles": ctx.counter(3), "tiles_plain": ctx.counter(2), "ctas": ctx.counter(4),
+        "filter": max(0, ctx.counter(7)) & 3,          # 0: fp64 DMMA, 1: fp16 mma.sync, 2: fp16 tcgen05 / TMEM
+        "pivots": max(0, ctx.counter(7)) >> 4,         # pivots of the K5t pivot pass (0: none)
     }
 
 

@@ -14,20 +14,7 @@ import torch
 import torch.distributed as dist
 
 
-def row_shard(rank, world, bincount):
-    """Rows [start, end) of 0-based part `rank` of `world` (reference wisetools.py:358-361)."""
-    return int(bincount / float(world) * rank), int(bincount / float(world) * (rank + 1))
-
-
-def sample_shard(rank, world, nsamples):
-    """Contiguous block of samples for `rank`: sizes differ by at most one."""
-    base, extra = divmod(int(nsamples), int(world))
-    start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
-
-
-def max_shard_rows(world, bincount):
-    return max(row_shard(r, world, bincount)[1] - row_shard(r, world, bincount)[0] for r in range(world))
+from .partition import max_shard_rows, row_shard, sample_shard  # noqa: E402,F401  (torch-free definitions)
 
 
 def allgather_rows(idx_local, dist_local, bincount, group=None, out_idx=None, out_dist=None, scratch=None):
