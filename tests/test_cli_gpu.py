@@ -231,17 +231,39 @@ def test_config2_shape_prep_and_test_path_vs_oracle():
 
 
 def test_newref_on_two_gpus_equals_reference(workdir, tiny):
-    """`newref -gpus 2`: the parts run on two devices from two host threads; same reference file."""
+    """`newref -gpus 2`: one process per GPU, getPart row shards, rows gathered over NCCL (no part files); and the
+    `-partfiles` form (host threads + part files, resumable per part).  Same reference file either way."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     refs = [str(workdir / ("r%02d.npz" % i)) for i in range(tiny['ref_counts'].shape[0])]
     out = str(workdir / "two.npz")
-    _run(["newref"] + refs + [out, "-refsize", "40", "-gpus", "2", "-parts", "5"])
+    _run(["newref"] + refs + [out, "-refsize", "40", "-gpus", "2"])
     r = np.load(out, allow_pickle=True)
     assert np.array_equal(r['indexes'], tiny['ref_indexes'])
     _close(r['distances'], tiny['ref_distances'])
-    assert not os.path.exists(str(workdir / "two_part_3.npz"))
+    assert not os.path.exists(str(workdir / "two_part_1.npz")) and not os.path.exists(str(workdir / "two_prep.npz"))
+    out = str(workdir / "twofiles.npz")
+    _run(["newref"] + refs + [out, "-refsize", "40", "-gpus", "2", "-parts", "5", "-partfiles"])
+    r2 = np.load(out, allow_pickle=True)
+    assert np.array_equal(r2['indexes'], r['indexes']) and np.array_equal(r2['distances'], r['distances'])
+    assert not os.path.exists(str(workdir / "twofiles_part_3.npz"))
+
+
+def test_testbatch_on_two_gpus_equals_one(workdir, tiny):
+    """`testbatch -gpus 2`: the samples are sharded over two processes / devices; every result file equals the single-GPU one."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    outdir = str(workdir / "batch2")
+    tests = [str(workdir / ("t%d.npz" % t)) for t in (0, 1, 3)]
+    _run(["testbatch"] + tests + [outdir, str(workdir / "goldref.npz"), "-minrefbins", "10", "-batch", "2", "-gpus", "2"])
+    for t in (0, 1, 3):
+        res = np.load(os.path.join(outdir, "t%d.npz" % t), allow_pickle=True)
+        one = np.load(os.path.join(str(workdir / "batch"), "t%d.npz" % t), allow_pickle=True)
+        assert np.array_equal(np.concatenate(list(res['results_z'])), np.concatenate(list(one['results_z'])), equal_nan=True)
+        assert np.array_equal(np.asarray(res['results_calls']), np.asarray(one['results_calls']))
+        assert float(res['asdef']) == float(one['asdef'])
 
 
 def test_parts_interchangeable_with_the_reference_workers(workdir, tiny):
