@@ -414,11 +414,14 @@ def parity_check(device, torch, X, X_host_np, bins, k, table_idx, table_dist, ra
     import c_oracle
     n = int(sum(bins))
     rng = np.random.default_rng(11)
-    starts = [int(v) for v in rng.integers(0, n - rows_per_range, size=4)]
+    heavy = float(n) * X.shape[1] > 2e8          # the 2000 x 10 kb matrix: an oracle row costs 1.7 Gflop - fewer, shorter ranges
+    if heavy:
+        rows_per_range = 8
+    starts = [int(v) for v in rng.integers(0, n - rows_per_range, size=2 if heavy else 4)]
     if world > 1 and rows_per:
         for r in range(1, world):           # straddle the boundary between the bins of rank r-1 and rank r
             b = min(n - rows_per_range, max(0, r * rows_per - rows_per_range // 2))
-            if len(starts) < 8:
+            if len(starts) < (4 if heavy else 8):
                 starts.append(int(b))
     ti, td = table_idx.cpu().numpy(), table_dist.cpu().numpy()
     Xh = X_host_np if X_host_np is not None else X.cpu().numpy()

@@ -136,9 +136,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // 256-bit read-only streaming load (SASS LDG.E.NA.256.CONSTANT): four consecutive doubles, no L1 allocation, the rest of
-// the 128-byte line prefetched into L2
+// the 256-byte block prefetched into L2 (DRAM sees 256-byte requests: the rows of a matrix beyond the L2 are gathered at random)
 __device__ __forceinline__ void ldg_nc_v4f64(const double* p, double& a, double& b, double& c, double& d) {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 __device__ __forceinline__ void sts_v2f64(uint32_t addr, double v0, double v1) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory");
@@ -903,8 +903,9 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     __syncthreads();
     const uint32_t xi_u32 = smem_u32(xi_s);
     for (int c0 = 0; c0 < p; c0 += FT) {
-        if (c0 + tid < p) {
-            const int j = ex_j[c0 + tid];
+        if (c0 + warp * 32 < p) {                                // warp-uniform; idle lanes shadow the last candidate
+            const bool live = c0 + tid < p;
+            const int j = ex_j[live ? c0 + tid : p - 1];
             const double* xr = a.X + (size_t)j * a.S;
             double accd = 0.0;
             int t0 = 0;
@@ -913,6 +914,9 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
                     double v[32];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) ldg_nc_v4f64(xr + t0 + 4 * u, v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    // ptxas would sink the loads between the dependent adds (three in flight, 96 contiguous bytes); memory
+                    // operations do not move across a warp barrier, so all eight are issued here: 256 contiguous bytes per lane
+                    __syncwarp();
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
                         double x0, x1;
@@ -943,9 +947,12 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
                     accd = __dadd_rn(accd, __dmul_rn(d, d));
                 }
             }
-            const bool ok = accd < 1e10;     // wisetools.py:312-314: strict `<` against the 1e10 start value; NaN fails
-            ex_d[c0 + tid] = ok ? accd : INFINITY;
-            ex_j[c0 + tid] = ok ? j : 0x7fffffff;
+            __syncwarp();                    // every lane has read its candidate's bin before the live lanes overwrite theirs
+            if (live) {
+                const bool ok = accd < 1e10;     // wisetools.py:312-314: strict `<` against the 1e10 start value; NaN fails
+                ex_d[c0 + tid] = ok ? accd : INFINITY;
+                ex_j[c0 + tid] = ok ? j : 0x7fffffff;
+            }
         }
     }
     __syncthreads();
