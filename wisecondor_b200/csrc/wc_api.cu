@@ -65,6 +65,7 @@ extern "C" void wc_destroy(wc_ctx* ctx) {
     for (int i = 0; i < WC_NBUF; ++i)
         if (ctx->buf[i].p) cudaFree(ctx->buf[i].p);
     for (int i = 0; i < 2 * WC_NPHASE; ++i) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->search_plan && ctx->search_plan_free) ctx->search_plan_free(ctx->search_plan);
     delete ctx;
 }
 

@@ -38,7 +38,7 @@ struct wc_buf {
     size_t bytes = 0;
 };
 
-enum { WC_NBUF = 48, WC_NPHASE = 10, WC_NCOUNTER = 8 };
+enum { WC_NBUF = 56, WC_NPHASE = 12, WC_NCOUNTER = 12 };
 
 // Workspace slots (one grow-only device buffer each).
 enum {
@@ -49,7 +49,8 @@ enum {
     SLOT_T_COPY = 24, SLOT_T_ZT, SLOT_T_RT, SLOT_T_NT, SLOT_T_SD, SLOT_T_FLAGS, SLOT_T_TOTALS, SLOT_T_PROJ,   // test
     SLOT_T_REVCNT = 44, SLOT_T_REVCUR, SLOT_T_DIRTY, SLOT_T_PAIRS,
     SLOT_S_ZC = 32, SLOT_S_META, SLOT_S_STATUS, SLOT_S_RC, SLOT_S_AUX,                                                       // segmentation
-    SLOT_P_FIRST = 40                                                                                  // newref prep
+    SLOT_P_FIRST = 40,                                                                                 // newref prep
+    SLOT_FIN_J = 48, SLOT_FIN_D, SLOT_FIN_P, SLOT_FIN_GRP                                              // K6 split form: shortlists, exact distances, work list
 };
 
 // State of a sharded symmetric search between its three calls (wc_newref_shard_begin / _sweep / _finish).
@@ -79,16 +80,22 @@ struct wc_ctx {
     const int* zs_npairs_d = nullptr;    // device counters of the last wc_zscore_batch: listed pairs of pass 1..repeats-1
     int zs_repeats = 0;
     long long zs_pair_limit = 0, zs_all_pairs = 0;
+    void* search_plan = nullptr;         // host plan of the last search (wc_search.cu: SearchPlan), freed through search_plan_free
+    void (*search_plan_free)(void*) = nullptr;
     unsigned long long sched_hash = 0;   // fingerprint of the K5 schedule metadata currently on the device
     unsigned timed_mask = 0;        // phases whose event pair is recorded but not yet read (asynchronous calls)
     int k5_stages = 0;              // 0 = automatic TMA ring depth
     int k5_group = 0;               // CTAs sharing a row block per scheduling round of K5 (0 = automatic)
     int k5_sym = 8;                 // symmetric search: 0 = off, f >= 2 = on with 1/f of the block pairs in the first pass
     int k5_f16 = 2;                 // filter of K5: 0 fp64 (DMMA), 1 fp16 on mma.sync (HMMA), 2 fp16 on tcgen05 / TMEM (UTCHMMA)
+    int k5_f16_checked = 1;         // 1: K4h's fp16 range check is read at the end of the call (no sync before K5), 0: right after K4h
     int k5_pivots = 1;              // K5t: pivot pass before a symmetric search (0 = off)
     unsigned long long piv_hash = 0;   // fingerprint of the pivot pass' piece table on the device
     float* dbg_scores = nullptr;    // wc_debug_filter_scores: where K5t dumps its filter distances (caller-owned), or NULL
     int dbg_ld = 0;
+    const int* k6_stats_d = nullptr;   // device counters of the last split K6: [0] live entries, [1] shortlisted candidates
+    int k6_split = 1;               // K6: 1 = select -> streaming re-score (bulk copies) -> rank, 0 = fused kernel
+    int k6_chunk = 0, k6_warps = 0, k6_prod = 0;     // K6c tuning: samples per chunk, consumer / producer warps (0 = default)
     int k5_lag = 0;                 // chunks the trailing consumer warps of K5 lag behind the leading ones
     int debug_profile = 0;          // K5 writes per-CTA cycle counters when set (wc_debug_profile)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)

@@ -99,6 +99,7 @@ struct TopkArgs {
     int in_cap;
     const u64* col_thr;          // thresholds indexed by GLOBAL bin (== row_thr when the launch starts at row 0)
     double madd;                 // margin(v) = mcoef * (n_i + |v|) + madd  (0 for the fp64 filter)
+    const double* madd_p;        // when set: madd lives on the device (written by wc_f16_margin_kernel - no host round trip)
     const float* n32;            // fp16 filter: the bins' squared norms in fp32, +inf for padding rows
     const float* coln32;         // K5t: norms of the COLUMN rows (== n32, or the pivot matrix' norms in the pivot pass)
     const int* col_ids;          // K5t pivot pass: global bin of every row of the pivot matrix (nullptr: columns are bins)
@@ -157,6 +158,8 @@ inline u64 host_key_of_tau(double tau) {
     return bits;
 }
 __device__ __forceinline__ double dist_of_key(u64 key) { return -2.0 * __longlong_as_double((long long)key); }
+template <typename Args>
+__device__ __forceinline__ double madd_of(const Args& a) { return a.madd_p != nullptr ? __ldg(a.madd_p) : a.madd; }
 
 // Warp-collective prune of one row's candidate buffer, on score keys (unsigned order == distance order).  The
 // buffer is copied once into the warp's shared scratch with independent L2 loads; an integer bisection finds a
@@ -359,9 +362,9 @@ wc_dist_topk_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs a) 
             int* rj = cj + (size_t)(r0w + rw) * a.cap;
             __threadfence_block();
             if (a.cap <= 512)
-                prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
+                prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, madd_of(a), lane, w_sk, w_sj, &thr, &kept);
             else
-                prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
+                prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, madd_of(a), lane, w_sk, w_sj, &thr, &kept);
             if (lane == 0) {
                 if (kept > a.cap - BN) {       // a tie plateau wider than the buffer: exact fallback
                     w_flag[rw] = 1;
@@ -712,9 +715,17 @@ struct FinArgs {
     const int* in_cnt;
     int in_cap;
     double madd;            // window(v) = v + mcoef * (n_i + |v|) + madd
+    const double* madd_p;   // when set: madd lives on the device
     const u64* row_thr;     // [rows] the tightest threshold key K5 published for the row (entries beyond it cannot rank), or nullptr
     int in_nsrc;            // incoming sources (1; one per rank after the exchange of a sharded symmetric search)
     int in_src_rows;        // rows between two sources: source s holds row r at (s * in_src_rows + r)
+    // split form (select -> streaming re-score -> rank): the shortlist leaves the CTA
+    int* sl_j;              // [rows][shortcap] shortlisted bins
+    int* sl_p;              // [rows] shortlist length; -1: the row is finished elsewhere (no candidates / exhaustive fallback)
+    int* grp;               // work list of the re-score: (row << 4 | group of 32 shortlist slots)
+    int* grp_count;
+    const int* row_list;    // rows this launch handles (grid-stride), or nullptr: row = blockIdx.x
+    const int* row_count;
 };
 
 // One CTA per target row.
@@ -725,9 +736,9 @@ struct FinArgs {
 //     operands: sequential over samples, separately rounded subtract / multiply / add); one thread per
 //     candidate, candidate rows staged through shared memory by cp.async in 32-sample chunks, double buffered.
 //  3. rank by (distance, index), write the first k with indices remapped to other-chromosome coordinates.
-template <int FT>      // threads = shortlisted candidates re-scored per round: 128, or 160 behind the wider window of the fp16 filters
-__global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
-    extern __shared__ __align__(32) unsigned char fin_raw[];
+// SPLIT: stop after step 1 and hand the shortlist to the streaming re-score (wc_fin_rescore_kernel) through global memory.
+template <int FT, bool SPLIT>      // threads = shortlisted candidates re-scored per round: 128, or 160 behind the wider window of the fp16 filters
+__device__ __forceinline__ void finalize_row(const FinArgs& a, const int rloc, unsigned char* fin_raw) {
     constexpr int ecap = FIN_ECAP;                                         // collected entries: [ecap] keys, [ecap] bins
     double* ex_d = reinterpret_cast<double*>(fin_raw + (size_t)ecap * 12); // shortcap
     int* ex_j = reinterpret_cast<int*>(ex_d + a.shortcap);                 // shortcap
@@ -736,7 +747,6 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     __shared__ int s_total, s_flag, s_p, s_bstar, s_valid;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rloc = blockIdx.x;
     const int row = a.row_begin + rloc;
     const int rb = rloc / BM, rl = rloc % BM;
     const int seg0 = a.rb_seg_first[rb], nseg = a.rb_seg_count[rb];
@@ -795,11 +805,15 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     __syncthreads();
     const int total = s_total;
     if (s_flag) {
-        if (tid == 0) a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+        if (tid == 0) {
+            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+            if (SPLIT) a.sl_p[rloc] = -1;
+        }
         return;
     }
     if (total == 0) {
         for (int e = tid; e < a.k; e += FT) { out_i[e] = -1; out_d[e] = 1e10; }
+        if (SPLIT && tid == 0) a.sl_p[rloc] = -1;
         return;
     }
     // The select passes visit every live entry of the row: from shared memory when the collection fitted (the normal case),
@@ -872,7 +886,7 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < FT / 32; ++w) vstar = fmax(vstar, s_red[0][w]);
-    const double window = vstar + a.mcoef * (a.norms[row] + fabs(vstar)) + a.madd;
+    const double window = vstar + a.mcoef * (a.norms[row] + fabs(vstar)) + madd_of(a);
     for_each_entry([&](u64 key, int j) {
         if (dist_of_key(key) <= window) {
             const int slot = atomicAdd(&s_p, 1);
@@ -882,7 +896,20 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     __syncthreads();
     const int p = s_p;
     if (p > a.shortcap) {                               // tie plateau wider than the shortlist: exact fallback
-        if (tid == 0) a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+        if (tid == 0) {
+            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+            if (SPLIT) a.sl_p[rloc] = -1;
+        }
+        return;
+    }
+    if (SPLIT) {                                        // the shortlist goes to the streaming re-score, 32 slots per work item
+        for (int e = tid; e < p; e += FT) a.sl_j[(size_t)rloc * a.shortcap + e] = ex_j[e];
+        if (tid == 0) {
+            a.sl_p[rloc] = p;
+            const int ng = (p + 31) >> 5;
+            const int base = atomicAdd(a.grp_count, ng);
+            for (int g = 0; g < ng; ++g) a.grp[base + g] = (rloc << 4) | g;
+        }
         return;
     }
 
@@ -975,6 +1002,22 @@ __global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
     atomicAdd(&s_valid, nvalid_local);
     __syncthreads();
     for (int e = s_valid + tid; e < a.k; e += FT) { out_i[e] = -1; out_d[e] = 1e10; }
+}
+
+// One CTA per target row (grid = rows), or - with a row list (the rows the warp-per-row select of the split form passed on:
+// more live entries than a warp holds) - a fixed grid striding over the list.
+template <int FT, bool SPLIT>
+__global__ void __launch_bounds__(FT) wc_finalize_kernel(const FinArgs a) {
+    extern __shared__ __align__(32) unsigned char fin_raw[];
+    if (a.row_list == nullptr) {
+        finalize_row<FT, SPLIT>(a, (int)blockIdx.x, fin_raw);
+        return;
+    }
+    const int n = *a.row_count;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        finalize_row<FT, SPLIT>(a, a.row_list[b], fin_raw);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1078,6 +1121,8 @@ namespace {
 // together.  The CTAs then sit on (nearly) the same B panel at the same time - it is read from DRAM once per round -
 // and the live A panels (grid/G of them) stay L2-resident.  Row blocks left after the last full round are cut into
 // contiguous ranges that level the CTAs' tile counts (water-filling), so the balance of the plain equal split is kept.
+#include "wc_search_fin.cuh"      // K6 split form: streaming re-score + rank, and the K6 launch shared by both search entries
+
 struct Piece { int cta, rb, q0, q1, step, seg, pass; };
 void schedule_pieces(const std::vector<int>& prefix, int nrb, int grid, int G, bool rounds_on, int pass,
                      std::vector<Piece>& pieces) {
@@ -1287,6 +1332,26 @@ extern "C" int wc_debug_sym_plan(int N, const int* chrom_bins_h, int nchrom, int
     return WC_OK;
 }
 
+namespace {
+// madd of the fp16 filter from K4h's statistics (stats[0] = bits of the largest norm): out = 2 eps nmax + 2^-20 sqrt(S nmax)
+__global__ void wc_f16_margin_kernel(const unsigned long long* __restrict__ stats, int S, double eps16, double* __restrict__ out) {
+    const double nmax = __longlong_as_double((long long)stats[0]);
+    out[0] = 2.0 * eps16 * nmax + ldexp(1.0, -20) * sqrt((double)S * nmax);
+}
+}  // namespace
+
+namespace {
+// Host plan of a search (see wc_newref_topk), cached in the context between identical calls.
+struct SearchPlan {
+    unsigned long long key = 0, content_hash = 0;
+    bool valid = false;
+    std::vector<int> row_cs, row_ce, skip_lo, skip_n, rb_seg_first, rb_seg_count, cta_piece_begin, piece_tab, sym_tab;
+    int nrb = 0, total_tiles = 0, grid = 0, sym = 0, sym_frac = 0, gridA = 0, gridB = 0, grid0 = 0, nseg = 0;
+    long long tilesA = 0, tilesB = 0;
+    size_t listA_size = 0;
+};
+}  // namespace
+
 extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int S, const int* chrom_bins_h,
                               int nchrom, int row_begin, int row_end, int refsize, int32_t* idx_d, double* dist_d,
                               void* stream_v) {
@@ -1322,7 +1387,26 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     const size_t Npad = (size_t)(N + BN - 1) / BN * BN + BN;
     const double mcoef = 16.0 * (double)(S + 16) * 1.1102230246251565e-16;
 
-    // ---- per-row exclusion ranges and the (row block, column tile) work list -----------------------------
+    // ---- host plan: exclusion ranges, work list, schedule.  A pure function of (N, chromosome sizes, row range, refsize, SM
+    //      count, options): repeated calls on the same problem (bench loops, the parts of one newref) reuse it - building it
+    //      costs ~0.5 ms of host time at 50 kb during which the GPU would idle ----
+    unsigned long long plan_key = 1469598103934665603ull;
+    {
+        auto mixk = [&](const void* p, size_t bytes) {
+            const unsigned char* c = static_cast<const unsigned char*>(p);
+            for (size_t i = 0; i < bytes; ++i) { plan_key ^= c[i]; plan_key *= 1099511628211ull; }
+        };
+        mixk(chrom_bins_h, (size_t)nchrom * sizeof(int));
+        const int dims[10] = {N, nchrom, row_begin, row_end, refsize, ctx->sm_count, ctx->k5_sym, ctx->k5_group, ctx->k5_f16, 0x5ea7c4};
+        mixk(dims, sizeof(dims));
+    }
+    if (ctx->search_plan == nullptr) {
+        ctx->search_plan = new SearchPlan();
+        ctx->search_plan_free = [](void* q) { delete static_cast<SearchPlan*>(q); };
+    }
+    SearchPlan& P = *static_cast<SearchPlan*>(ctx->search_plan);
+    if (P.key != plan_key || !P.valid) {
+    P.valid = false;
     std::vector<int> row_cs(N), row_ce(N);
     {
         int pos = 0;
@@ -1455,6 +1539,38 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         sym_tab.insert(sym_tab.end(), listB.begin(), listB.end());
     }
 
+    P.row_cs.swap(row_cs); P.row_ce.swap(row_ce); P.skip_lo.swap(skip_lo); P.skip_n.swap(skip_n);
+    P.rb_seg_first.swap(rb_seg_first); P.rb_seg_count.swap(rb_seg_count); P.cta_piece_begin.swap(cta_piece_begin);
+    P.piece_tab.swap(piece_tab); P.sym_tab.swap(sym_tab);
+    P.nrb = nrb; P.total_tiles = total_tiles; P.grid = grid; P.sym = sym ? 1 : 0; P.sym_frac = sym_frac; P.gridA = gridA; P.gridB = gridB;
+    P.grid0 = grid0; P.nseg = nseg; P.tilesA = tilesA; P.tilesB = tilesB; P.listA_size = listA.size();
+    {   // fingerprint of what the device copy of the metadata must hold
+        unsigned long long h = 1469598103934665603ull;
+        auto mix = [&](const void* p, size_t bytes) {
+            const unsigned char* c = static_cast<const unsigned char*>(p);
+            for (size_t i = 0; i < bytes; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+        };
+        mix(chrom_bins_h, (size_t)nchrom * sizeof(int));
+        const int dims[8] = {N, row_begin, row_end, grid0, nrb, nseg, sym ? sym_frac : 0, gridB};
+        mix(dims, sizeof(dims));
+        mix(P.piece_tab.data(), P.piece_tab.size() * sizeof(int));
+        mix(P.cta_piece_begin.data(), P.cta_piece_begin.size() * sizeof(int));
+        P.content_hash = h;
+    }
+    P.key = plan_key;
+    P.valid = true;
+    }
+    const std::vector<int>& row_cs = P.row_cs; const std::vector<int>& row_ce = P.row_ce;
+    const std::vector<int>& skip_lo = P.skip_lo; const std::vector<int>& skip_n = P.skip_n;
+    const std::vector<int>& rb_seg_first = P.rb_seg_first; const std::vector<int>& rb_seg_count = P.rb_seg_count;
+    const std::vector<int>& cta_piece_begin = P.cta_piece_begin; const std::vector<int>& piece_tab = P.piece_tab;
+    const std::vector<int>& sym_tab = P.sym_tab;
+    const int nrb = P.nrb, total_tiles = P.total_tiles, grid = P.grid, gridA = P.gridA, gridB = P.gridB, grid0 = P.grid0, nseg = P.nseg;
+    const bool sym = P.sym != 0;
+    const int sym_frac = P.sym_frac;
+    const long long tilesA = P.tilesA, tilesB = P.tilesB;
+    const size_t listA_size = P.listA_size;
+
     // ---- workspace ----------------------------------------------------------------------------------------
     double* Xc; double* norms; int* d_row_cs; int* d_row_ce; int* d_meta;
     u64* cand_key; int* cand_j; int* seg_cnt; int* seg_flag; int* slow;
@@ -1493,20 +1609,10 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     int* d_sym = d_pieces + piece_tab.size();
 
     {
-        // the metadata is a pure function of (N, chromosome sizes, row range, grid): repeated calls on the same problem
-        // (bench loops, the parts of one newref on one GPU) find it on the device already
-        unsigned long long h = 1469598103934665603ull;
-        auto mix = [&](const void* p, size_t bytes) {
-            const unsigned char* c = static_cast<const unsigned char*>(p);
-            for (size_t i = 0; i < bytes; ++i) { h ^= c[i]; h *= 1099511628211ull; }
-        };
+        // repeated calls on the same problem find the metadata on the device already
+        unsigned long long h = P.content_hash;
         const unsigned long long ptrs[2] = {(unsigned long long)(uintptr_t)d_row_cs, (unsigned long long)(uintptr_t)d_meta};
-        mix(ptrs, sizeof(ptrs));
-        mix(chrom_bins_h, (size_t)nchrom * sizeof(int));
-        const int dims[8] = {N, row_begin, row_end, grid0, nrb, nseg, sym ? sym_frac : 0, gridB};
-        mix(dims, sizeof(dims));
-        mix(piece_tab.data(), piece_tab.size() * sizeof(int));
-        mix(cta_piece_begin.data(), cta_piece_begin.size() * sizeof(int));
+        for (int i = 0; i < 2; ++i) { h ^= ptrs[i]; h *= 1099511628211ull; }
         if (h != ctx->sched_hash) {
             WC_CUDA(cudaMemcpyAsync(d_row_cs, row_cs.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, stream));
             WC_CUDA(cudaMemcpyAsync(d_row_ce, row_ce.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1534,20 +1640,29 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     const int ldh = (S + BKH - 1) / BKH * BKH;
     float* n32 = nullptr;
     double nmax = 0.0;
+    const double eps16 = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (double)ldh * ldexp(1.0, -23) + ldexp(1.0, -21);
+    const unsigned long long* f16_stats_d = nullptr;       // set: K4h's range flag is checked at the end of the call
     WC_CUDA(cudaEventRecord(ctx->ev[0], stream));
     if (f16) {
         unsigned long long* stats;
         if ((rc = wc_reserve(ctx, SLOT_N32, Npad * sizeof(float), (void**)&n32))) return rc;
-        if ((rc = wc_reserve(ctx, SLOT_F16STAT, 2 * sizeof(unsigned long long), (void**)&stats))) return rc;
+        if ((rc = wc_reserve(ctx, SLOT_F16STAT, 4 * sizeof(unsigned long long), (void**)&stats))) return rc;
         WC_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), stream));
         wc_prepare_f16_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ldh,
                                                                                   reinterpret_cast<__half*>(Xc), norms, n32, stats);
         WC_CUDA(cudaGetLastError());
-        unsigned long long st_h[2] = {0, 0};
-        WC_CUDA(cudaMemcpyAsync(st_h, stats, sizeof(st_h), cudaMemcpyDeviceToHost, stream));
-        WC_CUDA(cudaStreamSynchronize(stream));
-        memcpy(&nmax, &st_h[0], sizeof(double));
-        if (st_h[1] != 0) f16 = false;            // |x - 1| > 60000 somewhere: outside fp16's range
+        if (ctx->k5_f16_checked != 0) {
+            // the range check and the largest norm come back at the end of the call (with the fallback-row counter): no
+            // host round trip between K4h and K5; a matrix outside fp16's range repeats the call with the fp64 filter
+            f16_stats_d = stats;
+            wc_f16_margin_kernel<<<1, 1, 0, stream>>>(stats, S, eps16, reinterpret_cast<double*>(stats + 2));
+        } else {
+            unsigned long long st_h[2] = {0, 0};
+            WC_CUDA(cudaMemcpyAsync(st_h, stats, sizeof(st_h), cudaMemcpyDeviceToHost, stream));
+            WC_CUDA(cudaStreamSynchronize(stream));
+            memcpy(&nmax, &st_h[0], sizeof(double));
+            if (st_h[1] != 0) f16 = false;            // |x - 1| > 60000 somewhere: outside fp16's range
+        }
     }
     if (!f16) {
         const int blocks = (int)((Npad * 32 + 255) / 256);
@@ -1557,7 +1672,6 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     WC_CUDA(cudaEventRecord(ctx->ev[1], stream));
     // error of the fp16 filter: |d~ - d| <= eps * (n_i + n_j) + sub; eps = operand rounding (2 x 2^-11), fp32 accumulation
     // of ldh products (taken one bit worse than IEEE), the fp32 epilogue; sub = fp16 subnormal spacing on tiny values
-    const double eps16 = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (double)ldh * ldexp(1.0, -23) + ldexp(1.0, -21);
     const double filt_mcoef = f16 ? 2.0 * eps16 : mcoef;
     const double filt_madd = f16 ? 2.0 * eps16 * nmax + ldexp(1.0, -20) * sqrt((double)S * nmax) : 0.0;
 
@@ -1596,6 +1710,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     ta.tile_list = nullptr; ta.rb_list_off = nullptr; ta.final_prune = sym ? 1 : 0;
     ta.in_key = in_key; ta.in_j = in_j; ta.in_cnt = in_cnt; ta.in_cap = in_cap; ta.col_thr = row_thr;
     ta.madd = filt_madd; ta.n32 = n32;
+    ta.madd_p = f16_stats_d != nullptr ? reinterpret_cast<const double*>(f16_stats_d + 2) : nullptr;
     ta.dbg = f16 && tc ? ctx->dbg_scores : nullptr; ta.dbg_ld = ctx->dbg_ld;
     ta.prof = nullptr;
     ta.trace = nullptr;
@@ -1667,7 +1782,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         launch(false, gridA);
         WC_CUDA(cudaGetLastError());
         WC_CUDA(cudaEventRecord(ctx->ev[16], stream));
-        ta.tile_list = d_sym + 2 * nb1 + (int)listA.size();              // pass B
+        ta.tile_list = d_sym + 2 * nb1 + (int)listA_size;              // pass B
         ta.rb_list_off = d_sym + nb1;
         ta.cta_piece_begin = d_cta_piece + (gridA + 1);
         launch(true, gridB);
@@ -1684,23 +1799,30 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     fa.mcoef = filt_mcoef; fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
     fa.vec = (S % 4 == 0 && (reinterpret_cast<uintptr_t>(corrected_d) & 31) == 0) ? 4 : 1;
     fa.in_key = in_key; fa.in_j = in_j; fa.in_cnt = in_cnt; fa.in_cap = in_cap; fa.in_nsrc = 1; fa.in_src_rows = 0;
-    fa.madd = filt_madd; fa.row_thr = row_thr;
-    const size_t fin_smem = (size_t)FIN_ECAP * 12 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
+    fa.madd = filt_madd; fa.row_thr = row_thr; fa.madd_p = ta.madd_p;
     WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
-    if (f16) {
-        WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-        wc_finalize_kernel<160><<<rows, 160, fin_smem, stream>>>(fa);
-    } else {
-        WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<FIN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-        wc_finalize_kernel<FIN_THREADS><<<rows, FIN_THREADS, fin_smem, stream>>>(fa);
-    }
-    WC_CUDA(cudaGetLastError());
+    long long fin_launches = 0;
+    if ((rc = launch_finalize(ctx, stream, fa, (int)rows, f16 != 0, &fin_launches))) return rc;
     WC_CUDA(cudaEventRecord(ctx->ev[5], stream));
 
-    int nslow = 0;
+    int nslow = 0, k6_stats[4] = {0, 0, 0, 0};
     WC_CUDA(cudaMemcpyAsync(&nslow, slow, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (ctx->k6_stats_d != nullptr) WC_CUDA(cudaMemcpyAsync(k6_stats, ctx->k6_stats_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    unsigned long long f16_flag = 0;
+    if (f16_stats_d != nullptr) WC_CUDA(cudaMemcpyAsync(&f16_flag, f16_stats_d + 1, sizeof(f16_flag), cudaMemcpyDeviceToHost, stream));
     WC_CUDA(cudaStreamSynchronize(stream));
-    long long launches = (sym ? 6 : 5) + pivot_launches;          // two fills, K4, K5 (one or two passes; pivot select + gather + pass), K6
+    if (f16_flag != 0) {                                 // |x - 1| > 60000 somewhere: outside fp16's range - the fp64 filter
+        const int keep = ctx->k5_f16;
+        ctx->k5_f16 = 0;
+        rc = wc_newref_topk(ctx, corrected_d, N, S, chrom_bins_h, nchrom, row_begin, row_end, refsize, idx_d, dist_d, stream_v);
+        ctx->k5_f16 = keep;
+        return rc;
+    }
+    ctx->counter[8] = k6_stats[1];                       // K6 split form: live entries / shortlisted candidates over all rows
+    ctx->counter[9] = k6_stats[2];
+    ctx->counter[10] = k6_stats[0];
+    ctx->counter[11] = k6_stats[3];
+    long long launches = (sym ? 5 : 4) + pivot_launches + fin_launches;   // two fills, K4, K5 (one or two passes; pivot select + gather + pass), K6 (1 fused, or reset + select + re-score + rank)
     if (nslow > 0) {
         const int batch = 64;
         double* scratch;
@@ -1813,6 +1935,10 @@ extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
         ctx->k5_pivots = value != 0 ? 1 : 0;
         return WC_OK;
     }
+    if (strcmp(key, "k6_split") == 0) { ctx->k6_split = value != 0 ? 1 : 0; return WC_OK; }      // K6: split (streaming re-score) / fused
+    if (strcmp(key, "k6_chunk") == 0) { WC_CHECK_ARG(value >= 0 && value <= 480); ctx->k6_chunk = (int)value; return WC_OK; }
+    if (strcmp(key, "k6_warps") == 0) { WC_CHECK_ARG(value >= 0 && value <= 16); ctx->k6_warps = (int)value; return WC_OK; }
+    if (strcmp(key, "k6_prod") == 0) { WC_CHECK_ARG(value >= 0 && value <= 8); ctx->k6_prod = (int)value; return WC_OK; }
     if (strcmp(key, "k5_stages") == 0) {
         WC_CHECK_ARG(value == 0 || (value >= 3 && value <= MAX_STAGES));
         ctx->k5_stages = (int)value;

@@ -177,9 +177,9 @@ wc_dist_topk_f16_kernel(const __grid_constant__ CUtensorMap tmap, const TopkArgs
             int* rj = cj + (size_t)(r0w + rw) * a.cap;
             __threadfence_block();
             if (a.cap <= 512)
-                prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
+                prune_row<16>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, madd_of(a), lane, w_sk, w_sj, &thr, &kept);
             else
-                prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, a.madd, lane, w_sk, w_sj, &thr, &kept);
+                prune_row<32>(rk, rj, n, a.k, w_nrm[rw], a.mcoef, madd_of(a), lane, w_sk, w_sj, &thr, &kept);
             if (lane == 0) {
                 if (kept > a.cap - BN) {
                     w_flag[rw] = 1;

@@ -1,0 +1,544 @@
+// wisecondor_b200 - K6 in split form: select (wc_finalize_kernel<FT, true>) -> streaming exact re-score -> rank.
+// Textually included by wc_search.cu inside its anonymous namespace (uses FinArgs, pair_less and the mbarrier helpers).
+#pragma once
+
+// ---------------------------------------------------------------------------------------------------------
+// K6a  wc_fin_select_kernel: one WARP per target bin picks its shortlist
+// ---------------------------------------------------------------------------------------------------------
+// Same decision as step 0-1 of wc_finalize_kernel (entries within the filter's error window of the k-th smallest filter
+// distance; everything beyond the row's final threshold dropped first), organised for memory-level parallelism: the row's
+// entries sit in ~10 separate buffers (one per K5 segment, plus the incoming buffers) that are cold in L2 when K6 starts,
+// and the CTA-per-row kernel walked them source after source - two dependent DRAM round trips per source and warp, 0.77 ms
+// at 600 x 50 kb for 0.5 GB.  Here a lane reads the counts of a source each (one round trip), a shared prefix table maps a
+// flat entry number to (source, offset), and every lane has SEL_U independent entry loads in flight (second round trip).
+// The k-th smallest key is found by integer bisection on keys held in registers (as in prune_row), exact up to ties.
+// Rows with more than SEL_ECAP live entries or more than SEL_MAXSRC sources (never-pruned rows of small matrices) go to `big_list`
+// and are handled by wc_finalize_kernel<FT, true> afterwards.
+constexpr int SEL_WARPS = 4;
+constexpr int SEL_ECAP = 1024;               // live entries of a row held by its warp: 32 keys per lane (typical: 400-800)
+constexpr int SEL_EPL = SEL_ECAP / 32;
+constexpr int SEL_U = 4;                     // entry loads in flight per lane
+constexpr int SEL_MAXSRC = 255;           // sources of a row: two per K5 piece of its row block, plus the incoming buffers
+constexpr size_t SEL_WARP_BYTES = (size_t)SEL_ECAP * 12 + (SEL_MAXSRC + 1) * 4 + 12;      // keys, bins, prefix table
+constexpr size_t SEL_WARP_STRIDE = (SEL_WARP_BYTES + 15) / 16 * 16;
+
+__global__ void __launch_bounds__(SEL_WARPS * 32) wc_fin_select_kernel(const FinArgs a, int* __restrict__ big_list,
+                                                                       int* __restrict__ big_count, int* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char sel_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rloc = blockIdx.x * SEL_WARPS + warp;
+    const int rows = a.row_end - a.row_begin;
+    if (rloc >= rows) return;
+    u64* en_k = reinterpret_cast<u64*>(sel_raw + (size_t)warp * SEL_WARP_STRIDE);
+    int* en_j = reinterpret_cast<int*>(en_k + SEL_ECAP);
+    int* pre = en_j + SEL_ECAP;                                   // [nsrc + 1] exclusive prefix of the sources' counts
+    const int row = a.row_begin + rloc;
+    const int rb = rloc / BM, rl = rloc % BM;
+    const int seg0 = a.rb_seg_first[rb], nseg = a.rb_seg_count[rb];
+    const int nsrc = nseg + (a.in_key != nullptr ? a.in_nsrc : 0);
+    int* out_i = a.idx_out + (size_t)rloc * a.k;
+    double* out_d = a.dist_out + (size_t)rloc * a.k;
+    auto to_big = [&]() {
+        if (lane == 0) {
+            big_list[atomicAdd(big_count, 1)] = rloc;
+            a.sl_p[rloc] = -1;                                     // the fallback kernel overwrites it
+        }
+    };
+    if (nsrc > SEL_MAXSRC) { to_big(); return; }
+    // ---- counts and flags of all sources: one round trip ----
+    int flagged = 0;
+    for (int s0 = 0; s0 < nsrc; s0 += 32) {
+        const int s = s0 + lane;
+        int n = 0;
+        if (s < nsrc) {
+            if (s < nseg) {
+                n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
+                flagged |= a.seg_flag[(size_t)(seg0 + s) * BM + rl];
+            } else {
+                n = a.in_cnt[(size_t)(s - nseg) * a.in_src_rows + rloc];
+                if (n > a.in_cap) { flagged = 1; n = a.in_cap; }   // more offers than the buffer holds: exact fallback
+            }
+        }
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int base = s0 == 0 ? 0 : pre[s0];
+        if (s < nsrc) pre[s + 1] = base + incl;
+        if (s0 == 0 && lane == 0) pre[0] = 0;
+        __syncwarp();
+    }
+    if (__any_sync(0xffffffffu, flagged != 0)) {
+        if (lane == 0) {
+            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+            a.sl_p[rloc] = -1;
+        }
+        return;
+    }
+    const int total_raw = pre[nsrc];
+    const u64 tfinal = a.row_thr != nullptr ? __ldcg(a.row_thr + rloc) : ~0ull;
+    // ---- entries: SEL_U independent loads per lane and round; those beyond the row's final threshold are dead weight ----
+    int kept = 0;
+    for (int t0 = 0; t0 < total_raw; t0 += 32 * SEL_U) {
+        u64 key[SEL_U];
+        int jj[SEL_U];
+#pragma unroll
+        for (int u = 0; u < SEL_U; ++u) {
+            const int t = t0 + u * 32 + lane;
+            key[u] = ~0ull;
+            jj[u] = 0;
+            if (t < total_raw) {
+                int lo = 0, hi = nsrc;                              // largest s with pre[s] <= t
+                while (hi - lo > 1) {
+                    const int m = (lo + hi) >> 1;
+                    if (pre[m] <= t) lo = m; else hi = m;
+                }
+                const int e = t - pre[lo];
+                size_t off;
+                const u64* kb;
+                const int* jb;
+                if (lo < nseg) {
+                    off = ((size_t)(seg0 + lo) * BM + rl) * a.cap + e;
+                    kb = a.cand_key;
+                    jb = a.cand_j;
+                } else {
+                    off = ((size_t)(lo - nseg) * a.in_src_rows + rloc) * a.in_cap + e;
+                    kb = a.in_key;
+                    jb = a.in_j;
+                }
+                key[u] = kb[off];
+                jj[u] = jb[off];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SEL_U; ++u) {
+            const bool keep = t0 + u * 32 + lane < total_raw && key[u] <= tfinal;
+            const unsigned bm = __ballot_sync(0xffffffffu, keep);
+            const int pos = kept + __popc(bm & ((1u << lane) - 1u));
+            if (keep && pos < SEL_ECAP) {
+                en_k[pos] = key[u];
+                en_j[pos] = jj[u];
+            }
+            kept += __popc(bm);
+        }
+    }
+    if (kept > SEL_ECAP) { to_big(); return; }
+    if (kept == 0) {
+        for (int e = lane; e < a.k; e += 32) { out_i[e] = -1; out_d[e] = 1e10; }
+        if (lane == 0) a.sl_p[rloc] = -1;
+        return;
+    }
+    __syncwarp();
+    // ---- k-th smallest key (unsigned order == distance order) by bisection on a register copy ----
+    u64 d[SEL_EPL];
+#pragma unroll
+    for (int t = 0; t < SEL_EPL; ++t) d[t] = t * 32 + lane < kept ? en_k[t * 32 + lane] : ~0ull;
+    u64 lo = ~0ull, hi = 0ull;
+#pragma unroll
+    for (int t = 0; t < SEL_EPL; ++t) {
+        if (t * 32 + lane < kept) {
+            lo = d[t] < lo ? d[t] : lo;
+            hi = d[t] > hi ? d[t] : hi;
+        }
+    }
+    lo = warp_min_u64(lo);
+    hi = warp_max_u64(hi);
+    u64 blo = lo, bhi = hi, cut = hi;            // count(<= cut) >= min(k, kept) throughout
+    int c_hi = kept;
+    for (int it = 0; it < 70 && c_hi > a.k; ++it) {
+        if (bhi - blo < 2) break;                // bracket exhausted (ties at the k-th place): keep the current cut
+        const u64 mid = blo + ((bhi - blo) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int t = 0; t < SEL_EPL; ++t) c += d[t] <= mid ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (c >= a.k) { bhi = mid; c_hi = c; cut = mid; } else { blo = mid; }
+    }
+    u64 vstar = 0ull;
+#pragma unroll
+    for (int t = 0; t < SEL_EPL; ++t)
+        if (d[t] <= cut && d[t] > vstar) vstar = d[t];
+    vstar = warp_max_u64(vstar);
+    const double dv = dist_of_key(vstar);
+    // (filter distances <= 0 - rounding noise of duplicates - order backwards as keys: the window then starts at 0, and their
+    // keys, sign bit clear, pass any positive window)
+    double window = fmax(dv, 0.0) + a.mcoef * (a.norms[row] + fabs(dv)) + madd_of(a);
+    if (!(window > 1e-300)) window = 1e-300;
+    const u64 wkey = key_of_tau(window);
+    // ---- shortlist: entries within the window, in entry order ----
+    int p = 0;
+#pragma unroll
+    for (int t = 0; t < SEL_EPL; ++t) {
+        const bool keep = t * 32 + lane < kept && d[t] <= wkey;
+        const unsigned bm = __ballot_sync(0xffffffffu, keep);
+        const int pos = p + __popc(bm & ((1u << lane) - 1u));
+        if (keep && pos < a.shortcap) a.sl_j[(size_t)rloc * a.shortcap + pos] = en_j[t * 32 + lane];
+        p += __popc(bm);
+    }
+    if (lane == 0) {
+        if (p > a.shortcap) {                    // tie plateau wider than the shortlist: exact fallback
+            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+            a.sl_p[rloc] = -1;
+        } else {
+            a.sl_p[rloc] = p;
+            const int ng = (p + 31) >> 5;
+            const int base = atomicAdd(a.grp_count, ng);
+            for (int g = 0; g < ng; ++g) a.grp[base + g] = (rloc << 4) | g;
+            if (stats != nullptr) { atomicAdd(stats, kept); atomicAdd(stats + 1, p); atomicMax(stats + 2, kept); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6c  wc_fin_rescore_kernel<W, NP>: the exact distances of every shortlisted (target bin, candidate bin) pair
+// ---------------------------------------------------------------------------------------------------------
+// getRefForBins' distance (/root/reference/wisetools.py:302 on Fortran-ordered operands): sum over the samples, strictly in
+// sample order, of separately rounded (x_j - x_i)^2.  The arithmetic is a 3-instruction dependent chain per sample and per
+// candidate - nothing to speed up there; what bounds the step is bringing ~125 candidate rows of S doubles per target bin
+// (28 GB at 600 x 50 kb, 466 GB at 2000 x 10 kb) to the threads.  Register-streaming loads (the fused kernel: one 32-byte
+// sector per lane and instruction, 32 different lines per warp instruction) hold the L1 tag stage at one line per cycle:
+// ~60 % of its throughput is all the kernel got, at 53 % of L2 and 30 % of DRAM throughput.  Here the rows never pass through L1:
+//   * one persistent CTA per SM, W consumer warps + NP producer warps, a ring of NSLOT shared-memory slots;
+//   * a work item = 32 shortlist slots of one target bin; a slot holds one chunk (C samples) of the 32 candidate rows and of
+//     the target's own row, each brought by ONE bulk copy (cp.async.bulk global -> shared, SASS UBLKCP, C * 8 contiguous
+//     bytes) that completes on the slot's mbarrier - the producer lanes only issue, nothing is staged through registers;
+//   * a consumer lane owns one candidate: it walks its row of the slot with 128-bit shared-memory loads (rows are
+//     C * 8 + 16 bytes apart, an odd number of 16-byte units: conflict-free) against the broadcast target chunk;
+//   * items are interleaved over CTAs and warps: item G = (wave * W + w) * gridDim + block; every consumer warp has a private
+//     ring of D = NSLOT / W slots which its chunks (wave * nchunks + c) walk round-robin - one producer and one consumer per
+//     slot, both in order, so a phase parity names a use unambiguously.
+struct RescoreArgs {
+    const double* X;
+    int S;
+    int row_begin;
+    int shortcap;
+    const int* sl_j;
+    double* sl_d;            // [rows][shortcap] exact distances, slot for slot
+    const int* sl_p;
+    const int* grp;
+    const int* grp_count;
+    int C;                   // samples per chunk (multiple of 4)
+    int nchunks;
+    int stride;              // bytes between two rows of a slot: C * 8 + 16
+    int nslot;               // W * D ring slots
+};
+
+constexpr int RS_HEADER = 1024;       // mbarriers: full[64], empty[64]
+constexpr int RS_MAX_SLOTS = 64;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int W, int R>      // W consumer warps, R producer warps per consumer warp
+__global__ void __launch_bounds__((W + W * R) * 32, 1) wc_fin_rescore_kernel(const RescoreArgs a) {
+    extern __shared__ __align__(128) unsigned char rs_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(rs_raw);
+    uint64_t* empty = full + RS_MAX_SLOTS;
+    const uint32_t slots_u32 = smem_u32(rs_raw + RS_HEADER);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nslot = a.nslot;
+    const int D = nslot / W;                   // ring depth per consumer warp
+    const uint32_t slot_bytes = 33u * (uint32_t)a.stride;
+    if (tid == 0) {
+        for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int ngroups = *a.grp_count;
+    const int grid = gridDim.x, b = blockIdx.x;
+    const int per_wave = W * grid;
+    const int nfull = ngroups / per_wave;
+    const int rem = ngroups - nfull * per_wave;
+    const int nact = rem > b ? (rem - b + grid - 1) / grid : 0;      // warps of this CTA with an item in the last wave
+    const int nwaves = nfull + (nact > 0 ? 1 : 0);
+    const int nchunks = a.nchunks, C = a.C;
+    const size_t row_bytes = (size_t)a.S * 8;
+
+    if (warp < W) {
+        // ===== consumers: lane = candidate =====
+        const int w = warp;
+        for (int wave = 0; wave < nwaves; ++wave) {
+            const int wact = wave < nfull ? W : nact;
+            if (w >= wact) break;
+            const int desc = a.grp[(size_t)(wave * W + w) * grid + b];
+            const int rloc = desc >> 4, gi = desc & 15;
+            const int p = a.sl_p[rloc];
+            const int cnt = min(32, p - gi * 32);
+            const int mylane = lane < cnt ? lane : cnt - 1;          // idle lanes shadow the last candidate
+            double acc = 0.0;
+            const int k0 = wave * nchunks;
+            for (int c = 0; c < nchunks; ++c) {
+                const int use = (k0 + c) / D, slot = w * D + (k0 + c) - use * D;
+                mbar_wait(&full[slot], (uint32_t)(use & 1));
+                const uint32_t sb = slots_u32 + (uint32_t)slot * slot_bytes;
+                const uint32_t cb = sb + (uint32_t)mylane * (uint32_t)a.stride;
+                const uint32_t xb = sb + 32u * (uint32_t)a.stride;
+                const int n = min(C, a.S - c * C);                   // even
+                int t = 0;
+                for (; t + 8 <= n; t += 8) {
+                    double v[8], x[8];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        lds_v2f64(cb + (uint32_t)(t + 2 * u) * 8u, v[2 * u], v[2 * u + 1]);
+                        lds_v2f64(xb + (uint32_t)(t + 2 * u) * 8u, x[2 * u], x[2 * u + 1]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const double d = __dsub_rn(v[u], x[u]);
+                        acc = __dadd_rn(acc, __dmul_rn(d, d));
+                    }
+                }
+                for (; t < n; t += 2) {
+                    double v0, v1, x0, x1;
+                    lds_v2f64(cb + (uint32_t)t * 8u, v0, v1);
+                    lds_v2f64(xb + (uint32_t)t * 8u, x0, x1);
+                    double d = __dsub_rn(v0, x0);
+                    acc = __dadd_rn(acc, __dmul_rn(d, d));
+                    d = __dsub_rn(v1, x1);
+                    acc = __dadd_rn(acc, __dmul_rn(d, d));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+            }
+            if (lane < cnt) a.sl_d[(size_t)rloc * a.shortcap + gi * 32 + lane] = acc;
+        }
+    } else {
+        // ===== producers: warp (w, r) issues the copies of the lanes l = r (mod R) of consumer warp w's slots =====
+        // A per-lane bulk copy is a serial loop over the active lanes (UBLKCP takes uniform operands: ~70 cycles per copy and
+        // warp, measured) - the issue rate, not the memory system, bounds the kernel unless several warps share a slot's copies.
+        const int w = (warp - W) % W, r = (warp - W) / W;
+        const bool mine = lane % R == r;
+        for (int wave = 0; wave < nwaves; ++wave) {
+            const int wact = wave < nfull ? W : nact;
+            if (w >= wact) break;
+            const int desc = a.grp[(size_t)(wave * W + w) * grid + b];
+            const int rloc = desc >> 4, gi = desc & 15;
+            const int p = a.sl_p[rloc];
+            const int cnt = min(32, p - gi * 32);
+            const double* src = nullptr;
+            if (mine && lane < cnt) src = a.X + (size_t)a.sl_j[(size_t)rloc * a.shortcap + gi * 32 + lane] * a.S;
+            const double* xsrc = a.X + (size_t)(a.row_begin + rloc) * a.S;
+            const int k0 = wave * nchunks;
+            for (int c = 0; c < nchunks; ++c) {
+                const uint32_t bytes = (uint32_t)min(C, a.S - c * C) * 8u;
+                const size_t off = (size_t)c * C;
+                const int use = (k0 + c) / D, slot = w * D + (k0 + c) - use * D;
+                if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
+                const uint32_t sb = slots_u32 + (uint32_t)slot * slot_bytes;
+                if (r == 0 && lane == 0) {
+                    mbar_arrive_expect_tx(&full[slot], (uint32_t)(cnt + 1) * bytes);
+                    bulk_g2s(sb + 32u * (uint32_t)a.stride, xsrc + off, bytes, &full[slot]);
+                }
+                if (src != nullptr) bulk_g2s(sb + (uint32_t)lane * (uint32_t)a.stride, src + off, bytes, &full[slot]);
+            }
+        }
+    }
+    (void)row_bytes;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6d  wc_fin_rank_kernel: one warp per target bin ranks its re-scored shortlist by (distance, bin) and writes the first k
+// ---------------------------------------------------------------------------------------------------------
+struct RankArgs {
+    int rows, k, shortcap;
+    const int* sl_j;
+    const double* sl_d;
+    const int* sl_p;
+    const int* row_cs;
+    const int* row_ce;
+    int row_begin;
+    int* idx_out;
+    double* dist_out;
+};
+constexpr int RK_WARPS = 8;
+
+// Bitonic sort of 32 * EPL (key, bin) pairs held EPL per lane (element e = t * 32 + lane), ascending by (key, bin):
+// compare-exchange distances below 32 go through shuffles, the others stay inside the lane.
+template <int EPL>
+__device__ __forceinline__ void rank_sort(u64 (&key)[EPL], int (&bin)[EPL], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * EPL; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int t = 0; t < EPL; ++t) {
+                const int e = t * 32 + lane;
+                const bool up = (e & size) == 0;                    // this block sorts ascending
+                if (stride >= 32) {
+                    const int t2 = t ^ (stride >> 5);
+                    if (t2 > t) {                                    // one compare-exchange per pair, both ends in this lane
+                        const bool less2 = key[t2] < key[t] || (key[t2] == key[t] && bin[t2] < bin[t]);
+                        if (less2 == up) {
+                            const u64 tk = key[t]; key[t] = key[t2]; key[t2] = tk;
+                            const int tb = bin[t]; bin[t] = bin[t2]; bin[t2] = tb;
+                        }
+                    }
+                } else {
+                    const u64 ok = __shfl_xor_sync(0xffffffffu, key[t], stride);
+                    const int ob = __shfl_xor_sync(0xffffffffu, bin[t], stride);
+                    const bool lower = (lane & stride) == 0;         // this end keeps the smaller one when ascending
+                    const bool other_less = ok < key[t] || (ok == key[t] && ob < bin[t]);
+                    const bool take = (lower == up) ? other_less : !other_less && !(ok == key[t] && ob == bin[t]);
+                    if (take) { key[t] = ok; bin[t] = ob; }
+                }
+            }
+        }
+    }
+}
+
+template <int EPL>
+__device__ __forceinline__ void rank_row(const RankArgs& a, int rloc, int p, int lane) {
+    u64 key[EPL];
+    int bin[EPL];
+    int nvalid = 0;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+        const int e = t * 32 + lane;
+        key[t] = ~0ull;                                              // padding sorts last
+        bin[t] = 0x7fffffff;
+        if (e < p) {
+            const double d = a.sl_d[(size_t)rloc * a.shortcap + e];
+            const bool ok = d < 1e10;       // wisetools.py:312-314: strict `<` against the 1e10 start value; NaN fails
+            // distances are sums of squares: their bit patterns order like unsigned integers (no FP64 compare in the sort)
+            if (ok) { key[t] = (u64)__double_as_longlong(d); bin[t] = a.sl_j[(size_t)rloc * a.shortcap + e]; }
+            nvalid += ok ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    rank_sort<EPL>(key, bin, lane);
+    const int row = a.row_begin + rloc;
+    const int cs = a.row_cs[row], ce = a.row_ce[row];
+    int* out_i = a.idx_out + (size_t)rloc * a.k;
+    double* out_d = a.dist_out + (size_t)rloc * a.k;
+    const int nout = nvalid < a.k ? nvalid : a.k;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+        const int e = t * 32 + lane;
+        if (e < nout) {
+            out_i[e] = bin[t] >= ce ? bin[t] - (ce - cs) : bin[t];
+            out_d[e] = __longlong_as_double((long long)key[t]);
+        }
+    }
+    for (int e = nvalid + lane; e < a.k; e += 32) { out_i[e] = -1; out_d[e] = 1e10; }
+}
+
+__global__ void __launch_bounds__(RK_WARPS * 32) wc_fin_rank_kernel(const RankArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rloc = blockIdx.x * RK_WARPS + warp;
+    if (rloc >= a.rows) return;
+    const int p = a.sl_p[rloc];
+    if (p < 0) return;                                          // fillers written by the select, or the exhaustive kernel's row
+    if (p <= 128) rank_row<4>(a, rloc, p, lane);
+    else if (p <= 256) rank_row<8>(a, rloc, p, lane);
+    else rank_row<16>(a, rloc, p, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host: K6 of a search call (both the single-GPU call and the finish of a sharded symmetric search)
+// ---------------------------------------------------------------------------------------------------------
+template <int W, int R>
+static int launch_rescore(const RescoreArgs& ra, int grid, size_t smem, cudaStream_t stream) {
+    WC_CUDA(cudaFuncSetAttribute(wc_fin_rescore_kernel<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wc_fin_rescore_kernel<W, R><<<grid, (W + W * R) * 32, smem, stream>>>(ra);
+    return WC_OK;
+}
+
+// Returns the number of kernel launches through *launches.  fa.sl_* / fa.grp* are filled here.
+static int launch_finalize(wc_ctx* ctx, cudaStream_t stream, FinArgs fa, int rows, bool wide, long long* launches) {
+    const size_t fin_smem = (size_t)FIN_ECAP * 12 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
+    // the streaming re-score needs 16-byte aligned rows (bulk copies): an even number of samples
+    const bool split = ctx->k6_split != 0 && fa.S % 2 == 0 && fa.S >= 8 && (reinterpret_cast<uintptr_t>(fa.X) & 15) == 0 && rows > 0;
+    fa.sl_j = nullptr; fa.sl_p = nullptr; fa.grp = nullptr; fa.grp_count = nullptr; fa.row_list = nullptr; fa.row_count = nullptr;
+    ctx->k6_stats_d = nullptr;
+    ctx->phase_ms[10] = 0.0;
+    ctx->timed_mask &= ~(1u << 10);
+    if (!split) {
+        if (wide) {
+            WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<160, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+            wc_finalize_kernel<160, false><<<rows, 160, fin_smem, stream>>>(fa);
+        } else {
+            WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<FIN_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+            wc_finalize_kernel<FIN_THREADS, false><<<rows, FIN_THREADS, fin_smem, stream>>>(fa);
+        }
+        WC_CUDA(cudaGetLastError());
+        *launches = 1;
+        return WC_OK;
+    }
+    int rc;
+    double* sl_d;
+    const int gpr = fa.shortcap / 32;                      // work items per row at most
+    if ((rc = wc_reserve(ctx, SLOT_FIN_J, (size_t)rows * fa.shortcap * sizeof(int), (void**)&fa.sl_j))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_FIN_D, (size_t)rows * fa.shortcap * sizeof(double), (void**)&sl_d))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_FIN_P, ((size_t)rows + 8) * sizeof(int), (void**)&fa.sl_p))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_FIN_GRP, (size_t)rows * (gpr + 1) * sizeof(int), (void**)&fa.grp))) return rc;
+    // sl_p[rows .. rows + 3]: work-item counter, rows passed on to the CTA-per-row select, live entries / shortlist sizes (stats)
+    fa.grp_count = fa.sl_p + rows;
+    int* big_count = fa.sl_p + rows + 1;
+    int* stats = fa.sl_p + rows + 2;
+    int* big_list = fa.grp + (size_t)rows * gpr;
+    WC_CUDA(cudaMemsetAsync(fa.grp_count, 0, 5 * sizeof(int), stream));
+    fa.row_list = nullptr; fa.row_count = nullptr;
+    const size_t sel_smem = SEL_WARPS * SEL_WARP_STRIDE;
+    WC_CUDA(cudaFuncSetAttribute(wc_fin_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    wc_fin_select_kernel<<<(rows + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, sel_smem, stream>>>(fa, big_list, big_count, stats);
+    WC_CUDA(cudaGetLastError());
+    {   // rows with more live entries than a warp holds (never-pruned rows of small matrices): the CTA-per-row select
+        fa.row_list = big_list; fa.row_count = big_count;
+        const int g = std::min(rows, 8 * ctx->sm_count);
+        if (wide) {
+            WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<160, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+            wc_finalize_kernel<160, true><<<g, 160, fin_smem, stream>>>(fa);
+        } else {
+            WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<FIN_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+            wc_finalize_kernel<FIN_THREADS, true><<<g, FIN_THREADS, fin_smem, stream>>>(fa);
+        }
+        WC_CUDA(cudaGetLastError());
+    }
+    WC_CUDA(cudaEventRecord(ctx->ev[20], stream));
+    RescoreArgs ra;
+    ra.X = fa.X; ra.S = fa.S; ra.row_begin = fa.row_begin; ra.shortcap = fa.shortcap; ra.sl_j = fa.sl_j; ra.sl_d = sl_d;
+    ra.sl_p = fa.sl_p; ra.grp = fa.grp; ra.grp_count = fa.grp_count;
+    int C = ctx->k6_chunk > 0 ? ctx->k6_chunk : 100;
+    C = std::max(4, std::min(C & ~3, 480));
+    if (C > fa.S) C = (fa.S + 3) & ~3;
+    ra.C = C;
+    ra.nchunks = (fa.S + C - 1) / C;
+    ra.stride = C * 8 + 16;
+    const size_t slot_bytes = (size_t)33 * ra.stride;
+    ra.nslot = (int)std::min<size_t>(RS_MAX_SLOTS, ((size_t)226 * 1024 - RS_HEADER) / slot_bytes);
+    const int W = ctx->k6_warps > 0 ? ctx->k6_warps : 4;
+    const int R = ctx->k6_prod > 0 ? ctx->k6_prod : 2;
+    if (ra.nslot < 2 * W) { wc_set_error("K6: chunk of %d samples leaves %d ring slots for %d consumer warps", C, ra.nslot, W); return WC_ERR_ARG; }
+    ra.nslot = ra.nslot / W * W;
+    const size_t smem = RS_HEADER + (size_t)ra.nslot * slot_bytes;
+    const int grid = ctx->sm_count;
+    if (W == 2 && R == 4) rc = launch_rescore<2, 4>(ra, grid, smem, stream);
+    else if (W == 2 && R == 8) rc = launch_rescore<2, 8>(ra, grid, smem, stream);
+    else if (W == 4 && R == 1) rc = launch_rescore<4, 1>(ra, grid, smem, stream);
+    else if (W == 4 && R == 2) rc = launch_rescore<4, 2>(ra, grid, smem, stream);
+    else if (W == 4 && R == 4) rc = launch_rescore<4, 4>(ra, grid, smem, stream);
+    else if (W == 4 && R == 7) rc = launch_rescore<4, 7>(ra, grid, smem, stream);
+    else if (W == 8 && R == 1) rc = launch_rescore<8, 1>(ra, grid, smem, stream);
+    else if (W == 8 && R == 2) rc = launch_rescore<8, 2>(ra, grid, smem, stream);
+    else if (W == 8 && R == 3) rc = launch_rescore<8, 3>(ra, grid, smem, stream);
+    else { wc_set_error("K6: no kernel for %d consumer warps x %d producer warps each", W, R); return WC_ERR_ARG; }
+    if (rc) return rc;
+    WC_CUDA(cudaGetLastError());
+    WC_CUDA(cudaEventRecord(ctx->ev[21], stream));
+    RankArgs ka;
+    ka.rows = rows; ka.k = fa.k; ka.shortcap = fa.shortcap; ka.sl_j = fa.sl_j; ka.sl_d = sl_d; ka.sl_p = fa.sl_p;
+    ka.row_cs = fa.row_cs; ka.row_ce = fa.row_ce; ka.row_begin = fa.row_begin; ka.idx_out = fa.idx_out; ka.dist_out = fa.dist_out;
+    wc_fin_rank_kernel<<<(rows + RK_WARPS - 1) / RK_WARPS, RK_WARPS * 32, 0, stream>>>(ka);
+    WC_CUDA(cudaGetLastError());
+    ctx->timed_mask |= 1u << 10;                           // phase 10: the re-score alone (read on demand)
+    ctx->k6_stats_d = big_count;                           // [0] rows passed on, [1] live entries, [2] shortlisted candidates, [3] most live entries of a row
+    *launches = 4;                                         // select (warp per row), select (row list), re-score, rank
+    return WC_OK;
+}

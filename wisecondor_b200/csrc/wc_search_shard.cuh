@@ -90,6 +90,7 @@ int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned
     ta.rb_list_off = pass == 0 ? d_offA : d_offB;
     ta.final_prune = 1;
     ta.in_key = in_key_d; ta.in_j = in_j_d; ta.in_cnt = in_cnt_d; ta.in_cap = pl.in_cap;
+    ta.madd_p = nullptr;
     ta.madd = pl.madd; ta.n32 = pl.f16 ? static_cast<float*>(ctx->buf[SLOT_N32].p) : nullptr;
     ta.dbg = nullptr; ta.dbg_ld = 0; ta.coln32 = ta.n32; ta.col_ids = nullptr;
     const bool tc = pl.f16 == 2;
@@ -369,21 +370,22 @@ extern "C" int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* rec
         fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
         fa.vec = (pl.S % 4 == 0 && (reinterpret_cast<uintptr_t>(pl.corrected) & 31) == 0) ? 4 : 1;
         fa.in_key = recv_key_d; fa.in_j = recv_j_d; fa.in_cnt = recv_cnt_d; fa.in_cap = pl.in_cap;
-        fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per; fa.madd = pl.madd;
+        fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per; fa.madd = pl.madd; fa.madd_p = nullptr;
         fa.row_thr = pl.thr != nullptr ? pl.thr + pl.row0 : nullptr;
-        const size_t fin_smem = (size_t)FIN_ECAP * 12 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
         WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
-        if (pl.f16) {
-            WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-            wc_finalize_kernel<160><<<rows, 160, fin_smem, stream>>>(fa);
-        } else {
-            WC_CUDA(cudaFuncSetAttribute(wc_finalize_kernel<FIN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-            wc_finalize_kernel<FIN_THREADS><<<rows, FIN_THREADS, fin_smem, stream>>>(fa);
-        }
-        WC_CUDA(cudaGetLastError());
+        long long fin_launches = 0;
+        int rcf;
+        if ((rcf = launch_finalize(ctx, stream, fa, rows, pl.f16 != 0, &fin_launches))) return rcf;
+        launches += fin_launches - 1;
         WC_CUDA(cudaEventRecord(ctx->ev[5], stream));
+        int k6_stats[4] = {0, 0, 0, 0};
         WC_CUDA(cudaMemcpyAsync(&nslow, slow, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (ctx->k6_stats_d != nullptr) WC_CUDA(cudaMemcpyAsync(k6_stats, ctx->k6_stats_d, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         WC_CUDA(cudaStreamSynchronize(stream));
+        ctx->counter[8] = k6_stats[1];
+        ctx->counter[9] = k6_stats[2];
+    ctx->counter[10] = k6_stats[0];
+    ctx->counter[11] = k6_stats[3];
         if (nslow > 0) {
             const int batch = 64;
             double* scratch;

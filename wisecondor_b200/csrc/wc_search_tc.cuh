@@ -319,7 +319,7 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             }
             if (valid && total >= a.k) {
                 const double dv = (double)hi;
-                double tau = dv + a.mcoef * ((double)ni + fabs(dv)) + a.madd;
+                double tau = dv + a.mcoef * ((double)ni + fabs(dv)) + madd_of(a);
                 if (!(tau > 1e-300)) tau = 1e-300;
                 atomicMin(a.row_thr + (row - a.row_begin), key_of_tau(tau));
             }
@@ -414,9 +414,9 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                     __threadfence_block();
                     __syncwarp();
                     if (a.cap <= 512)
-                        prune_row<16>(wk + (size_t)src * a.cap, wj + (size_t)src * a.cap, n, a.k, nr, a.mcoef, a.madd, lane, nullptr, nullptr, &nthr, &kept);
+                        prune_row<16>(wk + (size_t)src * a.cap, wj + (size_t)src * a.cap, n, a.k, nr, a.mcoef, madd_of(a), lane, nullptr, nullptr, &nthr, &kept);
                     else
-                        prune_row<32>(wk + (size_t)src * a.cap, wj + (size_t)src * a.cap, n, a.k, nr, a.mcoef, a.madd, lane, nullptr, nullptr, &nthr, &kept);
+                        prune_row<32>(wk + (size_t)src * a.cap, wj + (size_t)src * a.cap, n, a.k, nr, a.mcoef, madd_of(a), lane, nullptr, nullptr, &nthr, &kept);
                     if (lane == src) {
                         if (kept > a.cap - BN) {             // a tie plateau wider than the buffer: exact fallback
                             w_flag[lane] = 1;

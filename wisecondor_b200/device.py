@@ -110,10 +110,15 @@ def last_search_stats(device=0):
     return {
         "center_norms_ms": ctx.phase_ms(0), "dist_topk_ms": ctx.phase_ms(1), "finalize_ms": ctx.phase_ms(2),
         "dist_topk_first_pass_ms": ctx.phase_ms(8),
+        "finalize_rescore_ms": ctx.phase_ms(10),       # K6 split form: the streaming exact re-score alone (0: fused kernel)
         "exhaustive_ms": ctx.phase_ms(3), "launches": ctx.counter(0), "exhaustive_rows": ctx.counter(1),
         "tiles": ctx.counter(3), "tiles_plain": ctx.counter(2), "ctas": ctx.counter(4),
         "filter": max(0, ctx.counter(7)) & 3,          # 0: fp64 DMMA, 1: fp16 mma.sync, 2: fp16 tcgen05 / TMEM
         "pivots": max(0, ctx.counter(7)) >> 4,         # pivots of the K5t pivot pass (0: none)
+        "k6_live_entries": ctx.counter(8),             # K6 split form: entries within the rows' final thresholds, all rows
+        "k6_shortlisted": ctx.counter(9),              # ... and candidates re-scored exactly (0: fused kernel)
+        "k6_live_max": ctx.counter(11),                # most live entries of one row among the warp-selected rows
+        "k6_rows_cta_select": ctx.counter(10),         # rows the warp-per-row select passed on to the CTA-per-row one
     }
 
 
