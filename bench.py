@@ -544,6 +544,8 @@ def main():
             r0, r1 = sym_search.row0, max(sym_search.row0, sym_search.row1)
             rows = r1 - r0
 
+    timing = {"on": False}
+
     def step():
         if sym_search is not None:
             sym_search.run(X, bins)      # threshold all-reduce + candidate all-to-all inside
@@ -551,7 +553,11 @@ def main():
             return
         device.newref_topk(X, bins, r0, r1, k, out_idx[:rows], out_dist[:rows])
         if world > 1:       # NCCL all-gather of the row shards over NVLink: every rank ends with the whole table
+            if timing["on"]:
+                ag_ev[0].record()
             shard.allgather_rows(out_idx[:rows], out_dist[:rows], n, out_idx=full_idx, out_dist=full_dist, scratch=scratch)
+            if timing["on"]:
+                ag_ev[1].record()
 
     def barrier():
         if world > 1:
@@ -568,14 +574,23 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     k5_ms, k4_ms, k6_ms, launches = [], [], [], 0
     k5a_ms, work_ratio, filt = [], 1.0, 0
+    k6c_ms, shortlisted, ag_ms = [], 0, []
+    ag_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     barrier()
     t_wall0 = time.time()
     for i in range(args.steps):
         flush.fill_(i)                       # L2 flush between timed iterations (outside the event pairs)
+        timing["on"] = True
         ev[i][0].record()
         step()
         ev[i][1].record()
+        timing["on"] = False
         st = device.last_search_stats(local)
+        k6c_ms.append(st.get("finalize_rescore_ms", 0.0))
+        shortlisted = int(st.get("k6_shortlisted", 0))
+        if world > 1 and sym_search is None:
+            ag_ev[1].synchronize()
+            ag_ms.append(ag_ev[0].elapsed_time(ag_ev[1]))
         k4_ms.append(st["center_norms_ms"])
         k5_ms.append(st["dist_topk_ms"])
         k6_ms.append(st["finalize_ms"] + st["exhaustive_ms"])
@@ -643,7 +658,7 @@ def main():
             mp, mp_src = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)"
         traffic = {}
         try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full captures
-            with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "traffic_r03.json")) as fh:
                 traffic = json.load(fh).get(args.workload if world == 1 else "", {})
         except Exception:
             pass
@@ -672,18 +687,42 @@ def main():
                    "note": "kernel_ms covers every K5 launch of a step (pivot pass, threshold pass, symmetric pass); work_ratio < 1: "
                            "symmetric search, each unordered pair of bin blocks contracted once; achieved / frac count the flops issued",
                    "peak_source": k5_desc[2], "share_of_step": k5 / ms_per_step}
-        # K6: the exact re-score must read, per target bin, the rows of at least `refsize` candidates and its own (S doubles
-        # each) and write refsize (index, distance) pairs: (refsize + 1) * S * 8 + refsize * 12 bytes per target bin
+        # K6 = select (warp per target bin) -> K6c streaming exact re-score -> rank.  K6c is the one long kernel: every
+        # shortlisted (target, candidate) pair needs the candidate's row of S doubles at the SM, strictly in sample order
+        # (wisetools.py:302) - its algorithmic bytes are pairs x S x 8 (plus the target's own chunks, one per 32 pairs).
+        # `traffic` (DRAM bytes, ncu) is BELOW that: the hot candidate rows are served by the L2, so the HBM fraction can
+        # exceed 1 when most of the matrix fits the 126 MB L2; the L2 -> SM figure (tools/l2_peak.cu) is printed next to it.
         rows_mine = r1 - r0
-        k6_bytes = float(rows_mine) * ((k + 1) * S * 8.0 + k * 12.0)
+        k6c = float(np.mean(k6c_ms)) if k6c_ms else 0.0
         hbm = float(mp["hbm_gbs"])
-        roof_k6 = {"bound": "hbm", "kernel": "wc_finalize_kernel (K6: exact fp64 re-score in the reference's operation order, gathered "
-                                             "candidate rows, ranking)",
-                   "achieved": k6_bytes / (k6 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": k6_bytes / (k6 * 1e-3) / 1e9 / hbm,
-                   "traffic": traffic.get("k6"), "bytes_per_launch": k6_bytes, "kernel_ms": k6,
-                   "note": "algorithmic bytes = target bins x ((refsize + 1) rows of S doubles + refsize (index, distance) pairs); the "
-                           "shortlist behind the fp16 filter is ~25 % longer than refsize, and about 60 % of the gathered rows hit the L2",
-                   "peak_source": "%s hbm_gbs (device copy)" % mp_src, "share_of_step": k6 / ms_per_step}
+        l2_peak = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "l2_peak_r03.json")) as fh:
+                l2_peak = float(json.loads(fh.readline())["ldg128_gbs"])
+        except Exception:
+            pass
+        if k6c > 0.0 and shortlisted > 0:
+            k6_bytes = float(shortlisted) * S * 8.0 * (1.0 + 1.0 / 32.0) + float(shortlisted) * 12.0
+            k6_ms_kernel = k6c
+            k6_name = ("wc_fin_rescore_kernel (K6c: exact fp64 re-score in the reference's operation order; candidate rows by "
+                       "cp.async.bulk into a shared-memory ring, one persistent CTA per SM)")
+            k6_note = ("algorithmic bytes = re-scored (target, candidate) pairs x S x 8 B (+ the target's chunk per 32 pairs, + the "
+                       "(index, distance) result); %.1f pairs per target bin for refsize %d (the fp16 filter's error window); "
+                       "frac > 1 is possible: hot candidate rows come from the L2, see traffic / l2" % (shortlisted / float(max(1, rows_mine)), k))
+        else:       # fused K6 (odd S, k6_split = 0)
+            k6_bytes = float(rows_mine) * ((k + 1) * S * 8.0 + k * 12.0)
+            k6_ms_kernel = k6
+            k6_name = "wc_finalize_kernel (K6 fused: select, exact fp64 re-score in the reference's operation order, ranking)"
+            k6_note = "algorithmic bytes = target bins x ((refsize + 1) rows of S doubles + refsize (index, distance) pairs)"
+        k6_gbs = k6_bytes / (k6_ms_kernel * 1e-3) / 1e9
+        roof_k6 = {"bound": "hbm", "kernel": k6_name,
+                   "achieved": k6_gbs, "peak": hbm, "unit": "GB/s", "frac": k6_gbs / hbm,
+                   "traffic": traffic.get("k6c" if k6c > 0.0 else "k6"), "bytes_per_launch": k6_bytes, "kernel_ms": k6_ms_kernel,
+                   "l2": {"peak_gbs": l2_peak, "frac": (k6_gbs / l2_peak) if l2_peak else None,
+                          "peak_source": "profiles/l2_peak_r03.json (tools/l2_peak.cu: 128-bit loads over an L2-resident 48 MiB buffer)"},
+                   "k6_total_ms": k6, "select_and_rank_ms": (k6 - k6c) if k6c > 0.0 else None,
+                   "note": k6_note, "peak_source": "%s hbm_gbs (device copy)" % mp_src, "share_of_step": k6_ms_kernel / ms_per_step}
+        k6 = k6_ms_kernel if k6c > 0.0 else k6
         roofline, roof_other = (roof_k5, roof_k6) if k5 >= k6 else (roof_k6, roof_k5)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -697,7 +736,10 @@ def main():
                            "rows sharded by getPart over %d GPU(s)%s" % (world, " + NCCL all-gather" if world > 1 else "")),
                        "sharded_symmetric_trial": sym_note,
                        "l2": "512 MiB buffer written between timed iterations (L2 flush)"},
-            "phases_ms": {"center_norms": float(np.mean(k4_ms)), "dist_topk": k5, "finalize": float(np.mean(k6_ms))},
+            "phases_ms": {"center_norms": float(np.mean(k4_ms)), "dist_topk": k5, "finalize": float(np.mean(k6_ms)),
+                          "finalize_rescore": float(np.mean(k6c_ms)) if k6c_ms else 0.0,
+                          "allgather": float(np.mean(ag_ms)) if ag_ms else 0.0,
+                          "host_and_gaps": ms_per_step - float(np.mean(k4_ms)) - k5 - float(np.mean(k6_ms)) - (float(np.mean(ag_ms)) if ag_ms else 0.0)},
             "roofline": roofline, "roofline_second_kernel": roof_other, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }

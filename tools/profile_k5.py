@@ -33,8 +33,8 @@ out = {"workload": name, "lag": (sys.argv[2] if len(sys.argv) > 2 else "default"
        "cycles_total_max": p[:, 0].max(), "cycles_total_mean": p[:, 0].mean(), "cycles_total_min": p[:, 0].min(),
        "wait_tma_frac": (p[:, 1] / p[:, 0]).mean(), "epilogue_frac": (p[:, 2] / p[:, 0]).mean(),
        "prune_frac": (p[:, 3] / p[:, 0]).mean(), "tiles_per_cta": p[:, 4].mean(),
-       "cycles_per_tile": (p[:, 0] / p[:, 4]).mean(), "prunes_warp0_mean": p[:, 5].mean(),
-       "emitted_thread0_mean": p[:, 6].mean(),
+       "cycles_per_tile": (p[:, 0] / p[:, 4]).mean(), "col_side_frac": (p[:, 5] / p[:, 0]).mean(),
+       "survivors_frac": (p[:, 6] / p[:, 0]).mean(), "flush_frac": (p[:, 7] / p[:, 0]).mean(),
        "ideal_cycles_per_tile": 128 * 128 * S / 64.0}
 print(json.dumps(out))
 if g + 64 <= 320 and "-t" in sys.argv:

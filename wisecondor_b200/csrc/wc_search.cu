@@ -100,6 +100,7 @@ struct TopkArgs {
     const u64* col_thr;          // thresholds indexed by GLOBAL bin (== row_thr when the launch starts at row 0)
     double madd;                 // margin(v) = mcoef * (n_i + |v|) + madd  (0 for the fp64 filter)
     const double* madd_p;        // when set: madd lives on the device (written by wc_f16_margin_kernel - no host round trip)
+    int kb_last;                 // K5t: column of the B operand's last 64-sample chunk (folded norms: its second version)
     const float* n32;            // fp16 filter: the bins' squared norms in fp32, +inf for padding rows
     const float* coln32;         // K5t: norms of the COLUMN rows (== n32, or the pivot matrix' norms in the pivot pass)
     const int* col_ids;          // K5t pivot pass: global bin of every row of the pivot matrix (nullptr: columns are bins)
@@ -1223,7 +1224,7 @@ void block_skips(int N, const int* chrom_bins_h, int nchrom, std::vector<int>& r
 namespace {
 // Tensor map of a row-major fp16 matrix [rows][ldh] with boxes of 64 halves x 128 rows, SWIZZLE_128B (the operand tiles of
 // K5h / K5t).
-int encode_f16_map(wc_ctx* ctx, CUtensorMap* tmap, const void* base, int ldh, size_t rows) {
+int encode_f16_map(wc_ctx* ctx, CUtensorMap* tmap, const void* base, int ldh, size_t rows) {      // ldh: row width = row stride, in halves
     if (!ctx->encode_tiled) {
         wc_set_error("cuTensorMapEncodeTiled is not available from this driver");
         return WC_ERR_CUDA;
@@ -1252,7 +1253,7 @@ int pivot_count(int N, int k) {
 // ta.row_begin) from their distances to the R bins of smallest norm.  `ta` arrives prepared for the search proper (norms,
 // exclusion ranges, candidate buffers, margins, row_thr, n32); rb_seg_first[rb] names a segment of row block rb whose
 // candidate buffers serve as scratch - the search proper overwrites them afterwards.
-int tc_pivot_pass(wc_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmap_a, TopkArgs ta, const __half* Xh, int ldh, int N,
+int tc_pivot_pass(wc_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmap_a, TopkArgs ta, const __half* Xh, int ldh, int ldx, int N,
                   int nrb, const std::vector<int>& rb_seg_first, int R) {
     int* ids; __half* P; float* n32p; int* meta;
     int rc;
@@ -1282,7 +1283,7 @@ int tc_pivot_pass(wc_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmap_a, T
         ctx->piv_hash = h;
     }
     wc_pivot_select_kernel<<<1, 1024, 0, stream>>>(ta.n32, N, R, ids);
-    wc_pivot_gather_kernel<<<R, 128, 0, stream>>>(Xh, ldh, ta.n32, ids, P, n32p);
+    wc_pivot_gather_kernel<<<R, 128, 0, stream>>>(Xh, ldh, ldx, ta.n32, ids, P, n32p);
     WC_CUDA(cudaGetLastError());
     CUtensorMap tmap_p;
     if ((rc = encode_f16_map(ctx, &tmap_p, P, ldh, (size_t)R))) return rc;
@@ -1290,6 +1291,7 @@ int tc_pivot_pass(wc_ctx* ctx, cudaStream_t stream, const CUtensorMap& tmap_a, T
     ta.tile_list = nullptr; ta.rb_list_off = nullptr; ta.final_prune = 1;
     ta.in_key = nullptr; ta.in_j = nullptr; ta.in_cnt = nullptr; ta.in_cap = 0; ta.col_thr = nullptr;
     ta.coln32 = n32p; ta.col_ids = ids; ta.dbg = nullptr; ta.dbg_ld = 0; ta.prof = nullptr; ta.trace = nullptr;
+    ta.kb_last = ldh - BKH;               // the pivot matrix carries the B version of the last chunk in place
     WC_CUDA(cudaFuncSetAttribute(wc_dist_topk_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     wc_dist_topk_tc_kernel<2, false><<<gridP, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmap_a, tmap_p, ta);
     WC_CUDA(cudaGetLastError());
@@ -1575,7 +1577,8 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     double* Xc; double* norms; int* d_row_cs; int* d_row_ce; int* d_meta;
     u64* cand_key; int* cand_j; int* seg_cnt; int* seg_flag; int* slow;
     int rc;
-    if ((rc = wc_reserve(ctx, SLOT_XC, Npad * ld * sizeof(double), (void**)&Xc))) return rc;
+    // (the fp16 matrix of K5t - rows of S + 4 halves padded to whole chunks, plus one more chunk - can exceed it for tiny S)
+    if ((rc = wc_reserve(ctx, SLOT_XC, std::max(Npad * ld * sizeof(double), Npad * ((size_t)(S + 4 + 2 * BKH) / BKH * BKH + BKH) * sizeof(__half)), (void**)&Xc))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_NORMS, Npad * sizeof(double), (void**)&norms))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_ROWCS, (size_t)N * sizeof(int), (void**)&d_row_cs))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_ROWCE, (size_t)N * sizeof(int), (void**)&d_row_ce))) return rc;
@@ -1637,10 +1640,16 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     // holds finite values fp16 cannot represent.
     bool f16 = ctx->k5_f16 != 0;
     const bool tc = ctx->k5_f16 == 2;          // tcgen05 / TMEM filter (K5t); 1 = mma.sync filter (K5h)
-    const int ldh = (S + BKH - 1) / BKH * BKH;
+    // K5t folds the norms into the contraction: four more columns, and a second version of the last chunk (wc_prepare_f16_kernel)
+    const int ldh = tc ? (S + 4 + BKH - 1) / BKH * BKH : (S + BKH - 1) / BKH * BKH;
+    const int ldx = tc ? ldh + BKH : ldh;                 // row stride of the fp16 matrix, in halves
     float* n32 = nullptr;
     double nmax = 0.0;
-    const double eps16 = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (double)ldh * ldexp(1.0, -23) + ldexp(1.0, -21);
+    // error of the fp16 filter: |d~ - d| <= eps * (n_i + n_j) + sub; eps = operand rounding (2 x 2^-11), fp32 accumulation
+    // of ldh products (taken one bit worse than IEEE; twice that with the norms among the summands: the partial sums are
+    // bounded by n_i + n_j instead of half of it), the norms' two-half split and the fp32 compare (2^-20)
+    const double eps16 = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (tc ? 2.0 : 1.0) * (double)ldh * ldexp(1.0, -23) +
+                         (tc ? ldexp(1.0, -20) : ldexp(1.0, -21));
     const unsigned long long* f16_stats_d = nullptr;       // set: K4h's range flag is checked at the end of the call
     WC_CUDA(cudaEventRecord(ctx->ev[0], stream));
     if (f16) {
@@ -1648,7 +1657,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         if ((rc = wc_reserve(ctx, SLOT_N32, Npad * sizeof(float), (void**)&n32))) return rc;
         if ((rc = wc_reserve(ctx, SLOT_F16STAT, 4 * sizeof(unsigned long long), (void**)&stats))) return rc;
         WC_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), stream));
-        wc_prepare_f16_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ldh,
+        wc_prepare_f16_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ldh, ldx, tc ? 1 : 0,
                                                                                   reinterpret_cast<__half*>(Xc), norms, n32, stats);
         WC_CUDA(cudaGetLastError());
         if (ctx->k5_f16_checked != 0) {
@@ -1682,8 +1691,8 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
             wc_set_error("cuTensorMapEncodeTiled is not available from this driver");
             return WC_ERR_CUDA;
         }
-        cuuint64_t dims[2] = {(cuuint64_t)(f16 ? ldh : ld), (cuuint64_t)Npad};
-        cuuint64_t strides[1] = {f16 ? (cuuint64_t)ldh * sizeof(__half) : (cuuint64_t)ld * sizeof(double)};
+        cuuint64_t dims[2] = {(cuuint64_t)(f16 ? ldx : ld), (cuuint64_t)Npad};
+        cuuint64_t strides[1] = {f16 ? (cuuint64_t)ldx * sizeof(__half) : (cuuint64_t)ld * sizeof(double)};
         cuuint32_t box[2] = {(cuuint32_t)(f16 ? BKH : BK), BM};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = reinterpret_cast<PFN_encodeTiled>(ctx->encode_tiled)(
@@ -1706,6 +1715,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     ta.lag = ctx->k5_lag;
     ta.nstages = cap <= 512 ? (sym ? 4 : 5) : 3;          // the symmetric pass keeps 8 KiB of column thresholds in shared memory
     if (f16) { ta.nstages = 4; ta.nkc = ldh / BKH; }
+    ta.kb_last = f16 ? (tc ? ldh : ldh - BKH) : 0;
     if (ctx->k5_stages >= 3 && ctx->k5_stages <= MAX_STAGES) ta.nstages = ctx->k5_stages;
     ta.tile_list = nullptr; ta.rb_list_off = nullptr; ta.final_prune = sym ? 1 : 0;
     ta.in_key = in_key; ta.in_j = in_j; ta.in_cnt = in_cnt; ta.in_cap = in_cap; ta.col_thr = row_thr;
@@ -1769,7 +1779,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     // pivot pass (K5t): every target bin of the call starts the search proper with a threshold close to its final one
     const int R = (use_tc && !dbg && ctx->k5_pivots != 0 && rows >= 2 * BM) ? pivot_count(N, k) : 0;
     if (R > 0) {
-        if ((rc = tc_pivot_pass(ctx, stream, tmap, ta, reinterpret_cast<const __half*>(Xc), ldh, N, nrb, rb_seg_first, R))) return rc;
+        if ((rc = tc_pivot_pass(ctx, stream, tmap, ta, reinterpret_cast<const __half*>(Xc), ldh, ldx, N, nrb, rb_seg_first, R))) return rc;
         pivot_launches = 3;
     }
     WC_CUDA(cudaEventRecord(ctx->ev[17], stream));

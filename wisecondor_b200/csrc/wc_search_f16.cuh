@@ -31,32 +31,49 @@ __device__ __forceinline__ float tau32_of_key(u64 key) { return __double2float_r
 
 // K4h: X' = X - 1 in fp16 (padded with zeros to whole 64-sample chunks), n_i in fp64 (margins) and fp32 (epilogue;
 // +inf for padding rows so that they never pass), the largest finite norm and a flag for values fp16 cannot hold.
-__global__ void wc_prepare_f16_kernel(const double* __restrict__ X, int N, int Npad, int S, int ldh,
+// fold (K5t): the norms ride in the contraction.  The last four columns of the last 64-sample chunk hold (h_i, l_i, 1, 1)
+// with h_i + l_i = -n_i / 2 split into two halves (relative error 2^-22), and a second copy of that chunk, 64 columns further
+// (row stride ldx = ldh + 64), holds (1, 1, h_i, l_i) there: with the A operand reading the first version and the B operand the
+// second, the accumulator is x'_i . x'_j - n_i / 2 - n_j / 2 = -d~_ij / 2 and the epilogue needs no arithmetic before its
+// compares.  Needs S + 4 <= ldh and n / 2 inside fp16's range (else the range flag: fp64 filter).
+__global__ void wc_prepare_f16_kernel(const double* __restrict__ X, int N, int Npad, int S, int ldh, int ldx, int fold,
                                       __half* __restrict__ Xh, double* __restrict__ norms, float* __restrict__ n32,
                                       unsigned long long* __restrict__ stats) {
     const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= Npad) return;
-    __half* dst = Xh + (size_t)row * ldh;
+    __half* dst = Xh + (size_t)row * ldx;
     double acc = 0.0;
     bool big = false;
     if (row < N) {
         const double* src = X + (size_t)row * S;
         for (int s = lane; s < ldh; s += 32) {
             const double v = s < S ? src[s] - 1.0 : 0.0;
-            dst[s] = __double2half(v);
+            const __half hv = __double2half(v);
+            dst[s] = hv;
+            if (fold && s >= ldh - BKH) dst[s + BKH] = hv;
             acc = fma(v, v, acc);
             if (fabs(v) > 60000.0 && fabs(v) < INFINITY) big = true;
         }
     } else {
-        for (int s = lane; s < ldh; s += 32) dst[s] = __float2half(0.0f);
+        for (int s = lane; s < ldx; s += 32) dst[s] = __float2half(0.0f);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     big = __any_sync(0xffffffffu, big);
+    __syncwarp();                                   // the zeros of the spare columns are written: lane 0 overwrites four of them
     if (lane == 0) {
         norms[row] = row < N ? acc : 0.0;
         n32[row] = row < N ? (float)acc : INFINITY;
+        if (fold && row < N) {
+            const double nh = -0.5 * acc;
+            if (!(acc * 0.5 <= 60000.0)) big = true;
+            const __half h = __double2half(nh);
+            const __half l = __double2half(nh - (double)__half2float(h));
+            const __half one = __float2half(1.0f);
+            dst[ldh - 4] = h;   dst[ldh - 3] = l;   dst[ldh - 2] = one; dst[ldh - 1] = one;      // as the A operand
+            dst[ldx - 4] = one; dst[ldx - 3] = one; dst[ldx - 2] = h;   dst[ldx - 1] = l;        // as the B operand
+        }
         if (row < N && acc < INFINITY) atomicMax(stats, (unsigned long long)__double_as_longlong(acc));   // acc >= 0
         if (big) atomicOr(stats + 1, 1ull);
     }

@@ -47,8 +47,9 @@ int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned
     }
     CUtensorMap tmap;
     {
-        cuuint64_t dims[2] = {(cuuint64_t)(pl.f16 ? pl.ldh : pl.ld), (cuuint64_t)pl.Npad};
-        cuuint64_t strides[1] = {pl.f16 ? (cuuint64_t)pl.ldh * sizeof(__half) : (cuuint64_t)pl.ld * sizeof(double)};
+        const int ldx = pl.f16 == 2 ? pl.ldh + BKH : pl.ldh;       // K5t: folded norms, a second version of the last chunk
+        cuuint64_t dims[2] = {(cuuint64_t)(pl.f16 ? ldx : pl.ld), (cuuint64_t)pl.Npad};
+        cuuint64_t strides[1] = {pl.f16 ? (cuuint64_t)ldx * sizeof(__half) : (cuuint64_t)pl.ld * sizeof(double)};
         cuuint32_t box[2] = {(cuuint32_t)(pl.f16 ? BKH : BK), BM};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = reinterpret_cast<PFN_encodeTiled>(ctx->encode_tiled)(
@@ -91,11 +92,12 @@ int shard_launch_pass(wc_ctx* ctx, int pass, unsigned long long* thr_d, unsigned
     ta.final_prune = 1;
     ta.in_key = in_key_d; ta.in_j = in_j_d; ta.in_cnt = in_cnt_d; ta.in_cap = pl.in_cap;
     ta.madd_p = nullptr;
+    ta.kb_last = pl.f16 ? (pl.f16 == 2 ? pl.ldh : pl.ldh - BKH) : 0;
     ta.madd = pl.madd; ta.n32 = pl.f16 ? static_cast<float*>(ctx->buf[SLOT_N32].p) : nullptr;
     ta.dbg = nullptr; ta.dbg_ld = 0; ta.coln32 = ta.n32; ta.col_ids = nullptr;
     const bool tc = pl.f16 == 2;
     if (pass == 2)
-        return tc_pivot_pass(ctx, stream, tmap, ta, static_cast<const __half*>(ctx->buf[SLOT_XC].p), pl.ldh, pl.N, pl.nrb, *seg_first, pivots);
+        return tc_pivot_pass(ctx, stream, tmap, ta, static_cast<const __half*>(ctx->buf[SLOT_XC].p), pl.ldh, pl.f16 == 2 ? pl.ldh + BKH : pl.ldh, pl.N, pl.nrb, *seg_first, pivots);
     if (tc) {
         auto kern = pass == 0 ? wc_dist_topk_tc_kernel<0, false> : wc_dist_topk_tc_kernel<1, false>;
         WC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
@@ -239,7 +241,7 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
     double* Xc; double* norms; int* d_row_cs; int* d_row_ce; int* d_meta;
     u64* cand_key; int* cand_j; int* seg_cnt; int* seg_flag; int* slow;
     int rc;
-    if ((rc = wc_reserve(ctx, SLOT_XC, Npad * ld * sizeof(double), (void**)&Xc))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_XC, std::max(Npad * ld * sizeof(double), Npad * ((size_t)(S + 4 + 2 * BKH) / BKH * BKH + BKH) * sizeof(__half)), (void**)&Xc))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_NORMS, Npad * sizeof(double), (void**)&norms))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_ROWCS, (size_t)N * sizeof(int), (void**)&d_row_cs))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_ROWCE, (size_t)N * sizeof(int), (void**)&d_row_ce))) return rc;
@@ -260,7 +262,9 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
 
     // option k5_f16: fp16 tensor-core filter (every rank holds the whole matrix, so all ranks take the same decision)
     bool f16 = ctx->k5_f16 != 0;
-    const int ldh = (S + BKH - 1) / BKH * BKH;
+    const bool tcf = ctx->k5_f16 == 2;                    // K5t: norms folded into the contraction (wc_prepare_f16_kernel)
+    const int ldh = tcf ? (S + 4 + BKH - 1) / BKH * BKH : (S + BKH - 1) / BKH * BKH;
+    const int ldx = tcf ? ldh + BKH : ldh;
     double nmax = 0.0;
     WC_CUDA(cudaEventRecord(ctx->ev[0], stream));
     if (f16) {
@@ -269,7 +273,7 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
         if ((rc = wc_reserve(ctx, SLOT_N32, Npad * sizeof(float), (void**)&n32))) return rc;
         if ((rc = wc_reserve(ctx, SLOT_F16STAT, 2 * sizeof(unsigned long long), (void**)&stats))) return rc;
         WC_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), stream));
-        wc_prepare_f16_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ldh,
+        wc_prepare_f16_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ldh, ldx, tcf ? 1 : 0,
                                                                                   reinterpret_cast<__half*>(Xc), norms, n32, stats);
         WC_CUDA(cudaGetLastError());
         unsigned long long st_h[2] = {0, 0};
@@ -282,7 +286,8 @@ extern "C" int wc_newref_shard_begin(wc_ctx* ctx, const double* corrected_d, int
         wc_prepare_kernel<<<(int)((Npad * 32 + 255) / 256), 256, 0, stream>>>(corrected_d, N, (int)Npad, S, ld, Sx, Xc, norms);
     WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[1], stream));
-    const double eps16 = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (double)ldh * ldexp(1.0, -23) + ldexp(1.0, -21);
+    const double eps16 = ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + (tcf ? 2.0 : 1.0) * (double)ldh * ldexp(1.0, -23) +
+                         (tcf ? ldexp(1.0, -20) : ldexp(1.0, -21));          // see wc_newref_topk
     const double tau_init = f16 ? 3e38 : 1e10 * (1.0 + 1e-6);
     wc_fill_u64_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(thr_d, (size_t)N, host_key_of_tau(tau_init));
     wc_fill_u64_kernel<<<(unsigned)((d.thr_len - N + 255) / 256), 256, 0, stream>>>(thr_d + N, d.thr_len - (size_t)N, KEY_NEVER);

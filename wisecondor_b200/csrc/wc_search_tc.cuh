@@ -32,11 +32,11 @@ constexpr int TC_STAGES = 3;                        // 144 KiB in flight: the L2
 constexpr int TC_STAGE_BYTES = 3 * TILE_BYTES;      // A, B0, B1 boxes: 128 rows x 64 halves x 2 B = 16 KiB each
 constexpr int TC_NB = 2 * BN;                       // columns of a full item (two candidate blocks)
 constexpr int TC_STG = 256;                         // per-warp staging entries (8 bytes each) for column-side candidates
-constexpr int TC_LIST = 256;                        // per-warp (row, column) pairs of one 32-column chunk handled by the dense path
 constexpr int TC_PIVOTS = 512;                      // pivots of the pivot pass: their distances to 128 bins fill the tensor memory
 constexpr int TC_EPI_WARPS = 8;                     // two per TMEM lane quarter: columns [0, 128) and [128, 256) of an item
 constexpr int TC_SEGS_PER_PIECE = 2;                // each column half keeps its own candidate buffers (no shared row state)
 constexpr uint32_t TC_TMEM_COLS = 512;
+constexpr int TC_PARK_LD = 36;                      // words between two rows of a parked chunk (16-byte aligned, conflict-free 128-bit stores)
 
 struct __align__(16) TcState {
     uint64_t full[TC_STAGES];
@@ -44,15 +44,12 @@ struct __align__(16) TcState {
     uint64_t tfull[2];
     uint64_t tempty[2];
     uint32_t tmem_base;
-    int alloc[8];                // per epilogue warp: (row-side | column-side << 16) list slots handed out in the current chunk
 };
 
 constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES                 // operand ring
                                  + 2 * 2 * TC_NB * sizeof(float)                     // column norms + thresholds, 2 buffers
                                  + (size_t)TC_EPI_WARPS * TC_STG * sizeof(uint2)     // column-side staging
-                                 + (size_t)TC_EPI_WARPS * 32 * 33 * sizeof(float)    // per-warp parking of one 32 x 32 chunk
-                                 + (size_t)TC_EPI_WARPS * 2 * TC_LIST * sizeof(unsigned short)   // (row, column) lists
-                                 + (size_t)TC_EPI_WARPS * 32 * (sizeof(int) + 1)     // per-row candidate counts and overflow flags
+                                 + (size_t)TC_EPI_WARPS * 32 * TC_PARK_LD * sizeof(float)    // per-warp parking of one 32 x 32 chunk
                                  + sizeof(TcState);
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -124,11 +121,8 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     float* s_nj = reinterpret_cast<float*>(smem_raw + (size_t)TC_STAGES * TC_STAGE_BYTES);    // [2][TC_NB]
     float* s_tj = s_nj + 2 * TC_NB;                                                            // [2][TC_NB]  (pivot pass: the pivots' bins, as int)
     uint2* s_stg = reinterpret_cast<uint2*>(s_tj + 2 * TC_NB);                                 // [8][TC_STG]
-    float* s_park = reinterpret_cast<float*>(s_stg + TC_EPI_WARPS * TC_STG);                   // [8][32][33]
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_park + TC_EPI_WARPS * 32 * 33);   // [8][2][TC_LIST]
-    int* s_cnt = reinterpret_cast<int*>(s_list + TC_EPI_WARPS * 2 * TC_LIST);                  // [8][32]
-    unsigned char* s_flag = reinterpret_cast<unsigned char*>(s_cnt + TC_EPI_WARPS * 32);       // [8][32]
-    TcState& sm = *reinterpret_cast<TcState*>(s_flag + TC_EPI_WARPS * 32);
+    float* s_park = reinterpret_cast<float*>(s_stg + TC_EPI_WARPS * TC_STG);                   // [8][32][TC_PARK_LD]
+    TcState& sm = *reinterpret_cast<TcState*>(s_park + TC_EPI_WARPS * 32 * TC_PARK_LD);
     const int tid = threadIdx.x;
     const int warp_all = tid >> 5, lane = tid & 31;
 
@@ -193,9 +187,10 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                         while (!mbar_try_wait(&sm.empty[stage], phase ^ 1u)) __nanosleep(64);
                         unsigned char* st = tiles + (size_t)stage * TC_STAGE_BYTES;
                         mbar_arrive_expect_tx(&sm.full[stage], (two ? 3 : 2) * TILE_BYTES);
+                        const int kb = kc == a.nkc - 1 ? a.kb_last : kc * BKH;      // folded norms: the B version of the last chunk
                         tma_load_2d(st, &tmap, kc * BKH, row0, &sm.full[stage]);
-                        tma_load_2d(st + TILE_BYTES, &tmap_b, kc * BKH, c0, &sm.full[stage]);
-                        if (two) tma_load_2d(st + 2 * TILE_BYTES, &tmap_b, kc * BKH, c1, &sm.full[stage]);
+                        tma_load_2d(st + TILE_BYTES, &tmap_b, kb, c0, &sm.full[stage]);
+                        if (two) tma_load_2d(st + 2 * TILE_BYTES, &tmap_b, kb, c1, &sm.full[stage]);
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -283,11 +278,11 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                     unsigned m = 0;
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const float4 nj = *reinterpret_cast<const float4*>(s_nj + ch * 32 + 4 * u);
-                        const float d0 = fmaf(-2.0f, __uint_as_float(v[4 * u + 0]), ni + nj.x);
-                        const float d1 = fmaf(-2.0f, __uint_as_float(v[4 * u + 1]), ni + nj.y);
-                        const float d2 = fmaf(-2.0f, __uint_as_float(v[4 * u + 2]), ni + nj.z);
-                        const float d3 = fmaf(-2.0f, __uint_as_float(v[4 * u + 3]), ni + nj.w);
+                        // the accumulator holds -d~ / 2 (norms folded into the contraction, wc_prepare_f16_kernel)
+                        const float d0 = -2.0f * __uint_as_float(v[4 * u + 0]);
+                        const float d1 = -2.0f * __uint_as_float(v[4 * u + 1]);
+                        const float d2 = -2.0f * __uint_as_float(v[4 * u + 2]);
+                        const float d3 = -2.0f * __uint_as_float(v[4 * u + 3]);
                         if (d0 <= cut) m |= 1u << (4 * u + 0);
                         if (d1 <= cut) m |= 1u << (4 * u + 1);
                         if (d2 <= cut) m |= 1u << (4 * u + 2);
@@ -335,47 +330,44 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         const int g = (warp_all - 4) >> 2;          // column half of the item this warp handles (candidate block 0 / 1)
         const int we = warp_all - 4;                // epilogue warp index 0..7 (per-warp shared-memory areas)
         const int r = e * 32 + lane;                // row of the tile = TMEM lane
-        uint2* w_stg = s_stg + we * TC_STG;         // (float d~ bits, bin j | source lane << 27) of column-side candidates
-        int stg_n = 0;                              // staged entries: warp-uniform, lives in a register
-        float* w_park = s_park + we * (32 * 33);    // the chunk's 32 x 32 distances: entry (column b, lane l) at [b * 33 + l]
-        unsigned short* w_rlist = s_list + we * (2 * TC_LIST);       // row-side (column b << 5 | lane) pairs of the chunk
-        unsigned short* w_clist = w_rlist + TC_LIST;                 // column-side pairs
-        int* w_cnt = s_cnt + we * 32;               // candidate counts of the warp's 32 rows in ITS segment
-        unsigned char* w_flag = s_flag + we * 32;
-        int* w_alloc = &sm.alloc[we];
-        if (lane == 0) *w_alloc = 0;
-        __syncwarp();
+        uint2* w_stg = s_stg + we * TC_STG;         // (accumulator bits, bin j) of column-side candidates
+        float* w_park = s_park + we * (32 * TC_PARK_LD);   // the chunk's 32 x 32 accumulator values: entry (lane l, column b) at [l * TC_PARK_LD + b]
+        int cnt = 0;                                // candidates of this thread's row in ITS segment: the row has one writer
+        bool flag = false;                          // the row's buffer overflowed (tie plateau): exact fallback
         const size_t seg_stride = (size_t)BM * a.cap;
-        long long pf_epi = 0, pf_prune = 0, pf_nprune = 0, pf_emit = 0, pf_wait = 0;
+        long long pf_epi = 0, pf_prune = 0, pf_nprune = 0, pf_emit = 0, pf_wait = 0, pf_col = 0, pf_flush = 0, pf_surv = 0;
         const long long pf_t0 = clock64();
 
         // Append the staged column-side candidates to their bins' incoming buffers: four global atomics in flight per lane
         // before the first result is needed.  rowbase = first bin of this warp's 32 rows.
+        int stg_n = 0;                              // staged entries: warp-uniform, lives in a register
         auto flush_incoming = [&](int rowbase) {
+            const long long pf_f0 = clock64();
             __syncwarp();
             for (int base = 0; base < stg_n; base += 128) {
-                uint2 v[4];
+                uint2 sv[4];
                 int w[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int x = base + u * 32 + lane;
                     w[u] = -1;
                     if (x < stg_n) {
-                        v[u] = w_stg[x];
-                        w[u] = atomicAdd(a.in_cnt + (int)(v[u].y & 0x7ffffffu), 1);
+                        sv[u] = w_stg[x];
+                        w[u] = atomicAdd(a.in_cnt + (int)(sv[u].y & 0x7ffffffu), 1);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (w[u] >= 0 && w[u] < a.in_cap) {
-                        const size_t o = (size_t)(v[u].y & 0x7ffffffu) * a.in_cap + w[u];
-                        a.in_key[o] = tc_key_of_f32(__uint_as_float(v[u].x));
-                        a.in_j[o] = rowbase + (int)(v[u].y >> 27);
+                        const size_t o = (size_t)(sv[u].y & 0x7ffffffu) * a.in_cap + w[u];
+                        a.in_key[o] = tc_key_of_f32(__uint_as_float(sv[u].x));
+                        a.in_j[o] = rowbase + (int)(sv[u].y >> 27);
                     }
                 }
             }
             __syncwarp();
             stg_n = 0;
+            pf_flush += clock64() - pf_f0;
         };
 
         int it = 0;
@@ -389,23 +381,20 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             const int row = rowbase + lane;
             const bool valid = row < a.row_end;
             const double nrm = valid ? a.norms[row] : 0.0;
-            const float ni = valid ? a.n32[row] : INFINITY;          // +inf: no entry of an invalid row ever passes
             const int cs = valid ? a.row_cs[row] : 0;
             const unsigned clen = valid ? (unsigned)(a.row_ce[row] - cs) : 0u;
             u64 thr = valid ? __ldcg(a.row_thr + (row - a.row_begin)) : KEY_NEVER;
             u64* wk = a.cand_key + (size_t)seg * seg_stride + (size_t)(e * 32) * a.cap;       // buffers of the warp's 32 rows
             int* wj = a.cand_j + (size_t)seg * seg_stride + (size_t)(e * 32) * a.cap;
-            __syncwarp();
-            w_cnt[lane] = 0;
-            w_flag[lane] = 0;
-            __syncwarp();
+            cnt = 0;
+            flag = false;
 
             // warp-collective prune of the rows named in `need`; the owning lane adopts the result
             auto prune_rows = [&](unsigned need) {
                 while (need) {
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
-                    int n = w_cnt[src];
+                    int n = __shfl_sync(0xffffffffu, cnt, src);
                     if (n > a.cap) n = a.cap;
                     const double nr = __shfl_sync(0xffffffffu, nrm, src);
                     u64 nthr;
@@ -419,13 +408,13 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                         prune_row<32>(wk + (size_t)src * a.cap, wj + (size_t)src * a.cap, n, a.k, nr, a.mcoef, madd_of(a), lane, nullptr, nullptr, &nthr, &kept);
                     if (lane == src) {
                         if (kept > a.cap - BN) {             // a tie plateau wider than the buffer: exact fallback
-                            w_flag[lane] = 1;
+                            flag = true;
                             thr = KEY_NEVER;
-                            w_cnt[lane] = 0;
+                            cnt = 0;
                         } else {
                             const u64 other = atomicMin(a.row_thr + (row - a.row_begin), nthr);   // publish; adopt a tighter one
                             thr = other < nthr ? other : nthr;
-                            w_cnt[lane] = kept;
+                            cnt = kept;
                         }
                     }
                     __syncwarp();
@@ -441,20 +430,19 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 const int buf = it & 1;
                 const int cg = g == 0 ? c0 : c1;      // first bin of this warp's candidate block
                 const bool mine = g == 0 || two;      // an odd last item has no second block: the second warpgroup only keeps step
-                // column tables of the block (norms; SYM: thresholds) and the row's shared threshold: issued before the wait
-                const float njr = mine ? a.coln32[cg + r] : INFINITY;
+                // the block's column thresholds (SYM) and the row's shared threshold: issued before the wait
                 u64 ctr = KEY_NEVER;
                 if (SYM && mine) ctr = __ldcg(a.col_thr + cg + r);
                 if (valid) {
                     const u64 shared_thr = __ldcg(a.row_thr + (row - a.row_begin));
                     if (shared_thr < thr) thr = shared_thr;
                 }
-                float* nj_t = s_nj + buf * TC_NB + g * BN;           // this warpgroup's half of the tables
-                float* tj_t = s_tj + buf * TC_NB + g * BN;
-                nj_t[r] = njr;
-                if (SYM) tj_t[r] = tc_tau32_of_key(ctr);
-                const float taui = tc_tau32_of_key(thr);
-                named_bar_sync(1 + g, 128);                         // tables visible to the four warps of the warpgroup
+                float* tj_t = s_tj + buf * TC_NB + g * BN;           // this warpgroup's half of the table: tau_j / 2
+                if (SYM) tj_t[r] = 0.5f * tc_tau32_of_key(ctr);
+                // The accumulator holds u = -d~ / 2 (norms folded into the contraction): "d~ <= tau" is "u + tau / 2 >= 0", the
+                // SIGN BIT of one add - no compare, no select.  -inf: nothing of an invalid row passes.
+                const float hti = valid ? 0.5f * tc_tau32_of_key(thr) : -INFINITY;
+                if (SYM) named_bar_sync(1 + g, 128);                // table visible to the four warps of the warpgroup
                 const long long pf_w0 = clock64();
                 mbar_wait(&sm.tfull[buf], (uint32_t)((it >> 1) & 1));
                 tc_fence_after();
@@ -479,42 +467,37 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                     const int cb = ch * 32;          // column within the warp's block (0..127)
                     const int colbase = cg + cb;     // global bin of the chunk's first column
                     unsigned mask = 0, cmask = 0;
-                    float dv[32];
+                    {   // Sign bits gathered by funnel shifts, most significant entry first; four independent chains per side.
+                        unsigned pm[4] = {0u, 0u, 0u, 0u}, qm[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float4 nj = *reinterpret_cast<const float4*>(nj_t + cb + 4 * u);
-                        dv[4 * u + 0] = fmaf(-2.0f, __uint_as_float(v[4 * u + 0]), ni + nj.x);
-                        dv[4 * u + 1] = fmaf(-2.0f, __uint_as_float(v[4 * u + 1]), ni + nj.y);
-                        dv[4 * u + 2] = fmaf(-2.0f, __uint_as_float(v[4 * u + 2]), ni + nj.z);
-                        dv[4 * u + 3] = fmaf(-2.0f, __uint_as_float(v[4 * u + 3]), ni + nj.w);
-                    }
-                    {   // eight independent partial masks per side: no 32-deep dependency chain on one register
-                        unsigned pm[8], qm[8];
+                        for (int u = 7; u >= 0; --u) {
+                            float4 tj = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (SYM) tj = *reinterpret_cast<const float4*>(tj_t + cb + 4 * u);
+                            const float tjv[4] = {tj.x, tj.y, tj.z, tj.w};
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            pm[u] = (dv[4 * u + 0] <= taui ? 1u : 0u) | (dv[4 * u + 1] <= taui ? 2u : 0u) |
-                                    (dv[4 * u + 2] <= taui ? 4u : 0u) | (dv[4 * u + 3] <= taui ? 8u : 0u);
-                            qm[u] = 0u;
-                            if (SYM) {
-                                const float4 tj = *reinterpret_cast<const float4*>(tj_t + cb + 4 * u);
-                                qm[u] = (dv[4 * u + 0] <= tj.x ? 1u : 0u) | (dv[4 * u + 1] <= tj.y ? 2u : 0u) |
-                                        (dv[4 * u + 2] <= tj.z ? 4u : 0u) | (dv[4 * u + 3] <= tj.w ? 8u : 0u);
+                            for (int w = 3; w >= 0; --w) {
+                                const float uv = __uint_as_float(v[4 * u + w]);
+                                pm[u >> 1] = __funnelshift_l(__float_as_uint(uv + hti), pm[u >> 1], 1);
+                                if (SYM) qm[u >> 1] = __funnelshift_l(__float_as_uint(uv + tjv[w]), qm[u >> 1], 1);
                             }
                         }
-                        mask = (pm[0] | (pm[1] << 4)) | ((pm[2] << 8) | (pm[3] << 12)) | ((pm[4] << 16) | (pm[5] << 20)) | ((pm[6] << 24) | (pm[7] << 28));
-                        if (SYM)
-                            cmask = (qm[0] | (qm[1] << 4)) | ((qm[2] << 8) | (qm[3] << 12)) | ((qm[4] << 16) | (qm[5] << 20)) | ((qm[6] << 24) | (qm[7] << 28));
+                        mask = ~((pm[0] | (pm[1] << 8)) | ((pm[2] << 16) | (pm[3] << 24)));     // a set sign bit = beyond the threshold
+                        if (SYM) cmask = ~((qm[0] | (qm[1] << 8)) | ((qm[2] << 16) | (qm[3] << 24)));
                     }
                     if (DBG) {
                         if (valid && a.dbg != nullptr) {
 #pragma unroll
                             for (int b = 0; b < 32; ++b)
-                                if (colbase + b < a.dbg_ld) a.dbg[(size_t)(row - a.row_begin) * a.dbg_ld + colbase + b] = dv[b];
+                                if (colbase + b < a.dbg_ld) a.dbg[(size_t)(row - a.row_begin) * a.dbg_ld + colbase + b] = -2.0f * __uint_as_float(v[b]);
                         }
                     }
-                    // Columns of the row's own chromosome never count (a symmetric relation: it serves both sides); a passing
-                    // distance is finite by construction (thresholds are finite, padding rows / columns carry +inf norms).
+                    // Columns beyond the last bin (zero padding: u = 0 would pass) and, on the column side, rows beyond the last
+                    // target bin never count; nor do the columns of the row's own chromosome (a symmetric relation: both sides).
                     {
+                        const int ncol = a.N - colbase;
+                        const unsigned vm = ncol >= 32 ? 0xffffffffu : (ncol <= 0 ? 0u : (1u << ncol) - 1u);
+                        mask &= vm;
+                        cmask = valid ? (cmask & vm) : 0u;
                         int lo = cs - colbase, hi = lo + (int)clen;
                         lo = lo < 0 ? 0 : lo;
                         hi = hi > 32 ? 32 : hi;
@@ -524,102 +507,85 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                             cmask &= ~excl;
                         }
                     }
-                    // ---- survivors: compacted over the warp, then handled 32 at a time (no per-thread serial work) ----
+                    // ---- survivors (~0.7 per thread and chunk on each side once thresholds are tight) ----
+                    // Row side: a row has ONE writer, this thread - its count lives in a register, entries go straight to the row's
+                    // buffer.  Column side: slots of the warp's staging area by a warp scan.  No atomics, no list indirection, no
+                    // warp barrier on the way (r02: lists + shared-memory atomics + four barriers per chunk cost 2 x the MMA time).
                     const int rn = __popc(mask), cn = SYM ? __popc(cmask) : 0;
-                    const int packed = rn | (cn << 16);
-                    if (__any_sync(0xffffffffu, packed != 0)) {
-                        // list slots: one shared-memory atomic per lane with survivors (the lists need no order)
-                        int mine = 0;
-                        if (packed != 0) mine = atomicAdd(w_alloc, packed);
+                    const long long pf_s0 = clock64();
+                    if (__any_sync(0xffffffffu, (mask | cmask) != 0u)) {
+                        // v[] is indexed by a run-time bit below: parked in this thread's row of the warp's patch (rows 36 words apart:
+                        // the eight 128-bit stores are conflict-free)
 #pragma unroll
-                        for (int b = 0; b < 32; ++b) w_park[b * 33 + lane] = dv[b];
-                        __syncwarp();
-                        const int tot = *w_alloc;
-                        const int rt = tot & 0xffff, ct = tot >> 16;
-                        __syncwarp();
-                        if (lane == 0) *w_alloc = 0;
-                        if (rt <= TC_LIST && ct <= TC_LIST) {
-                            int pr = mine & 0xffff, pq = mine >> 16;
-                            while (mask) {
-                                const int bit = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                w_rlist[pr++] = (unsigned short)((bit << 5) | lane);
+                        for (int u = 0; u < 8; ++u)
+                            *reinterpret_cast<uint4*>(w_park + lane * TC_PARK_LD + 4 * u) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                        while (mask) {
+                            const int bit = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            if (cnt < a.cap) {
+                                wk[(size_t)lane * a.cap + cnt] = tc_key_of_f32(-2.0f * w_park[lane * TC_PARK_LD + bit]);
+                                wj[(size_t)lane * a.cap + cnt] = colbase + bit;
+                            } else {
+                                flag = true;
                             }
-                            while (cmask) {
-                                const int bit = __ffs(cmask) - 1;
-                                cmask &= cmask - 1;
-                                w_clist[pq++] = (unsigned short)((bit << 5) | lane);
+                            ++cnt;
+                        }
+                        const long long pf_c0 = clock64();
+                        if (SYM) {
+                            int incl = cn;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                                if (lane >= o) incl += t;
                             }
-                            __syncwarp();
-                            for (int x = lane; x < rt; x += 32) {          // row side: into the rows' candidate buffers
-                                const int en = w_rlist[x];
-                                const int l = en & 31, b = en >> 5;
-                                const int pos = atomicAdd(&w_cnt[l], 1);
-                                if (pos < a.cap) {
-                                    wk[(size_t)l * a.cap + pos] = tc_key_of_f32(w_park[b * 33 + l]);
-                                    wj[(size_t)l * a.cap + pos] = colbase + b;
-                                } else {
-                                    w_flag[l] = 1;
+                            const int ct = __shfl_sync(0xffffffffu, incl, 31);
+                            if (ct > TC_STG) {
+                                // more than the staging area holds (loose thresholds at the start of a pass): straight to the bins
+                                while (cmask) {
+                                    const int bit = __ffs(cmask) - 1;
+                                    cmask &= cmask - 1;
+                                    const int j = colbase + bit;
+                                    const int w = atomicAdd(a.in_cnt + j, 1);
+                                    if (w < a.in_cap) {
+                                        a.in_key[(size_t)j * a.in_cap + w] = tc_key_of_f32(-2.0f * w_park[lane * TC_PARK_LD + bit]);
+                                        a.in_j[(size_t)j * a.in_cap + w] = row;
+                                    }
                                 }
-                            }
-                            if (SYM && ct != 0) {                           // column side: into the warp's staging area
+                            } else if (ct != 0) {
                                 if (stg_n + ct > TC_STG) flush_incoming(rowbase);
-                                for (int x = lane; x < ct; x += 32) {
-                                    const int en = w_clist[x];
-                                    const int l = en & 31, b = en >> 5;
-                                    w_stg[stg_n + x] = make_uint2(__float_as_uint(w_park[b * 33 + l]), (unsigned)(colbase + b) | ((unsigned)l << 27));
+                                int q = stg_n + incl - cn;
+                                while (cmask) {
+                                    const int bit = __ffs(cmask) - 1;
+                                    cmask &= cmask - 1;
+                                    w_stg[q++] = make_uint2(__float_as_uint(-2.0f * w_park[lane * TC_PARK_LD + bit]), (unsigned)(colbase + bit) | ((unsigned)lane << 27));
                                 }
                                 stg_n += ct;
                             }
-                            pf_emit += rn + cn;
-                        } else {
-                            // more survivors than the lists hold (loose thresholds at the start of a threshold pass): every
-                            // thread serves its own row
-                            __syncwarp();
-                            while (mask) {
-                                const int bit = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                const int pos = atomicAdd(&w_cnt[lane], 1);
-                                if (pos < a.cap) {
-                                    wk[(size_t)lane * a.cap + pos] = tc_key_of_f32(w_park[bit * 33 + lane]);
-                                    wj[(size_t)lane * a.cap + pos] = colbase + bit;
-                                } else {
-                                    w_flag[lane] = 1;
-                                }
-                            }
-                            while (cmask) {
-                                const int bit = __ffs(cmask) - 1;
-                                cmask &= cmask - 1;
-                                const int j = colbase + bit;
-                                const int w = atomicAdd(a.in_cnt + j, 1);
-                                if (w < a.in_cap) {
-                                    a.in_key[(size_t)j * a.in_cap + w] = tc_key_of_f32(w_park[bit * 33 + lane]);
-                                    a.in_j[(size_t)j * a.in_cap + w] = row;
-                                }
-                            }
                         }
-                        __syncwarp();
+                        pf_emit += rn + cn;
+                        pf_col += clock64() - pf_c0;
                     }
+                    pf_surv += clock64() - pf_s0;
                 }
                 const long long pf_p0 = clock64();
                 pf_epi += pf_p0 - pf_e0;
                 // ---- prune rows whose buffer could overflow during the next item ----
-                prune_rows(__ballot_sync(0xffffffffu, w_cnt[lane] > a.cap - BN && !w_flag[lane]));
+                prune_rows(__ballot_sync(0xffffffffu, cnt > a.cap - BN && !flag));
                 pf_prune += clock64() - pf_p0;
             }
             // piece finished
             __syncwarp();
             if (SYM) flush_incoming(rowbase);
             if (a.final_prune)      // every row leaves its best threshold behind (the column side of later tiles is filtered by it)
-                prune_rows(__ballot_sync(0xffffffffu, w_cnt[lane] > a.k + 24 && w_cnt[lane] <= a.cap && !w_flag[lane]));
+                prune_rows(__ballot_sync(0xffffffffu, cnt > a.k + 24 && cnt <= a.cap && !flag));
             __syncwarp();
-            a.seg_cnt[(size_t)seg * BM + r] = w_cnt[lane] > a.cap ? a.cap : w_cnt[lane];
-            a.seg_flag[(size_t)seg * BM + r] = w_flag[lane];
+            a.seg_cnt[(size_t)seg * BM + r] = cnt > a.cap ? a.cap : cnt;
+            a.seg_flag[(size_t)seg * BM + r] = flag ? 1 : 0;
         }
         if (a.prof != nullptr && we == 0 && lane == 0) {
             long long* o = a.prof + (size_t)blockIdx.x * 8;
             o[0] = clock64() - pf_t0; o[1] = pf_wait; o[2] = pf_epi; o[3] = pf_prune;
-            o[4] = it; o[5] = pf_nprune; o[6] = pf_emit; o[7] = 0;
+            o[4] = it; o[5] = pf_col; o[6] = pf_surv; o[7] = pf_flush;
         }
     }
 
@@ -728,12 +694,14 @@ __global__ void __launch_bounds__(1024) wc_pivot_select_kernel(const float* __re
 }
 
 // P[r] = the fp16 row of pivot r, its norm next to it
-__global__ void wc_pivot_gather_kernel(const __half* __restrict__ Xh, int ldh, const float* __restrict__ n32,
+// (folded norms, ldx = ldh + 64: the pivots are B operands - their last chunk is the row's second version of it)
+__global__ void wc_pivot_gather_kernel(const __half* __restrict__ Xh, int ldh, int ldx, const float* __restrict__ n32,
                                        const int* __restrict__ ids, __half* __restrict__ P, float* __restrict__ n32p) {
     const int r = blockIdx.x;
     const int src = ids[r];
-    const uint4* s = reinterpret_cast<const uint4*>(Xh + (size_t)src * ldh);
+    const uint4* s = reinterpret_cast<const uint4*>(Xh + (size_t)src * ldx);
     uint4* d = reinterpret_cast<uint4*>(P + (size_t)r * ldh);
-    for (int i = threadIdx.x; i < ldh / 8; i += blockDim.x) d[i] = s[i];
+    const int last = (ldh - BKH) / 8, shift = (ldx - ldh) / 8;
+    for (int i = threadIdx.x; i < ldh / 8; i += blockDim.x) d[i] = s[i >= last ? i + shift : i];
     if (threadIdx.x == 0) n32p[r] = n32[src];
 }
