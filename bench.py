@@ -316,12 +316,18 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
     copy_out = torch.cuda.Stream(device=dev)
     in_flight = []          # (device tensors, copy-finished event) of the batches whose results are still travelling
 
-    def run(from_host):
+    host_cwz = torch.empty((B, 22), dtype=torch.float64).pin_memory()
+    host_sd = torch.empty((B,), dtype=torch.float64).pin_memory()
+
+    def run(from_host, full=False):
         counts = counts_pinned.to(dev, non_blocking=True) if from_host else counts_dev
         T = device.test_prep(counts, masked_raw, mean, comps)
         z, r, sizes, asdef = device.zscore_batch(T, B, table, thr, 5)
-        cwz, cleaned, calls = device.segment_batch(z, sizes, bins, list(range(22)), 25, thr, 3)
-        if from_host:       # results go to pinned host memory on a second stream while the next batch computes
+        cwz, cleaned, calls = device.segment_batch(z, sizes, bins, list(range(22)), 25, thr, 3)   # calls: on the host already
+        if from_host and not full:      # compact result: calls, chromosome-wide z, sigma average (what a report needs)
+            host_cwz.copy_(torch.as_tensor(cwz).reshape(B, -1)[:, :22], non_blocking=True)
+            host_sd.copy_(torch.as_tensor(asdef).reshape(-1)[:B], non_blocking=True)
+        if from_host and full:  # also the per-bin vectors, on a second stream while the next batch computes
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(dev))
             with torch.cuda.stream(copy_out):
@@ -355,18 +361,22 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
     e1.record()
     torch.cuda.synchronize(dev)
     dev_ms = e0.elapsed_time(e1) / steps
-    run(True)
-    torch.cuda.synchronize(dev)
     e2e_steps = max(steps, 4)
-    t0 = time.time()
-    for _ in range(e2e_steps):
-        run(True)
-    torch.cuda.synchronize(dev)           # includes the last batch's device-to-host copies
-    e2e_s = (time.time() - t0) / e2e_steps
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    e2e_both = []
+    for full in (False, True):
+        run(True, full)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.time()
+        for _ in range(e2e_steps):
+            run(True, full)
+        torch.cuda.synchronize(dev)           # includes the last batch's device-to-host copies
+        e2e_both.append((time.time() - t0) / e2e_steps)
+    t = torch.tensor([dev_ms] + e2e_both, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    dev_ms, e2e_s, e2e_full_s = float(t[0].item()), float(t[1].item()), float(t[2].item())
     if rank != 0:
         return None
     zms, sms = float(np.mean(zs)), float(np.mean(sg))
@@ -382,6 +392,14 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
             hbm = float(json.load(fh)["hbm_gbs"])
     except Exception:
         pass
+    l2_peak = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "l2_peak_r03.json")) as fh:
+            l2_peak = float(json.loads(fh.readline())["ldg128_gbs"])
+    except Exception:
+        pass
+    props = torch.cuda.get_device_properties(dev)
+    issue_peak = props.multi_processor_count * 4 * 32 * 1.965e9
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_test(bins, idx_full.cpu().numpy(), dist_h, cut, thr)
@@ -396,9 +414,23 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
                        "whole z-score phase (marks, work lists, sigma average and transposes included); operands come "
                        "from L2, not HBM",
         "segment_run_evals_per_s": entries / (sms * 1e-3),
-        "e2e": {"value": world * B / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * n * 4, "d2h_bytes_per_step": B * n * 20,
-                "api": "device.test_prep + zscore_batch + segment_batch from pinned host counts; z, r, refsizes copied back "
-                       "to pinned host memory on a second stream overlapping the next batch, %d batches" % e2e_steps},
+        "roofline": {
+            "K8": {"bound": "l2", "achieved": gathers / (zms * 1e-3) / 1e9, "peak": l2_peak, "unit": "GB/s",
+                   "frac": (gathers / (zms * 1e-3) / 1e9 / l2_peak) if l2_peak else None,
+                   "note": "executed gather bytes of the whole z-score phase against the L2 -> SM figure of tools/l2_peak.cu "
+                           "(profiles/l2_peak_r03.json); the working copy of a 32-sample tile (15 MB) is L2-resident"},
+            "K9": {"bound": "issue", "achieved": entries / (sms * 1e-3), "peak": issue_peak / 3.0, "unit": "run evaluations/s",
+                   "frac": entries / (sms * 1e-3) / (issue_peak / 3.0),
+                   "note": "fp32 sweep: FADD + FMUL + FMNMX per run evaluation; ceiling = SMs x 4 schedulers x 32 lanes x "
+                           "max SM clock / 3 instructions"}},
+        "e2e": {"value": world * B / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * n * 4,
+                "d2h_bytes_per_step": B * (22 + 1) * 8 + ncalls * 24,
+                "api": "device.test_prep + zscore_batch + segment_batch from pinned host counts; calls, chromosome-wide z and "
+                       "sigma averages back (the compact result a report needs), %d batches" % e2e_steps},
+        "e2e_full": {"value": world * B / e2e_full_s, "unit": "samples/s", "h2d_bytes_per_step": B * n * 4,
+                     "d2h_bytes_per_step": B * n * 20 + B * (22 + 1) * 8 + ncalls * 24,
+                     "api": "as e2e, plus the per-bin z, ratio and refsize vectors of every sample copied back to pinned host "
+                            "memory on a second stream overlapping the next batch (what a result npz holds)"},
         "parallelism": "samples sharded over %d GPU(s), no communication" % world,
     }
 

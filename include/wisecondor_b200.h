@@ -99,6 +99,8 @@ int wc_set_option(wc_ctx* ctx, const char* key, double value);
  * out_d[(i - row_begin) * ld + j] (DEVICE float, caller-owned).  NULL switches it off.  Used by the tests that measure the
  * filter's error against the margin its exactness argument assumes. */
 int wc_debug_filter_scores(wc_ctx* ctx, float* out_d, int ld);
+/* debug: K5t's pivot selection alone - the R bins of smallest fp32 norm (ties by bin), sorted by bin; device pointers */
+int wc_debug_pivot_select(wc_ctx* ctx, const float* n32_d, int N, int R, int* ids_d);
 
 /* ABI version of this header; wc_abi_version() returns the one the library was built from (the binding refuses a mismatch). */
 #define WC_ABI_VERSION 2

@@ -146,3 +146,22 @@ def test_f16_filter_sharded_symmetric_search(monkeypatch):
         for world in (2, 3):
             idx, dist, stats = _emulated_ranks(X, bins, 100, world)
             _assert_same(idx, dist, oidx, odist)
+
+
+def test_pivot_selection_is_the_r_smallest_norms_sorted_by_bin():
+    """K5t's pivot pass starts from the R bins of smallest norm (ties by bin index), sorted by bin (wc_pivot_select_kernel)."""
+    import torch
+    from wisecondor_b200 import _cabi
+    rng = np.random.default_rng(3)
+    ctx = _cabi.context(0)
+    for n, r, ties in ((57633, 512, False), (4100, 512, True), (288113, 512, False), (2048, 512, True)):
+        v = rng.random(n).astype(np.float32) * 50.0
+        if ties:
+            v = np.round(v)                       # massive ties, also at the R-th place
+        v[rng.integers(0, n, 5)] = np.inf         # padding-like entries never come first
+        order = np.lexsort((np.arange(n), v))[:r]
+        want = np.sort(order)
+        vd = torch.from_numpy(v).cuda()
+        ids = torch.empty(r, dtype=torch.int32, device="cuda")
+        _cabi.check(_cabi.lib().wc_debug_pivot_select(ctx.handle, vd.data_ptr(), n, r, ids.data_ptr()))
+        assert np.array_equal(ids.cpu().numpy(), want)

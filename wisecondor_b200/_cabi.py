@@ -12,7 +12,7 @@ _LIB = None
 ABI_VERSION = 2      # include/wisecondor_b200.h: WC_ABI_VERSION
 
 SYMBOLS = [
-    "wc_create", "wc_destroy", "wc_last_error", "wc_version", "wc_abi_version", "wc_debug_filter_scores", "wc_sm_count", "wc_last_phase_ms",
+    "wc_create", "wc_destroy", "wc_last_error", "wc_version", "wc_abi_version", "wc_debug_filter_scores", "wc_debug_pivot_select", "wc_sm_count", "wc_last_phase_ms",
     "wc_last_counter", "wc_device_count", "wc_dev_alloc", "wc_dev_free", "wc_copy_h2d", "wc_copy_d2h", "wc_dev_sync", "wc_newref_topk", "wc_newref_topk_host",
     "wc_newref_shard_dims", "wc_newref_shard_begin", "wc_newref_shard_sweep", "wc_newref_shard_finish", "wc_debug_sym_plan", "wc_debug_profile", "wc_set_option",
     "wc_newref_mask", "wc_newref_normalize", "wc_pca_gram", "wc_pca_apply",
@@ -46,6 +46,8 @@ def lib():
                               "(python -m wisecondor_b200.build --force)" % (path, have, ABI_VERSION))
     L.wc_debug_filter_scores.restype = ci
     L.wc_debug_filter_scores.argtypes = [vp, vp, ci]
+    L.wc_debug_pivot_select.restype = ci
+    L.wc_debug_pivot_select.argtypes = [vp, vp, ci, ci, vp]
     L.wc_create.restype = vp
     L.wc_create.argtypes = [ci]
     L.wc_destroy.restype = None

@@ -1918,6 +1918,16 @@ extern "C" int wc_debug_filter_scores(wc_ctx* ctx, float* out_d, int ld) {
     return WC_OK;
 }
 
+// Debug: the pivot selection of K5t alone - the R bins of smallest norm (ties by bin), sorted by bin (device pointers).
+extern "C" int wc_debug_pivot_select(wc_ctx* ctx, const float* n32_d, int N, int R, int* ids_d) {
+    WC_CHECK_ARG(ctx != nullptr && n32_d != nullptr && ids_d != nullptr && N > 0 && R > 0 && R <= N);
+    WC_CUDA(cudaSetDevice(ctx->device));
+    wc_pivot_select_kernel<<<1, 1024>>>(n32_d, N, R, ids_d);
+    WC_CUDA(cudaGetLastError());
+    WC_CUDA(cudaDeviceSynchronize());
+    return WC_OK;
+}
+
 // Tuning knobs (debug / experiments).  key "k5_lag": chunks by which the trailing consumer warps lag (0..4).
 extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
     WC_CHECK_ARG(ctx != nullptr && key != nullptr);

@@ -358,37 +358,66 @@ struct RankArgs {
 };
 constexpr int RK_WARPS = 8;
 
-// Bitonic sort of 32 * EPL (key, bin) pairs held EPL per lane (element e = t * 32 + lane), ascending by (key, bin):
-// compare-exchange distances below 32 go through shuffles, the others stay inside the lane.
-template <int EPL>
-__device__ __forceinline__ void rank_sort(u64 (&key)[EPL], int (&bin)[EPL], int lane) {
+// (key a, bin ja) < (key b, bin jb) as one 96-bit subtraction with borrow: 0xffffffff if less, else 0
+__device__ __forceinline__ unsigned pair_less96(u64 a, int ja, u64 b, int jb) {
+    unsigned r;
+    asm("{\n"
+        ".reg .u32 t;\n"
+        "sub.cc.u32 t, %1, %4;\n"
+        "subc.cc.u32 t, %2, %5;\n"
+        "subc.cc.u32 t, %3, %6;\n"
+        "subc.u32 %0, 0, 0;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"((unsigned)ja), "r"((unsigned)(a & 0xffffffffu)), "r"((unsigned)(a >> 32)), "r"((unsigned)jb),
+          "r"((unsigned)(b & 0xffffffffu)), "r"((unsigned)(b >> 32)));
+    return r;
+}
+
+// One compare-exchange step at distance STRIDE of the bitonic network (blocks of `size` sort up / down alternately).
+// Pairs are distinct except for padding entries, which are identical - either choice is the same.
+template <int EPL, int STRIDE>
+__device__ __forceinline__ void rank_step(u64 (&key)[EPL], int (&bin)[EPL], int lane, int size) {
 #pragma unroll
-    for (int size = 2; size <= 32 * EPL; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-            for (int t = 0; t < EPL; ++t) {
-                const int e = t * 32 + lane;
-                const bool up = (e & size) == 0;                    // this block sorts ascending
-                if (stride >= 32) {
-                    const int t2 = t ^ (stride >> 5);
-                    if (t2 > t) {                                    // one compare-exchange per pair, both ends in this lane
-                        const bool less2 = key[t2] < key[t] || (key[t2] == key[t] && bin[t2] < bin[t]);
-                        if (less2 == up) {
-                            const u64 tk = key[t]; key[t] = key[t2]; key[t2] = tk;
-                            const int tb = bin[t]; bin[t] = bin[t2]; bin[t2] = tb;
-                        }
-                    }
-                } else {
-                    const u64 ok = __shfl_xor_sync(0xffffffffu, key[t], stride);
-                    const int ob = __shfl_xor_sync(0xffffffffu, bin[t], stride);
-                    const bool lower = (lane & stride) == 0;         // this end keeps the smaller one when ascending
-                    const bool other_less = ok < key[t] || (ok == key[t] && ob < bin[t]);
-                    const bool take = (lower == up) ? other_less : !other_less && !(ok == key[t] && ob == bin[t]);
-                    if (take) { key[t] = ok; bin[t] = ob; }
+    for (int t = 0; t < EPL; ++t) {
+        const int e = t * 32 + lane;
+        const bool up = (e & size) == 0;                    // this block sorts ascending
+        if (STRIDE >= 32) {
+            const int t2 = t ^ (STRIDE >> 5);
+            if (t2 > t) {                                    // one compare-exchange per pair, both ends in this lane
+                const bool less2 = pair_less96(key[t2], bin[t2], key[t], bin[t]) != 0u;
+                if (less2 == up) {
+                    const u64 tk = key[t]; key[t] = key[t2]; key[t2] = tk;
+                    const int tb = bin[t]; bin[t] = bin[t2]; bin[t2] = tb;
                 }
             }
+        } else {
+            const u64 ok = __shfl_xor_sync(0xffffffffu, key[t], STRIDE);
+            const int ob = __shfl_xor_sync(0xffffffffu, bin[t], STRIDE);
+            const bool want_min = ((lane & STRIDE) == 0) == up;       // this end keeps the smaller one
+            const bool other_less = pair_less96(ok, ob, key[t], bin[t]) != 0u;
+            if (other_less == want_min) { key[t] = ok; bin[t] = ob; }
         }
+    }
+}
+
+// Bitonic sort of 32 * EPL (key, bin) pairs held EPL per lane (element e = t * 32 + lane), ascending by (key, bin):
+// compare-exchange distances below 32 go through shuffles, the others stay inside the lane.  The loop over the block size is
+// a run-time loop around ONE copy of every distance's step (the fully unrolled network is 0.7 MB of code for the three
+// instantiations).
+template <int EPL>
+__device__ __forceinline__ void rank_sort(u64 (&key)[EPL], int (&bin)[EPL], int lane) {
+#pragma unroll 1
+    for (int size = 2; size <= 32 * EPL; size <<= 1) {
+        if (EPL >= 16 && size > 256) rank_step<EPL, (EPL >= 16 ? 256 : 1)>(key, bin, lane, size);
+        if (EPL >= 8 && size > 128) rank_step<EPL, (EPL >= 8 ? 128 : 1)>(key, bin, lane, size);
+        if (EPL >= 4 && size > 64) rank_step<EPL, (EPL >= 4 ? 64 : 1)>(key, bin, lane, size);
+        if (EPL >= 2 && size > 32) rank_step<EPL, (EPL >= 2 ? 32 : 1)>(key, bin, lane, size);
+        if (size > 16) rank_step<EPL, 16>(key, bin, lane, size);
+        if (size > 8) rank_step<EPL, 8>(key, bin, lane, size);
+        if (size > 4) rank_step<EPL, 4>(key, bin, lane, size);
+        if (size > 2) rank_step<EPL, 2>(key, bin, lane, size);
+        rank_step<EPL, 1>(key, bin, lane, size);
     }
 }
 
