@@ -258,6 +258,8 @@ def test_testbatch_on_two_gpus_equals_one(workdir, tiny):
     outdir = str(workdir / "batch2")
     tests = [str(workdir / ("t%d.npz" % t)) for t in (0, 1, 3)]
     _run(["testbatch"] + tests + [outdir, str(workdir / "goldref.npz"), "-minrefbins", "10", "-batch", "2", "-gpus", "2"])
+    if not os.path.isdir(str(workdir / "batch")):       # (the single-GPU run of test_testbatch_equals_single_runs, when deselected)
+        _run(["testbatch"] + tests + [str(workdir / "batch"), str(workdir / "goldref.npz"), "-minrefbins", "10", "-batch", "2"])
     for t in (0, 1, 3):
         res = np.load(os.path.join(outdir, "t%d.npz" % t), allow_pickle=True)
         one = np.load(os.path.join(str(workdir / "batch"), "t%d.npz" % t), allow_pickle=True)

@@ -727,6 +727,7 @@ struct FinArgs {
     int* grp_count;
     const int* row_list;    // rows this launch handles (grid-stride), or nullptr: row = blockIdx.x
     const int* row_count;
+    int* stats;             // split form: [0] live entries, [1] shortlisted candidates, [2] most live entries of a row; or nullptr
 };
 
 // One CTA per target row.
@@ -910,6 +911,7 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int rloc, u
             const int ng = (p + 31) >> 5;
             const int base = atomicAdd(a.grp_count, ng);
             for (int g = 0; g < ng; ++g) a.grp[base + g] = (rloc << 4) | g;
+            if (a.stats != nullptr) { atomicAdd(a.stats, total); atomicAdd(a.stats + 1, p); }
         }
         return;
     }

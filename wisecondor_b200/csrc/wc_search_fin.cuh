@@ -246,7 +246,7 @@ __global__ void __launch_bounds__((W + W * R) * 32, 1) wc_fin_rescore_kernel(con
     const int D = nslot / W;                   // ring depth per consumer warp
     const uint32_t slot_bytes = 33u * (uint32_t)a.stride;
     if (tid == 0) {
-        for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 32); }      // every consumer lane releases its slot itself
         mbar_fence_init();
     }
     __syncthreads();
@@ -303,8 +303,7 @@ __global__ void __launch_bounds__((W + W * R) * 32, 1) wc_fin_rescore_kernel(con
                     d = __dsub_rn(v1, x1);
                     acc = __dadd_rn(acc, __dmul_rn(d, d));
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[slot]);
+                mbar_arrive(&empty[slot]);       // (release: this lane's reads of the slot are done)
             }
             if (lane < cnt) a.sl_d[(size_t)rloc * a.shortcap + gi * 32 + lane] = acc;
         }
@@ -484,7 +483,7 @@ static int launch_finalize(wc_ctx* ctx, cudaStream_t stream, FinArgs fa, int row
     const size_t fin_smem = (size_t)FIN_ECAP * 12 + (size_t)fa.shortcap * 12 + HIST_BINS * 4;
     // the streaming re-score needs 16-byte aligned rows (bulk copies): an even number of samples
     const bool split = ctx->k6_split != 0 && fa.S % 2 == 0 && fa.S >= 8 && (reinterpret_cast<uintptr_t>(fa.X) & 15) == 0 && rows > 0;
-    fa.sl_j = nullptr; fa.sl_p = nullptr; fa.grp = nullptr; fa.grp_count = nullptr; fa.row_list = nullptr; fa.row_count = nullptr;
+    fa.sl_j = nullptr; fa.sl_p = nullptr; fa.grp = nullptr; fa.grp_count = nullptr; fa.row_list = nullptr; fa.row_count = nullptr; fa.stats = nullptr;
     ctx->k6_stats_d = nullptr;
     ctx->phase_ms[10] = 0.0;
     ctx->timed_mask &= ~(1u << 10);
@@ -513,7 +512,7 @@ static int launch_finalize(wc_ctx* ctx, cudaStream_t stream, FinArgs fa, int row
     int* stats = fa.sl_p + rows + 2;
     int* big_list = fa.grp + (size_t)rows * gpr;
     WC_CUDA(cudaMemsetAsync(fa.grp_count, 0, 5 * sizeof(int), stream));
-    fa.row_list = nullptr; fa.row_count = nullptr;
+    fa.row_list = nullptr; fa.row_count = nullptr; fa.stats = stats;
     const size_t sel_smem = SEL_WARPS * SEL_WARP_STRIDE;
     WC_CUDA(cudaFuncSetAttribute(wc_fin_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     wc_fin_select_kernel<<<(rows + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, sel_smem, stream>>>(fa, big_list, big_count, stats);
