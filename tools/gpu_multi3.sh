@@ -19,7 +19,7 @@ except Exception as e:
     print(sys.argv[1], "ERR", e)
 PY
 }
-for SH in rows sym; do
+for SH in sym; do
 F=$OUT/bench_newref_600x50kb_g${N}_${SH}_$TAG
 timeout 900 $TR --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --shard $SH --no-test > $F.json 2> $F.err; summ $F.json; tail -2 $F.err
 done

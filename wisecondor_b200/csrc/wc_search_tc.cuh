@@ -519,16 +519,30 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
                             *reinterpret_cast<uint4*>(w_park + lane * TC_PARK_LD + 4 * u) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-                        while (mask) {
+                        while (mask) {                  // two survivors per round: their value -> key -> store chains overlap
                             const int bit = __ffs(mask) - 1;
                             mask &= mask - 1;
+                            const int bit2 = mask ? __ffs(mask) - 1 : -1;
+                            mask &= mask - 1;           // (0 stays 0)
+                            const float u1 = w_park[lane * TC_PARK_LD + bit];
+                            const float u2 = w_park[lane * TC_PARK_LD + (bit2 < 0 ? bit : bit2)];
+                            const u64 k1 = tc_key_of_f32(-2.0f * u1), k2 = tc_key_of_f32(-2.0f * u2);
                             if (cnt < a.cap) {
-                                wk[(size_t)lane * a.cap + cnt] = tc_key_of_f32(-2.0f * w_park[lane * TC_PARK_LD + bit]);
+                                wk[(size_t)lane * a.cap + cnt] = k1;
                                 wj[(size_t)lane * a.cap + cnt] = colbase + bit;
                             } else {
                                 flag = true;
                             }
                             ++cnt;
+                            if (bit2 >= 0) {
+                                if (cnt < a.cap) {
+                                    wk[(size_t)lane * a.cap + cnt] = k2;
+                                    wj[(size_t)lane * a.cap + cnt] = colbase + bit2;
+                                } else {
+                                    flag = true;
+                                }
+                                ++cnt;
+                            }
                         }
                         const long long pf_c0 = clock64();
                         if (SYM) {
