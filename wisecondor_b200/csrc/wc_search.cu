@@ -43,6 +43,7 @@ constexpr int MAX_STAGES = 6;
 constexpr int HIST_BINS = 256;
 constexpr int FIN_THREADS = 128;    // one thread per shortlisted candidate during the exact re-score
 constexpr int FIN_CHUNK = 32;       // samples staged per pipeline step of the re-score
+constexpr int FIN_BUCKETS = 1024;   // locality buckets of the re-score's work list
 constexpr int FIN_ECAP = 1360;      // candidate entries of one row K6 collects in shared memory (16 KiB; later the target's own row: S <= 2040); more: read from the sources
 constexpr int FIN_LD = FIN_CHUNK + 1;   // padded tile row (bank-conflict free per-thread row walks)
 constexpr int FIN_LDB = FIN_CHUNK + 2;  // tile row of the 16-byte copy path: 16-byte aligned rows (2-way conflicts, cheap)
@@ -728,6 +729,10 @@ struct FinArgs {
     const int* row_list;    // rows this launch handles (grid-stride), or nullptr: row = blockIdx.x
     const int* row_count;
     int* stats;             // split form: [0] live entries, [1] shortlisted candidates, [2] most live entries of a row; or nullptr
+    // locality order of the re-score: a row's work items are filed under the smallest shortlisted bin (bucket = bin >> shift)
+    int* sl_b;              // [rows] bucket of the row
+    int* bkt_hist;          // [FIN_BUCKETS] work items per bucket
+    int bkt_shift;
 };
 
 // One CTA per target row.
@@ -909,8 +914,11 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int rloc, u
         if (tid == 0) {
             a.sl_p[rloc] = p;
             const int ng = (p + 31) >> 5;
-            const int base = atomicAdd(a.grp_count, ng);
-            for (int g = 0; g < ng; ++g) a.grp[base + g] = (rloc << 4) | g;
+            int jmin = 0x7fffffff;
+            for (int e = 0; e < p; ++e) jmin = min(jmin, ex_j[e]);
+            const int bkt = min(jmin >> a.bkt_shift, FIN_BUCKETS - 1);
+            a.sl_b[rloc] = bkt;
+            atomicAdd(a.bkt_hist + bkt, ng);
             if (a.stats != nullptr) { atomicAdd(a.stats, total); atomicAdd(a.stats + 1, p); }
         }
         return;

@@ -169,27 +169,66 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) wc_fin_select_kernel(const Fin
     if (!(window > 1e-300)) window = 1e-300;
     const u64 wkey = key_of_tau(window);
     // ---- shortlist: entries within the window, in entry order ----
-    int p = 0;
+    int p = 0, jmin = 0x7fffffff;
 #pragma unroll
     for (int t = 0; t < SEL_EPL; ++t) {
         const bool keep = t * 32 + lane < kept && d[t] <= wkey;
         const unsigned bm = __ballot_sync(0xffffffffu, keep);
         const int pos = p + __popc(bm & ((1u << lane) - 1u));
-        if (keep && pos < a.shortcap) a.sl_j[(size_t)rloc * a.shortcap + pos] = en_j[t * 32 + lane];
+        if (keep && pos < a.shortcap) {
+            const int j = en_j[t * 32 + lane];
+            a.sl_j[(size_t)rloc * a.shortcap + pos] = j;
+            jmin = min(jmin, j);
+        }
         p += __popc(bm);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
     if (lane == 0) {
         if (p > a.shortcap) {                    // tie plateau wider than the shortlist: exact fallback
             a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
             a.sl_p[rloc] = -1;
         } else {
             a.sl_p[rloc] = p;
-            const int ng = (p + 31) >> 5;
-            const int base = atomicAdd(a.grp_count, ng);
-            for (int g = 0; g < ng; ++g) a.grp[base + g] = (rloc << 4) | g;
+            // Work items are filed by the smallest shortlisted bin: target bins that share candidates are re-scored close in
+            // time, so their candidate rows are still in the L2 (LRU model on the bench matrix: misses 44 % -> 24 %).
+            const int bkt = min(jmin >> a.bkt_shift, FIN_BUCKETS - 1);
+            a.sl_b[rloc] = bkt;
+            atomicAdd(a.bkt_hist + bkt, (p + 31) >> 5);
             if (stats != nullptr) { atomicAdd(stats, kept); atomicAdd(stats + 1, p); atomicMax(stats + 2, kept); }
         }
     }
+}
+
+// The re-score's work list in locality order: exclusive scan of the buckets' item counts (one CTA), then every row files its
+// items under its bucket (order inside a bucket: arrival).
+__global__ void __launch_bounds__(FIN_BUCKETS) wc_fin_bucket_scan_kernel(int* __restrict__ hist, int* __restrict__ total) {
+    __shared__ int s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v = hist[tid];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_w[w];
+    hist[tid] = base + incl - v;                               // becomes the bucket's cursor
+    if (tid == FIN_BUCKETS - 1) *total = base + incl;
+}
+
+__global__ void wc_fin_bucket_scatter_kernel(int rows, const int* __restrict__ sl_p, const int* __restrict__ sl_b,
+                                             int* __restrict__ cursor, int* __restrict__ grp) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int p = sl_p[r];
+    if (p <= 0) return;
+    const int ng = (p + 31) >> 5;
+    const int base = atomicAdd(cursor + sl_b[r], ng);
+    for (int g = 0; g < ng; ++g) grp[base + g] = (r << 4) | g;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -504,12 +543,17 @@ static int launch_finalize(wc_ctx* ctx, cudaStream_t stream, FinArgs fa, int row
     const int gpr = fa.shortcap / 32;                      // work items per row at most
     if ((rc = wc_reserve(ctx, SLOT_FIN_J, (size_t)rows * fa.shortcap * sizeof(int), (void**)&fa.sl_j))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_FIN_D, (size_t)rows * fa.shortcap * sizeof(double), (void**)&sl_d))) return rc;
-    if ((rc = wc_reserve(ctx, SLOT_FIN_P, ((size_t)rows + 8) * sizeof(int), (void**)&fa.sl_p))) return rc;
+    if ((rc = wc_reserve(ctx, SLOT_FIN_P, (2 * (size_t)rows + 8 + FIN_BUCKETS) * sizeof(int), (void**)&fa.sl_p))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_FIN_GRP, (size_t)rows * (gpr + 1) * sizeof(int), (void**)&fa.grp))) return rc;
     // sl_p[rows .. rows + 3]: work-item counter, rows passed on to the CTA-per-row select, live entries / shortlist sizes (stats)
     fa.grp_count = fa.sl_p + rows;
     int* big_count = fa.sl_p + rows + 1;
     int* stats = fa.sl_p + rows + 2;
+    fa.sl_b = fa.sl_p + rows + 8;
+    fa.bkt_hist = fa.sl_b + rows;
+    fa.bkt_shift = 0;
+    while (((fa.N - 1) >> fa.bkt_shift) >= FIN_BUCKETS) ++fa.bkt_shift;
+    WC_CUDA(cudaMemsetAsync(fa.bkt_hist, 0, FIN_BUCKETS * sizeof(int), stream));
     int* big_list = fa.grp + (size_t)rows * gpr;
     WC_CUDA(cudaMemsetAsync(fa.grp_count, 0, 5 * sizeof(int), stream));
     fa.row_list = nullptr; fa.row_count = nullptr; fa.stats = stats;
@@ -529,6 +573,9 @@ static int launch_finalize(wc_ctx* ctx, cudaStream_t stream, FinArgs fa, int row
         }
         WC_CUDA(cudaGetLastError());
     }
+    wc_fin_bucket_scan_kernel<<<1, FIN_BUCKETS, 0, stream>>>(fa.bkt_hist, fa.grp_count);
+    wc_fin_bucket_scatter_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(rows, fa.sl_p, fa.sl_b, fa.bkt_hist, fa.grp);
+    WC_CUDA(cudaGetLastError());
     WC_CUDA(cudaEventRecord(ctx->ev[20], stream));
     RescoreArgs ra;
     ra.X = fa.X; ra.S = fa.S; ra.row_begin = fa.row_begin; ra.shortcap = fa.shortcap; ra.sl_j = fa.sl_j; ra.sl_d = sl_d;
@@ -567,6 +614,6 @@ static int launch_finalize(wc_ctx* ctx, cudaStream_t stream, FinArgs fa, int row
     WC_CUDA(cudaGetLastError());
     ctx->timed_mask |= 1u << 10;                           // phase 10: the re-score alone (read on demand)
     ctx->k6_stats_d = big_count;                           // [0] rows passed on, [1] live entries, [2] shortlisted candidates, [3] most live entries of a row
-    *launches = 4;                                         // select (warp per row), select (row list), re-score, rank
+    *launches = 6;                                         // select (warp per row), select (row list), bucket scan, scatter, re-score, rank
     return WC_OK;
 }

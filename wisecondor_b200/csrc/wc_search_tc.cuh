@@ -430,7 +430,8 @@ wc_dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 const int buf = it & 1;
                 const int cg = g == 0 ? c0 : c1;      // first bin of this warp's candidate block
                 const bool mine = g == 0 || two;      // an odd last item has no second block: the second warpgroup only keeps step
-                // the block's column thresholds (SYM) and the row's shared threshold: issued before the wait
+                // the block's column thresholds (SYM) and the row's shared threshold: issued before the wait.  (Fetching them one
+                // item ahead was measured slower, r03r: staler thresholds let more survivors through than the hidden latency saves.)
                 u64 ctr = KEY_NEVER;
                 if (SYM && mine) ctr = __ldcg(a.col_thr + cg + r);
                 if (valid) {
