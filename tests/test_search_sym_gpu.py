@@ -96,3 +96,20 @@ def test_partial_ranges_and_small_genomes_take_the_plain_path(sym):
     Xs = synth.corrected_like(small, 20, seed=8)
     idx, dist = device.newref_topk_host(Xs, small, 0, 750, 10)
     assert device.last_search_stats(0)["launches"] in (5, 10)
+
+
+def test_rescore_by_tma_gather4_returns_the_same_table(sym):
+    """Option k6_g4: K6c fetches the candidate rows four per TMA request (tile::gather4) - same table as the bulk-copy form."""
+    from wisecondor_b200 import _cabi
+    bins = [int(b) for b in np.array(synth.chrom_bins(250000)) // 2]
+    X = synth.corrected_like(bins, 130, seed=21)
+    idx, dist, st = _gpu_search(X, bins, 100)
+    ctx = _cabi.context(0)
+    _cabi.check(_cabi.lib().wc_set_option(ctx.handle, b"k6_g4", 1.0))
+    try:
+        gidx, gdist, gst = _gpu_search(X, bins, 100)
+    finally:
+        _cabi.check(_cabi.lib().wc_set_option(ctx.handle, b"k6_g4", 0.0))
+    _assert_same(gidx, gdist, idx, dist)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, 256, 100)
+    _assert_same(gidx[:256], gdist[:256], oidx, odist)

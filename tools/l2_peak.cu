@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda.h>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
@@ -71,6 +72,40 @@ __global__ void __launch_bounds__(NW * 32, 1) bulk_kernel(const unsigned char* _
     }
 }
 
+// gather4: one TMA request brings 4 rows x `C` doubles (tile::gather4 of a 2-D tensor map with a 1-row box)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) gather4_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int C, int iters) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm);                  // [NW * 32][2]
+    const int slot = (4 * C * 8 + 127) / 128 * 128;
+    unsigned char* slots = sm + ((NW * 32 * 2 * 8 + 127) / 128 * 128);
+    const int tid = threadIdx.x;
+    for (int s = 0; s < 2; ++s)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[tid * 2 + s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    unsigned pos = (blockIdx.x * blockDim.x + tid) * 977u;
+    for (int it = 0; it < iters + 2; ++it) {
+        const int s = it & 1;
+        if (it >= 2) {
+            uint32_t ok = 0;
+            const uint32_t par = (uint32_t)(((it - 2) >> 1) & 1);
+            while (!ok)
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(ok) : "r"(smem_u32(&bars[tid * 2 + s])), "r"(par) : "memory");
+        }
+        if (it >= iters) continue;
+        const int r0 = (int)(pos % (unsigned)rows), r1 = (int)((pos * 3u + 1u) % (unsigned)rows), r2 = (int)((pos * 5u + 2u) % (unsigned)rows),
+                  r3 = (int)((pos * 7u + 3u) % (unsigned)rows);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[tid * 2 + s])), "r"(4 * C * 8) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                     ::"r"(smem_u32(slots + ((size_t)tid * 2 + s) * slot)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3),
+                       "r"(smem_u32(&bars[tid * 2 + s]))
+                     : "memory");
+        pos += 7919u;
+    }
+}
+
 int main(int argc, char** argv) {
     const size_t mib = argc > 1 ? (size_t)atoi(argv[1]) : 48;
     const size_t bytes = mib << 20;
@@ -123,6 +158,47 @@ int main(int argc, char** argv) {
             best = ms < best ? ms : best;
         }
         printf(", \"bulk%d_gbs\": %.1f", chunk, (double)sms * NW * 32 * iters * chunk / (best * 1e-3) / 1e9);
+    }
+    {   // gather4 requests: rows of 128 doubles, box of C columns x 1 row
+        typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        const int rowlen = 128;
+        const int nrows = (int)(bytes / (rowlen * 8));
+        const int Cs[3] = {32, 64, 100};
+        for (int ci = 0; ci < 3; ++ci) {
+            const int C = Cs[ci];
+            CUtensorMap tm;
+            cuuint64_t dims[2] = {(cuuint64_t)rowlen, (cuuint64_t)nrows};
+            cuuint64_t strides[1] = {(cuuint64_t)rowlen * 8};
+            cuuint32_t box[2] = {(cuuint32_t)C, 1};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = reinterpret_cast<PFN>(fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, buf, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { printf(", \"gather4_%d_err\": %d", C, (int)r); continue; }
+            constexpr int NW = 1;
+            const int slot = (4 * C * 8 + 127) / 128 * 128;
+            const size_t smem = ((NW * 32 * 2 * 8 + 127) / 128 * 128) + (size_t)NW * 32 * 2 * slot;
+            if (smem > 227 * 1024) continue;
+            CK(cudaFuncSetAttribute(gather4_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int iters = 4000;
+            gather4_kernel<NW><<<sms, NW * 32, smem>>>(tm, nrows, C, 100);
+            CK(cudaDeviceSynchronize());
+            float best = 1e30f;
+            for (int rr = 0; rr < 5; ++rr) {
+                CK(cudaEventRecord(e0));
+                gather4_kernel<NW><<<sms, NW * 32, smem>>>(tm, nrows, C, iters);
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                float ms;
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                best = ms < best ? ms : best;
+            }
+            printf(", \"gather4_%dB_gbs\": %.1f, \"gather4_%dB_requests_per_us_per_sm\": %.2f", 4 * C * 8, (double)sms * NW * 32 * iters * 4.0 * C * 8 / (best * 1e-3) / 1e9,
+                   4 * C * 8, (double)NW * 32 * iters / (best * 1e3));
+        }
     }
     printf("}\n");
     return 0;

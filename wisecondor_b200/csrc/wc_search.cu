@@ -1966,6 +1966,7 @@ extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
         return WC_OK;
     }
     if (strcmp(key, "k6_split") == 0) { ctx->k6_split = value != 0 ? 1 : 0; return WC_OK; }      // K6: split (streaming re-score) / fused
+    if (strcmp(key, "k6_g4") == 0) { ctx->k6_g4 = value != 0 ? 1 : 0; return WC_OK; }
     if (strcmp(key, "k6_chunk") == 0) { WC_CHECK_ARG(value >= 0 && value <= 480); ctx->k6_chunk = (int)value; return WC_OK; }
     if (strcmp(key, "k6_warps") == 0) { WC_CHECK_ARG(value >= 0 && value <= 16); ctx->k6_warps = (int)value; return WC_OK; }
     if (strcmp(key, "k6_prod") == 0) { WC_CHECK_ARG(value >= 0 && value <= 8); ctx->k6_prod = (int)value; return WC_OK; }

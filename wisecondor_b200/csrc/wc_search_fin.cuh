@@ -261,8 +261,11 @@ struct RescoreArgs {
     const int* grp_count;
     int C;                   // samples per chunk (multiple of 4)
     int nchunks;
-    int stride;              // bytes between two rows of a slot: C * 8 + 16
+    int stride;              // bytes between two rows of a slot: C * 8 + 16 (gather4: box width * 8, rows of a group contiguous)
     int nslot;               // W * D ring slots
+    // gather4 form: a slot = 8 groups of 4 rows (one TMA request each) G bytes apart, then the target's chunk
+    int gstride;             // G: bytes between two groups (a multiple of 128)
+    int slot_bytes;
 };
 
 constexpr int RS_HEADER = 1024;       // mbarriers: full[64], empty[64]
@@ -274,8 +277,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
-template <int W, int R>      // W consumer warps, R producer warps per consumer warp
-__global__ void __launch_bounds__((W + W * R) * 32, 1) wc_fin_rescore_kernel(const RescoreArgs a) {
+// One TMA request for FOUR candidate rows: tile::gather4 of a 2-D tensor map over X with a (box width x 1 row) box.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+        : "memory");
+}
+constexpr int RS_G4_SHIFT = 8;        // odd groups start 8 samples early: their rows sit 64 bytes further -> conflict-free 128-bit loads
+
+// G4 (option k6_g4, off by default): the candidate rows arrive four per TMA request (tile::gather4) instead of one bulk copy
+// each - 9 requests per slot instead of 33 (profiles/l2_peak_r03u.json: 24 requests / us / SM from one issuing warp for 1, 2
+// or 3.2 KB per request).  Measured r03v: 2.81 against 2.71 ms - the request rate is not what bounds the kernel, the
+// shared-memory bandwidth is (every operand byte is written once by the TMA unit and read once by a lane).  The four rows
+// of a group land contiguously (box width * 8 bytes apart, an odd number of 16-byte units), the groups G bytes apart (TMA
+// destinations are 128-byte aligned); odd groups read their box RS_G4_SHIFT samples early, so that the eight lanes of a
+// 128-bit shared-memory load phase (two groups) touch eight different bank groups.
+template <int W, int R, bool G4>      // W consumer warps, R producer warps per consumer warp
+__global__ void __launch_bounds__((W + W * R) * 32, 1) wc_fin_rescore_kernel(const __grid_constant__ CUtensorMap xmap, const RescoreArgs a) {
     extern __shared__ __align__(128) unsigned char rs_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(rs_raw);
     uint64_t* empty = full + RS_MAX_SLOTS;
@@ -283,10 +302,11 @@ __global__ void __launch_bounds__((W + W * R) * 32, 1) wc_fin_rescore_kernel(con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nslot = a.nslot;
     const int D = nslot / W;                   // ring depth per consumer warp
-    const uint32_t slot_bytes = 33u * (uint32_t)a.stride;
+    const uint32_t slot_bytes = G4 ? (uint32_t)a.slot_bytes : 33u * (uint32_t)a.stride;
     if (tid == 0) {
         for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 32); }      // every consumer lane releases its slot itself
         mbar_fence_init();
+        if (G4) tma_prefetch_desc(&xmap);
     }
     __syncthreads();
     const int ngroups = *a.grp_count;
@@ -316,8 +336,11 @@ __global__ void __launch_bounds__((W + W * R) * 32, 1) wc_fin_rescore_kernel(con
                 const int use = (k0 + c) / D, slot = w * D + (k0 + c) - use * D;
                 mbar_wait(&full[slot], (uint32_t)(use & 1));
                 const uint32_t sb = slots_u32 + (uint32_t)slot * slot_bytes;
-                const uint32_t cb = sb + (uint32_t)mylane * (uint32_t)a.stride;
-                const uint32_t xb = sb + 32u * (uint32_t)a.stride;
+                // gather4: every lane has a row of its own (idle lanes: a duplicate of the last candidate's)
+                const uint32_t cb = G4 ? sb + (uint32_t)(lane >> 2) * (uint32_t)a.gstride + (uint32_t)(lane & 3) * (uint32_t)a.stride +
+                                             (((lane >> 2) & 1) ? RS_G4_SHIFT * 8u : 0u)
+                                       : sb + (uint32_t)mylane * (uint32_t)a.stride;
+                const uint32_t xb = G4 ? sb + 8u * (uint32_t)a.gstride : sb + 32u * (uint32_t)a.stride;
                 const int n = min(C, a.S - c * C);                   // even
                 int t = 0;
                 for (; t + 8 <= n; t += 8) {
@@ -360,7 +383,16 @@ __global__ void __launch_bounds__((W + W * R) * 32, 1) wc_fin_rescore_kernel(con
             const int p = a.sl_p[rloc];
             const int cnt = min(32, p - gi * 32);
             const double* src = nullptr;
-            if (mine && lane < cnt) src = a.X + (size_t)a.sl_j[(size_t)rloc * a.shortcap + gi * 32 + lane] * a.S;
+            if (!G4 && mine && lane < cnt) src = a.X + (size_t)a.sl_j[(size_t)rloc * a.shortcap + gi * 32 + lane] * a.S;
+            int j0 = 0, j1 = 0, j2 = 0, j3 = 0;
+            bool issue = false;
+            if (G4) {      // lane 4q holds the four bins of group q (lanes beyond the item's candidates repeat its last one)
+                j0 = a.sl_j[(size_t)rloc * a.shortcap + gi * 32 + min(lane, cnt - 1)];
+                j1 = __shfl_down_sync(0xffffffffu, j0, 1);
+                j2 = __shfl_down_sync(0xffffffffu, j0, 2);
+                j3 = __shfl_down_sync(0xffffffffu, j0, 3);
+                issue = (lane & 3) == 0 && (lane >> 2) % R == r;
+            }
             const double* xsrc = a.X + (size_t)(a.row_begin + rloc) * a.S;
             const int k0 = wave * nchunks;
             for (int c = 0; c < nchunks; ++c) {
@@ -369,11 +401,22 @@ __global__ void __launch_bounds__((W + W * R) * 32, 1) wc_fin_rescore_kernel(con
                 const int use = (k0 + c) / D, slot = w * D + (k0 + c) - use * D;
                 if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
                 const uint32_t sb = slots_u32 + (uint32_t)slot * slot_bytes;
-                if (r == 0 && lane == 0) {
-                    mbar_arrive_expect_tx(&full[slot], (uint32_t)(cnt + 1) * bytes);
-                    bulk_g2s(sb + 32u * (uint32_t)a.stride, xsrc + off, bytes, &full[slot]);
+                if (G4) {
+                    if (r == 0 && lane == 0) {      // a box counts in full, also where it reaches beyond the row (zero fill)
+                        mbar_arrive_expect_tx(&full[slot], 32u * (uint32_t)a.stride + bytes);
+                        bulk_g2s(sb + 8u * (uint32_t)a.gstride, xsrc + off, bytes, &full[slot]);
+                    }
+                    if (issue) {
+                        const int q = lane >> 2;
+                        tma_gather4(sb + (uint32_t)q * (uint32_t)a.gstride, &xmap, c * C - ((q & 1) ? RS_G4_SHIFT : 0), j0, j1, j2, j3, &full[slot]);
+                    }
+                } else {
+                    if (r == 0 && lane == 0) {
+                        mbar_arrive_expect_tx(&full[slot], (uint32_t)(cnt + 1) * bytes);
+                        bulk_g2s(sb + 32u * (uint32_t)a.stride, xsrc + off, bytes, &full[slot]);
+                    }
+                    if (src != nullptr) bulk_g2s(sb + (uint32_t)lane * (uint32_t)a.stride, src + off, bytes, &full[slot]);
                 }
-                if (src != nullptr) bulk_g2s(sb + (uint32_t)lane * (uint32_t)a.stride, src + off, bytes, &full[slot]);
             }
         }
     }
@@ -511,9 +554,14 @@ __global__ void __launch_bounds__(RK_WARPS * 32) wc_fin_rank_kernel(const RankAr
 // host: K6 of a search call (both the single-GPU call and the finish of a sharded symmetric search)
 // ---------------------------------------------------------------------------------------------------------
 template <int W, int R>
-static int launch_rescore(const RescoreArgs& ra, int grid, size_t smem, cudaStream_t stream) {
-    WC_CUDA(cudaFuncSetAttribute(wc_fin_rescore_kernel<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wc_fin_rescore_kernel<W, R><<<grid, (W + W * R) * 32, smem, stream>>>(ra);
+static int launch_rescore(const RescoreArgs& ra, const CUtensorMap& xmap, bool g4, int grid, size_t smem, cudaStream_t stream) {
+    if (g4) {
+        WC_CUDA(cudaFuncSetAttribute(wc_fin_rescore_kernel<W, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wc_fin_rescore_kernel<W, R, true><<<grid, (W + W * R) * 32, smem, stream>>>(xmap, ra);
+        return WC_OK;
+    }
+    WC_CUDA(cudaFuncSetAttribute(wc_fin_rescore_kernel<W, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wc_fin_rescore_kernel<W, R, false><<<grid, (W + W * R) * 32, smem, stream>>>(xmap, ra);
     return WC_OK;
 }
 
@@ -580,29 +628,64 @@ static int launch_finalize(wc_ctx* ctx, cudaStream_t stream, FinArgs fa, int row
     RescoreArgs ra;
     ra.X = fa.X; ra.S = fa.S; ra.row_begin = fa.row_begin; ra.shortcap = fa.shortcap; ra.sl_j = fa.sl_j; ra.sl_d = sl_d;
     ra.sl_p = fa.sl_p; ra.grp = fa.grp; ra.grp_count = fa.grp_count;
-    int C = ctx->k6_chunk > 0 ? ctx->k6_chunk : 100;
-    C = std::max(4, std::min(C & ~3, 480));
-    if (C > fa.S) C = (fa.S + 3) & ~3;
-    ra.C = C;
-    ra.nchunks = (fa.S + C - 1) / C;
-    ra.stride = C * 8 + 16;
-    const size_t slot_bytes = (size_t)33 * ra.stride;
-    ra.nslot = (int)std::min<size_t>(RS_MAX_SLOTS, ((size_t)226 * 1024 - RS_HEADER) / slot_bytes);
     const int W = ctx->k6_warps > 0 ? ctx->k6_warps : 4;
     const int R = ctx->k6_prod > 0 ? ctx->k6_prod : 2;
+    // gather4 form: four candidate rows per TMA request (needs the tensor-map encoder and a matrix of at least one box)
+    bool g4 = ctx->k6_g4 != 0 && ctx->encode_tiled != nullptr && fa.S >= 64 && fa.N >= 4;
+    int C = ctx->k6_chunk > 0 ? ctx->k6_chunk : (g4 ? 86 : 100);
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    size_t slot_bytes = 0;
+    if (g4) {
+        // chunks of about C samples that tile S evenly; box = chunk + RS_G4_SHIFT samples, half of it an odd number (rows of
+        // a group an odd number of 16-byte units apart)
+        const int nch = (fa.S + C - 1) / C;
+        C = (fa.S + nch - 1) / nch;
+        C += C & 1;
+        if ((((C + RS_G4_SHIFT) / 2) & 1) == 0) C += 2;
+        const int cbox = C + RS_G4_SHIFT;
+        if (cbox > 256) g4 = false;
+        else {
+            ra.C = C;
+            ra.nchunks = (fa.S + C - 1) / C;
+            ra.stride = cbox * 8;
+            ra.gstride = (4 * ra.stride + 127) / 128 * 128;
+            ra.slot_bytes = 8 * ra.gstride + (C * 8 + 127) / 128 * 128;
+            slot_bytes = (size_t)ra.slot_bytes;
+            cuuint64_t dims[2] = {(cuuint64_t)fa.S, (cuuint64_t)fa.N};
+            cuuint64_t strides[1] = {(cuuint64_t)fa.S * sizeof(double)};
+            cuuint32_t box[2] = {(cuuint32_t)cbox, 1};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = reinterpret_cast<PFN_encodeTiled>(ctx->encode_tiled)(
+                &xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(fa.X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) g4 = false;
+        }
+    }
+    if (!g4) {
+        C = ctx->k6_chunk > 0 ? ctx->k6_chunk : 100;
+        C = std::max(4, std::min(C & ~3, 480));
+        if (C > fa.S) C = (fa.S + 3) & ~3;
+        ra.C = C;
+        ra.nchunks = (fa.S + C - 1) / C;
+        ra.stride = C * 8 + 16;
+        ra.gstride = 0; ra.slot_bytes = 0;
+        slot_bytes = (size_t)33 * ra.stride;
+    }
+    ra.nslot = (int)std::min<size_t>(RS_MAX_SLOTS, ((size_t)226 * 1024 - RS_HEADER) / slot_bytes);
     if (ra.nslot < 2 * W) { wc_set_error("K6: chunk of %d samples leaves %d ring slots for %d consumer warps", C, ra.nslot, W); return WC_ERR_ARG; }
     ra.nslot = ra.nslot / W * W;
     const size_t smem = RS_HEADER + (size_t)ra.nslot * slot_bytes;
     const int grid = ctx->sm_count;
-    if (W == 2 && R == 4) rc = launch_rescore<2, 4>(ra, grid, smem, stream);
-    else if (W == 2 && R == 8) rc = launch_rescore<2, 8>(ra, grid, smem, stream);
-    else if (W == 4 && R == 1) rc = launch_rescore<4, 1>(ra, grid, smem, stream);
-    else if (W == 4 && R == 2) rc = launch_rescore<4, 2>(ra, grid, smem, stream);
-    else if (W == 4 && R == 4) rc = launch_rescore<4, 4>(ra, grid, smem, stream);
-    else if (W == 4 && R == 7) rc = launch_rescore<4, 7>(ra, grid, smem, stream);
-    else if (W == 8 && R == 1) rc = launch_rescore<8, 1>(ra, grid, smem, stream);
-    else if (W == 8 && R == 2) rc = launch_rescore<8, 2>(ra, grid, smem, stream);
-    else if (W == 8 && R == 3) rc = launch_rescore<8, 3>(ra, grid, smem, stream);
+    if (W == 2 && R == 4) rc = launch_rescore<2, 4>(ra, xmap, g4, grid, smem, stream);
+    else if (W == 2 && R == 8) rc = launch_rescore<2, 8>(ra, xmap, g4, grid, smem, stream);
+    else if (W == 4 && R == 1) rc = launch_rescore<4, 1>(ra, xmap, g4, grid, smem, stream);
+    else if (W == 4 && R == 2) rc = launch_rescore<4, 2>(ra, xmap, g4, grid, smem, stream);
+    else if (W == 4 && R == 4) rc = launch_rescore<4, 4>(ra, xmap, g4, grid, smem, stream);
+    else if (W == 4 && R == 7) rc = launch_rescore<4, 7>(ra, xmap, g4, grid, smem, stream);
+    else if (W == 8 && R == 1) rc = launch_rescore<8, 1>(ra, xmap, g4, grid, smem, stream);
+    else if (W == 8 && R == 2) rc = launch_rescore<8, 2>(ra, xmap, g4, grid, smem, stream);
+    else if (W == 8 && R == 3) rc = launch_rescore<8, 3>(ra, xmap, g4, grid, smem, stream);
     else { wc_set_error("K6: no kernel for %d consumer warps x %d producer warps each", W, R); return WC_ERR_ARG; }
     if (rc) return rc;
     WC_CUDA(cudaGetLastError());
