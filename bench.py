@@ -419,10 +419,11 @@ def bench_test_path(args, torch, dist, device, dev, rank, world, local, X, bins,
                    "frac": (gathers / (zms * 1e-3) / 1e9 / l2_peak) if l2_peak else None,
                    "note": "executed gather bytes of the whole z-score phase against the L2 -> SM figure of tools/l2_peak.cu "
                            "(profiles/l2_peak_r03.json); the working copy of a 32-sample tile (15 MB) is L2-resident"},
-            "K9": {"bound": "issue", "achieved": entries / (sms * 1e-3), "peak": issue_peak / 3.0, "unit": "run evaluations/s",
-                   "frac": entries / (sms * 1e-3) / (issue_peak / 3.0),
-                   "note": "fp32 sweep: FADD + FMUL + FMNMX per run evaluation; ceiling = SMs x 4 schedulers x 32 lanes x "
-                           "max SM clock / 3 instructions"}},
+            "K9": {"bound": "issue", "achieved": entries / (sms * 1e-3), "peak": issue_peak / 2.4, "unit": "run evaluations/s",
+                   "frac": entries / (sms * 1e-3) / (issue_peak / 2.4),
+                   "note": "fp32 sweep: FADD + FMNMX(|.|) per run evaluation and two shared-memory loads per five of them "
+                           "(the 1/sqrt(length) multiply once per length); ceiling = SMs x 4 schedulers x 32 lanes x max SM "
+                           "clock / 2.4 instructions; the whole segmentation phase (exact re-scores, recursion) is in the time"}},
         "e2e": {"value": world * B / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * n * 4,
                 "d2h_bytes_per_step": B * (22 + 1) * 8 + ncalls * 24,
                 "api": "device.test_prep + zscore_batch + segment_batch from pinned host counts; calls, chromosome-wide z and "

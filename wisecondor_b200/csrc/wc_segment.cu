@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
 
         // -- sweep by diagonals, in fp32 (it only locates): lane owns the run lengths L0 .. L0+4 (their 1/sqrt in
         //    registers) and walks the start x; P[x] is one broadcast read per step, P[x+L0+r] a 5-deep register window
-        //    fed by one conflict-free read.  Per run: FADD, FMUL, FMNMX(|.|) --
+        //    fed by one conflict-free read.  Per run: FADD, FMNMX(|.|); one FMUL per length at the end --
         float best = 0.f;                             // max over this thread's runs of |score|
         const int ntiles = (m + SEG_TILE - 1) / SEG_TILE;
         {
@@ -321,9 +321,11 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
                             const float px = P[x + j];
 #pragma unroll
                             for (int r = 0; r < SEG_R; ++r) {
-                                const float v = __fmul_rn(__fsub_rn(ww[(j + r) % SEG_R], px), isq[r]);
-                                if (!MINEFF) bh[r] = fmaxf(bh[r], fabsf(v));
-                                else if (fabsf(v) > bh[r] && passes(x + j, L0 + r)) bh[r] = fabsf(v);   // only record attempts pay
+                                // |fl(d * s)| is non-decreasing in |d| for s > 0 (rounding is monotone): the maximum of the
+                                // scores is the score of the largest |difference| - the multiply happens once per length
+                                const float v = fabsf(__fsub_rn(ww[(j + r) % SEG_R], px));
+                                if (!MINEFF) bh[r] = fmaxf(bh[r], v);
+                                else if (v > bh[r] && passes(x + j, L0 + r)) bh[r] = v;   // only record attempts pay
                             }
                         }
                     }
@@ -332,10 +334,11 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
                 for (int r = 0; r < SEG_R; ++r) {                  // ragged end: the remaining starts of each length
                     const int L = L0 + r;
                     for (int xx = x; xx + L <= hi; ++xx) {
-                        const float v = __fmul_rn(__fsub_rn(P[xx + L], P[xx]), isq[r]);
-                        if (!MINEFF) bh[r] = fmaxf(bh[r], fabsf(v));
-                        else if (fabsf(v) > bh[r] && passes(xx, L)) bh[r] = fabsf(v);
+                        const float v = fabsf(__fsub_rn(P[xx + L], P[xx]));
+                        if (!MINEFF) bh[r] = fmaxf(bh[r], v);
+                        else if (v > bh[r] && passes(xx, L)) bh[r] = v;
                     }
+                    bh[r] = __fmul_rn(bh[r], isq[r]);               // the length's extreme score
                     if (L <= m) { dh[L] = bh[r]; best = fmaxf(best, bh[r]); }
                 }
             }
