@@ -451,8 +451,12 @@ __global__ void __launch_bounds__(256) wc_sigma_kernel(const double* __restrict_
             const double* col = &tile[c & 1][0][lane];
 #pragma unroll 8
             for (int bin = 0; bin < nb; ++bin) {
+                // a skipped bin adds +0.0 (sum >= +0 throughout: the same bits as not adding): the select sits before the
+                // add, so the loop-carried chain is one DADD per bin
                 const double v = col[bin * 32];
-                if (!isnan(v)) { sum = __dadd_rn(sum, v); ++num; }
+                const bool ok = !isnan(v);
+                sum = __dadd_rn(sum, ok ? v : 0.0);
+                num += ok ? 1 : 0;
             }
         }
         __syncthreads();
