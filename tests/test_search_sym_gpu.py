@@ -53,9 +53,9 @@ def test_symmetric_equals_plain_search_and_halves_the_tiles(sym):
     sym(0)
     pidx, pdist, pst = _gpu_search(X, bins, 100)
     _assert_same(idx, dist, pidx, pdist)
-    # plain: two fills, K4, K5, K6 (one fused kernel, or two selects + bucket scan + scatter + re-score + rank) (+ pivot select, gather, pass with the
+    # plain: two fills, K4, K5, K6 (one fused kernel, or two selects + bucket scan + scatter + re-score + rank; twice when the host call finalises in two row ranges) (+ pivot select, gather, pass with the
     # tcgen05 filter); symmetric: one K5 launch more
-    assert pst["launches"] in (5, 10, 13) and st["launches"] == pst["launches"] + 1
+    assert pst["launches"] in (5, 6, 10, 16, 8, 9, 13, 19) and st["launches"] == pst["launches"] + 1
     assert 0.5 < st["tiles"] / pst["tiles"] < 0.62                             # 1/8 + 7/16 = 0.5625 of the plain tiles
     assert st["tiles_plain"] == pst["tiles"] == pst["tiles_plain"]
     assert st["exhaustive_rows"] == pst["exhaustive_rows"] == 0
@@ -89,13 +89,13 @@ def test_partial_ranges_and_small_genomes_take_the_plain_path(sym):
     from wisecondor_b200 import device
     idx, dist = device.newref_topk_host(X, bins, 100, 900, 10)
     st = device.last_search_stats(0)
-    assert st["launches"] - (3 if st["pivots"] else 0) in (5, 10) and st["tiles"] == st["tiles_plain"]  # one K5 pass (+ the pivot pass)
+    assert st["launches"] - (3 if st["pivots"] else 0) in (5, 6, 10, 16) and st["tiles"] == st["tiles_plain"]  # one K5 pass (+ the pivot pass)
     oidx, odist = c_oracle.get_reference_rows(X, bins, 100, 900, 10)
     _assert_same(idx, dist, oidx, odist)
     small = [300, 200, 250]
     Xs = synth.corrected_like(small, 20, seed=8)
     idx, dist = device.newref_topk_host(Xs, small, 0, 750, 10)
-    assert device.last_search_stats(0)["launches"] in (5, 10)
+    assert device.last_search_stats(0)["launches"] in (5, 6, 10, 16)
 
 
 def test_rescore_by_tma_gather4_returns_the_same_table(sym):

@@ -66,6 +66,7 @@ extern "C" void wc_destroy(wc_ctx* ctx) {
         if (ctx->buf[i].p) cudaFree(ctx->buf[i].p);
     for (int i = 0; i < 2 * WC_NPHASE; ++i) cudaEventDestroy(ctx->ev[i]);
     if (ctx->search_plan && ctx->search_plan_free) ctx->search_plan_free(ctx->search_plan);
+    if (ctx->d2h_stream) { cudaStreamDestroy(ctx->d2h_stream); cudaEventDestroy(ctx->d2h_ev); }
     delete ctx;
 }
 

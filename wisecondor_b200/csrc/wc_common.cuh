@@ -80,6 +80,9 @@ struct wc_ctx {
     const int* zs_npairs_d = nullptr;    // device counters of the last wc_zscore_batch: listed pairs of pass 1..repeats-1
     int zs_repeats = 0;
     long long zs_pair_limit = 0, zs_all_pairs = 0;
+    // wc_newref_topk_host: where the search may start copying the first half of its table while the second half is re-scored
+    int32_t* d2h_idx_h = nullptr; double* d2h_dist_h = nullptr; size_t d2h_rows_done = 0;
+    cudaStream_t d2h_stream = nullptr; cudaEvent_t d2h_ev = nullptr;
     void* search_plan = nullptr;         // host plan of the last search (wc_search.cu: SearchPlan), freed through search_plan_free
     void (*search_plan_free)(void*) = nullptr;
     unsigned long long sched_hash = 0;   // fingerprint of the K5 schedule metadata currently on the device

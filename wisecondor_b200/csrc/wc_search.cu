@@ -711,6 +711,7 @@ struct FinArgs {
     double* dist_out;
     int* slow_list;
     int* slow_count;
+    int slow_bias;          // added to a row's number in slow_list (a call finalised in two row ranges: the second range's offset)
     int vec;                // 4: rows are 32-byte aligned (S % 4 == 0): 256-bit loads; 1: scalar loads
     const u64* in_key;      // symmetric search: the row's incoming (column-side) candidates, or nullptr
     const int* in_j;
@@ -813,7 +814,7 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int rloc, u
     const int total = s_total;
     if (s_flag) {
         if (tid == 0) {
-            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc + a.slow_bias;
             if (SPLIT) a.sl_p[rloc] = -1;
         }
         return;
@@ -904,7 +905,7 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int rloc, u
     const int p = s_p;
     if (p > a.shortcap) {                               // tie plateau wider than the shortlist: exact fallback
         if (tid == 0) {
-            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc + a.slow_bias;
             if (SPLIT) a.sl_p[rloc] = -1;
         }
         return;
@@ -1468,6 +1469,9 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         G = 1;
         if (matrix_bytes > 64e6)
             while (G < 8 && (double)(grid / G) * tile_bytes > 48e6) G *= 2;
+        // the tcgen05 filter's panels are a quarter of the size, but four CTAs per row block also level the CTAs' finish times
+        // (measured at 600 x 50 kb, profiles/tc_group_50kb_r03ab.txt: G = 1, 2, 4, 8 -> K5 3.30, 2.97, 2.77, 2.83 ms)
+        if (ctx->k5_f16 == 2 && G == 2) G = 4;
     }
     const bool rounds_on = matrix_bytes > 64e6 || ctx->k5_group > 0;
 
@@ -1820,9 +1824,36 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     fa.vec = (S % 4 == 0 && (reinterpret_cast<uintptr_t>(corrected_d) & 31) == 0) ? 4 : 1;
     fa.in_key = in_key; fa.in_j = in_j; fa.in_cnt = in_cnt; fa.in_cap = in_cap; fa.in_nsrc = 1; fa.in_src_rows = 0;
     fa.madd = filt_madd; fa.row_thr = row_thr; fa.madd_p = ta.madd_p;
+    fa.slow_bias = 0;
     WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
     long long fin_launches = 0;
-    if ((rc = launch_finalize(ctx, stream, fa, (int)rows, f16 != 0, &fin_launches))) return rc;
+    // Called from wc_newref_topk_host: the table's first half travels to the host while the second half is still being
+    // re-scored (K6 in two row ranges, the copy on a non-blocking stream behind an event).
+    const int split_rows = (ctx->d2h_idx_h != nullptr && rows >= 16 * BM) ? (int)(rows / 2) / BM * BM : 0;
+    ctx->d2h_rows_done = 0;
+    if (split_rows > 0) {
+        FinArgs f1 = fa;
+        f1.row_end = row_begin + split_rows;
+        long long l1 = 0, l2 = 0;
+        if ((rc = launch_finalize(ctx, stream, f1, split_rows, f16 != 0, &l1))) return rc;
+        WC_CUDA(cudaEventRecord(ctx->d2h_ev, stream));
+        WC_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->d2h_ev, 0));
+        WC_CUDA(cudaMemcpyAsync(ctx->d2h_idx_h, idx_d, (size_t)split_rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        WC_CUDA(cudaMemcpyAsync(ctx->d2h_dist_h, dist_d, (size_t)split_rows * k * sizeof(double), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        ctx->d2h_rows_done = (size_t)split_rows;
+        FinArgs f2 = fa;
+        const int hb = split_rows / BM;
+        f2.row_begin = row_begin + split_rows;
+        f2.rb_seg_first += hb; f2.rb_seg_count += hb;
+        f2.idx_out += (size_t)split_rows * k; f2.dist_out += (size_t)split_rows * k;
+        f2.slow_bias = split_rows;
+        if (f2.row_thr != nullptr) f2.row_thr += split_rows;
+        if (f2.in_key != nullptr) { f2.in_key += (size_t)split_rows * in_cap; f2.in_j += (size_t)split_rows * in_cap; f2.in_cnt += split_rows; }
+        if ((rc = launch_finalize(ctx, stream, f2, (int)rows - split_rows, f16 != 0, &l2))) return rc;
+        fin_launches = l1 + l2;
+    } else {
+        if ((rc = launch_finalize(ctx, stream, fa, (int)rows, f16 != 0, &fin_launches))) return rc;
+    }
     WC_CUDA(cudaEventRecord(ctx->ev[5], stream));
 
     int nslow = 0, k6_stats[4] = {0, 0, 0, 0};
@@ -1844,6 +1875,7 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     ctx->counter[11] = k6_stats[3];
     long long launches = (sym ? 5 : 4) + pivot_launches + fin_launches;   // two fills, K4, K5 (one or two passes; pivot select + gather + pass), K6 (1 fused, or reset + select + re-score + rank)
     if (nslow > 0) {
+        ctx->d2h_rows_done = 0;                          // rows of the first half may be among them: the host copies everything again
         const int batch = 64;
         double* scratch;
         if ((rc = wc_reserve(ctx, SLOT_SCRATCH, (size_t)std::min(nslow, batch) * N * sizeof(double), (void**)&scratch)))
@@ -1890,13 +1922,21 @@ extern "C" int wc_newref_topk_host(wc_ctx* ctx, const double* corrected_h, int N
     if ((rc = wc_reserve(ctx, SLOT_IO_IDX, std::max<size_t>(rows, 1) * refsize * sizeof(int32_t), (void**)&idx))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_IO_DIST, std::max<size_t>(rows, 1) * refsize * sizeof(double), (void**)&dist))) return rc;
     WC_CUDA(cudaMemcpyAsync(X, corrected_h, (size_t)N * S * sizeof(double), cudaMemcpyHostToDevice, 0));
+    if (rows) WC_CHECK_ARG(idx_h != nullptr && dist_h != nullptr);
+    if (ctx->d2h_stream == nullptr) {
+        WC_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        WC_CUDA(cudaEventCreateWithFlags(&ctx->d2h_ev, cudaEventDisableTiming));
+    }
+    ctx->d2h_idx_h = idx_h; ctx->d2h_dist_h = dist_h; ctx->d2h_rows_done = 0;       // lets the search start the copy of its first half early
     rc = wc_newref_topk(ctx, X, N, S, chrom_bins_h, nchrom, row_begin, row_end, refsize, idx, dist, nullptr);
-    if (rc) return rc;
+    const size_t done = rc ? 0 : ctx->d2h_rows_done;
+    ctx->d2h_idx_h = nullptr; ctx->d2h_dist_h = nullptr; ctx->d2h_rows_done = 0;
+    if (rc) { cudaStreamSynchronize(ctx->d2h_stream); return rc; }
     if (rows) {
-        WC_CHECK_ARG(idx_h != nullptr && dist_h != nullptr);
-        WC_CUDA(cudaMemcpyAsync(idx_h, idx, rows * refsize * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-        WC_CUDA(cudaMemcpyAsync(dist_h, dist, rows * refsize * sizeof(double), cudaMemcpyDeviceToHost, 0));
+        WC_CUDA(cudaMemcpyAsync(idx_h + done * refsize, idx + done * refsize, (rows - done) * refsize * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+        WC_CUDA(cudaMemcpyAsync(dist_h + done * refsize, dist + done * refsize, (rows - done) * refsize * sizeof(double), cudaMemcpyDeviceToHost, 0));
         WC_CUDA(cudaStreamSynchronize(0));
+        WC_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
     }
     return WC_OK;
 }

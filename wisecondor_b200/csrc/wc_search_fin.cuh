@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) wc_fin_select_kernel(const Fin
     }
     if (__any_sync(0xffffffffu, flagged != 0)) {
         if (lane == 0) {
-            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc + a.slow_bias;
             a.sl_p[rloc] = -1;
         }
         return;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) wc_fin_select_kernel(const Fin
     for (int o = 16; o > 0; o >>= 1) jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
     if (lane == 0) {
         if (p > a.shortcap) {                    // tie plateau wider than the shortlist: exact fallback
-            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc;
+            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc + a.slow_bias;
             a.sl_p[rloc] = -1;
         } else {
             a.sl_p[rloc] = p;

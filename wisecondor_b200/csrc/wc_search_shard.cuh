@@ -372,7 +372,7 @@ extern "C" int wc_newref_shard_finish(wc_ctx* ctx, const unsigned long long* rec
         fa.cand_key = static_cast<u64*>(ctx->buf[SLOT_CAND_D].p); fa.cand_j = static_cast<int*>(ctx->buf[SLOT_CAND_J].p);
         fa.seg_cnt = static_cast<int*>(ctx->buf[SLOT_SEGCNT].p); fa.seg_flag = static_cast<int*>(ctx->buf[SLOT_SEGFLAG].p);
         fa.cap = pl.cap; fa.k = pl.k; fa.shortcap = pl.k <= (pl.f16 ? 96 : 128) ? 256 : 512; fa.mcoef = pl.mcoef;
-        fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow;
+        fa.idx_out = idx_d; fa.dist_out = dist_d; fa.slow_list = slow + 1; fa.slow_count = slow; fa.slow_bias = 0;
         fa.vec = (pl.S % 4 == 0 && (reinterpret_cast<uintptr_t>(pl.corrected) & 31) == 0) ? 4 : 1;
         fa.in_key = recv_key_d; fa.in_j = recv_j_d; fa.in_cnt = recv_cnt_d; fa.in_cap = pl.in_cap;
         fa.in_nsrc = pl.world; fa.in_src_rows = pl.rows_per; fa.madd = pl.madd; fa.madd_p = nullptr;
