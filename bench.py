@@ -555,13 +555,15 @@ def main():
     r0, r1 = shard.row_shard(rank, world, n)        # = the reference's getPart(rank, world, N)
     rows = r1 - r0
     rows_max = shard.max_shard_rows(world, n)
-    out_idx = torch.empty((rows_max, k), dtype=torch.int32, device=dev)
-    out_dist = torch.empty((rows_max, k), dtype=torch.float64, device=dev)
     if world > 1:
-        scratch = (out_idx, out_dist, torch.empty((world * rows_max, k), dtype=torch.int32, device=dev),
-                   torch.empty((world * rows_max, k), dtype=torch.float64, device=dev))
+        # the rows' all-gather is one NCCL collective over a packed (indexes | distances) block; the search writes into it
+        scratch = shard.RowGather(n, k, world, dev)
+        out_idx, out_dist = scratch.idx_local, scratch.dist_local
         full_idx = torch.empty((n, k), dtype=torch.int32, device=dev)
         full_dist = torch.empty((n, k), dtype=torch.float64, device=dev)
+    else:
+        out_idx = torch.empty((rows_max, k), dtype=torch.int32, device=dev)
+        out_dist = torch.empty((rows_max, k), dtype=torch.float64, device=dev)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # 512 MiB > 126 MB L2
 
     # N > 1: the block pairs of the symmetric search divided over the ranks (shard.SymmetricShardedSearch), if a trial run

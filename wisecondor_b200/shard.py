@@ -17,35 +17,53 @@ import torch.distributed as dist
 from .partition import max_shard_rows, row_shard, sample_shard  # noqa: E402,F401  (torch-free definitions)
 
 
+class RowGather(object):
+    """Buffers of the rows' all-gather: a rank's (rows x k) int32 indexes and float64 distances live side by side in ONE
+    byte block (padded to the largest part), so the gather is ONE collective (all_gather_into_tensor); `idx_local` /
+    `dist_local` are views of this rank's block - a search that writes into them needs no staging copy."""
+
+    def __init__(self, bincount, k, world, device):
+        self.bincount, self.k, self.world = int(bincount), int(k), int(world)
+        self.rmax = max_shard_rows(world, bincount)
+        self.ib = (self.rmax * self.k * 4 + 15) // 16 * 16               # the distances start 16-byte aligned
+        self.db = self.rmax * self.k * 8
+        self.block = self.ib + self.db
+        self.local = torch.empty(self.block, dtype=torch.uint8, device=device)
+        self.all = torch.empty(world * self.block, dtype=torch.uint8, device=device)
+        self.idx_local, self.dist_local = self._views(self.local, 0)
+        self.lens = [row_shard(r, world, bincount)[1] - row_shard(r, world, bincount)[0] for r in range(world)]
+
+    def _views(self, buf, r):
+        o = r * self.block
+        idx = buf[o:o + self.rmax * self.k * 4].view(torch.int32).view(self.rmax, self.k)
+        dst = buf[o + self.ib:o + self.ib + self.db].view(torch.float64).view(self.rmax, self.k)
+        return idx, dst
+
+    def gather(self, group=None, out_idx=None, out_dist=None):
+        dist.all_gather_into_tensor(self.all, self.local, group=group)
+        if out_idx is None:
+            out_idx = torch.empty((self.bincount, self.k), dtype=torch.int32, device=self.local.device)
+            out_dist = torch.empty((self.bincount, self.k), dtype=torch.float64, device=self.local.device)
+        parts = [self._views(self.all, r) for r in range(self.world)]
+        torch.cat([parts[r][0][:self.lens[r]] for r in range(self.world)], out=out_idx)       # drop the padding rows
+        torch.cat([parts[r][1][:self.lens[r]] for r in range(self.world)], out=out_dist)
+        return out_idx, out_dist
+
+
 def allgather_rows(idx_local, dist_local, bincount, group=None, out_idx=None, out_dist=None, scratch=None):
     """Concatenate every rank's (rows x k) result block in rank order -> (bincount x k) on every rank.
 
-    Parts differ by at most one row, so blocks are padded to the largest part for all_gather_into_tensor and the
-    padding rows are dropped afterwards.  `scratch` may carry preallocated (pad_idx, pad_dist, all_idx, all_dist)."""
+    Parts differ by at most one row, so blocks are padded to the largest part; indexes and distances travel in one
+    collective (RowGather).  `scratch` may carry a RowGather whose idx_local / dist_local the search wrote into."""
     world = dist.get_world_size(group)
     k = idx_local.shape[1]
-    dev = idx_local.device
-    rmax = max_shard_rows(world, bincount)
-    if scratch is None:
-        scratch = (torch.empty((rmax, k), dtype=idx_local.dtype, device=dev),
-                   torch.empty((rmax, k), dtype=dist_local.dtype, device=dev),
-                   torch.empty((world * rmax, k), dtype=idx_local.dtype, device=dev),
-                   torch.empty((world * rmax, k), dtype=dist_local.dtype, device=dev))
-    pad_idx, pad_dist, all_idx, all_dist = scratch
+    rg = scratch if isinstance(scratch, RowGather) else RowGather(bincount, k, world, idx_local.device)
     rows = idx_local.shape[0]
-    if pad_idx.data_ptr() != idx_local.data_ptr():      # the caller may have let the search write into the scratch
-        pad_idx[:rows].copy_(idx_local)
-    if pad_dist.data_ptr() != dist_local.data_ptr():
-        pad_dist[:rows].copy_(dist_local)
-    dist.all_gather_into_tensor(all_idx, pad_idx, group=group)
-    dist.all_gather_into_tensor(all_dist, pad_dist, group=group)
-    if out_idx is None:
-        out_idx = torch.empty((bincount, k), dtype=idx_local.dtype, device=dev)
-        out_dist = torch.empty((bincount, k), dtype=dist_local.dtype, device=dev)
-    lens = [row_shard(r, world, bincount)[1] - row_shard(r, world, bincount)[0] for r in range(world)]
-    torch.cat([all_idx[r * rmax:r * rmax + lens[r]] for r in range(world)], out=out_idx)      # drop the padding rows
-    torch.cat([all_dist[r * rmax:r * rmax + lens[r]] for r in range(world)], out=out_dist)
-    return out_idx, out_dist
+    if rg.idx_local.data_ptr() != idx_local.data_ptr():
+        rg.idx_local[:rows].copy_(idx_local)
+    if rg.dist_local.data_ptr() != dist_local.data_ptr():
+        rg.dist_local[:rows].copy_(dist_local)
+    return rg.gather(group=group, out_idx=out_idx, out_dist=out_dist)
 
 
 class ShardedSearch(object):
