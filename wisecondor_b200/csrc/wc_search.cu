@@ -1469,9 +1469,6 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
         G = 1;
         if (matrix_bytes > 64e6)
             while (G < 8 && (double)(grid / G) * tile_bytes > 48e6) G *= 2;
-        // the tcgen05 filter's panels are a quarter of the size, but four CTAs per row block also level the CTAs' finish times
-        // (measured at 600 x 50 kb, profiles/tc_group_50kb_r03ab.txt: G = 1, 2, 4, 8 -> K5 3.30, 2.97, 2.77, 2.83 ms)
-        if (ctx->k5_f16 == 2 && G == 2) G = 4;
     }
     const bool rounds_on = matrix_bytes > 64e6 || ctx->k5_group > 0;
 
@@ -1487,6 +1484,10 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     // Work: (1/sym_frac + (1 - 1/sym_frac) / 2) of the plain search.
     const int sym_frac = ctx->k5_sym;
     const bool sym = sym_frac >= 2 && row_begin == 0 && row_end == N && nrb >= 24;
+    // symmetric pass of the tcgen05 filter: four CTAs per row block level the CTAs' finish times (measured at 600 x 50 kb,
+    // profiles/tc_group_50kb_r03ab.txt: G = 1, 2, 4, 8 -> K5 3.30, 2.97, 2.77, 2.83 ms; the plain pass of a row range is
+    // as fast with two)
+    if (sym && ctx->k5_group <= 0 && ctx->k5_f16 == 2 && G == 2) G = 4;
     std::vector<Piece> pieces;
     std::vector<int> listA, listB, offA, offB;
     int gridA = 0, gridB = 0;
