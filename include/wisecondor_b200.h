@@ -92,7 +92,12 @@ int wc_debug_profile(wc_ctx* ctx, int enable, long long* out_h, int max_ctas);
  *   "k5_group"  CTAs sharing a row block per scheduling round (0 = automatic), "k5_stages" TMA ring depth (0 = automatic),
  *   "k5_lag"    chunks (0..4) by which half of the distance kernel's MMA warps trail the other half,
  *   "k5_f16"    the FILTER of the distance kernel (the exact fp64 re-score that decides the result is the same for all):
- *               0 = fp64 contraction on DMMA, 1 = fp16 on mma.sync, 2 = fp16 on tcgen05 with TMEM accumulators. */
+ *               0 = fp64 contraction on DMMA, 1 = fp16 on mma.sync, 2 = fp16 on tcgen05 with TMEM accumulators (default),
+ *   "k5_pivots" 1 = pivot pass before the search proper with the tcgen05 filter (default), 0 = none,
+ *   "k6_split"  the exact re-score: 1 = select -> streaming re-score on bulk copies -> rank (default; needs an even number
+ *               of samples), 0 = one fused kernel; "k6_chunk" samples per bulk copy, "k6_warps" consumer warps per SM,
+ *               "k6_prod" producer warps per consumer warp (0 = defaults 100 / 4 / 2), "k6_g4" 1 = candidate rows four per
+ *               TMA request (tile::gather4) instead of one bulk copy each (default 0: measured no faster). */
 int wc_set_option(wc_ctx* ctx, const char* key, double value);
 
 /* Debug: searches that run the tcgen05 filter (k5_f16 = 2) also store every filter distance they compute into

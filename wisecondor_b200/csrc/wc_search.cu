@@ -45,8 +45,6 @@ constexpr int FIN_THREADS = 128;    // one thread per shortlisted candidate duri
 constexpr int FIN_CHUNK = 32;       // samples staged per pipeline step of the re-score
 constexpr int FIN_BUCKETS = 1024;   // locality buckets of the re-score's work list
 constexpr int FIN_ECAP = 1360;      // candidate entries of one row K6 collects in shared memory (16 KiB; later the target's own row: S <= 2040); more: read from the sources
-constexpr int FIN_LD = FIN_CHUNK + 1;   // padded tile row (bank-conflict free per-thread row walks)
-constexpr int FIN_LDB = FIN_CHUNK + 2;  // tile row of the 16-byte copy path: 16-byte aligned rows (2-way conflicts, cheap)
 constexpr int EXH_THREADS = 256;
 constexpr int STG = 128;            // per-warp staging entries for column-side candidates (symmetric pass)
 constexpr u64 KEY_NEVER = 0ull;     // threshold key of an inactive row: no finite negative score passes
