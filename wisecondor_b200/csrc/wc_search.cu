@@ -1931,6 +1931,7 @@ extern "C" int wc_newref_topk_host(wc_ctx* ctx, const double* corrected_h, int N
     const size_t done = rc ? 0 : ctx->d2h_rows_done;
     ctx->d2h_idx_h = nullptr; ctx->d2h_dist_h = nullptr; ctx->d2h_rows_done = 0;
     if (rc) { cudaStreamSynchronize(ctx->d2h_stream); return rc; }
+    if (done == 0) WC_CUDA(cudaStreamSynchronize(ctx->d2h_stream));      // an early copy that was called off must not land after the final one
     if (rows) {
         WC_CUDA(cudaMemcpyAsync(idx_h + done * refsize, idx + done * refsize, (rows - done) * refsize * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
         WC_CUDA(cudaMemcpyAsync(dist_h + done * refsize, dist + done * refsize, (rows - done) * refsize * sizeof(double), cudaMemcpyDeviceToHost, 0));
