@@ -14,6 +14,7 @@ Run from the repo root in the build container (needs /root/reference):  python t
 """
 import contextlib
 import io
+import json
 import os
 import shutil
 import subprocess
@@ -200,14 +201,52 @@ def golden_functions():
     print("functions.npz: %d arrays, %d segmentation calls" % (len(out), out['seg_calls'].shape[0]))
 
 
+def report_files(tmp):
+    """A sample npz with the read counts `convert` stores and a result npz with the keys `test` writes (wisecondor.py:273-281)
+    that `report` reads; calls with effect sizes on both sides of the default -mineffect 1.5.  Shared with the CPU test."""
+    bins = TINY_BINS
+    rng = np.random.default_rng(41)
+    row = rng.integers(50, 400, size=sum(bins))
+    write_sample_npz(os.path.join(tmp, "s.npz"), row, bins, TINY_BINSIZE)
+    s = dict(np.load(os.path.join(tmp, "s.npz"), allow_pickle=True))
+    quality = {'mapped': 9123456, 'unmapped': 23456, 'no_coordinate': 1200, 'filter_rmdup': 345678, 'filter_mapq': 456789,
+               'pre_retro': 8400000, 'post_retro': 8312345, 'pair_fail': 77}
+    np.savez_compressed(os.path.join(tmp, "s.npz"), arguments={'binsize': 1000000.0, 'retdist': 4, 'retthres': 4, 'infile': 'a.bam'},
+                        runtime={}, sample=s['sample'].item(), quality=quality)
+    calls = [[3, 10, 29, 7.123456, 0.0312], [7, 0, 39, -12.5, -0.0849], [1, 30, 30, 5.9, 0.004], [12, 4, 9, -6.25, -0.015001],
+             [20, 2, 3, 6.0, 0.015]]
+    np.savez_compressed(os.path.join(tmp, "o.npz"), binsize=TINY_BINSIZE, threshold_z=5.2345, asdef=0.04567, aasdef=0.0512349,
+                        arguments={'minzscore': None, 'repeats': 5, 'minrefbins': 25, 'mineffectsize': 0.0},
+                        runtime={}, results_calls=np.array(calls, dtype=object))
+
+
+def golden_report():
+    """The reference's `report` on report_files(), default and explicit -mineffect."""
+    tmp = tempfile.mkdtemp(prefix="wc_golden_")
+    try:
+        report_files(tmp)
+        out = {}
+        for name, extra in (("default", []), ("mineffect0", ["-mineffect", "0"]), ("mineffect5", ["-mineffect", "5"])):
+            out[name] = run_ref_cli(["report", "s.npz", "o.npz"] + extra, tmp)
+        with open(os.path.join(HERE, "report.json"), "w") as f:
+            json.dump(out, f, indent=1, sort_keys=True)
+        print("report.json: %d variants, %d lines each at most" % (len(out), max(len(v.splitlines()) for v in out.values())))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     if not os.path.isfile(os.path.join(REF, "wisetools.py")):
         rc = subprocess.call([sys.executable, os.path.join(ROOT, "oracle", "make_ref.py")])
         if rc != 0:
             print("the reference is not available: golden vectors can only be regenerated in the build container")
             return 1
+    if '--report-only' in sys.argv:
+        golden_report()
+        return 0
     golden_functions()
     golden_cli_tiny()
+    golden_report()
     return 0
 
 

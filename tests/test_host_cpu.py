@@ -85,6 +85,25 @@ def test_scale_inflate_cutoff_host_functions():
     assert counts.dtype == np.int32 and counts.shape[0] == sum(len(sample[str(c)]) + (c % 3) - 1 for c in range(1, 23))
 
 
+@pytest.mark.parametrize("variant,extra", [("default", []), ("mineffect0", ["-mineffect", "0"]), ("mineffect5", ["-mineffect", "5"])])
+def test_report_prints_what_the_reference_prints(tmp_path, monkeypatch, capsys, variant, extra):
+    """`report` (reference wisecondor.py:304-342) against the reference's own output on the same two npz files
+    (tests/golden/report.json, written by make_golden.golden_report)."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden
+    import wisecondor
+    make_golden.report_files(str(tmp_path))
+    monkeypatch.chdir(tmp_path)
+    capsys.readouterr()
+    wisecondor.main(["report", "s.npz", "o.npz"] + extra)
+    got = capsys.readouterr().out
+    with open(os.path.join(os.path.dirname(__file__), "golden", "report.json")) as f:
+        want = json.load(f)[variant]
+    assert got == want
+
+
 def test_cli_surface_matches_reference():
     import wisecondor
     p = wisecondor.buildParser()

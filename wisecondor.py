@@ -12,9 +12,10 @@ wisecondor.py (/root/reference/wisecondor.py:345-521), so scripts such as the re
     testbatch   infiles... outdir reference [same flags as test]      (new: many samples per launch)
 
 The arithmetic of every one of them runs in libwisecondor_b200.so (hand-written sm_100a kernels) through
-wisecondor_b200.wisetools; there is no CPU fallback.  `convert`, `plot` and `report` are host-only tools of the
-reference that this build does not replace (BAM binning stays on the host with pysam; plotting and reporting only read
-the result npz, whose keys are unchanged) - they are declared so that the interface is complete and say so when used.
+wisecondor_b200.wisetools; there is no CPU fallback.  `report` (text formatting of a sample npz and a result npz) is
+kept as a host tool.  `convert` and `plot` are host-only tools of the reference that this build does not replace (BAM
+binning stays on the host with pysam; plotting only reads the result npz, whose keys are unchanged) - they are declared
+so that the interface is complete and say so when used.
 
 The tool functions keep the reference's names (toolNewref, toolTest, ...) because every npz stores
 `arguments=vars(args)`, which pickles `args.func` by name (/root/reference/README.md:154).
@@ -415,7 +416,51 @@ def _hostOnly(name, why):
 
 toolConvert = _hostOnly('convert', 'BAM read-start binning stays on the host (pysam)')
 toolPlot = _hostOnly('plot', 'it only reads the result npz (matplotlib)')
-toolReport = _hostOnly('report', 'it only reads the sample and result npz')
+
+
+def toolReport(args):
+    """Text report of one tested sample (reference wisecondor.py:304-342): the arguments of `convert` and `test`, the read
+    counts `convert` kept in the sample npz, the z-score threshold and the two sigma averages, and one line per call
+    whose effect size exceeds -mineffect percent.  Host only (formatting of two npz files, nothing for the device), the
+    same text as the reference prints so that scripts parsing it keep working."""
+    sample = _load(args.testfile)
+    result = _load(args.resultfile)
+    binsize = result['binsize'].item()
+    out = []
+
+    def section(title):
+        out.append('\n# %s #' % title)
+
+    for title, stored in (('Arguments used in convert:', sample['arguments'].item()),
+                          ('Arguments used in test:', result['arguments'].item())):
+        section(title)
+        out.extend('%s = %s' % (key, stored[key]) for key in stored)
+
+    q = sample['quality'].item()
+    section('BAM information:')
+    for label, key in (('Reads mapped:  ', 'mapped'), ('Reads unmapped:', 'unmapped'), ('Reads nocoord: ', 'no_coordinate'),
+                       ('Reads rmdup:   ', 'filter_rmdup'), ('Reads lowqual: ', 'filter_mapq')):
+        out.append('%s\t %s' % (label, q[key]))
+    # what went into the tower filter: the reads counted before it, without the coordinate-less ones, with the duplicates
+    # and low-quality reads counted back in (the reference's own bookkeeping, wisecondor.py:328-331)
+    retro_in = q['pre_retro'] - q['no_coordinate'] + q['filter_rmdup'] + q['filter_mapq']
+    section('RETRO filtering:')
+    out.append('Reads in:     \t %s' % retro_in)
+    out.append('Reads removed:\t %s' % (retro_in - q['post_retro']))
+    out.append('Reads out:    \t %s' % q['post_retro'])
+
+    section('Z-Score checks:')
+    out.append('Z-Score used:\t %.2f' % result['threshold_z'].item())
+    out.append('AvgStdDev:   \t %.2f%%' % (float(result['asdef']) * 100))
+    out.append('AvgAllStdDev:\t %.2f%%' % (float(result['aasdef']) * 100))
+
+    section('Test results:')
+    out.append('z-score\teffect\tmbsize\tlocation')
+    for chrom, first, last, z, effect in result['results_calls']:
+        if args.mineffect < abs(effect * 100):
+            out.append('%.2f\t%.2f\t%.2f\t%.0f:%.0f-%.0f' % (z, effect * 100, (last - first + 1) * binsize / 1e6, chrom,
+                                                            first * binsize, (last + 1) * binsize))
+    print('\n'.join(out))
 
 
 def _intList(text):

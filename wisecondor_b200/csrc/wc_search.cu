@@ -722,6 +722,7 @@ struct FinArgs {
     int in_src_rows;        // rows between two sources: source s holds row r at (s * in_src_rows + r)
     // split form (select -> streaming re-score -> rank): the shortlist leaves the CTA
     int* sl_j;              // [rows][shortcap] shortlisted bins
+    u64* sl_k;              // [rows][shortcap] their filter keys (histogram select only; the re-score's distance slots)
     int* sl_p;              // [rows] shortlist length; -1: the row is finished elsewhere (no candidates / exhaustive fallback)
     int* grp;               // work list of the re-score: (row << 4 | group of 32 shortlist slots)
     int* grp_count;
@@ -2007,6 +2008,7 @@ extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
     }
     if (strcmp(key, "k6_split") == 0) { ctx->k6_split = value != 0 ? 1 : 0; return WC_OK; }      // K6: split (streaming re-score) / fused
     if (strcmp(key, "k6_g4") == 0) { ctx->k6_g4 = value != 0 ? 1 : 0; return WC_OK; }
+    if (strcmp(key, "k6_select") == 0) { ctx->k6_select = value != 0 ? 1 : 0; return WC_OK; }
     if (strcmp(key, "k6_chunk") == 0) { WC_CHECK_ARG(value >= 0 && value <= 480); ctx->k6_chunk = (int)value; return WC_OK; }
     if (strcmp(key, "k6_warps") == 0) { WC_CHECK_ARG(value >= 0 && value <= 16); ctx->k6_warps = (int)value; return WC_OK; }
     if (strcmp(key, "k6_prod") == 0) { WC_CHECK_ARG(value >= 0 && value <= 8); ctx->k6_prod = (int)value; return WC_OK; }

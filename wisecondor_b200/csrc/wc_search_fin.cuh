@@ -200,6 +200,285 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) wc_fin_select_kernel(const Fin
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K6a'  wc_fin_select_hist_kernel: the same decision without holding the row's entries (option k6_select = 1)
+// ---------------------------------------------------------------------------------------------------------
+// The warp-per-row select above keeps a row's live entries in shared memory (12 KB per warp: 16 warps per SM) and rows
+// with more than 1024 of them go to the CTA-per-row kernel (most rows at 10 kb).  Here the entries are streamed twice
+// and never held: pass 1 histograms the live filter distances over 1024 equal buckets of [0, d(final threshold)]; the
+// bucket b* holding the k-th smallest gives v* = its upper edge (a bound of the k-th smallest from above); pass 2 re-reads
+// the entries (L2-hot), emits those inside the window of v* and histograms the entries of b* 1024 times finer, which
+// tightens v* to 2^-20 of the range: the few entries the finer window excludes are squeezed out of the emitted list in
+// place.  Any bound from above gives the same final table; the tight one matters because the re-score's cost goes by
+// started groups of 32 candidates (r04a, 2000 x 10 kb: 1.6 % more candidates from the one-level bound, 17 % more re-score
+// time).  4 KB of shared memory per warp, 64 registers: 32 warps per SM in flight against the cold buffers' latency, and
+// no limit on a row's entries.
+constexpr int SELH_WARPS = 8;
+constexpr int SELH_BINS = 1024;
+
+__global__ void __launch_bounds__(SELH_WARPS * 32) wc_fin_select_hist_kernel(const FinArgs a, int* __restrict__ big_list,
+                                                                            int* __restrict__ big_count, int* __restrict__ stats) {
+    __shared__ int s_hist[SELH_WARPS][SELH_BINS];
+    __shared__ int s_pre[SELH_WARPS][SEL_MAXSRC + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rloc = blockIdx.x * SELH_WARPS + warp;
+    const int rows = a.row_end - a.row_begin;
+    if (rloc >= rows) return;
+    int* hist = s_hist[warp];
+    int* pre = s_pre[warp];
+    const int row = a.row_begin + rloc;
+    const int rb = rloc / BM, rl = rloc % BM;
+    const int seg0 = a.rb_seg_first[rb], nseg = a.rb_seg_count[rb];
+    const int nsrc = nseg + (a.in_key != nullptr ? a.in_nsrc : 0);
+    int* out_i = a.idx_out + (size_t)rloc * a.k;
+    double* out_d = a.dist_out + (size_t)rloc * a.k;
+    if (nsrc > SEL_MAXSRC) {
+        if (lane == 0) { big_list[atomicAdd(big_count, 1)] = rloc; a.sl_p[rloc] = -1; }
+        return;
+    }
+    for (int b = lane; b < SELH_BINS; b += 32) hist[b] = 0;
+    int flagged = 0;
+    for (int s0 = 0; s0 < nsrc; s0 += 32) {
+        const int s = s0 + lane;
+        int n = 0;
+        if (s < nsrc) {
+            if (s < nseg) {
+                n = a.seg_cnt[(size_t)(seg0 + s) * BM + rl];
+                flagged |= a.seg_flag[(size_t)(seg0 + s) * BM + rl];
+            } else {
+                n = a.in_cnt[(size_t)(s - nseg) * a.in_src_rows + rloc];
+                if (n > a.in_cap) { flagged = 1; n = a.in_cap; }
+            }
+        }
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int base = s0 == 0 ? 0 : pre[s0];
+        if (s < nsrc) pre[s + 1] = base + incl;
+        if (s0 == 0 && lane == 0) pre[0] = 0;
+        __syncwarp();
+    }
+    if (__any_sync(0xffffffffu, flagged != 0)) {
+        if (lane == 0) { a.slow_list[atomicAdd(a.slow_count, 1)] = rloc + a.slow_bias; a.sl_p[rloc] = -1; }
+        return;
+    }
+    const int total_raw = pre[nsrc];
+    const u64 tfinal = a.row_thr != nullptr ? __ldcg(a.row_thr + rloc) : ~0ull;
+    // entry t of the row: (key, bin); ~0 beyond the end
+    auto entry = [&](int t, u64& key, int& j) {
+        key = ~0ull;
+        j = 0;
+        if (t < total_raw) {
+            int lo = 0, hi = nsrc;
+            while (hi - lo > 1) {
+                const int m = (lo + hi) >> 1;
+                if (pre[m] <= t) lo = m; else hi = m;
+            }
+            const int e = t - pre[lo];
+            if (lo < nseg) {
+                const size_t off = ((size_t)(seg0 + lo) * BM + rl) * a.cap + e;
+                key = a.cand_key[off];
+                j = a.cand_j[off];
+            } else {
+                const size_t off = ((size_t)(lo - nseg) * a.in_src_rows + rloc) * a.in_cap + e;
+                key = a.in_key[off];
+                j = a.in_j[off];
+            }
+        }
+    };
+    // ---- pass 1: histogram of the live filter distances ----
+    // bucket scale: distances in [d0, dmax] = [0, the row's final threshold].  A row nobody published a threshold for still
+    // carries the initial one (1e10 or 3e38, or ~0 without a table): one more pass for the smallest and largest entry
+    // below 1e10 (entries from there on - fillers, inf, NaN - rank last and are dropped at the end, wisetools.py:312-314).
+    double d0 = 0.0, dmax = dist_of_key(tfinal);
+    if (!(dmax < 1e10)) {
+        double mn = INFINITY, mx = -INFINITY;
+        for (int t0 = 0; t0 < total_raw; t0 += 32 * SEL_U) {
+            u64 key[SEL_U];
+            int jj[SEL_U];
+#pragma unroll
+            for (int u = 0; u < SEL_U; ++u) entry(t0 + u * 32 + lane, key[u], jj[u]);
+#pragma unroll
+            for (int u = 0; u < SEL_U; ++u) {
+                const double d = dist_of_key(key[u]);
+                if (t0 + u * 32 + lane < total_raw && key[u] <= tfinal && d < 1e10) { mn = fmin(mn, d); mx = fmax(mx, d); }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (mx >= mn) { d0 = mn; dmax = mx; } else { dmax = 0.0; }          // no entry below 1e10: nothing to shortlist
+    }
+    // (a span below 1e-5 of the values: one bucket - the upper edge d0 + (b + 1) / scale must not drown in d0's rounding)
+    const float scale = dmax - d0 > 1e-5 * fabs(dmax) ? (float)SELH_BINS / (float)(dmax - d0) : 0.0f;
+    // bucket of a distance: below d0 -> 0; NaN, inf and anything beyond the range -> the last one (they rank last)
+    auto bucket = [&](double d) -> int {
+        const float x = (float)(d - d0) * scale;
+        return x < (float)SELH_BINS ? (x >= 0.0f ? (int)x : 0) : SELH_BINS - 1;
+    };
+    int kept = 0;
+    for (int t0 = 0; t0 < total_raw; t0 += 32 * SEL_U) {
+        u64 key[SEL_U];
+        int jj[SEL_U];
+#pragma unroll
+        for (int u = 0; u < SEL_U; ++u) entry(t0 + u * 32 + lane, key[u], jj[u]);
+#pragma unroll
+        for (int u = 0; u < SEL_U; ++u) {
+            const bool live = t0 + u * 32 + lane < total_raw && key[u] <= tfinal;
+            if (live) atomicAdd(&hist[bucket(dist_of_key(key[u]))], 1);
+            kept += __popc(__ballot_sync(0xffffffffu, live));
+        }
+    }
+    if (kept == 0) {
+        for (int e = lane; e < a.k; e += 32) { out_i[e] = -1; out_d[e] = 1e10; }
+        if (lane == 0) a.sl_p[rloc] = -1;
+        return;
+    }
+    __syncwarp();
+    // ---- the bucket holding the k-th smallest; v* = its upper edge ----
+    // kth_bucket(kk, below): the bucket of the kk-th smallest counted entry (-1: fewer than kk) and the number of entries in
+    // the buckets before it.  Lane l sums buckets [l * PER, (l + 1) * PER) (reads rotated by the lane: conflict-free), a warp
+    // scan finds the lane whose range holds the kk-th, its buckets are then scanned one per lane (PER / 32 rounds).
+    auto kth_bucket = [&](int kk, int& below) -> int {
+        constexpr int PER = SELH_BINS / 32;
+        static_assert(PER % 32 == 0, "one bank per lane in the rotated read");
+        int sum = 0;
+#pragma unroll 8
+        for (int t = 0; t < PER; ++t) sum += hist[lane * PER + ((t + lane) & (PER - 1))];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, incl >= kk);
+        below = 0;
+        if (!m) return -1;
+        const int lstar = __ffs(m) - 1;
+        int base = __shfl_sync(0xffffffffu, incl - sum, lstar);
+        for (int r = 0; r < PER / 32; ++r) {
+            const int v = hist[lstar * PER + r * 32 + lane];
+            int inc2 = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int w = __shfl_up_sync(0xffffffffu, inc2, o);
+                if (lane >= o) inc2 += w;
+            }
+            const unsigned m2 = __ballot_sync(0xffffffffu, base + inc2 >= kk);
+            if (m2) {
+                const int l2 = __ffs(m2) - 1;
+                below = base + __shfl_sync(0xffffffffu, inc2 - v, l2);
+                return lstar * PER + r * 32 + l2;
+            }
+            base += __shfl_sync(0xffffffffu, inc2, 31);
+        }
+        return -1;                                               // (not reached: the lane's total covers kk)
+    };
+    int below = 0;
+    int bstar = kth_bucket(a.k, below);
+    // every live entry of buckets <= bstar has d - d0 < (bstar + 1) / scale up to the float rounding of the bucket index
+    // (conversion, multiply: 2^-23) and of the division below (2 ulp): the edge is taken 2^-20 up.  The last bucket, or fewer
+    // than k live entries: all of them, i.e. dmax
+    const bool refine = bstar >= 0 && bstar < SELH_BINS - 1 && scale > 0.0f;
+    double vstar = dmax;
+    if (refine) vstar = fmin(dmax, d0 + (double)(__fdividef((float)(bstar + 1), scale) * (1.0f + 8.0f * 1.1920929e-7f)));
+    auto window_key = [&](double v) -> u64 {
+        double window = fmax(v, 0.0) + a.mcoef * (a.norms[row] + fabs(v)) + madd_of(a);
+        if (!(window > 1e-300)) window = 1e-300;
+        const u64 wk = key_of_tau(window);
+        return wk > tfinal ? tfinal : wk;                        // never beyond the row's final threshold
+    };
+    const u64 wkey = window_key(vstar);
+    // ---- pass 2: the shortlist under v*'s window (bins to sl_j, keys next to them in the re-score's distance slots), and
+    // a second histogram that resolves bucket b* 1024 times finer (the re-score's cost goes by started groups of 32
+    // candidates: a shortlist a few entries longer than the exact k-th smallest asks for often starts one more) ----
+    // (the refinement pays only where it can save a started group: it takes out about as many entries as pass 1 counted in
+    // the bucket of the window's edge - twice that, plus two, is the test after pass 2)
+    const int edge_cnt = refine ? hist[bucket(dist_of_key(wkey))] : 0;
+    __syncwarp();
+    for (int bb = lane; bb < SELH_BINS; bb += 32) hist[bb] = 0;
+    __syncwarp();
+    const double dscale = (double)scale;
+    u64* my_k = a.sl_k + (size_t)rloc * a.shortcap;
+    int* my_j = a.sl_j + (size_t)rloc * a.shortcap;
+    int p = 0, jmin = 0x7fffffff;
+    for (int t0 = 0; t0 < total_raw; t0 += 32 * SEL_U) {
+        u64 key[SEL_U];
+        int jj[SEL_U];
+#pragma unroll
+        for (int u = 0; u < SEL_U; ++u) entry(t0 + u * 32 + lane, key[u], jj[u]);
+#pragma unroll
+        for (int u = 0; u < SEL_U; ++u) {
+            const bool keep = t0 + u * 32 + lane < total_raw && key[u] <= wkey;
+            const unsigned bm = __ballot_sync(0xffffffffu, keep);
+            const int pos = p + __popc(bm & ((1u << lane) - 1u));
+            if (keep && pos < a.shortcap) {
+                my_j[pos] = jj[u];
+                my_k[pos] = key[u];
+                jmin = min(jmin, jj[u]);
+            }
+            p += __popc(bm);
+            if (refine && keep) {                                // (every entry of bucket b* is inside v*'s window)
+                const double d = dist_of_key(key[u]);
+                if (bucket(d) == bstar) {
+                    const double f = ((d - d0) * dscale - (double)bstar) * (double)SELH_BINS;
+                    atomicAdd(&hist[f < (double)SELH_BINS ? (f >= 0.0 ? (int)f : 0) : SELH_BINS - 1], 1);
+                }
+            }
+        }
+    }
+    if (p > a.shortcap) {                                        // tie plateau wider than the shortlist: exact fallback
+        if (lane == 0) {
+            a.slow_list[atomicAdd(a.slow_count, 1)] = rloc + a.slow_bias;
+            a.sl_p[rloc] = -1;
+        }
+        return;
+    }
+    __syncwarp();
+    if (refine && p > a.k && ((p - 1) >> 5) != ((max(a.k, p - 2 * edge_cnt - 2) - 1) >> 5)) {
+        int below2 = 0;
+        const int sstar = kth_bucket(a.k - below, below2);
+        // sub-bucket s of b* holds (d - d0) * scale in [b* + s / 1024, b* + (s + 1) / 1024) (the ends of b* clamp into the
+        // first and the last one): below the last one its upper edge, a thousandth of its width up for the rounding of
+        // f, bounds the k-th smallest
+        if (sstar >= 0 && sstar < SELH_BINS - 1) {
+            const double v2 = d0 + ((double)bstar + ((double)(sstar + 1) + 1e-3) / (double)SELH_BINS) / dscale;
+            const u64 wkey2 = window_key(fmin(vstar, v2));
+            if (wkey2 < wkey) {                                  // drop what the finer bound excludes, order kept
+                int q = 0;
+                jmin = 0x7fffffff;
+                for (int e0 = 0; e0 < p; e0 += 32) {
+                    const int e = e0 + lane;
+                    const bool keep = e < p && __ldcg(my_k + e) <= wkey2;
+                    const int j = e < p ? __ldcg(my_j + e) : 0;
+                    __syncwarp();                                // slots of this round are read before any is rewritten
+                    const unsigned bm = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        my_j[q + __popc(bm & ((1u << lane) - 1u))] = j;
+                        jmin = min(jmin, j);
+                    }
+                    q += __popc(bm);
+                }
+                p = q;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
+    if (lane == 0) {
+        a.sl_p[rloc] = p;
+        const int bkt = min(jmin >> a.bkt_shift, FIN_BUCKETS - 1);
+        a.sl_b[rloc] = bkt;
+        atomicAdd(a.bkt_hist + bkt, (p + 31) >> 5);
+        if (stats != nullptr) { atomicAdd(stats, kept); atomicAdd(stats + 1, p); atomicMax(stats + 2, kept); }
+    }
+}
+
 // The re-score's work list in locality order: exclusive scan of the buckets' item counts (one CTA), then every row files its
 // items under its bucket (order inside a bucket: arrival).
 __global__ void __launch_bounds__(FIN_BUCKETS) wc_fin_bucket_scan_kernel(int* __restrict__ hist, int* __restrict__ total) {
@@ -591,6 +870,7 @@ static int launch_finalize(wc_ctx* ctx, cudaStream_t stream, FinArgs fa, int row
     const int gpr = fa.shortcap / 32;                      // work items per row at most
     if ((rc = wc_reserve(ctx, SLOT_FIN_J, (size_t)rows * fa.shortcap * sizeof(int), (void**)&fa.sl_j))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_FIN_D, (size_t)rows * fa.shortcap * sizeof(double), (void**)&sl_d))) return rc;
+    fa.sl_k = reinterpret_cast<u64*>(sl_d);               // K6a' parks the shortlisted keys where K6c later writes the distances
     if ((rc = wc_reserve(ctx, SLOT_FIN_P, (2 * (size_t)rows + 8 + FIN_BUCKETS) * sizeof(int), (void**)&fa.sl_p))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_FIN_GRP, (size_t)rows * (gpr + 1) * sizeof(int), (void**)&fa.grp))) return rc;
     // sl_p[rows .. rows + 3]: work-item counter, rows passed on to the CTA-per-row select, live entries / shortlist sizes (stats)
@@ -605,9 +885,13 @@ static int launch_finalize(wc_ctx* ctx, cudaStream_t stream, FinArgs fa, int row
     int* big_list = fa.grp + (size_t)rows * gpr;
     WC_CUDA(cudaMemsetAsync(fa.grp_count, 0, 5 * sizeof(int), stream));
     fa.row_list = nullptr; fa.row_count = nullptr; fa.stats = stats;
-    const size_t sel_smem = SEL_WARPS * SEL_WARP_STRIDE;
-    WC_CUDA(cudaFuncSetAttribute(wc_fin_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-    wc_fin_select_kernel<<<(rows + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, sel_smem, stream>>>(fa, big_list, big_count, stats);
+    if (ctx->k6_select != 0) {
+        wc_fin_select_hist_kernel<<<(rows + SELH_WARPS - 1) / SELH_WARPS, SELH_WARPS * 32, 0, stream>>>(fa, big_list, big_count, stats);
+    } else {
+        const size_t sel_smem = SEL_WARPS * SEL_WARP_STRIDE;
+        WC_CUDA(cudaFuncSetAttribute(wc_fin_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+        wc_fin_select_kernel<<<(rows + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, sel_smem, stream>>>(fa, big_list, big_count, stats);
+    }
     WC_CUDA(cudaGetLastError());
     {   // rows with more live entries than a warp holds (never-pruned rows of small matrices): the CTA-per-row select
         fa.row_list = big_list; fa.row_count = big_count;
