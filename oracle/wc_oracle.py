@@ -297,10 +297,12 @@ def fill_triangle(region, region_r=None, min_effect=0):
     k = 0
     for x in range(n):
         for y in range(x, n):
-            if min_effect != 0 and abs(np.median(region_r[x:y + 1]) - 1) < min_effect:
-                out[k] = 0
-            else:
+            # the reference's own form of the test (wisetools.py:483): a NaN median (a NaN ratio in the run) compares
+            # False and zeroes the entry
+            if min_effect == 0 or abs(np.median(region_r[x:y + 1]) - 1) >= min_effect:
                 out[k] = run_value(region, x, y)
+            else:
+                out[k] = 0
             k += 1
     return out
 

@@ -20,6 +20,7 @@ import shutil
 import subprocess
 import sys
 import tempfile
+import warnings
 
 import numpy as np
 
@@ -235,6 +236,48 @@ def golden_report():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def segmin_nonfinite_cases():
+    """(name, z, r) regions with inf / NaN z-scores (reference sigma 0, wisetools.py:431) and inf / NaN ratios (reference
+    mean 0) under the effect-size filter.  Shared with the tests."""
+    rng = np.random.default_rng(77)
+    cases = []
+
+    def base(n=72):
+        z = rng.normal(0, 1, size=n)
+        r = 1.0 + rng.normal(0, 0.01, size=n)
+        z[20:40] += 2.0
+        r[20:40] += 0.08
+        return z, r
+
+    z, r = base(); z[25] = np.inf; cases.append(("posinf_inside", z, r))
+    z, r = base(); z[30] = -np.inf; cases.append(("neginf_inside", z, r))
+    z, r = base(); z[50] = np.nan; cases.append(("nan_outside", z, r))
+    z, r = base(); z[30] = -np.inf; z[55] = np.inf; cases.append(("both_signs", z, r))
+    z, r = base(); z[8] = np.nan; r[8] = np.nan; cases.append(("nan_ratio", z, r))
+    z, r = base(); z[28] = np.inf; r[28] = np.inf; z[60] = np.nan; r[60] = np.nan; cases.append(("inf_ratio", z, r))
+    z, r = base(); z[66] = np.inf; cases.append(("posinf_never_passes", z, r))
+    z, r = base(); z[22] = np.nan; z[23] = np.inf; z[45] = -np.inf; r[44:48] -= 0.09; cases.append(("many", z, r))
+    z, r = base(); r[3] = np.nan; r[35] = np.nan; cases.append(("nan_ratio_finite_z", z, r))
+    return cases
+
+
+def golden_segmin_nonfinite():
+    """fillTriMin + segmentTri of the reference on segmin_nonfinite_cases() (np.seterr('ignore') as wisecondor.py sets)."""
+    sys.path.insert(0, REF)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import wisetools as ref_wt
+    out = {}
+    with np.errstate(all='ignore'), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, z, r in segmin_nonfinite_cases():
+            tri = ref_wt.fillTriMin(z, r, 0.05)
+            segs = tri.segmentTri(3.5, 3)
+            out[name + "_cw"] = tri.getValue(0, len(z) - 1)
+            out[name + "_calls"] = np.array([[s[1][0], s[1][1], s[0]] for s in segs], dtype=float).reshape(-1, 3)
+            print(name, len(segs), [(s[1], float(s[0])) for s in segs][:6])
+    np.savez_compressed(os.path.join(HERE, "segmin_nonfinite.npz"), **out)
+
+
 def main():
     if not os.path.isfile(os.path.join(REF, "wisetools.py")):
         rc = subprocess.call([sys.executable, os.path.join(ROOT, "oracle", "make_ref.py")])
@@ -244,9 +287,13 @@ def main():
     if '--report-only' in sys.argv:
         golden_report()
         return 0
+    if '--segmin-only' in sys.argv:
+        golden_segmin_nonfinite()
+        return 0
     golden_functions()
     golden_cli_tiny()
     golden_report()
+    golden_segmin_nonfinite()
     return 0
 
 

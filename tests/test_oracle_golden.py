@@ -151,6 +151,27 @@ def test_segmentation_min_effect(fn):
                           fn['segmin_calls'].reshape(-1, 3))
 
 
+def _segmin_nonfinite():
+    import sys
+    import warnings
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    warnings.filterwarnings("ignore", category=RuntimeWarning)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "segmin_nonfinite.npz"))
+    return [(name, z, r, gold[name + "_cw"], gold[name + "_calls"]) for name, z, r in make_golden.segmin_nonfinite_cases()]
+
+
+def test_segmentation_min_effect_non_finite():
+    """inf / NaN z-scores and ratios under the effect-size filter: the reference lets them flow through fillTriMin and
+    segmentTri under np.seterr('ignore') (wisetools.py:475-487, triarray.py:59-84); golden = its own output."""
+    for name, z, r, cw_want, calls_want in _segmin_nonfinite():
+        with np.errstate(all="ignore"):
+            cw, segs = wc_oracle.segment_region(z, 3.5, 3, r, 0.05)
+        assert np.array_equal(np.array([cw]), np.array([cw_want]), equal_nan=True), name
+        got = np.array([[s[1][0], s[1][1], s[0]] for s in segs], dtype=float).reshape(-1, 3)
+        assert np.array_equal(got, calls_want.reshape(-1, 3), equal_nan=True), name
+
+
 # ---- the whole test tool ---------------------------------------------------------------------------------------
 def test_tool_test_matches_reference_cli(tiny):
     from wisecondor_b200 import synth

@@ -369,39 +369,18 @@ def toolTestBatch(args):
     with concurrent.futures.ThreadPoolExecutor(max_workers=max(2, int(args.iothreads))) as pool:
         loads = [pool.submit(load, f) for f in args.infiles]
         saves = []
-        failed = []
         for first in range(0, len(args.infiles), nbatch):
             files = args.infiles[first:first + nbatch]
             loaded = [f.result() for f in loads[first:first + nbatch]]
-            try:
-                results = _testSamples([l[0] for l in loaded], [l[1] for l in loaded], ref, args)
-            except Exception as exc:
-                # -mineffectsize with a non-finite z-score in a kept bin (a reference bin set of zero spread) is the one input
-                # the segmentation kernel rejects: one such sample must not take the rest of its batch down with it
-                if 'non-finite z-scores' not in str(exc) or len(files) == 1:
-                    raise
-                results = []
-                for infile, l in zip(files, loaded):
-                    try:
-                        results.append(_testSamples([l[0]], [l[1]], ref, args)[0])
-                    except Exception as one:
-                        if 'non-finite z-scores' not in str(one):
-                            raise
-                        print('ERROR:', infile, 'skipped -', one)
-                        failed.append(infile)
-                        results.append(None)
+            results = _testSamples([l[0] for l in loaded], [l[1] for l in loaded], ref, args)
             for infile, res in zip(files, results):
-                if res is not None:
-                    saves.append(pool.submit(_saveResult, os.path.join(args.outdir, os.path.basename(infile)), args,
-                                             ref['binsize'], res))
+                saves.append(pool.submit(_saveResult, os.path.join(args.outdir, os.path.basename(infile)), args,
+                                         ref['binsize'], res))
             for i in range(first, first + len(files)):
                 loads[i] = None                      # release the sample dicts
         for f in saves:
             f.result()                               # surface write errors
     print('Time spent on testing', len(args.infiles), 'samples:', round(time.time() - t0, 3), 'seconds')
-    if failed:
-        print('ERROR:', len(failed), 'sample(s) not tested:', ' '.join(failed))
-        sys.exit(1)
 
 
 # ---- host-only tools of the reference that are not part of this build -------------------------------------------------

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) wc_fin_select_kernel(const Fin
 constexpr int SELH_WARPS = 8;
 constexpr int SELH_BINS = 1024;
 
-__global__ void __launch_bounds__(SELH_WARPS * 32) wc_fin_select_hist_kernel(const FinArgs a, int* __restrict__ big_list,
+__global__ void __launch_bounds__(SELH_WARPS * 32, 5) wc_fin_select_hist_kernel(const FinArgs a, int* __restrict__ big_list,
                                                                             int* __restrict__ big_count, int* __restrict__ stats) {
     __shared__ int s_hist[SELH_WARPS][SELH_BINS];
     __shared__ int s_pre[SELH_WARPS][SEL_MAXSRC + 1];

@@ -53,7 +53,7 @@ struct SegArgs {
     int max_calls;
     int pcap;                // capacity of the per-chromosome arrays (>= longest chromosome + 1)
     unsigned* aux_g;         // when the side arrays do not fit in shared memory next to P: [blocks][pcap * aux_words] global
-    int* status;             // [0] |= 1 call overflow, 2 range-stack overflow, 4 non-finite z with the effect-size filter
+    int* status;             // [0] |= 1 call overflow, 2 range-stack overflow
 };
 
 struct Best {                // lexicographic champion: value, then first occurrence (x, then y)
@@ -81,16 +81,18 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     extern __shared__ __align__(16) unsigned char seg_raw[];
     float* P = reinterpret_cast<float*>(seg_raw);                 // [pcap] prefix sums (fp32 copy), P[i] = sum zc[0..i)
     // side arrays: in shared memory after P when they fit, else a per-CTA slice of global scratch
-    float* dh = a.aux_g ? reinterpret_cast<float*>(a.aux_g + (size_t)blockIdx.x * a.pcap * (MINEFF ? 3 : 1))
+    float* dh = a.aux_g ? reinterpret_cast<float*>(a.aux_g + (size_t)blockIdx.x * a.pcap * (MINEFF ? 4 : 1))
                         : P + a.pcap;                             // [pcap] per run length: max |score| of the sweep
     int* CH = reinterpret_cast<int*>(dh + a.pcap);                // [pcap] MINEFF: #{j < i : rc[j] >= c_hi}
     int* CL = CH + a.pcap;                                        // [pcap] MINEFF: #{j < i : rc[j] <= c_lo}
+    int* CN = CL + a.pcap;                                        // [pcap] MINEFF: #{j < i : rc[j] is NaN} (only if there is one)
     __shared__ double s_red[2][SEG_WARPS];
     __shared__ Best s_best[2][SEG_WARPS];
     __shared__ int s_scan[SEG_WARPS];
     __shared__ int s_lo[SEG_STACK], s_hi[SEG_STACK];
     __shared__ int s_rows[SEG_ROWCAP];
-    __shared__ int s_nrows, s_sp, s_n, s_bad;
+    __shared__ int s_nrows, s_sp, s_n, s_bad, s_rnan;
+    __shared__ unsigned long long s_cand[3];     // MINEFF: first passing NaN / +inf / -inf entry of a range, (x << 32) | y
     __shared__ double s_A, s_Pm;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     const double* rrow = MINEFF ? a.r + (size_t)b * a.N + cstart : nullptr;
 
     // ---- 1. compaction of the kept bins (wisecondor.py:215-218: refSizes >= minrefbins) -------------------------
-    if (tid == 0) { s_n = 0; s_bad = 0; }
+    if (tid == 0) { s_n = 0; s_bad = 0; s_rnan = 0; }
     __syncthreads();
     for (int base = 0; base < clen; base += SEG_THREADS) {
         const int i = base + tid;
@@ -116,7 +118,11 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         for (int w = 0; w < warp; ++w) off += s_scan[w];
         if (keep) {
             zc[off + __popc(bal & ((1u << lane) - 1u))] = v;
-            if (MINEFF) rc[off + __popc(bal & ((1u << lane) - 1u))] = rrow[i];
+            if (MINEFF) {
+                const double rv = rrow[i];
+                rc[off + __popc(bal & ((1u << lane) - 1u))] = rv;
+                if (isnan(rv)) s_rnan = 1;
+            }
             if (!isfinite(v)) s_bad = 1;
         }
         __syncthreads();
@@ -136,13 +142,9 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
     // +-inf / NaN z (a kept bin whose reference sigma is 0, wisetools.py:431 under np.seterr('ignore')): the reference's
     // argmax/argmin then see inf / NaN run values; handled per range below.  Prefix sums skip the non-finite bins.
     const bool has_bad = s_bad != 0;
-    if (MINEFF && has_bad) {                        // the effect-size filter on inf / NaN runs is not implemented
-        if (tid == 0) {
-            atomicOr(a.status, 4);
-            a.cwz[(size_t)b * a.nsel + slot] = __longlong_as_double(0x7ff8000000000000ll);
-        }
-        return;
-    }
+    // A NaN ratio (0 / 0: an empty bin whose reference bins are empty too) makes np_median of every run that holds it NaN
+    // and the filter's comparison False (wisetools.py:483): such runs are zeroed.  +-inf ratios order like any value.
+    const bool has_rnan = MINEFF && s_rnan != 0;
 
     // ---- 2. prefix sums and A = sum |z| (the scale of the error window) ---------------------------------------------
     {
@@ -212,10 +214,16 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
             }
             CH[n] = ch; CL[n] = cl;
         }
+        if (has_rnan && tid == 32) {
+            int cn = 0;
+            for (int i = 0; i < n; ++i) { CN[i] = cn; cn += isnan(rc[i]) ? 1 : 0; }
+            CN[n] = cn;
+        }
         __syncthreads();
     }
     auto passes = [&](int x, int L) -> bool {          // abs(np_median(regionR[x:y+1]) - 1) >= threshold (wisetools.py:483)
         if (!MINEFF) return true;
+        if (has_rnan && CN[x + L] != CN[x]) return false;
         const int mid = L >> 1;
         const int nh = CH[x + L] - CH[x], nl = CL[x + L] - CL[x];
         if (L & 1) return nh >= mid + 1 || nl >= mid + 1;            // the median is the middle element
@@ -258,7 +266,61 @@ __global__ void __launch_bounds__(SEG_THREADS) wc_segment_kernel(const SegArgs a
         if (tid == 0) s_sp = sp - 1;
         const int m = hi - lo;
 
-        if (has_bad) {
+        if (MINEFF && has_bad) {
+            // With the effect-size filter an inf / NaN run only counts where its median test passes (the others are 0):
+            // the first NaN entry in row-major order (numpy's argmax / argmin, triarray.py:62-66), else the first +inf
+            // entry (the maximum), else the first -inf entry (abs(min) > max, :68-70).  A row's run values go finite ->
+            // +-inf -> NaN as y grows; one thread per row x walks y and tests the non-finite stretch (rare path: O(m^2)
+            // median tests in all).  No passing non-finite entry: the finite sweep below decides - runs holding a
+            // non-finite bin do not pass there either.
+            if (tid < 3) s_cand[tid] = ~0ull;
+            __syncthreads();
+            for (int xb = lo; xb < hi; xb += SEG_THREADS) {
+                const int x = xb + tid;
+                if (x < hi) {
+                    bool sn = false, sp = false, sm = false, gotp = false, gotm = false;
+                    for (int y = x; y < hi; ++y) {
+                        const double v = zc[y];
+                        if (!isfinite(v)) {
+                            if (isnan(v)) sn = true; else if (v > 0.0) sp = true; else sm = true;
+                        }
+                        const int kind = (sn || (sp && sm)) ? 0 : (sp ? 1 : (sm ? 2 : -1));
+                        if (kind < 0 || (kind == 1 && gotp) || (kind == 2 && gotm)) continue;
+                        if (passes(x, y - x + 1)) {
+                            atomicMin(&s_cand[kind], ((unsigned long long)x << 32) | (unsigned)y);
+                            if (kind == 0) break;                  // the rest of the row comes later in the order
+                            if (kind == 1) gotp = true; else gotm = true;
+                        }
+                    }
+                }
+                __syncthreads();
+                const bool stop = s_cand[0] != ~0ull;              // a NaN entry in these rows: no later row precedes it
+                __syncthreads();
+                if (stop) break;
+            }
+            const unsigned long long cn = s_cand[0], cp = s_cand[1], cm = s_cand[2];
+            if ((cn & cp & cm) != ~0ull) {
+                __syncthreads();                     // s_cand is rewritten by the next range
+                if (tid == 0) {
+                    const unsigned long long at = cn != ~0ull ? cn : (cp != ~0ull ? cp : cm);
+                    wc_call c;
+                    c.sample = b; c.chrom = slot; c.x = (int)(at >> 32); c.y = (int)(at & 0xffffffffu);
+                    c.z = cn != ~0ull ? __longlong_as_double(0x7ff8000000000000ll) : (cp != ~0ull ? INFINITY : -INFINITY);
+                    const int slot_i = atomicAdd(&a.ncalls[b], 1);
+                    if (slot_i < a.max_calls) a.calls[(size_t)b * a.max_calls + slot_i] = c; else atomicOr(a.status, 1);
+                    int spn = s_sp;
+                    if ((c.y - lo) + 1 < m - a.min_search) {            // triarray.py:79
+                        if (spn < SEG_STACK) { s_lo[spn] = c.y + 1; s_hi[spn] = hi; ++spn; } else atomicOr(a.status, 2);
+                    }
+                    if (c.x - lo > a.min_search) {                      // triarray.py:76
+                        if (spn < SEG_STACK) { s_lo[spn] = lo; s_hi[spn] = c.x; ++spn; } else atomicOr(a.status, 2);
+                    }
+                    s_sp = spn;
+                }
+                continue;
+            }
+        }
+        if (!MINEFF && has_bad) {
             // Run values that contain a NaN, or both +inf and -inf, are NaN; a run with only +inf (-inf) bins is +inf
             // (-inf).  numpy's argmax/argmin return the first NaN entry if there is one (triarray.py:62-66), and a run
             // [x..y] that is NaN makes [lo..y] NaN too, so the first NaN entry is (lo, first y at which [lo..y] turns NaN).
@@ -486,7 +548,7 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const double* r_
     if ((rc = wc_reserve(ctx, SLOT_S_META, (size_t)3 * nsel * sizeof(int), (void**)&meta_d))) return rc;
     if ((rc = wc_reserve(ctx, SLOT_S_STATUS, 4 * sizeof(int), (void**)&status_d))) return rc;
     const int pcap = (maxlen + 8) & ~1;
-    const size_t aux_bytes = (size_t)pcap * (sizeof(unsigned) + (mineff ? 2 * sizeof(int) : 0));
+    const size_t aux_bytes = (size_t)pcap * (sizeof(unsigned) + (mineff ? 3 * sizeof(int) : 0));
     size_t smem = (size_t)pcap * sizeof(float) + aux_bytes;
     unsigned* aux_g = nullptr;
     if (smem > 220 * 1024) {                      // keep only the prefix sums in shared memory
@@ -520,10 +582,6 @@ extern "C" int wc_segment_batch(wc_ctx* ctx, const double* z_d, const double* r_
     WC_CUDA(cudaStreamSynchronize(stream));       // meta/status host buffers; the call is documented as synchronous
     ctx->timed_mask |= 1u << 5;
     ctx->counter[6] = 1;
-    if (status & 4) {
-        wc_set_error("segmentation: non-finite z-scores in kept bins together with mineffectsize != 0 is not supported");
-        return WC_ERR_ARG;
-    }
     if (status & 2) { wc_set_error("segmentation: more than %d pending ranges on one chromosome", SEG_STACK); return WC_ERR_INTERNAL; }
     if (status & 1) { wc_set_error("segmentation: more than max_calls=%d calls for one sample", max_calls); return WC_ERR_ARG; }
     return WC_OK;
