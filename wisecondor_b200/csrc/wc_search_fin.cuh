@@ -265,28 +265,44 @@ __global__ void __launch_bounds__(SELH_WARPS * 32, 5) wc_fin_select_hist_kernel(
         if (lane == 0) { a.slow_list[atomicAdd(a.slow_count, 1)] = rloc + a.slow_bias; a.sl_p[rloc] = -1; }
         return;
     }
-    const int total_raw = pre[nsrc];
     const u64 tfinal = a.row_thr != nullptr ? __ldcg(a.row_thr + rloc) : ~0ull;
-    // entry t of the row: (key, bin); ~0 beyond the end
-    auto entry = [&](int t, u64& key, int& j) {
-        key = ~0ull;
-        j = 0;
-        if (t < total_raw) {
-            int lo = 0, hi = nsrc;
-            while (hi - lo > 1) {
-                const int m = (lo + hi) >> 1;
-                if (pre[m] <= t) lo = m; else hi = m;
+    // sweep(f): f(key, bin, valid) for every entry of the row, source by source in rounds of 32 entries (lane = entry), SEL_U
+    // rounds' loads in flight; the cursor (source, round) is warp-uniform, so f may vote.  (r04e: a flat entry number mapped
+    // to its source by a binary search over the prefix table cost half of the kernel's 6 170 instructions per row.)
+    auto sweep = [&](auto&& f) {
+        int s = 0, e0 = 0, ns = nsrc > 0 ? pre[1] : 0;           // source, first entry of its next round, its entry count
+        bool more = true;
+        while (more) {
+            u64 key[SEL_U];
+            int jj[SEL_U];
+            bool ok[SEL_U];
+#pragma unroll
+            for (int u = 0; u < SEL_U; ++u) {
+                while (s < nsrc && e0 >= ns) { ++s; e0 = 0; ns = s < nsrc ? pre[s + 1] - pre[s] : 0; }
+                key[u] = ~0ull;
+                jj[u] = 0;
+                ok[u] = false;
+                if (s < nsrc) {
+                    const int e = e0 + lane;
+                    if (e < ns) {
+                        ok[u] = true;
+                        if (s < nseg) {
+                            const size_t off = ((size_t)(seg0 + s) * BM + rl) * a.cap + e;
+                            key[u] = a.cand_key[off];
+                            jj[u] = a.cand_j[off];
+                        } else {
+                            const size_t off = ((size_t)(s - nseg) * a.in_src_rows + rloc) * a.in_cap + e;
+                            key[u] = a.in_key[off];
+                            jj[u] = a.in_j[off];
+                        }
+                    }
+                    e0 += 32;
+                } else {
+                    more = false;
+                }
             }
-            const int e = t - pre[lo];
-            if (lo < nseg) {
-                const size_t off = ((size_t)(seg0 + lo) * BM + rl) * a.cap + e;
-                key = a.cand_key[off];
-                j = a.cand_j[off];
-            } else {
-                const size_t off = ((size_t)(lo - nseg) * a.in_src_rows + rloc) * a.in_cap + e;
-                key = a.in_key[off];
-                j = a.in_j[off];
-            }
+#pragma unroll
+            for (int u = 0; u < SEL_U; ++u) f(key[u], jj[u], ok[u]);
         }
     };
     // ---- pass 1: histogram of the live filter distances ----
@@ -296,17 +312,10 @@ __global__ void __launch_bounds__(SELH_WARPS * 32, 5) wc_fin_select_hist_kernel(
     double d0 = 0.0, dmax = dist_of_key(tfinal);
     if (!(dmax < 1e10)) {
         double mn = INFINITY, mx = -INFINITY;
-        for (int t0 = 0; t0 < total_raw; t0 += 32 * SEL_U) {
-            u64 key[SEL_U];
-            int jj[SEL_U];
-#pragma unroll
-            for (int u = 0; u < SEL_U; ++u) entry(t0 + u * 32 + lane, key[u], jj[u]);
-#pragma unroll
-            for (int u = 0; u < SEL_U; ++u) {
-                const double d = dist_of_key(key[u]);
-                if (t0 + u * 32 + lane < total_raw && key[u] <= tfinal && d < 1e10) { mn = fmin(mn, d); mx = fmax(mx, d); }
-            }
-        }
+        sweep([&](u64 key, int, bool valid) {
+            const double d = dist_of_key(key);
+            if (valid && key <= tfinal && d < 1e10) { mn = fmin(mn, d); mx = fmax(mx, d); }
+        });
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -322,18 +331,11 @@ __global__ void __launch_bounds__(SELH_WARPS * 32, 5) wc_fin_select_hist_kernel(
         return x < (float)SELH_BINS ? (x >= 0.0f ? (int)x : 0) : SELH_BINS - 1;
     };
     int kept = 0;
-    for (int t0 = 0; t0 < total_raw; t0 += 32 * SEL_U) {
-        u64 key[SEL_U];
-        int jj[SEL_U];
-#pragma unroll
-        for (int u = 0; u < SEL_U; ++u) entry(t0 + u * 32 + lane, key[u], jj[u]);
-#pragma unroll
-        for (int u = 0; u < SEL_U; ++u) {
-            const bool live = t0 + u * 32 + lane < total_raw && key[u] <= tfinal;
-            if (live) atomicAdd(&hist[bucket(dist_of_key(key[u]))], 1);
-            kept += __popc(__ballot_sync(0xffffffffu, live));
-        }
-    }
+    sweep([&](u64 key, int, bool valid) {
+        const bool live = valid && key <= tfinal;
+        if (live) atomicAdd(&hist[bucket(dist_of_key(key))], 1);
+        kept += __popc(__ballot_sync(0xffffffffu, live));
+    });
     if (kept == 0) {
         for (int e = lane; e < a.k; e += 32) { out_i[e] = -1; out_d[e] = 1e10; }
         if (lane == 0) a.sl_p[rloc] = -1;
@@ -407,31 +409,24 @@ __global__ void __launch_bounds__(SELH_WARPS * 32, 5) wc_fin_select_hist_kernel(
     u64* my_k = a.sl_k + (size_t)rloc * a.shortcap;
     int* my_j = a.sl_j + (size_t)rloc * a.shortcap;
     int p = 0, jmin = 0x7fffffff;
-    for (int t0 = 0; t0 < total_raw; t0 += 32 * SEL_U) {
-        u64 key[SEL_U];
-        int jj[SEL_U];
-#pragma unroll
-        for (int u = 0; u < SEL_U; ++u) entry(t0 + u * 32 + lane, key[u], jj[u]);
-#pragma unroll
-        for (int u = 0; u < SEL_U; ++u) {
-            const bool keep = t0 + u * 32 + lane < total_raw && key[u] <= wkey;
-            const unsigned bm = __ballot_sync(0xffffffffu, keep);
-            const int pos = p + __popc(bm & ((1u << lane) - 1u));
-            if (keep && pos < a.shortcap) {
-                my_j[pos] = jj[u];
-                my_k[pos] = key[u];
-                jmin = min(jmin, jj[u]);
-            }
-            p += __popc(bm);
-            if (refine && keep) {                                // (every entry of bucket b* is inside v*'s window)
-                const double d = dist_of_key(key[u]);
-                if (bucket(d) == bstar) {
-                    const double f = ((d - d0) * dscale - (double)bstar) * (double)SELH_BINS;
-                    atomicAdd(&hist[f < (double)SELH_BINS ? (f >= 0.0 ? (int)f : 0) : SELH_BINS - 1], 1);
-                }
+    sweep([&](u64 key, int j, bool valid) {
+        const bool keep = valid && key <= wkey;
+        const unsigned bm = __ballot_sync(0xffffffffu, keep);
+        const int pos = p + __popc(bm & ((1u << lane) - 1u));
+        if (keep && pos < a.shortcap) {
+            my_j[pos] = j;
+            my_k[pos] = key;
+            jmin = min(jmin, j);
+        }
+        p += __popc(bm);
+        if (refine && keep) {                                    // (every entry of bucket b* is inside v*'s window)
+            const double d = dist_of_key(key);
+            if (bucket(d) == bstar) {
+                const double f = ((d - d0) * dscale - (double)bstar) * (double)SELH_BINS;
+                atomicAdd(&hist[f < (double)SELH_BINS ? (f >= 0.0 ? (int)f : 0) : SELH_BINS - 1], 1);
             }
         }
-    }
+    });
     if (p > a.shortcap) {                                        // tie plateau wider than the shortlist: exact fallback
         if (lane == 0) {
             a.slow_list[atomicAdd(a.slow_count, 1)] = rloc + a.slow_bias;
