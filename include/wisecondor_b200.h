@@ -97,7 +97,11 @@ int wc_debug_profile(wc_ctx* ctx, int enable, long long* out_h, int max_ctas);
  *   "k6_split"  the exact re-score: 1 = select -> streaming re-score on bulk copies -> rank (default; needs an even number
  *               of samples), 0 = one fused kernel; "k6_chunk" samples per bulk copy, "k6_warps" consumer warps per SM,
  *               "k6_prod" producer warps per consumer warp (0 = defaults 100 / 4 / 2), "k6_g4" 1 = candidate rows four per
- *               TMA request (tile::gather4) instead of one bulk copy each (default 0: measured no faster). */
+ *               TMA request (tile::gather4) instead of one bulk copy each (default 0: measured no faster),
+ *   "k6_select" 1 = streaming two-level histogram select (default: no limit on a row's candidate entries), 0 = entries
+ *               held in shared memory + bisection (rows with more than 1024 entries: CTA-per-row select),
+ *   "k6_parts"  wc_newref_topk_host only: row ranges (1..16, default 4) the last stage runs in; every finished range but the
+ *               last is copied to the host while the next one is re-scored. */
 int wc_set_option(wc_ctx* ctx, const char* key, double value);
 
 /* Debug: searches that run the tcgen05 filter (k5_f16 = 2) also store every filter distance they compute into

@@ -128,7 +128,7 @@ class Context(object):
         if not self._h:
             raise WisecondorError("wc_create(%d) failed: %s" % (device, lib().wc_last_error().decode()))
         self.device = int(device)
-        for key in ("k5_group", "k5_stages", "k5_lag", "k5_sym", "k5_f16", "k5_pivots", "k6_split", "k6_select", "k6_g4", "k6_chunk", "k6_warps", "k6_prod"):        # experiment knobs; results never depend on them
+        for key in ("k5_group", "k5_stages", "k5_lag", "k5_sym", "k5_f16", "k5_pivots", "k6_split", "k6_select", "k6_parts", "k6_g4", "k6_chunk", "k6_warps", "k6_prod"):        # experiment knobs; results never depend on them
             val = os.environ.get("WC_" + key.upper())
             if val is not None:
                 check(lib().wc_set_option(self._h, key.encode(), float(val)))

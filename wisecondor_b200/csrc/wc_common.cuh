@@ -98,6 +98,7 @@ struct wc_ctx {
     int dbg_ld = 0;
     const int* k6_stats_d = nullptr;   // device counters of the last split K6: [0] live entries, [1] shortlisted candidates
     int k6_g4 = 0;                  // K6c: 1 = candidate rows four per TMA request (tile::gather4) instead of one bulk copy each (measured: no faster)
+    int k6_parts = 4;               // wc_newref_topk_host: row ranges K6 runs in (all but the last copied to the host while the next is re-scored)
     int k6_select = 1;              // K6a: 1 = streaming histogram select (entries never held), 0 = bisection on entries held in shared memory
     int k6_split = 1;               // K6: 1 = select -> streaming re-score (bulk copies) -> rank, 0 = fused kernel
     int k6_chunk = 0, k6_warps = 0, k6_prod = 0;     // K6c tuning: samples per chunk, consumer / producer warps (0 = default)

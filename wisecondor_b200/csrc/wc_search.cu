@@ -1827,32 +1827,33 @@ extern "C" int wc_newref_topk(wc_ctx* ctx, const double* corrected_d, int N, int
     fa.slow_bias = 0;
     WC_CUDA(cudaEventRecord(ctx->ev[4], stream));
     long long fin_launches = 0;
-    // Called from wc_newref_topk_host: the table's first half travels to the host while the second half is still being
-    // re-scored (K6 in two row ranges, the copy on a non-blocking stream behind an event).
-    const int split_rows = (ctx->d2h_idx_h != nullptr && rows >= 16 * BM) ? (int)(rows / 2) / BM * BM : 0;
+    // Called from wc_newref_topk_host: K6 runs in k6_parts row ranges and every finished range but the last travels to the
+    // host (a non-blocking stream behind an event) while the next one is re-scored - the copy left at the end is
+    // 1 / k6_parts of the table.
+    const int nparts = (ctx->d2h_idx_h != nullptr && rows >= 16 * BM) ? std::max(1, ctx->k6_parts) : 1;
     ctx->d2h_rows_done = 0;
-    if (split_rows > 0) {
-        FinArgs f1 = fa;
-        f1.row_end = row_begin + split_rows;
-        long long l1 = 0, l2 = 0;
-        if ((rc = launch_finalize(ctx, stream, f1, split_rows, f16 != 0, &l1))) return rc;
-        WC_CUDA(cudaEventRecord(ctx->d2h_ev, stream));
-        WC_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->d2h_ev, 0));
-        WC_CUDA(cudaMemcpyAsync(ctx->d2h_idx_h, idx_d, (size_t)split_rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->d2h_stream));
-        WC_CUDA(cudaMemcpyAsync(ctx->d2h_dist_h, dist_d, (size_t)split_rows * k * sizeof(double), cudaMemcpyDeviceToHost, ctx->d2h_stream));
-        ctx->d2h_rows_done = (size_t)split_rows;
-        FinArgs f2 = fa;
-        const int hb = split_rows / BM;
-        f2.row_begin = row_begin + split_rows;
-        f2.rb_seg_first += hb; f2.rb_seg_count += hb;
-        f2.idx_out += (size_t)split_rows * k; f2.dist_out += (size_t)split_rows * k;
-        f2.slow_bias = split_rows;
-        if (f2.row_thr != nullptr) f2.row_thr += split_rows;
-        if (f2.in_key != nullptr) { f2.in_key += (size_t)split_rows * in_cap; f2.in_j += (size_t)split_rows * in_cap; f2.in_cnt += split_rows; }
-        if ((rc = launch_finalize(ctx, stream, f2, (int)rows - split_rows, f16 != 0, &l2))) return rc;
-        fin_launches = l1 + l2;
-    } else {
-        if ((rc = launch_finalize(ctx, stream, fa, (int)rows, f16 != 0, &fin_launches))) return rc;
+    for (int pi = 0, r0 = 0; pi < nparts; ++pi) {
+        const int r1 = pi + 1 == nparts ? (int)rows : (int)((long long)rows * (pi + 1) / nparts) / BM * BM;
+        if (r1 <= r0) continue;
+        FinArgs f = fa;
+        const int hb = r0 / BM;
+        f.row_begin = row_begin + r0; f.row_end = row_begin + r1;
+        f.rb_seg_first += hb; f.rb_seg_count += hb;
+        f.idx_out += (size_t)r0 * k; f.dist_out += (size_t)r0 * k;
+        f.slow_bias = r0;
+        if (f.row_thr != nullptr) f.row_thr += r0;
+        if (f.in_key != nullptr) { f.in_key += (size_t)r0 * in_cap; f.in_j += (size_t)r0 * in_cap; f.in_cnt += r0; }
+        long long l = 0;
+        if ((rc = launch_finalize(ctx, stream, f, r1 - r0, f16 != 0, &l))) return rc;
+        fin_launches += l;
+        if (pi + 1 < nparts) {
+            WC_CUDA(cudaEventRecord(ctx->d2h_ev, stream));
+            WC_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->d2h_ev, 0));
+            WC_CUDA(cudaMemcpyAsync(ctx->d2h_idx_h + (size_t)r0 * k, idx_d + (size_t)r0 * k, (size_t)(r1 - r0) * k * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            WC_CUDA(cudaMemcpyAsync(ctx->d2h_dist_h + (size_t)r0 * k, dist_d + (size_t)r0 * k, (size_t)(r1 - r0) * k * sizeof(double), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            ctx->d2h_rows_done = (size_t)r1;
+        }
+        r0 = r1;
     }
     WC_CUDA(cudaEventRecord(ctx->ev[5], stream));
 
@@ -2009,6 +2010,7 @@ extern "C" int wc_set_option(wc_ctx* ctx, const char* key, double value) {
     if (strcmp(key, "k6_split") == 0) { ctx->k6_split = value != 0 ? 1 : 0; return WC_OK; }      // K6: split (streaming re-score) / fused
     if (strcmp(key, "k6_g4") == 0) { ctx->k6_g4 = value != 0 ? 1 : 0; return WC_OK; }
     if (strcmp(key, "k6_select") == 0) { ctx->k6_select = value != 0 ? 1 : 0; return WC_OK; }
+    if (strcmp(key, "k6_parts") == 0) { WC_CHECK_ARG(value >= 1 && value <= 16); ctx->k6_parts = (int)value; return WC_OK; }
     if (strcmp(key, "k6_chunk") == 0) { WC_CHECK_ARG(value >= 0 && value <= 480); ctx->k6_chunk = (int)value; return WC_OK; }
     if (strcmp(key, "k6_warps") == 0) { WC_CHECK_ARG(value >= 0 && value <= 16); ctx->k6_warps = (int)value; return WC_OK; }
     if (strcmp(key, "k6_prod") == 0) { WC_CHECK_ARG(value >= 0 && value <= 8); ctx->k6_prod = (int)value; return WC_OK; }
