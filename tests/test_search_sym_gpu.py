@@ -53,9 +53,12 @@ def test_symmetric_equals_plain_search_and_halves_the_tiles(sym):
     sym(0)
     pidx, pdist, pst = _gpu_search(X, bins, 100)
     _assert_same(idx, dist, pidx, pdist)
-    # plain: two fills, K4, K5, K6 (one fused kernel, or two selects + bucket scan + scatter + re-score + rank; twice when the host call finalises in two row ranges) (+ pivot select, gather, pass with the
-    # tcgen05 filter); symmetric: one K5 launch more
-    assert pst["launches"] in (5, 6, 10, 16, 8, 9, 13, 19) and st["launches"] == pst["launches"] + 1
+    # plain: two fills, K4, K5, K6 (one fused kernel, or two selects + bucket scan + scatter + re-score + rank - once per row
+    # range the host call finalises in: option k6_parts, 1..16) (+ pivot select, gather, pass with the tcgen05 filter);
+    # symmetric: one K5 launch more
+    k6 = pst["launches"] - 4 - (3 if pst["pivots"] else 0)
+    assert k6 in (1, 2) or (k6 % 6 == 0 and 1 <= k6 // 6 <= 16)
+    assert st["launches"] == pst["launches"] + 1
     assert 0.5 < st["tiles"] / pst["tiles"] < 0.62                             # 1/8 + 7/16 = 0.5625 of the plain tiles
     assert st["tiles_plain"] == pst["tiles"] == pst["tiles_plain"]
     assert st["exhaustive_rows"] == pst["exhaustive_rows"] == 0
@@ -113,3 +116,25 @@ def test_rescore_by_tma_gather4_returns_the_same_table(sym):
     _assert_same(gidx, gdist, idx, dist)
     oidx, odist = c_oracle.get_reference_rows(X, bins, 0, 256, 100)
     _assert_same(gidx[:256], gdist[:256], oidx, odist)
+
+
+@pytest.mark.parametrize("S,k", [(130, 100), (50, 200), (64, 20)])
+def test_both_selects_return_the_same_table(sym, S, k):
+    """Option k6_select: the streaming two-level histogram select (default) and the select that holds a row's entries in
+    shared memory (rows with more than 1024 of them: CTA-per-row select) shortlist differently sized supersets of the
+    refsize nearest bins; the exact re-score and the rank make the same table of either.  Unpruned rows (small N, large k:
+    no published threshold, more entries than a warp holds) included."""
+    from wisecondor_b200 import _cabi
+    bins = [int(b) for b in np.array(synth.chrom_bins(250000)) // 2]
+    X = synth.corrected_like(bins, S, seed=23 + S)
+    idx, dist, st = _gpu_search(X, bins, k)
+    assert st["exhaustive_rows"] == 0
+    ctx = _cabi.context(0)
+    _cabi.check(_cabi.lib().wc_set_option(ctx.handle, b"k6_select", 0.0))
+    try:
+        hidx, hdist, hst = _gpu_search(X, bins, k)
+    finally:
+        _cabi.check(_cabi.lib().wc_set_option(ctx.handle, b"k6_select", 1.0))
+    _assert_same(hidx, hdist, idx, dist)
+    oidx, odist = c_oracle.get_reference_rows(X, bins, 0, 256, k)
+    _assert_same(idx[:256], dist[:256], oidx, odist)
