@@ -235,7 +235,8 @@ int wc_zscore_batch(wc_ctx* ctx, const double* test_d, const double* copy_init_d
  *   cwz_d          DEVICE B x nsel float64: zTriangle.getValue(0, n-1) (wisecondor.py:237)
  *   cleaned_bins_d DEVICE B x nsel int32: kept bins of each listed chromosome (`cleanedBins`, wisecondor.py:220-222)
  *   calls_d        DEVICE B x max_calls wc_call, ncalls_d DEVICE B int32: unordered; sort by (chrom, x)
- * Non-finite z of a kept bin (reference sigma 0) gives the NaN / inf calls numpy's argmax/argmin give the reference.
+ * Non-finite z of a kept bin (reference sigma 0) gives the NaN / inf calls numpy's argmax/argmin give the reference, with
+ * and without the effect-size filter (a NaN ratio fails the median test of every run that holds it, wisetools.py:483).
  * Synchronous. */
 int wc_segment_batch(wc_ctx* ctx, const double* z_d, const double* r_d, const int32_t* refsizes_d, int N, int B,
                      const int* chrom_bins_h, int nchrom, const int* chromosomes_h, int nsel, int minrefbins,
