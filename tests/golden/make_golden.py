@@ -278,6 +278,34 @@ def golden_segmin_nonfinite():
     np.savez_compressed(os.path.join(HERE, "segmin_nonfinite.npz"), **out)
 
 
+def golden_cli_tiny_mineff():
+    """The reference's `test -mineffectsize` (wisecondor.py:460, fillTriMin) on the tiny genome's test samples against the
+    reference npz of tiny_cli.npz (rebuilt from its arrays, as tests/test_cli_gpu.py does): 0.25 keeps the 1.3x gain of
+    sample 1 and zeroes the 0.8x loss of sample 2."""
+    tiny = np.load(os.path.join(HERE, "tiny_cli.npz"), allow_pickle=True)
+    bins = [int(b) for b in tiny['bins']]
+    tmp = tempfile.mkdtemp(prefix="wc_golden_")
+    try:
+        np.savez_compressed(os.path.join(tmp, "goldref.npz"), arguments={}, runtime={}, binsize=tiny['ref_binsize'],
+                            indexes=tiny['ref_indexes'], distances=tiny['ref_distances'],
+                            chromosome_sizes=tiny['ref_chromosome_sizes'], mask=tiny['ref_mask'],
+                            masked_sizes=tiny['ref_masked_sizes'], pca_components=tiny['ref_pca_components'],
+                            pca_mean=tiny['ref_pca_mean'])
+        out = {'mineffectsize': 0.25}
+        for t in range(tiny['test_counts'].shape[0]):
+            write_sample_npz(os.path.join(tmp, "t%d.npz" % t), tiny['test_counts'][t], bins, TINY_BINSIZE)
+            run_ref_cli(["test", "t%d.npz" % t, "o%d.npz" % t, "goldref.npz", "-minrefbins", "10", "-mineffectsize", "0.25"], tmp)
+            res = np.load(os.path.join(tmp, "o%d.npz" % t), allow_pickle=True)
+            out["res%d_cwz" % t] = res['results_cwz']
+            out["res%d_calls" % t] = np.asarray(res['results_calls'], dtype=float).reshape(-1, 5)
+            out["res%d_z" % t] = np.concatenate(list(res['results_z']))
+        np.savez_compressed(os.path.join(HERE, "tiny_cli_mineff.npz"), **out)
+        print("tiny_cli_mineff.npz: calls per test sample with / without the filter: %s / %s" % (
+            [out["res%d_calls" % t].shape[0] for t in range(4)], [tiny["res%d_calls" % t].shape[0] for t in range(4)]))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     if not os.path.isfile(os.path.join(REF, "wisetools.py")):
         rc = subprocess.call([sys.executable, os.path.join(ROOT, "oracle", "make_ref.py")])
@@ -287,6 +315,9 @@ def main():
     if '--report-only' in sys.argv:
         golden_report()
         return 0
+    if '--mineff-only' in sys.argv:
+        golden_cli_tiny_mineff()
+        return 0
     if '--segmin-only' in sys.argv:
         golden_segmin_nonfinite()
         return 0
@@ -294,6 +325,7 @@ def main():
     golden_cli_tiny()
     golden_report()
     golden_segmin_nonfinite()
+    golden_cli_tiny_mineff()
     return 0
 
 

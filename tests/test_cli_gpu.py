@@ -152,6 +152,27 @@ def test_test_tool_matches_reference(workdir, tiny):
         _check_result(res, tiny, t)
 
 
+def test_test_tool_with_mineffectsize_matches_reference(workdir, tiny):
+    """`test -mineffectsize 0.25` (wisecondor.py:460 -> fillTriMin) against what the reference's CLI wrote for the same
+    files (tests/golden/tiny_cli_mineff.npz, make_golden.golden_cli_tiny_mineff): the filter removes most calls."""
+    gold = np.load(os.path.join(GOLD, "tiny_cli_mineff.npz"), allow_pickle=True)
+    fewer = 0
+    for t in range(tiny['test_counts'].shape[0]):
+        out = str(workdir / ("m%d.npz" % t))
+        _run(["test", str(workdir / ("t%d.npz" % t)), out, str(workdir / "goldref.npz"), "-minrefbins", "10",
+              "-mineffectsize", str(float(gold['mineffectsize']))])
+        res = np.load(out, allow_pickle=True)
+        _close(np.concatenate(list(res['results_z'])), gold['res%d_z' % t])
+        _close(res['results_cwz'], gold['res%d_cwz' % t])
+        calls = np.asarray(res['results_calls'], dtype=float).reshape(-1, 5)
+        want = gold['res%d_calls' % t]
+        assert calls.shape == want.shape, t
+        assert np.array_equal(calls[:, :3], want[:, :3])
+        _close(calls[:, 3:], want[:, 3:])
+        fewer += int(want.shape[0] < tiny['res%d_calls' % t].shape[0])
+    assert fewer >= 2
+
+
 def test_testbatch_equals_single_runs(workdir, tiny):
     outdir = str(workdir / "batch")
     tests = [str(workdir / ("t%d.npz" % t)) for t in (0, 1, 3)]
