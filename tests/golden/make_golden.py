@@ -306,6 +306,60 @@ def golden_cli_tiny_mineff():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+FLAG_VARIANTS = [                                   # (name, test sample, sample bin size, extra flags of `test`)
+    ("chromosomes", 1, None, ["-chromosomes", "1,3,7,12", "-minzscore", "4.0"]),
+    ("multitest", 3, None, ["-multitest", "5"]),
+    ("minzscore_repeats1", 2, None, ["-minzscore", "3.2", "-repeats", "1"]),
+    ("rescaled_sample", 1, 500000, []),             # sample binned at 0.5 Mb: scaleSample sums pairs of bins (wisetools.py:20-44)
+]
+
+
+def split_counts(row, bins):
+    """A 0.5 Mb sample whose pairs of bins sum to the 1 Mb counts (an odd split, so both halves matter)."""
+    out, nb = [], []
+    pos = 0
+    for n in bins:
+        c = row[pos:pos + n].astype(np.int64)
+        fine = np.empty(2 * n, dtype=np.int64)
+        fine[0::2] = c // 3
+        fine[1::2] = c - c // 3
+        out.append(fine)
+        nb.append(2 * n)
+        pos += n
+    return np.concatenate(out), nb
+
+
+def golden_cli_tiny_flags():
+    """The reference's `test` with its remaining flags and with a sample of another bin size, same files as
+    golden_cli_tiny_mineff."""
+    tiny = np.load(os.path.join(HERE, "tiny_cli.npz"), allow_pickle=True)
+    bins = [int(b) for b in tiny['bins']]
+    tmp = tempfile.mkdtemp(prefix="wc_golden_")
+    try:
+        np.savez_compressed(os.path.join(tmp, "goldref.npz"), arguments={}, runtime={}, binsize=tiny['ref_binsize'],
+                            indexes=tiny['ref_indexes'], distances=tiny['ref_distances'],
+                            chromosome_sizes=tiny['ref_chromosome_sizes'], mask=tiny['ref_mask'],
+                            masked_sizes=tiny['ref_masked_sizes'], pca_components=tiny['ref_pca_components'],
+                            pca_mean=tiny['ref_pca_mean'])
+        out = {}
+        for name, t, sample_binsize, extra in FLAG_VARIANTS:
+            if sample_binsize is None:
+                write_sample_npz(os.path.join(tmp, name + ".npz"), tiny['test_counts'][t], bins, TINY_BINSIZE)
+            else:
+                fine, nb = split_counts(tiny['test_counts'][t], bins)
+                write_sample_npz(os.path.join(tmp, name + ".npz"), fine, nb, sample_binsize)
+            run_ref_cli(["test", name + ".npz", name + "_o.npz", "goldref.npz", "-minrefbins", "10"] + extra, tmp)
+            res = np.load(os.path.join(tmp, name + "_o.npz"), allow_pickle=True)
+            out[name + "_cwz"] = np.asarray(res['results_cwz'], dtype=float)
+            out[name + "_calls"] = np.asarray(res['results_calls'], dtype=float).reshape(-1, 5)
+            out[name + "_z"] = np.concatenate(list(res['results_z']))
+            out[name + "_scalars"] = np.array([res['threshold_z'], res['asdef'], res['aasdef']], dtype=float)
+            print(name, "calls", out[name + "_calls"].shape[0], "cwz", out[name + "_cwz"].shape, "threshold", float(res['threshold_z']))
+        np.savez_compressed(os.path.join(HERE, "tiny_cli_flags.npz"), **out)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     if not os.path.isfile(os.path.join(REF, "wisetools.py")):
         rc = subprocess.call([sys.executable, os.path.join(ROOT, "oracle", "make_ref.py")])
@@ -314,6 +368,9 @@ def main():
             return 1
     if '--report-only' in sys.argv:
         golden_report()
+        return 0
+    if '--flags-only' in sys.argv:
+        golden_cli_tiny_flags()
         return 0
     if '--mineff-only' in sys.argv:
         golden_cli_tiny_mineff()
@@ -326,6 +383,7 @@ def main():
     golden_report()
     golden_segmin_nonfinite()
     golden_cli_tiny_mineff()
+    golden_cli_tiny_flags()
     return 0
 
 

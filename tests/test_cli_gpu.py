@@ -173,6 +173,33 @@ def test_test_tool_with_mineffectsize_matches_reference(workdir, tiny):
     assert fewer >= 2
 
 
+def test_test_tool_flags_and_rescaled_sample_match_reference(workdir, tiny):
+    """`test` with -chromosomes / -minzscore / -multitest / -repeats and with a sample binned at half the reference's bin
+    size (scaleSample, wisetools.py:20-44) against the reference CLI's own output on the same files
+    (tests/golden/tiny_cli_flags.npz, make_golden.golden_cli_tiny_flags)."""
+    from make_golden import FLAG_VARIANTS, TINY_BINSIZE, split_counts, write_sample_npz
+    gold = np.load(os.path.join(GOLD, "tiny_cli_flags.npz"), allow_pickle=True)
+    bins = [int(b) for b in tiny['bins']]
+    for name, t, sample_binsize, extra in FLAG_VARIANTS:
+        infile = str(workdir / (name + ".npz"))
+        if sample_binsize is None:
+            write_sample_npz(infile, tiny['test_counts'][t], bins, TINY_BINSIZE)
+        else:
+            fine, nb = split_counts(tiny['test_counts'][t], bins)
+            write_sample_npz(infile, fine, nb, sample_binsize)
+        out = str(workdir / (name + "_o.npz"))
+        _run(["test", infile, out, str(workdir / "goldref.npz"), "-minrefbins", "10"] + extra)
+        res = np.load(out, allow_pickle=True)
+        _close(np.concatenate(list(res['results_z'])), gold[name + '_z'])
+        _close(np.asarray(res['results_cwz'], dtype=float), gold[name + '_cwz'])
+        calls = np.asarray(res['results_calls'], dtype=float).reshape(-1, 5)
+        want = gold[name + '_calls']
+        assert calls.shape == want.shape, name
+        assert np.array_equal(calls[:, :3], want[:, :3]), name
+        _close(calls[:, 3:], want[:, 3:])
+        _close([res['threshold_z'], res['asdef'], res['aasdef']], gold[name + '_scalars'])
+
+
 def test_testbatch_equals_single_runs(workdir, tiny):
     outdir = str(workdir / "batch")
     tests = [str(workdir / ("t%d.npz" % t)) for t in (0, 1, 3)]
