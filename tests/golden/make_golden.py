@@ -360,6 +360,28 @@ def golden_cli_tiny_flags():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def golden_cli_tiny_prep_binsize():
+    """The reference's `newrefprep -binsize 2000000` on the tiny genome's 1 Mb reference samples (every sample rescaled by
+    scaleSample before the mask / PCA, wisecondor.py:99-101)."""
+    tiny = np.load(os.path.join(HERE, "tiny_cli.npz"), allow_pickle=True)
+    bins = [int(b) for b in tiny['bins']]
+    tmp = tempfile.mkdtemp(prefix="wc_golden_")
+    try:
+        names = []
+        for i in range(tiny['ref_counts'].shape[0]):
+            names.append("r%02d.npz" % i)
+            write_sample_npz(os.path.join(tmp, names[-1]), tiny['ref_counts'][i], bins, TINY_BINSIZE)
+        run_ref_cli(["newrefprep"] + names + ["prep2.npz", "-binsize", "2000000"], tmp)
+        prep = np.load(os.path.join(tmp, "prep2.npz"), allow_pickle=True)
+        np.savez_compressed(os.path.join(HERE, "tiny_cli_prep_binsize.npz"), binsize=prep['binsize'], mask=prep['mask'],
+                            chromosomeBins=prep['chromosomeBins'], maskedChromBins=prep['maskedChromBins'],
+                            maskedChromBinSums=prep['maskedChromBinSums'], maskedData=np.ascontiguousarray(prep['maskedData']),
+                            correctedData=np.ascontiguousarray(prep['correctedData']))
+        print("tiny_cli_prep_binsize.npz: binsize", prep['binsize'], "bins", list(prep['chromosomeBins'])[:4], "masked", int(sum(prep['maskedChromBins'])))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     if not os.path.isfile(os.path.join(REF, "wisetools.py")):
         rc = subprocess.call([sys.executable, os.path.join(ROOT, "oracle", "make_ref.py")])
@@ -368,6 +390,9 @@ def main():
             return 1
     if '--report-only' in sys.argv:
         golden_report()
+        return 0
+    if '--prep-binsize-only' in sys.argv:
+        golden_cli_tiny_prep_binsize()
         return 0
     if '--flags-only' in sys.argv:
         golden_cli_tiny_flags()
@@ -384,6 +409,7 @@ def main():
     golden_segmin_nonfinite()
     golden_cli_tiny_mineff()
     golden_cli_tiny_flags()
+    golden_cli_tiny_prep_binsize()
     return 0
 
 

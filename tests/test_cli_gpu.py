@@ -117,6 +117,23 @@ def test_newref_cluster_steps_match_reference(workdir, tiny):
     assert np.array_equal(r['indexes'], oidx) and np.array_equal(r['distances'], odst)
 
 
+def test_newrefprep_with_binsize_matches_reference(workdir, tiny):
+    """`newrefprep -binsize 2000000` on 1 Mb samples (scaleSample on every sample before the mask and the PCA,
+    wisecondor.py:99-101) against the reference CLI's prep file (tests/golden/tiny_cli_prep_binsize.npz)."""
+    gold = np.load(os.path.join(GOLD, "tiny_cli_prep_binsize.npz"), allow_pickle=True)
+    refs = [str(workdir / ("r%02d.npz" % i)) for i in range(tiny['ref_counts'].shape[0])]
+    prep = str(workdir / "prep2.npz")
+    _run(["newrefprep"] + refs + [prep, "-binsize", "2000000"])
+    p = np.load(prep, allow_pickle=True)
+    assert p['binsize'].item() == gold['binsize'].item() == 2000000
+    assert np.array_equal(p['mask'], gold['mask'])
+    assert np.array_equal(p['chromosomeBins'], gold['chromosomeBins'])
+    assert np.array_equal(p['maskedChromBins'], gold['maskedChromBins'])
+    assert np.array_equal(p['maskedChromBinSums'], gold['maskedChromBinSums'])
+    assert np.array_equal(p['maskedData'], gold['maskedData'])
+    _close(p['correctedData'], gold['correctedData'])
+
+
 def test_newref_single_command_resumes_and_cleans_up(workdir, tiny):
     refs = [str(workdir / ("r%02d.npz" % i)) for i in range(tiny['ref_counts'].shape[0])]
     out = str(workdir / "whole.npz")
